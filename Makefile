@@ -1,0 +1,45 @@
+# Build recipe (also driven by __graft_entry__.build()).
+#   make lib      -> birdnest/audio_b200/libbnflac.so   (the product: sm_100a CUDA + C ABI)
+#   make oracle   -> oracle/_build/liboracle.so, flac_oracle   (test infrastructure)
+#   make corpus   -> corpus/_build/libbncorpus.so, bncorpus     (synthetic stream generator)
+#   make ref      -> oracle/_ref/refflac + LibFlac.dll copy      (only where /root/reference exists)
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall -Xptxas -v
+CSRC := birdnest/audio_b200/csrc
+LIB := birdnest/audio_b200/libbnflac.so
+
+all: lib oracle corpus host
+
+lib: $(LIB)
+$(LIB): $(CSRC)/kernels.cu $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/kernels.cu $(CSRC)/engine.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
+	@grep -E "error|warning" $(CSRC)/ptxas.log | grep -v "ptxas info" || true
+
+host: birdnest/audio_b200/flacdecoder_demo
+birdnest/audio_b200/flacdecoder_demo: $(CSRC)/flac_decoder.hpp $(CSRC)/flac_decoder_demo.cpp $(LIB)
+	g++ -O2 -std=c++17 -Wall -Iinclude -o $@ $(CSRC)/flac_decoder_demo.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
+
+oracle: oracle/_build/liboracle.so oracle/_build/flac_oracle
+oracle/_build/liboracle.so: oracle/flac_oracle.c oracle/flac_oracle.h
+	@mkdir -p oracle/_build
+	gcc -O3 -fPIC -shared -Wall -o $@ oracle/flac_oracle.c
+oracle/_build/flac_oracle: oracle/flac_oracle.c oracle/flac_oracle.h
+	@mkdir -p oracle/_build
+	gcc -O3 -Wall -DFO_MAIN -o $@ oracle/flac_oracle.c
+
+corpus: corpus/_build/libbncorpus.so corpus/_build/bncorpus
+corpus/_build/libbncorpus.so: corpus/bncorpus.c corpus/bncorpus.h
+	@mkdir -p corpus/_build
+	gcc -O3 -fPIC -shared -w -o $@ corpus/bncorpus.c -lm -lpthread
+corpus/_build/bncorpus: corpus/bncorpus.c corpus/bncorpus.h
+	@mkdir -p corpus/_build
+	gcc -O3 -w -DBNC_MAIN -o $@ corpus/bncorpus.c -lm -lpthread
+
+ref:
+	$(MAKE) -C oracle/refdll
+
+clean:
+	rm -rf $(LIB) oracle/_build corpus/_build birdnest/audio_b200/flacdecoder_demo
+
+.PHONY: all lib oracle corpus ref clean host

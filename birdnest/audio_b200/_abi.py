@@ -1,0 +1,272 @@
+"""ctypes binding of include/bnflac.h -- the same entry points the C# P/Invoke shim binds.
+
+The library is loaded lazily from this directory (libbnflac.so, built in-tree by `make lib` /
+__graft_entry__.build()).  A missing library is a hard error: there is no Python or CPU decode path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[C.CDLL] = None
+
+STATE_NAMES = ["SearchForMetadata", "ReadMetadata", "SearchForFrameSync", "ReadFrame", "EndOfStream", "OggError",
+               "SeekError", "Aborted", "MemoryAllocationError", "Uninitialized"]
+AL_FORMAT_NAMES = {0: "None", 0x1100: "Mono8", 0x1101: "Mono16", 0x1102: "Stereo8", 0x1103: "Stereo16"}
+
+ERR_ARG, ERR_NOT_FLAC, ERR_TRUNCATED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY, ERR_CAPACITY, ERR_ABORTED, ERR_UNSUPPORTED, ERR_STATE = range(-1, -11, -1)
+OPT_VERIFY_MD5 = 1
+
+
+class Opts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("shard_index", C.c_uint32),
+                ("shard_count", C.c_uint32), ("flags", C.c_uint32), ("read_chunk_frames", C.c_uint32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("min_blocksize", C.c_uint32), ("max_blocksize", C.c_uint32), ("min_framesize", C.c_uint32), ("max_framesize", C.c_uint32),
+                ("block_align", C.c_uint32), ("al_format", C.c_uint32), ("bytes_per_sample", C.c_uint32),
+                ("total_samples", C.c_uint64), ("pcm_bytes", C.c_uint64), ("length_reference", C.c_uint64),
+                ("duration_seconds", C.c_double), ("md5", C.c_uint8 * 16), ("first_frame_offset", C.c_uint64)]
+
+
+class FrameRec(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("length", C.c_uint32), ("blocksize", C.c_uint32), ("channels", C.c_uint8),
+                ("bits_per_sample", C.c_uint8), ("assignment", C.c_uint8), ("status", C.c_uint8), ("pad", C.c_uint32),
+                ("number", C.c_uint64), ("pcm_offset", C.c_uint64)]
+
+
+class SubframeRec(C.Structure):
+    _fields_ = [("bit_offset", C.c_uint32), ("type", C.c_uint8), ("order", C.c_uint8), ("wasted", C.c_uint8), ("flags", C.c_uint8)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("total", C.c_float), ("scan", C.c_float), ("crc", C.c_float), ("link", C.c_float), ("parse", C.c_float),
+                ("decode", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class Span(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("len", C.c_size_t)]
+
+
+class ClipResult(C.Structure):
+    _fields_ = [("pcm_offset", C.c_uint64), ("pcm_bytes", C.c_uint64), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("status", C.c_uint32), ("total_samples", C.c_uint64)]
+
+
+READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_size_t))
+
+# every symbol include/bnflac.h declares (tests check the export list against the header)
+_PROTOS = {
+    "bnflac_open_memory": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
+    "bnflac_open_callbacks": (C.c_int, [READ_CB, C.c_void_p, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
+    "bnflac_open_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
+    "bnflac_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "bnflac_state": (C.c_int, [C.c_void_p]),
+    "bnflac_close": (None, [C.c_void_p]),
+    "bnflac_read": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "bnflac_decode_all": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "bnflac_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "bnflac_decoded_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "bnflac_decode_batch": (C.c_int, [C.POINTER(Span), C.c_size_t, C.POINTER(Opts), C.c_void_p, C.c_size_t, C.c_int, C.POINTER(ClipResult), C.POINTER(C.c_uint64)]),
+    "bnflac_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(FrameRec)), C.POINTER(C.c_size_t)]),
+    "bnflac_subframes": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(SubframeRec)), C.POINTER(C.c_size_t)]),
+    "bnflac_errors": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
+    "bnflac_last_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "bnflac_strerror": (C.c_char_p, [C.c_int]),
+    "bnflac_state_name": (C.c_char_p, [C.c_int]),
+    "bnflac_frame_status_name": (C.c_char_p, [C.c_int]),
+    "bnflac_last_cuda_error": (C.c_char_p, []),
+    "bnflac_abi_version": (C.c_int, []),
+    "bnflac_device_count": (C.c_int, []),
+    "bnflac_kernel_launches": (C.c_uint64, []),
+}
+
+
+def lib_path() -> str:
+    return os.environ.get("BNFLAC_LIB", os.path.join(_HERE, "libbnflac.so"))
+
+
+def lib() -> C.CDLL:
+    """Load libbnflac.so (fails loudly if it has not been built: no fallback exists)."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not found: build it with `make lib` or __graft_entry__.build(); "
+                               "birdnest.audio_b200 has no CPU/Python decode path")
+        L = C.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class BnflacError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        L = lib()
+        msg = L.bnflac_strerror(code).decode()
+        if code == ERR_CUDA:
+            msg += ": " + L.bnflac_last_cuda_error().decode()
+        super().__init__(f"{where}: {msg} ({code})")
+        self.code = code
+
+
+def _check(rc: int, where: str) -> None:
+    if rc != 0:
+        raise BnflacError(rc, where)
+
+
+def _opts(device=-1, stream=0, shard_index=0, shard_count=0, flags=0) -> Opts:
+    o = Opts()
+    o.struct_size = C.sizeof(Opts)
+    o.device = device
+    o.stream = stream or None
+    o.shard_index = shard_index
+    o.shard_count = shard_count
+    o.flags = flags
+    return o
+
+
+def _addr(buf) -> int:
+    """Address of a writable/readable buffer: bytes, bytearray, numpy array, torch tensor (cpu) or int."""
+    if isinstance(buf, int):
+        return buf
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr()
+    if hasattr(buf, "ctypes"):
+        return buf.ctypes.data
+    if isinstance(buf, (bytes,)):
+        return C.cast(C.c_char_p(buf), C.c_void_p).value
+    return C.addressof((C.c_uint8 * len(buf)).from_buffer(buf))
+
+
+class Handle:
+    """Thin owner of a bnflac_t*."""
+
+    def __init__(self, ptr: int, keep=None):
+        self._p = C.c_void_p(ptr)
+        self._keep = keep
+
+    def close(self):
+        if self._p:
+            lib().bnflac_close(self._p)
+            self._p = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self) -> Info:
+        i = Info()
+        _check(lib().bnflac_info(self._p, C.byref(i)), "bnflac_info")
+        return i
+
+    def state(self) -> int:
+        return lib().bnflac_state(self._p)
+
+    def read_into(self, buf, count: Optional[int] = None) -> int:
+        n = len(buf) if count is None else count
+        r = lib().bnflac_read(self._p, _addr(buf), n)
+        if r < 0:
+            raise BnflacError(int(r), "bnflac_read")
+        return int(r)
+
+    def decode_all(self, buf=None) -> bytes | int:
+        """Decode to host memory.  With buf=None allocates a bytearray of the needed size and returns it."""
+        if buf is None:
+            size = self.decoded_size()
+            out = bytearray(size)
+            w = C.c_uint64()
+            if size:
+                _check(lib().bnflac_decode_all(self._p, _addr(out), size, C.byref(w)), "bnflac_decode_all")
+            return bytes(out[:w.value])
+        w = C.c_uint64()
+        n = buf.numel() * buf.element_size() if hasattr(buf, "numel") else len(buf)
+        _check(lib().bnflac_decode_all(self._p, _addr(buf), n, C.byref(w)), "bnflac_decode_all")
+        return int(w.value)
+
+    def decoded_size(self) -> int:
+        w = C.c_uint64()
+        _check(lib().bnflac_decoded_size(self._p, C.byref(w)), "bnflac_decoded_size")
+        return int(w.value)
+
+    def decode_device(self, d_dst: int = 0, cap: int = 0):
+        """Decode leaving the PCM in device memory; returns (device_ptr, bytes)."""
+        out = C.c_void_p()
+        w = C.c_uint64()
+        _check(lib().bnflac_decode_device(self._p, d_dst or None, cap, C.byref(out), C.byref(w)), "bnflac_decode_device")
+        return out.value, int(w.value)
+
+    def frames(self):
+        p = C.POINTER(FrameRec)()
+        n = C.c_size_t()
+        _check(lib().bnflac_frames(self._p, C.byref(p), C.byref(n)), "bnflac_frames")
+        return [p[i] for i in range(n.value)]
+
+    def subframes(self):
+        p = C.POINTER(SubframeRec)()
+        n = C.c_size_t()
+        _check(lib().bnflac_subframes(self._p, C.byref(p), C.byref(n)), "bnflac_subframes")
+        return [p[i] for i in range(n.value)]
+
+    def errors(self):
+        p = C.POINTER(C.c_uint32)()
+        n = C.c_size_t()
+        _check(lib().bnflac_errors(self._p, C.byref(p), C.byref(n)), "bnflac_errors")
+        return [int(p[i]) for i in range(n.value)]
+
+    def timing(self) -> Timing:
+        t = Timing()
+        _check(lib().bnflac_last_timing(self._p, C.byref(t)), "bnflac_last_timing")
+        return t
+
+
+def open_memory(data, device=-1, stream=0, shard_index=0, shard_count=0, flags=0) -> Handle:
+    o = _opts(device, stream, shard_index, shard_count, flags)
+    h = C.c_void_p()
+    n = data.numel() * data.element_size() if hasattr(data, "numel") else len(data)
+    _check(lib().bnflac_open_memory(_addr(data), n, C.byref(o), C.byref(h)), "bnflac_open_memory")
+    return Handle(h.value)
+
+
+def open_device(d_ptr: int, length: int, header: bytes, device=-1, stream=0, shard_index=0, shard_count=0, keep=None) -> Handle:
+    o = _opts(device, stream, shard_index, shard_count, 0)
+    h = C.c_void_p()
+    _check(lib().bnflac_open_device(d_ptr, length, _addr(header), len(header), C.byref(o), C.byref(h)), "bnflac_open_device")
+    return Handle(h.value, keep=(keep, header))
+
+
+def open_callbacks(read_fn, device=-1) -> Handle:
+    """read_fn(n) -> bytes (b'' at end of stream); mirrors the pull model of FLACDecoder.ReadCallback."""
+    def _cb(user, buf, nbytes):
+        want = nbytes[0]
+        try:
+            chunk = read_fn(want)
+        except Exception:
+            return 2
+        if chunk is None:
+            return 2
+        k = len(chunk)
+        if k:
+            C.memmove(buf, chunk, k)
+        nbytes[0] = k
+        return 1 if k < want else 0
+    cb = READ_CB(_cb)
+    o = _opts(device)
+    h = C.c_void_p()
+    _check(lib().bnflac_open_callbacks(cb, None, C.byref(o), C.byref(h)), "bnflac_open_callbacks")
+    return Handle(h.value)

@@ -1,0 +1,112 @@
+// bnflac_dev.h -- device-side tables shared by the kernels (kernels.cu) and the host engine (engine.cu).
+//
+// Data layout in HBM for one pipeline pass (one stream, one shard of a stream, or a batch of clips):
+//   in        : compressed bytes of every segment back to back, each segment start 16-byte aligned,
+//               64 zero bytes of padding after the last byte (bit readers may over-read, never fault)
+//   SegInfo[] : one per segment (= one FLAC stream or one shard of it)
+//   Chunk[]   : scan work units (<= SCAN_CHUNK bytes of one segment), built on the host
+//   Cand[]    : frame table, sorted by byte offset (K1 output)
+//   per-candidate arrays: seg_crc, next, flen, status, pcm_off, acc_idx, sub_bitoff[8]
+//   out       : interleaved little-endian packed PCM, frames back to back in stream order
+#pragma once
+#include <stdint.h>
+
+namespace bnf {
+
+constexpr int SCAN_CHUNK = 32768;      // bytes per scan CTA
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_SCAP = 4096;        // max frame candidates per chunk (min frame is 10 bytes -> 3277)
+constexpr int MAX_CH = 8;
+
+// per-candidate status
+enum : uint8_t {
+    ST_OK = 0,
+    ST_LOST = 1,         // (host side only) gap before this frame
+    ST_CRC = 3,          // CRC-16 mismatch: frame is delivered zero-filled (reference behaviour)
+    ST_UNPARSEABLE = 4,  // reserved field used: frame is skipped
+    ST_CHECK = 0xFE,     // span check inconclusive: K2 validates by parsing
+    ST_DROP = 0xFF       // false sync / covered by another frame
+};
+
+struct SegInfo {
+    uint64_t begin, end;          // byte range of frame data inside `in`
+    uint64_t own_begin, own_end;  // frames whose sync lies in [own_begin, own_end) belong to this shard
+    uint32_t bps, channels, sample_rate, min_bs, max_bs;
+    uint32_t max_frame_bytes;     // upper bound used when extending a CRC span over false syncs
+    uint32_t pad[2];
+};
+
+struct Chunk {
+    uint64_t begin;
+    uint32_t len;
+    uint32_t seg;
+};
+
+struct Cand {               // 32 bytes
+    uint64_t off;           // absolute byte offset of the sync code inside `in`
+    uint64_t number;        // coded frame number (fixed blocksize) or sample number (variable)
+    uint32_t bs;            // blocksize
+    uint32_t seg;
+    uint8_t hdr_len, bps, assign, flags;   // flags bit0: variable blocksize
+    uint32_t sample_rate;
+};
+
+struct SubInfo {            // K2 output, 8 bytes per (frame, channel)
+    uint32_t bit_offset;    // bit offset of the subframe header from the frame's first byte
+    uint8_t type;           // 0 CONSTANT 1 VERBATIM 2 FIXED 3 LPC
+    uint8_t order;
+    uint8_t wasted;
+    uint8_t flags;          // bit0: narrow (32-bit) accumulate per libFLAC's width rule; bit1: Rice2
+};
+
+struct Totals {             // written by the prefix-sum kernel
+    uint64_t pcm_bytes;     // bytes the pass produces
+    uint32_t n_accepted;    // frames delivered (OK or zero-filled)
+    uint32_t n_cand;        // candidates in the table
+    uint32_t overflow;      // bit0 scan-chunk overflow, bit1 candidate-table overflow
+    uint32_t max_order;     // largest predictor order among accepted frames
+    uint32_t any_wide;      // some LPC subframe needs 64-bit accumulation
+    uint32_t max_bs;
+};
+
+struct PassArgs {
+    const uint8_t* in;
+    uint64_t in_len;
+    const SegInfo* segs;
+    uint32_t nsegs;
+    const Chunk* chunks;
+    uint32_t nchunks;
+    // K1
+    Cand* cand_tmp;
+    Cand* cand;
+    uint32_t cand_cap;
+    uint32_t* chunk_base;
+    uint32_t* chunk_count;
+    uint32_t* chunk_scan;
+    uint32_t* counters;     // [0] total candidates appended, [1] overflow flags
+    uint16_t* seg_crc;
+    uint32_t* next;
+    uint32_t* flen;
+    uint8_t* status;
+    // K2
+    SubInfo* sub;
+    // prefix
+    uint64_t* pcm_off;
+    uint32_t* acc_idx;
+    Totals* totals;
+    // K3-5
+    uint8_t* out;
+    uint64_t out_cap;
+};
+
+// launchers (kernels.cu); all asynchronous on `stream`
+void launch_scan(const PassArgs& a, void* stream);
+void launch_order(const PassArgs& a, void* stream);
+void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
+void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
+void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
+void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream);
+void launch_decode(const PassArgs& a, uint32_t nacc_bound, uint32_t channels, uint32_t bytes_per_sample, uint32_t max_order, void* stream);
+int kernel_launch_count();   // kernels launched so far by this process (bench "gpu_launches")
+
+} // namespace bnf

@@ -1,0 +1,759 @@
+// kernels.cu -- sm_100a kernels of the bnflac decode pipeline (no tensor cores: nothing here is a contraction).
+//
+//   K1  k_scan      frame-sync scan (0xFFF8/0xFFF9) + header syntax + CRC-8  -> per-chunk sorted candidate lists
+//       k_chunk_scan / k_gather   order the per-chunk lists into one frame table
+//       k_crc       CRC-16 of every inter-candidate span (warp per span, GF(2) combine of lane pieces)
+//       k_link      span validation (CRC residue 0 + frame/sample-number continuity), false-sync elimination
+//   K2  k_parse     subframe header parse (CONSTANT / VERBATIM / FIXED 0-4 / LPC 1-32, wasted bits) and residual
+//                   skip: finds where every subframe starts, so K3-5 can run one thread per (frame, channel)
+//       k_prefix    accepted-frame compaction + PCM byte offsets
+//   K3-5 k_decode   Rice/Rice2/escape residual decode + FIXED/LPC restore (coefficients + history in registers)
+//                   + stereo decorrelation (warp shuffle between the two channel lanes) + interleave + 8/16/24-bit
+//                   little-endian pack, staged through shared memory into coalesced word stores
+//
+// Replaces what the reference reaches through FLAC__stream_decoder_process_single (LibFLACSharp.cs:54-55,
+// FLACDecoder.cs:215) and the interleave loops FLACDecoder.cs:552-576 / FLACFileReader.cs:214-243.
+#include "bnflac_dev.h"
+#include <cuda_runtime.h>
+
+namespace bnf {
+
+static int g_launches = 0;
+int kernel_launch_count() { return g_launches; }
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------ CRC helpers
+__device__ __forceinline__ uint32_t crc8_update(uint32_t c, uint32_t byte) {
+    c ^= byte;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c = (c & 0x80) ? ((c << 1) ^ 0x07) & 0xFF : (c << 1) & 0xFF;
+    return c;
+}
+__device__ __forceinline__ uint32_t crc16_update_bitwise(uint32_t c, uint32_t byte) {
+    c ^= byte << 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
+    return c;
+}
+// product of two residues modulo x^16 + x^15 + x^2 + 1
+__device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 15; i >= 0; --i) {
+        r <<= 1;
+        if (r & 0x10000u) r ^= 0x18005u;
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r & 0xFFFFu;
+}
+// x^(8*nbytes) mod P : appending nbytes bytes to a message multiplies its CRC by this
+__device__ uint32_t gf_xpow8(uint32_t nbytes) {
+    uint32_t result = 1, base = 0x100;
+    while (nbytes) {
+        if (nbytes & 1u) result = gf_mul(result, base);
+        base = gf_mul(base, base);
+        nbytes >>= 1;
+    }
+    return result;
+}
+
+// ------------------------------------------------------------------------------------------------ frame header
+struct Hdr {
+    uint64_t number;
+    uint32_t bs, sample_rate;
+    uint32_t hdr_len, bps, assign, variable, channels;
+};
+
+// Frame header syntax + CRC-8.  p must have 17 readable bytes.
+__device__ bool parse_header(const uint8_t* __restrict__ p, const SegInfo& s, Hdr& h) {
+    if (p[0] != 0xFF || (p[1] & 0xFE) != 0xF8) return false;
+    uint32_t b2 = p[2], b3 = p[3];
+    uint32_t bsc = b2 >> 4, src = b2 & 15, ca = b3 >> 4, ssc = (b3 >> 1) & 7;
+    if ((b3 & 1) || bsc == 0 || src == 15 || ca > 10 || ssc == 3 || ssc == 7) return false;
+    h.variable = p[1] & 1;
+    uint32_t q = 4;
+    uint32_t x = p[q++];
+    uint64_t num;
+    if (x < 0x80) num = x;
+    else {
+        int n = __clz(~(x << 24));   // leading ones
+        if (n == 1 || n > 7 || (!h.variable && n == 7)) return false;
+        num = (n == 7) ? 0 : (x & ((1u << (7 - n)) - 1));
+        for (int i = 1; i < n; i++) {
+            uint32_t y = p[q++];
+            if ((y >> 6) != 2) return false;
+            num = (num << 6) | (y & 0x3f);
+        }
+    }
+    h.number = num;
+    uint32_t bs;
+    if (bsc == 1) bs = 192;
+    else if (bsc <= 5) bs = 576u << (bsc - 2);
+    else if (bsc == 6) { bs = p[q] + 1u; q += 1; }
+    else if (bsc == 7) { bs = ((uint32_t)p[q] << 8 | p[q + 1]) + 1u; q += 2; }
+    else bs = 256u << (bsc - 8);
+    uint32_t sr;
+    switch (src) {
+    case 0: sr = s.sample_rate; break;
+    case 1: sr = 88200; break; case 2: sr = 176400; break; case 3: sr = 192000; break; case 4: sr = 8000; break;
+    case 5: sr = 16000; break; case 6: sr = 22050; break; case 7: sr = 24000; break; case 8: sr = 32000; break;
+    case 9: sr = 44100; break; case 10: sr = 48000; break; case 11: sr = 96000; break;
+    case 12: sr = p[q] * 1000u; q += 1; break;
+    case 13: sr = (uint32_t)p[q] << 8 | p[q + 1]; q += 2; break;
+    default: sr = ((uint32_t)p[q] << 8 | p[q + 1]) * 10u; q += 2; break;
+    }
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < q; i++) c = crc8_update(c, p[i]);
+    if (c != p[q]) return false;
+    q++;
+    h.bs = bs; h.sample_rate = sr; h.hdr_len = q; h.assign = ca;
+    h.channels = ca < 8 ? ca + 1 : 2;
+    static const uint8_t sst[8] = {0, 8, 12, 0, 16, 20, 24, 0};
+    h.bps = ssc == 0 ? s.bps : sst[ssc];
+    // the engine decodes streams whose frames agree with STREAMINFO (every real encoder; per-frame channel/bps
+    // changes are treated as false syncs)
+    if (h.channels != s.channels || h.bps != s.bps) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ K1a scan
+__device__ __forceinline__ uint32_t bytemask4(uint32_t eq) {   // 0xFF/0x00 per byte -> 4-bit mask
+    uint32_t x = (eq & 0x80808080u) >> 7;
+    return (x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xFu;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(PassArgs a) {
+    __shared__ uint32_t s_list[SCAN_SCAP];
+    __shared__ uint32_t s_sorted[SCAN_SCAP];
+    __shared__ uint32_t s_n, s_base;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t chunk = blockIdx.x; chunk < a.nchunks; chunk += gridDim.x) {
+        const Chunk c = a.chunks[chunk];
+        const SegInfo seg = a.segs[c.seg];
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        const uint64_t abeg = c.begin & ~15ull;
+        const uint32_t nunits = (uint32_t)((c.begin + c.len - abeg + 15) >> 4);
+        const uint32_t nloop = (nunits + 31) & ~31u;
+        for (uint32_t u = tid; u < nloop; u += SCAN_THREADS) {
+            const bool valid = u < nunits;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) v = __ldg(reinterpret_cast<const uint4*>(a.in + abeg) + u);
+            uint32_t nextb = __shfl_down_sync(FULL, v.x & 0xFFu, 1);
+            if (valid && (lane == 31 || u + 1 >= nunits)) nextb = a.in[abeg + 16ull * (u + 1)];   // padded input: always readable
+            uint32_t ff = bytemask4(__vcmpeq4(v.x, 0xFFFFFFFFu)) | bytemask4(__vcmpeq4(v.y, 0xFFFFFFFFu)) << 4 |
+                          bytemask4(__vcmpeq4(v.z, 0xFFFFFFFFu)) << 8 | bytemask4(__vcmpeq4(v.w, 0xFFFFFFFFu)) << 12;
+            if (ff) {
+                const uint32_t m = 0xFEFEFEFEu, k = 0xF8F8F8F8u;
+                uint32_t f8 = bytemask4(__vcmpeq4(v.x & m, k)) | bytemask4(__vcmpeq4(v.y & m, k)) << 4 |
+                              bytemask4(__vcmpeq4(v.z & m, k)) << 8 | bytemask4(__vcmpeq4(v.w & m, k)) << 12;
+                if ((nextb & 0xFE) == 0xF8) f8 |= 1u << 16;
+                uint32_t hits = ff & (f8 >> 1);
+                while (hits) {
+                    int p = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    uint64_t o = abeg + 16ull * u + p;
+                    if (o < c.begin || o >= c.begin + c.len) continue;
+                    Hdr h;
+                    if (!parse_header(a.in + o, seg, h)) continue;
+                    if (o + h.hdr_len + 2 > seg.end) continue;
+                    uint32_t slot = atomicAdd(&s_n, 1u);
+                    if (slot < SCAN_SCAP) s_list[slot] = (uint32_t)(o - c.begin);
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t n = s_n;
+        if (n > SCAN_SCAP) { n = SCAN_SCAP; if (tid == 0) atomicOr(&a.counters[1], 1u); }
+        // order the chunk's list by offset (n is ~chunk/frame size; rank sort)
+        for (uint32_t e = tid; e < n; e += SCAN_THREADS) {
+            uint32_t key = s_list[e], rank = 0;
+            for (uint32_t j = 0; j < n; j++) rank += (s_list[j] < key);
+            s_sorted[rank] = key;
+        }
+        if (tid == 0) {
+            uint32_t base = atomicAdd(&a.counters[0], n);
+            if (base + n > a.cand_cap) { atomicOr(&a.counters[1], 2u); n = base < a.cand_cap ? a.cand_cap - base : 0; }
+            s_base = base; s_n = n;
+            a.chunk_base[chunk] = base;
+            a.chunk_count[chunk] = n;
+        }
+        __syncthreads();
+        n = s_n;
+        for (uint32_t e = tid; e < n; e += SCAN_THREADS) {
+            uint64_t o = c.begin + s_sorted[e];
+            Hdr h;
+            parse_header(a.in + o, seg, h);
+            Cand cd;
+            cd.off = o; cd.number = h.number; cd.bs = h.bs; cd.seg = c.seg;
+            cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
+            cd.flags = (uint8_t)(h.variable | ((o < seg.own_begin || o >= seg.own_end) ? 2u : 0u));
+            cd.sample_rate = h.sample_rate;
+            a.cand_tmp[s_base + e] = cd;
+        }
+        __syncthreads();
+    }
+}
+
+// single-CTA exclusive scan of chunk_count -> chunk_scan
+__global__ void __launch_bounds__(1024) k_chunk_scan(PassArgs a) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t tid = threadIdx.x, n = a.nchunks;
+    const uint32_t per = (n + 1023) / 1024;
+    uint32_t b = tid * per, e = min(b + per, n), sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += a.chunk_count[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t v = tid >= d ? s_part[tid - d] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+    for (uint32_t i = b; i < e; i++) { a.chunk_scan[i] = run; run += a.chunk_count[i]; }
+}
+
+// move each chunk's (already sorted) list to its place in the global frame table
+__global__ void __launch_bounds__(256) k_gather(PassArgs a) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t chunk = warp; chunk < a.nchunks; chunk += nwarps) {
+        uint32_t n = a.chunk_count[chunk], src = a.chunk_base[chunk], dst = a.chunk_scan[chunk];
+        for (uint32_t r = lane; r < n; r += 32) a.cand[dst + r] = a.cand_tmp[src + r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1c CRC-16 of spans
+__device__ __forceinline__ uint32_t ncand(const PassArgs& a) { return min(a.counters[0], a.cand_cap); }
+
+__device__ __forceinline__ uint64_t span_end(const PassArgs& a, uint32_t i, uint32_t n, const Cand& ci) {
+    if (i + 1 < n) { const Cand& cn = a.cand[i + 1]; if (cn.seg == ci.seg) return cn.off; }
+    return a.segs[ci.seg].end;
+}
+
+__global__ void __launch_bounds__(256) k_crc(PassArgs a) {
+    __shared__ uint16_t s_tab[256];
+    {
+        uint32_t d = (uint32_t)threadIdx.x << 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) d = (d & 0x8000) ? ((d << 1) ^ 0x8005) & 0xFFFF : (d << 1) & 0xFFFF;
+        s_tab[threadIdx.x] = (uint16_t)d;
+    }
+    __syncthreads();
+    const uint32_t n = ncand(a);
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += nwarps) {
+        const Cand ci = a.cand[i];
+        const uint64_t e = span_end(a, i, n, ci);
+        const int64_t L = (int64_t)(e - ci.off);
+        const int64_t m = (L + 31) >> 5;
+        // zero bytes in front of a message do not change its CRC: lane pieces are laid out from the END so that all
+        // (virtual) pieces have the same length m and one factor x^(8m) serves the whole combine tree
+        int64_t pb = L - (int64_t)(32 - lane) * m, pe = pb + m;
+        if (pb < 0) pb = 0;
+        uint32_t crc = 0;
+        const uint8_t* p = a.in + ci.off;
+        for (int64_t b = pb; b < pe; b++) crc = ((crc << 8) ^ s_tab[(crc >> 8) ^ p[b]]) & 0xFFFF;
+        uint32_t f = gf_xpow8((uint32_t)m);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_down_sync(FULL, crc, d);
+            crc = gf_mul(crc, f) ^ o;
+            f = gf_mul(f, f);
+        }
+        if (lane == 0) a.seg_crc[i] = (uint16_t)crc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1d link / validate
+__device__ __forceinline__ bool continuous(const Cand& a, const Cand& b) {
+    if ((a.flags ^ b.flags) & 1) return false;
+    return (a.flags & 1) ? (b.number == a.number + a.bs) : (b.number == a.number + 1);
+}
+
+__global__ void __launch_bounds__(256) k_link(PassArgs a) {
+    const uint32_t n = ncand(a);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Cand ci = a.cand[i];
+    const SegInfo& sg = a.segs[ci.seg];
+    const uint64_t seg_end = sg.end;
+    const uint32_t max_frame = sg.max_frame_bytes;
+    uint32_t crc = a.seg_crc[i];
+    uint32_t j = i + 1;
+    uint8_t st = ST_DROP; uint32_t nx = i + 1; uint64_t fend = 0;
+    for (int tries = 0; tries < 64; tries++) {
+        const bool at_seg_end = !(j < n && a.cand[j].seg == ci.seg);
+        const uint64_t e = at_seg_end ? seg_end : a.cand[j].off;
+        if (crc == 0 && (at_seg_end || continuous(ci, a.cand[j]))) { st = ST_OK; nx = j; fend = e; break; }
+        if (at_seg_end || e - ci.off > max_frame) break;
+        // extend the span over candidate j (a false sync inside this frame)
+        const uint64_t e2 = (j + 1 < n && a.cand[j + 1].seg == ci.seg) ? a.cand[j + 1].off : seg_end;
+        crc = gf_mul(crc, gf_xpow8((uint32_t)(e2 - e))) ^ a.seg_crc[j];
+        j++;
+    }
+    if (st != ST_OK) {
+        // CRC failed: if a later candidate continues the numbering, this is a damaged frame (delivered zero-filled)
+        uint32_t k = i + 1;
+        for (;; k++) {
+            const bool at_seg_end = !(k < n && a.cand[k].seg == ci.seg);
+            if (at_seg_end) {
+                // last frame of the segment (or everything after is unrelated): K2 decides by parsing
+                if (seg_end - ci.off <= (uint64_t)max_frame + 65536) { st = ST_CHECK; nx = k; fend = seg_end; }
+                break;
+            }
+            if (a.cand[k].off - ci.off > max_frame) break;
+            if (continuous(ci, a.cand[k])) { st = ST_CRC; nx = k; fend = a.cand[k].off; break; }
+        }
+    }
+    a.status[i] = st;
+    a.next[i] = nx;
+    a.flen[i] = (uint32_t)(st == ST_DROP ? 0 : fend - ci.off);
+}
+
+// candidates that lie inside a validated frame are false syncs
+__global__ void __launch_bounds__(256) k_cover(PassArgs a) {
+    const uint32_t n = ncand(a);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (a.status[i] != ST_OK) return;
+    const uint32_t nx = a.next[i];
+    for (uint32_t j = i + 1; j < nx && j < n; j++) a.status[j] = ST_DROP;
+}
+
+// ------------------------------------------------------------------------------------------------ bit reader
+struct BitReader {
+    const uint32_t* wp;   // next 32-bit word to load
+    const uint32_t* wend; // first word past the (padded) input: loads beyond it read as zero
+    uint64_t buf;         // MSB-aligned window, at least 32 valid bits after every operation
+    int cnt;              // valid bits in buf
+
+    __device__ __forceinline__ uint32_t load() {
+        uint32_t w = wp < wend ? __ldg(wp) : 0u;
+        wp++;
+        return __byte_perm(w, 0, 0x0123);
+    }
+    __device__ __forceinline__ void set_limit(const uint8_t* base, uint64_t in_len) {
+        wend = reinterpret_cast<const uint32_t*>(base) + ((in_len + 3) >> 2);
+    }
+    __device__ __forceinline__ void init(const uint8_t* base, uint64_t bitpos) {
+        wp = reinterpret_cast<const uint32_t*>(base) + (bitpos >> 5);
+        uint32_t w0 = load(), w1 = load();
+        buf = ((uint64_t)w0 << 32) | w1;
+        cnt = 64;
+        int s = (int)(bitpos & 31);
+        if (s) skip(s);
+    }
+    __device__ __forceinline__ void skip(int n) {   // 0 <= n <= 32
+        buf <<= n;
+        cnt -= n;
+        if (cnt < 32) { buf |= (uint64_t)load() << (32 - cnt); cnt += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ uint32_t get(int n) {   // 0 <= n <= 32
+        uint32_t v = n ? (uint32_t)(buf >> (64 - n)) : 0u;
+        skip(n);
+        return v;
+    }
+    __device__ __forceinline__ int32_t gets(int n) {
+        int32_t v = n ? (int32_t)((int64_t)buf >> (64 - n)) : 0;
+        skip(n);
+        return v;
+    }
+    __device__ __forceinline__ uint64_t pos(const uint8_t* base) const {
+        return (uint64_t)(wp - reinterpret_cast<const uint32_t*>(base)) * 32 - (uint64_t)cnt;
+    }
+    // zeros before the terminating 1; `limit` bounds a runaway on damaged data
+    __device__ __forceinline__ uint32_t unary(uint32_t limit) {
+        uint32_t q = 0;
+        for (;;) {
+            uint32_t top = peek32();
+            if (top) { int z = __clz(top); skip(z + 1); return q + (uint32_t)z; }
+            q += 32; skip(32);
+            if (q > limit) return q;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ K2 parse
+// One thread per frame: walks the subframes, records where each starts and what it is, skips the residual.
+__device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
+
+__global__ void __launch_bounds__(128) k_parse(PassArgs a) {
+    const uint32_t n = ncand(a);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t st = a.status[i];
+    if (st != ST_OK && st != ST_CHECK) return;
+    const Cand c = a.cand[i];
+    if (c.flags & 2) return;   // frame belongs to the neighbouring shard (kept only as an end marker)
+    const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
+    const uint64_t frame_bit0 = c.off * 8;
+    const uint64_t end_bit = (c.off + a.flen[i]) * 8;
+    BitReader br;
+    br.set_limit(a.in, a.in_len);
+    br.init(a.in, frame_bit0 + 8ull * c.hdr_len);
+    bool bad = false, unparse = false;
+    uint32_t max_order = 0, any_wide = 0;
+    for (uint32_t ch = 0; ch < channels && !bad && !unparse; ch++) {
+        uint32_t bps = c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1u : 0u);
+        SubInfo si;
+        si.bit_offset = (uint32_t)(br.pos(a.in) - frame_bit0);
+        uint32_t x = br.get(8);
+        if (x & 0x80) { bad = true; break; }
+        uint32_t type = (x >> 1) & 0x3f, w = 0;
+        if (x & 1) { w = br.unary(64) + 1; if (w >= bps) { unparse = true; break; } bps -= w; }
+        si.wasted = (uint8_t)w; si.flags = 0; si.order = 0;
+        uint32_t order = 0; bool has_resid = false;
+        if (type == 0) { si.type = 0; br.skip(bps > 32 ? 32 : bps); }
+        else if (type == 1) {
+            si.type = 1;
+            // jump over blocksize * bps raw bits
+            uint64_t p = br.pos(a.in) + (uint64_t)c.bs * bps;
+            if (p > end_bit) { bad = true; break; }
+            br.init(a.in, p);
+        } else if (type >= 8 && type <= 12) { si.type = 2; order = type - 8; has_resid = true; }
+        else if (type >= 32) { si.type = 3; order = type - 31; has_resid = true; }
+        else { unparse = true; break; }
+        if (has_resid) {
+            si.order = (uint8_t)order;
+            if (order > c.bs) { unparse = true; break; }
+            if (order > max_order) max_order = order;
+            { uint64_t p = br.pos(a.in) + (uint64_t)order * bps; if (p > end_bit) { bad = true; break; } br.init(a.in, p); }
+            if (si.type == 3) {
+                uint32_t prec = br.get(4) + 1;
+                if (prec == 16) { unparse = true; break; }
+                int32_t shift = br.gets(5);
+                if (shift < 0) { unparse = true; break; }
+                uint64_t p = br.pos(a.in) + (uint64_t)order * prec;
+                br.init(a.in, p);
+                if (bps + prec + (uint32_t)ilog2u(order) <= 32) si.flags |= 1; else any_wide = 1;
+            } else si.flags |= 1;
+            uint32_t method = br.get(2);
+            if (method > 1) { unparse = true; break; }
+            if (method) si.flags |= 2;
+            const int plen = method ? 5 : 4; const uint32_t esc = method ? 31u : 15u;
+            uint32_t po = br.get(4);
+            uint32_t psize = c.bs >> po;
+            if (po > 0 ? psize < order : c.bs < order) { unparse = true; break; }
+            for (uint32_t p = 0; p < (1u << po) && !bad; p++) {
+                uint32_t cnt = (po == 0) ? c.bs - order : (p == 0 ? psize - order : psize);
+                uint32_t k = br.get(plen);
+                if (k == esc) {
+                    uint32_t nb = br.get(5);
+                    uint64_t q = br.pos(a.in) + (uint64_t)cnt * nb;
+                    if (q > end_bit) { bad = true; break; }
+                    br.init(a.in, q);
+                } else {
+                    for (uint32_t s = 0; s < cnt; s++) {
+                        uint32_t top = br.peek32();
+                        if (top) {
+                            int adv = __clz(top) + 1 + (int)k;       // <= 62
+                            if (adv > 32) { br.skip(32); adv -= 32; }
+                            br.skip(adv);
+                        } else {
+                            br.unary(1u << 16);
+                            br.skip((int)k);
+                            if (br.pos(a.in) > end_bit) { bad = true; break; }
+                        }
+                    }
+                    if (br.pos(a.in) > end_bit) { bad = true; break; }
+                }
+            }
+        }
+        a.sub[(uint64_t)i * MAX_CH + ch] = si;
+    }
+    if (!bad && !unparse) {
+        uint64_t p = (br.pos(a.in) + 7) & ~7ull;
+        if (st == ST_OK) {
+            if (p + 16 != end_bit) bad = true;     // parse disagrees with the CRC-validated span
+        } else {  // ST_CHECK: validate the way the reference does: CRC-16 over the bytes the parse consumed
+            if (p + 16 > end_bit) bad = true;
+            else {
+                const uint8_t* q = a.in + c.off;
+                uint32_t nbytes = (uint32_t)(p / 8 - c.off), crc = 0;
+                for (uint32_t b = 0; b < nbytes; b++) crc = crc16_update_bitwise(crc, q[b]);
+                uint32_t want = (uint32_t)q[nbytes] << 8 | q[nbytes + 1];
+                a.flen[i] = nbytes + 2;
+                st = (crc == want) ? ST_OK : ST_CRC;
+            }
+        }
+    }
+    if (unparse) st = ST_UNPARSEABLE;
+    else if (bad) st = (st == ST_CHECK) ? ST_DROP : ST_CRC;
+    a.status[i] = st;
+    if (st == ST_OK) {
+        if (max_order) atomicMax(&a.totals->max_order, max_order);
+        if (any_wide) atomicOr(&a.totals->any_wide, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ prefix
+__global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_sample) {
+    __shared__ uint64_t s_bytes[1024];
+    __shared__ uint32_t s_cnt[1024];
+    __shared__ uint32_t s_maxbs[32];
+    const uint32_t tid = threadIdx.x, n = ncand(a);
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = min(tid * per, n), e = min(b + per, n);
+    uint64_t bytes = 0; uint32_t cnt = 0, maxbs = 0;
+    for (uint32_t i = b; i < e; i++) {
+        uint8_t st = a.status[i];
+        const Cand& c = a.cand[i];
+        if ((st == ST_OK || st == ST_CRC) && !(c.flags & 2)) {
+            uint32_t ch = c.assign < 8 ? c.assign + 1u : 2u;
+            bytes += (uint64_t)c.bs * ch * bytes_per_sample; cnt++;
+            maxbs = max(maxbs, c.bs);
+        }
+    }
+    s_bytes[tid] = bytes; s_cnt[tid] = cnt;
+    maxbs = __reduce_max_sync(FULL, maxbs);
+    if ((tid & 31) == 0) s_maxbs[tid >> 5] = maxbs;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint64_t vb = tid >= d ? s_bytes[tid - d] : 0; uint32_t vc = tid >= d ? s_cnt[tid - d] : 0;
+        __syncthreads();
+        s_bytes[tid] += vb; s_cnt[tid] += vc;
+        __syncthreads();
+    }
+    uint64_t rb = s_bytes[tid] - bytes; uint32_t rc = s_cnt[tid] - cnt;
+    for (uint32_t i = b; i < e; i++) {
+        uint8_t st = a.status[i];
+        const Cand& c = a.cand[i];
+        if ((st == ST_OK || st == ST_CRC) && !(c.flags & 2)) {
+            uint32_t ch = c.assign < 8 ? c.assign + 1u : 2u;
+            a.pcm_off[i] = rb; a.acc_idx[rc] = i;
+            rb += (uint64_t)c.bs * ch * bytes_per_sample; rc++;
+        } else a.pcm_off[i] = rb;
+    }
+    if (tid == 1023) {
+        a.totals->pcm_bytes = s_bytes[1023]; a.totals->n_accepted = s_cnt[1023]; a.totals->n_cand = n;
+        a.totals->overflow = a.counters[1];
+    }
+    if (tid == 0) { uint32_t m = 0; for (int w = 0; w < 32; w++) m = max(m, s_maxbs[w]); a.totals->max_bs = m; }
+}
+
+// ------------------------------------------------------------------------------------------------ K3-5 decode
+constexpr int DEC_THREADS = 128;
+constexpr int DEC_T = 64;       // samples per channel staged per tile
+
+template <int ORD>
+struct SubDec {
+    BitReader br;
+    int32_t coef[ORD];
+    int32_t hist[ORD];          // hist[0] = most recent sample (before the wasted-bits shift)
+    uint32_t part_left, part_size;
+    int32_t cval;
+    int type, order, bps, wasted, shift, idx, k, plen, rawbits;
+    bool narrow, esc;
+
+    __device__ __forceinline__ void read_residual_header(uint32_t bs) {
+        uint32_t method = br.get(2);
+        plen = method ? 5 : 4;
+        uint32_t po = br.get(4);
+        part_size = bs >> po;
+        part_left = (po == 0 ? bs : part_size) - (uint32_t)order;
+        next_partition_params();
+    }
+    __device__ __forceinline__ void next_partition_params() {
+        uint32_t kk = br.get(plen);
+        esc = kk == (plen == 5 ? 31u : 15u);
+        k = (int)kk;
+        if (esc) rawbits = (int)br.get(5);
+    }
+    __device__ __forceinline__ void read_predictor(uint32_t bs) {
+        if (type == 3) {
+            int prec = (int)br.get(4) + 1;
+            shift = br.gets(5);
+            narrow = (bps + prec + ilog2u((uint32_t)order)) <= 32;
+#pragma unroll
+            for (int j = 0; j < ORD; j++) if (j < order) coef[j] = br.gets(prec);
+        } else {
+            shift = 0; narrow = true;
+            // FIXED predictors as LPC coefficient sets
+            const int o = order;
+            if (ORD >= 1 && o >= 1) coef[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
+            if (ORD >= 2 && o >= 2) coef[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
+            if (ORD >= 3 && o >= 3) coef[2] = o == 3 ? 1 : 4;
+            if (ORD >= 4 && o >= 4) coef[3] = -1;
+        }
+        read_residual_header(bs);
+    }
+    __device__ __forceinline__ void init(const uint8_t* in, uint64_t in_len, const Cand& c, const SubInfo& si, uint32_t ch) {
+        br.set_limit(in, in_len);
+        br.init(in, c.off * 8 + si.bit_offset);
+        uint32_t x = br.get(8);
+        if (x & 1) br.unary(64);
+        type = si.type; order = si.order; wasted = si.wasted;
+        bps = (int)c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1 : 0) - wasted;
+        idx = 0; shift = 0; narrow = true; esc = false; k = 0; rawbits = 0; plen = 4; part_left = 0; part_size = 0; cval = 0;
+#pragma unroll
+        for (int j = 0; j < ORD; j++) { coef[j] = 0; hist[j] = 0; }
+        if (type == 0) cval = br.gets(bps);
+        else if (type >= 2 && order == 0) read_predictor(c.bs);
+    }
+    __device__ __forceinline__ int32_t next(uint32_t bs) {
+        int32_t s;
+        if (type == 0) s = cval;
+        else if (type == 1 || idx < order) {
+            s = br.gets(bps);
+            if (type != 1 && idx == order - 1) read_predictor(bs);
+        } else {
+            while (part_left == 0) { part_left = part_size; next_partition_params(); }
+            part_left--;
+            int32_t r;
+            if (esc) r = br.gets(rawbits);
+            else {
+                uint32_t q = br.unary(1u << 24);
+                uint32_t u = (q << k) | br.get(k);
+                r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+            }
+            int64_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < ORD; j++) sum += (int64_t)coef[j] * hist[j];
+            if (narrow) sum = (int64_t)(int32_t)sum;      // libFLAC 1.2.1 accumulates in 32 bits here
+            s = (int32_t)((uint32_t)r + (uint32_t)(int32_t)(sum >> shift));
+        }
+#pragma unroll
+        for (int j = ORD - 1; j > 0; j--) hist[j] = hist[j - 1];
+        if (ORD > 0) hist[0] = s;
+        idx++;
+        return (int32_t)((uint32_t)s << wasted);
+    }
+};
+
+// bytes [0, nbytes) of the interleaved packed PCM of `ts` (flat int32 samples, B bytes each) -> dst, cooperatively by a warp
+__device__ __forceinline__ uint32_t sample_byte(const int32_t* ts, uint32_t b, uint32_t B) {
+    uint32_t q = b / B, r = b - q * B;
+    return ((uint32_t)ts[q] >> (8 * r)) & 0xFFu;
+}
+__device__ void store_packed(uint8_t* __restrict__ dst, uint32_t nbytes, const int32_t* __restrict__ ts, uint32_t B, int lane) {
+    uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
+    if (head > nbytes) head = nbytes;
+    if ((uint32_t)lane < head) dst[lane] = (uint8_t)sample_byte(ts, lane, B);
+    const uint32_t nw = (nbytes - head) >> 2;
+    uint32_t* __restrict__ dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (uint32_t j = lane; j < nw; j += 32) {
+        const uint32_t b0 = head + 4 * j;
+        uint32_t w;
+        if (B == 3) {
+            uint32_t q = (b0 * 0xAAABu) >> 17, r = b0 - 3 * q;
+            uint32_t s0 = (uint32_t)ts[q], s1 = (uint32_t)ts[q + 1];
+            w = r == 0 ? __byte_perm(s0, s1, 0x4210) : r == 1 ? __byte_perm(s0, s1, 0x5421) : __byte_perm(s0, s1, 0x6542);
+        } else if (B == 2 && !(b0 & 1)) {
+            uint32_t q = b0 >> 1;
+            w = __byte_perm((uint32_t)ts[q], (uint32_t)ts[q + 1], 0x5410);
+        } else if (B == 1) {
+            w = __byte_perm(__byte_perm((uint32_t)ts[b0], (uint32_t)ts[b0 + 1], 0x0040), __byte_perm((uint32_t)ts[b0 + 2], (uint32_t)ts[b0 + 3], 0x0040), 0x5410);
+        } else {
+            w = sample_byte(ts, b0, B) | sample_byte(ts, b0 + 1, B) << 8 | sample_byte(ts, b0 + 2, B) << 16 | sample_byte(ts, b0 + 3, B) << 24;
+        }
+        dw[j] = w;
+    }
+    const uint32_t tb = head + 4 * nw;
+    if (tb + lane < nbytes) dst[tb + lane] = (uint8_t)sample_byte(ts, tb + lane, B);
+}
+
+template <int ORD>
+__global__ void __launch_bounds__(DEC_THREADS) k_decode(PassArgs a, uint32_t C, uint32_t B) {
+    extern __shared__ int32_t s_tile[];
+    __shared__ uint32_t s_bs[DEC_THREADS];
+    __shared__ uint64_t s_po[DEC_THREADS];
+    __shared__ uint32_t s_maxbs;
+    const uint32_t F = DEC_THREADS / C;
+    const uint32_t stride = DEC_T * C + C;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_acc = a.totals->n_accepted;
+    const uint32_t fl = tid / C, ch = tid - fl * C;
+    for (uint32_t g = blockIdx.x; (uint64_t)g * F < n_acc; g += gridDim.x) {
+        const uint32_t k = g * F + fl;
+        const bool active = fl < F && k < n_acc;
+        if (tid == 0) s_maxbs = 0;
+        __syncthreads();
+        SubDec<ORD> dec;
+        uint32_t bs = 0, assign = 0; bool ok = false;
+        if (active) {
+            const uint32_t i = a.acc_idx[k];
+            const Cand c = a.cand[i];
+            bs = c.bs; assign = c.assign;
+            ok = a.status[i] == ST_OK;
+            const uint64_t po = a.pcm_off[i];
+            if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
+            if (ch == 0) { s_bs[fl] = bs; s_po[fl] = po; }
+            if (ok) dec.init(a.in, a.in_len, c, a.sub[(uint64_t)i * MAX_CH + ch], ch);
+            atomicMax(&s_maxbs, bs);
+        } else if (fl < F && ch == 0) s_bs[fl] = 0;
+        __syncthreads();
+        const uint32_t maxbs = s_maxbs;
+        int32_t* my = s_tile + fl * stride + ch;
+        for (uint32_t i0 = 0; i0 < maxbs; i0 += DEC_T) {
+#pragma unroll 1
+            for (uint32_t t = 0; t < DEC_T; t++) {
+                int32_t v = 0;
+                if (ok && i0 + t < bs) v = dec.next(bs);
+                if (C == 2) {
+                    int32_t o = __shfl_xor_sync(FULL, v, 1);
+                    if (assign == 8) { if (ch == 1) v = (int32_t)((uint32_t)o - (uint32_t)v); }
+                    else if (assign == 9) { if (ch == 0) v = (int32_t)((uint32_t)v + (uint32_t)o); }
+                    else if (assign == 10) {
+                        int32_t mid = ch == 0 ? v : o, side = ch == 0 ? o : v;
+                        uint32_t m2 = ((uint32_t)mid << 1) | ((uint32_t)side & 1u);
+                        v = ch == 0 ? ((int32_t)(m2 + (uint32_t)side) >> 1) : ((int32_t)(m2 - (uint32_t)side) >> 1);
+                    }
+                }
+                if (fl < F) my[t * C] = v;
+            }
+            __syncthreads();
+            for (uint32_t f = warp; f < F; f += DEC_THREADS / 32) {
+                const uint32_t fbs = s_bs[f];
+                if (i0 >= fbs) continue;
+                const uint32_t nt = min((uint32_t)DEC_T, fbs - i0);
+                store_packed(a.out + s_po[f] + (uint64_t)i0 * C * B, nt * C * B, s_tile + f * stride, B, lane);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+static inline uint32_t blocks_for(uint64_t n, uint32_t per) { uint64_t b = (n + per - 1) / per; return (uint32_t)(b ? b : 1); }
+
+void launch_scan(const PassArgs& a, void* stream) {
+    uint32_t grid = a.nchunks < 148u * 8 ? a.nchunks : 148u * 8;
+    if (!grid) grid = 1;
+    k_scan<<<grid, SCAN_THREADS, 0, S(stream)>>>(a); g_launches++;
+}
+void launch_order(const PassArgs& a, void* stream) {
+    k_chunk_scan<<<1, 1024, 0, S(stream)>>>(a); g_launches++;
+    k_gather<<<148 * 2, 256, 0, S(stream)>>>(a); g_launches++;
+}
+void launch_crc(const PassArgs& a, uint32_t nb, void* stream) {
+    uint32_t grid = blocks_for(nb, 8); if (grid > 148 * 8) grid = 148 * 8;
+    k_crc<<<grid, 256, 0, S(stream)>>>(a); g_launches++;
+}
+void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
+    k_link<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
+    k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
+}
+void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
+    k_parse<<<blocks_for(nb, 128), 128, 0, S(stream)>>>(a); g_launches++;
+}
+void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream) {
+    k_prefix<<<1, 1024, 0, S(stream)>>>(a, bytes_per_sample); g_launches++;
+}
+void launch_decode(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, void* stream) {
+    const uint32_t F = DEC_THREADS / C;
+    uint32_t grid = blocks_for(nacc, F); if (grid > 148 * 16) grid = 148 * 16;
+    size_t smem = (size_t)F * (DEC_T * C + C) * sizeof(int32_t);
+    if (max_order <= 4) k_decode<4><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
+    else if (max_order <= 8) k_decode<8><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
+    else if (max_order <= 12) k_decode<12><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
+    else k_decode<32><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
+    g_launches++;
+}
+
+} // namespace bnf

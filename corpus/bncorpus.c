@@ -115,6 +115,7 @@ void bnc_synth(int32_t* pcm, uint64_t n, uint32_t ch, uint32_t bps, uint32_t sr,
             s = s * 1664525u + 1013904223u;
             if (nb) noise = (noise + ((int32_t)(s >> (32 - nb)) - (int32_t)(1u << (nb - 1)))) / 2;
             v += noise;
+            if (kind == 2) v = 0;                                                      /* whole stream digital silence */
             if (kind == 1) {
                 switch (seg) {
                 case 1: v = 0; break;                                                  /* digital silence -> CONSTANT */

@@ -1,0 +1,153 @@
+/*
+ * bnflac.h -- C ABI of libbnflac.so, the B200-native FLAC decode engine that replaces the native
+ * codec behind BirdNest.Audio's `FLACDecoder : Stream`.
+ *
+ * Boundary being replaced (reference file:line, all under /root/reference/Library):
+ *   LibFLACSharp/LibFLACSharp.cs:42-85,175-185   the 16 FLAC__stream_decoder_* DllImports (cdecl, DLLName "LibFlac" :22)
+ *   LibFLACSharp/LibFLACSharp.cs:187-212          the callback delegate types (read/seek/tell/length/eof/write/metadata/error)
+ *   LibFLACSharp/LibFLACSharp.cs:24-36,262-268    StreamDecoderState / DecodeError enums (error vocabulary kept 1:1 below)
+ *   LibFLACSharp/LibFLACSharp.cs:282-319          FLACMetaData / FLACStreamInfo marshalled views  -> bnflac_info_t
+ *   BirdNest.Audio/FLACDecoder.cs:23,72           ctor: new -> init_stream -> process_until_end_of_metadata -> bnflac_open_*
+ *   BirdNest.Audio/FLACDecoder.cs:124-224         Read / RequestAnotherFLACPacket / process_single           -> bnflac_read
+ *   BirdNest.Audio/FLACDecoder.cs:325-363         ReadCallback (pull model, <=16 KiB per call)                -> bnflac_read_cb
+ *   BirdNest.Audio/FLACDecoder.cs:431-473         MetadataCallback (STREAMINFO -> properties, ALFormat)       -> bnflac_info
+ *   BirdNest.Audio/FLACDecoder.cs:520-580         WriteCallback (planar int32 -> interleaved LE 16-bit)       -> fused on the GPU
+ *   BirdNest.Audio.UnitTests/FLACFileReader.cs:208-254  16/24-bit N-channel interleave (layout followed for bps != 16, ch > 2)
+ *   BirdNest.Audio/FLACDecoder.cs:285-319,590-594 Dispose (finish+delete) / ErrorCallback                    -> bnflac_close / frame status
+ *
+ * Conventions: plain C, cdecl, opaque handles, caller-owned buffers are never retained past a call
+ * unless stated, int return 0 = OK / negative = bnflac_err.  A handle is single-threaded (like the
+ * reference); different handles may be used from different threads.  There is NO CPU decode path:
+ * every decode entry point fails with BNFLAC_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef BNFLAC_H
+#define BNFLAC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNFLAC_ABI_VERSION 1
+
+typedef struct bnflac bnflac_t;
+
+/* error codes; names mirror libFLAC's StreamDecoderState / DecodeError so the C# wrapper can keep the
+ * reference's exception texts ("FLAC: Could not {op} - {state}!", FLACDecoder.cs:98-105,590-594) */
+typedef enum {
+    BNFLAC_OK = 0,
+    BNFLAC_ERR_ARG = -1,            /* NULL / bad argument */
+    BNFLAC_ERR_NOT_FLAC = -2,       /* no "fLaC" marker / no STREAMINFO  (reference: init/metadata failure) */
+    BNFLAC_ERR_TRUNCATED = -3,      /* metadata runs past the end of the data */
+    BNFLAC_ERR_NO_DEVICE = -4,      /* no usable CUDA device: there is no CPU fallback */
+    BNFLAC_ERR_CUDA = -5,           /* CUDA runtime error (see bnflac_last_cuda_error) */
+    BNFLAC_ERR_MEMORY = -6,         /* StreamDecoderState.MemoryAllocationError */
+    BNFLAC_ERR_CAPACITY = -7,       /* destination too small */
+    BNFLAC_ERR_ABORTED = -8,        /* StreamDecoderState.Aborted (read callback returned abort) */
+    BNFLAC_ERR_UNSUPPORTED = -9,    /* stream shape outside engine limits (e.g. > 8 channels, blocksize > 65535) */
+    BNFLAC_ERR_STATE = -10          /* call not valid in this state (e.g. read after close) */
+} bnflac_err;
+
+/* decoder state, same numbering as LibFLACSharp.cs:24-36 */
+typedef enum {
+    BNFLAC_STATE_SEARCH_FOR_METADATA = 0, BNFLAC_STATE_READ_METADATA = 1, BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC = 2,
+    BNFLAC_STATE_READ_FRAME = 3, BNFLAC_STATE_END_OF_STREAM = 4, BNFLAC_STATE_OGG_ERROR = 5, BNFLAC_STATE_SEEK_ERROR = 6,
+    BNFLAC_STATE_ABORTED = 7, BNFLAC_STATE_MEMORY_ALLOCATION_ERROR = 8, BNFLAC_STATE_UNINITIALIZED = 9
+} bnflac_state_t;
+
+/* per-frame status, same numbering as DecodeError (LibFLACSharp.cs:262-268) shifted by one so 0 = OK */
+enum { BNFLAC_FRAME_OK = 0, BNFLAC_FRAME_LOST_SYNC = 1, BNFLAC_FRAME_BAD_HEADER = 2, BNFLAC_FRAME_CRC_MISMATCH = 3, BNFLAC_FRAME_UNPARSEABLE = 4 };
+
+/* OpenAL formats FLACDecoder.Format can take (FLACDecoder.cs:454-465); 0 = unmapped + logger warning */
+enum { BNFLAC_AL_NONE = 0, BNFLAC_AL_MONO8 = 0x1100, BNFLAC_AL_MONO16 = 0x1101, BNFLAC_AL_STEREO8 = 0x1102, BNFLAC_AL_STEREO16 = 0x1103 };
+
+typedef struct {
+    uint32_t struct_size;       /* = sizeof(bnflac_opts); 0-initialise the rest for defaults */
+    int32_t  device;            /* CUDA device ordinal, -1 = current device */
+    void*    stream;            /* cudaStream_t to launch on; NULL = library-owned stream */
+    uint32_t shard_index;       /* frame-range sharding: this handle owns shard_index of shard_count */
+    uint32_t shard_count;       /* 0 or 1 = whole stream */
+    uint32_t flags;             /* BNFLAC_OPT_* */
+    uint32_t read_chunk_frames; /* frames decoded per look-ahead batch by bnflac_read; 0 = default */
+} bnflac_opts;
+#define BNFLAC_OPT_VERIFY_MD5 1u   /* decode_all also checks md5(PCM) against STREAMINFO (host side, not timed) */
+
+/* what MetadataCallback derives (FLACDecoder.cs:431-473) plus the raw STREAMINFO fields */
+typedef struct {
+    uint32_t sample_rate, channels, bits_per_sample;
+    uint32_t min_blocksize, max_blocksize, min_framesize, max_framesize;
+    uint32_t block_align;       /* channels * (bits_per_sample/8)  (FLACDecoder.cs:448) */
+    uint32_t al_format;         /* BNFLAC_AL_* */
+    uint32_t bytes_per_sample;  /* ceil(bits_per_sample/8): width of one packed PCM sample in the output */
+    uint64_t total_samples;     /* per channel, 0 = unknown */
+    uint64_t pcm_bytes;         /* total_samples * channels * bytes_per_sample */
+    uint64_t length_reference;  /* FLACDecoder.Length as the reference computes it (block_align * total_samples, low 32 bits of total) */
+    double   duration_seconds;  /* FLACDecoder.Duration */
+    uint8_t  md5[16];
+    uint64_t first_frame_offset;
+} bnflac_info_t;
+
+/* pull-model source, the shape of FLACDecoder.ReadCallback (FLACDecoder.cs:325-363):
+ * fill buf with up to *bytes bytes, store the count in *bytes; return 0 continue, 1 end of stream, 2 abort */
+typedef int (*bnflac_read_cb)(void* user, uint8_t* buf, size_t* bytes);
+
+/* ---- open / info / close ------------------------------------------------------------------ */
+/* Opens a stream held in host memory.  The library copies what it needs to the device; `data` must stay
+ * valid until bnflac_close only if BNFLAC is asked to decode lazily (it always copies: caller keeps ownership). */
+int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts, bnflac_t** out);
+/* Opens from a pull callback (a C# Stream): pulls the whole stream in large requests, then as open_memory. */
+int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* opts, bnflac_t** out);
+/* Opens a stream whose bytes are ALREADY resident in device memory (d_data stays owned by the caller and must
+ * outlive the handle).  `header` = at least the first header_len bytes of the same stream in host memory
+ * (metadata is parsed on the host).  Benchmark / pipeline path. */
+int bnflac_open_device(const void* d_data, size_t len, const uint8_t* header, size_t header_len, const bnflac_opts* opts, bnflac_t** out);
+int bnflac_info(bnflac_t* h, bnflac_info_t* info);
+int bnflac_state(bnflac_t* h);                       /* bnflac_state_t */
+void bnflac_close(bnflac_t* h);                      /* finish + delete (FLACDecoder.cs:296-300) */
+
+/* ---- decode -------------------------------------------------------------------------------- */
+/* Stream read (FLACDecoder.Read, FLACDecoder.cs:124-205): interleaved little-endian PCM, bytes_per_sample each.
+ * Returns bytes written (== count unless the stream ended), 0 at end of stream, <0 = bnflac_err. */
+int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count);
+/* One shot to a host buffer (what OpenALDemo does with CopyTo(MemoryStream), Program.cs:33-38). */
+int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written);
+/* One shot, result left in device memory.  If d_dst is NULL the library allocates (owned by the handle, valid
+ * until the next decode or close) and returns it in *d_out; else writes into caller memory of capacity cap. */
+int bnflac_decode_device(bnflac_t* h, void* d_dst, size_t cap, void** d_out, uint64_t* written);
+/* Size in bytes the decode of this handle (its shard) will produce, known after the frame scan. */
+int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes);
+
+/* ---- batch of independent clips (BASELINE cfg4: sharded by file) --------------------------- */
+typedef struct { const uint8_t* data; size_t len; } bnflac_span;
+typedef struct { uint64_t pcm_offset, pcm_bytes; uint32_t sample_rate, channels, bits_per_sample, status; uint64_t total_samples; } bnflac_clip_result;
+/* Decodes n clips in one pipeline pass into one PCM buffer (clip i at results[i].pcm_offset).
+ * dst==NULL: only sizes are computed.  dst_is_device: dst is a device pointer. */
+int bnflac_decode_batch(const bnflac_span* clips, size_t n, const bnflac_opts* opts, uint8_t* dst, size_t cap, int dst_is_device,
+                        bnflac_clip_result* results, uint64_t* written);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+/* per-frame table of the last decode (host copies, owned by the handle) */
+typedef struct { uint64_t offset; uint32_t length, blocksize; uint8_t channels, bits_per_sample, assignment, status; uint32_t pad; uint64_t number; uint64_t pcm_offset; } bnflac_frame_t;
+int bnflac_frames(bnflac_t* h, const bnflac_frame_t** frames, size_t* n);
+/* per-subframe table (K2 output) of the last decode: 8 entries per frame */
+typedef struct { uint32_t bit_offset; uint8_t type, order, wasted, flags; } bnflac_subframe_t;
+int bnflac_subframes(bnflac_t* h, const bnflac_subframe_t** sub, size_t* n);
+/* number of error-callback events the reference would have raised (ErrorCallback, FLACDecoder.cs:590-594) and their codes */
+int bnflac_errors(bnflac_t* h, const uint32_t** codes, size_t* n);
+/* CUDA-event timings (ms) of the stages of the last decode on this handle */
+typedef struct { float total, scan, crc, link, parse, decode; uint32_t launches; uint32_t pad; } bnflac_timing;
+int bnflac_last_timing(bnflac_t* h, bnflac_timing* t);
+const char* bnflac_strerror(int err);
+const char* bnflac_state_name(int state);           /* "EndOfStream", ... as C# prints the enum */
+const char* bnflac_frame_status_name(int status);   /* "LostSync", "BadHeader", "FrameCrcMismatch", "UnparsableStream" */
+const char* bnflac_last_cuda_error(void);
+int bnflac_abi_version(void);
+int bnflac_device_count(void);
+/* kernels launched by this process so far (bench.py's gpu_launches is a difference of two reads) */
+uint64_t bnflac_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
