@@ -215,13 +215,13 @@ class Handle:
         p = C.POINTER(FrameRec)()
         n = C.c_size_t()
         _check(lib().bnflac_frames(self._p, C.byref(p), C.byref(n)), "bnflac_frames")
-        return [p[i] for i in range(n.value)]
+        return [FrameRec.from_buffer_copy(p[i]) for i in range(n.value)]
 
     def subframes(self):
         p = C.POINTER(SubframeRec)()
         n = C.c_size_t()
         _check(lib().bnflac_subframes(self._p, C.byref(p), C.byref(n)), "bnflac_subframes")
-        return [p[i] for i in range(n.value)]
+        return [SubframeRec.from_buffer_copy(p[i]) for i in range(n.value)]
 
     def errors(self):
         p = C.POINTER(C.c_uint32)()
