@@ -18,6 +18,7 @@ AL_FORMAT_NAMES = {0: "None", 0x1100: "Mono8", 0x1101: "Mono16", 0x1102: "Stereo
 
 ERR_ARG, ERR_NOT_FLAC, ERR_TRUNCATED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY, ERR_CAPACITY, ERR_ABORTED, ERR_UNSUPPORTED, ERR_STATE = range(-1, -11, -1)
 OPT_VERIFY_MD5 = 1
+OPT_BORROW_INPUT = 2
 
 
 class Opts(C.Structure):
@@ -240,7 +241,7 @@ def open_memory(data, device=-1, stream=0, shard_index=0, shard_count=0, flags=0
     h = C.c_void_p()
     n = data.numel() * data.element_size() if hasattr(data, "numel") else len(data)
     _check(lib().bnflac_open_memory(_addr(data), n, C.byref(o), C.byref(h)), "bnflac_open_memory")
-    return Handle(h.value)
+    return Handle(h.value, keep=data if (flags & OPT_BORROW_INPUT) else None)
 
 
 def open_device(d_ptr: int, length: int, header: bytes, device=-1, stream=0, shard_index=0, shard_count=0, keep=None) -> Handle:

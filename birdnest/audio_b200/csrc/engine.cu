@@ -157,6 +157,7 @@ struct bnflac {
 
     // input
     std::vector<uint8_t> host;          // copy of the stream when opened from host memory
+    const uint8_t* host_ptr = nullptr;  // the bytes to upload (== host.data() unless BNFLAC_OPT_BORROW_INPUT)
     const uint8_t* d_ext = nullptr;     // caller-owned device copy (open_device)
     size_t len = 0;
     uint64_t slice_begin = 0, slice_end = 0;   // byte range of the whole stream this handle (shard) keeps on the device
@@ -234,7 +235,7 @@ static int ensure_input(bnflac* h) {
     if (h->d_ext) { h->uploaded = true; return 0; }
     const size_t n = (size_t)(h->slice_end - h->slice_begin);
     int rc = h->d_in.reserve(n + 128); if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_in.p, h->host.data() + h->slice_begin, n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_in.p, h->host_ptr + h->slice_begin, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync((uint8_t*)h->d_in.p + n, 0, 128, h->stream));
     h->uploaded = true;
     return 0;
@@ -449,8 +450,12 @@ int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts,
     h->opts = default_opts(opts); h->len = len;
     bnflac_info_t probe; int rc = parse_metadata(data, len, &probe);      // fail before touching the device
     if (rc) { delete h; return rc; }
-    try { h->host.assign(data, data + len); } catch (...) { delete h; return BNFLAC_ERR_MEMORY; }
-    if ((rc = common_open(h, h->host.data(), len)) || (rc = setup_device(h))) { delete h; return rc; }
+    if (h->opts.flags & BNFLAC_OPT_BORROW_INPUT) h->host_ptr = data;
+    else {
+        try { h->host.assign(data, data + len); } catch (...) { delete h; return BNFLAC_ERR_MEMORY; }
+        h->host_ptr = h->host.data();
+    }
+    if ((rc = common_open(h, h->host_ptr, len)) || (rc = setup_device(h))) { delete h; return rc; }
     *out = h;
     return 0;
 }

@@ -72,6 +72,7 @@ typedef struct {
     uint32_t read_chunk_frames; /* frames decoded per look-ahead batch by bnflac_read; 0 = default */
 } bnflac_opts;
 #define BNFLAC_OPT_VERIFY_MD5 1u   /* decode_all also checks md5(PCM) against STREAMINFO (host side, not timed) */
+#define BNFLAC_OPT_BORROW_INPUT 2u /* open_memory does not copy `data`: the caller keeps it valid (and ideally pinned) until close */
 
 /* what MetadataCallback derives (FLACDecoder.cs:431-473) plus the raw STREAMINFO fields */
 typedef struct {
