@@ -378,108 +378,208 @@ struct BitReader {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ ring bit reader
+// Every lane walks its own serial bitstream.  The bytes are staged through shared memory by per-lane cp.async
+// (LDGSTS, 16 B each) into a private 4-block ring, two blocks ahead of the read position, so the serial parse never
+// waits on HBM: a block boundary is crossed once per RB_BLOCK bytes and the block needed next was requested one
+// full block earlier.  Reads are position based: two LDS + byte swaps + one funnel shift give a 32-bit window.
+constexpr int RB_BLOCK = 64;                    // bytes per ring block
+constexpr int RB_NBLK = 4;
+constexpr int RB_BYTES = RB_BLOCK * RB_NBLK;    // 256 B of ring per lane
+constexpr int RB_STRIDE = RB_BYTES + 16;        // lane stride (16 B skew spreads lanes over banks, keeps 16 B alignment)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
+__device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+__device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+
+struct RingBits {
+    uint32_t sring;        // shared-space address of this lane's ring
+    uint32_t pos;          // bit position relative to g0
+    uint32_t cur;          // block the read position is in (blocks cur, cur+1 resident, cur+2 in flight)
+    const uint8_t* g0;     // global address of ring word 0 (RB_BLOCK aligned)
+    const uint8_t* gend;   // end of the padded input: blocks past it are zero-filled
+
+    __device__ __forceinline__ void fetch(uint32_t b) {
+        const uint8_t* src = g0 + (uint64_t)b * RB_BLOCK;
+        const uint32_t dst = sring + (b & (RB_NBLK - 1)) * RB_BLOCK;
+#pragma unroll
+        for (int k = 0; k < RB_BLOCK / 16; k++) {
+            const uint8_t* s = src + 16 * k;
+            uint32_t n = (s + 16 <= gend) ? 16u : 0u;
+            if (!n) s = gend - 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16 * k), "l"(s), "r"(n) : "memory");
+        }
+    }
+    __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    __device__ __forceinline__ void refill_from(uint32_t blk) {   // make blocks blk, blk+1 resident and blk+2 in flight
+        if (blk == cur + 1) { fetch(blk + 2); commit(); }
+        else { fetch(blk); fetch(blk + 1); commit(); fetch(blk + 2); commit(); }
+        wait1();
+        cur = blk;
+    }
+    // in: base of the (256 B aligned) device input; abs_bit: absolute bit position in it
+    __device__ __forceinline__ void init(uint32_t sring_, const uint8_t* in, uint64_t in_len, uint64_t abs_bit) {
+        sring = sring_;
+        const uint64_t byte = abs_bit >> 3, b0 = byte & ~(uint64_t)(RB_BLOCK - 1);
+        g0 = in + b0; gend = in + (in_len & ~15ull);
+        pos = (uint32_t)(abs_bit - b0 * 8);
+        cur = 0xFFFFFFF0u;
+        refill_from(0);
+    }
+    __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
+    __device__ __forceinline__ uint32_t window() const {      // next 32 bits, MSB first
+        const uint32_t bo = (pos >> 3) & (RB_BYTES - 4);
+        const uint32_t a = lds32(sring + bo), b = lds32(sring + ((bo + 4) & (RB_BYTES - 4)));
+        return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), pos & 31);
+    }
+    __device__ __forceinline__ void advance(uint32_t n) {
+        pos += n;
+        const uint32_t blk = pos / (RB_BLOCK * 8);
+        if (blk != cur) refill_from(blk);
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); advance(n); return v; }          // n <= 32
+    __device__ __forceinline__ int32_t gets(uint32_t n) { int32_t v = n ? sar_c((int32_t)window(), 32 - n) : 0; advance(n); return v; }
+    __device__ __forceinline__ uint32_t unary(uint32_t limit) {
+        uint32_t q = 0;
+        for (;;) {
+            uint32_t w = window();
+            if (w) { uint32_t z = __clz(w); advance(z + 1); return q + z; }
+            q += 32; advance(32);
+            if (q > limit) return q;
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ K2 parse
 // One thread per frame: walks the subframes, records where each starts and what it is, skips the residual.
 __device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
+constexpr int PARSE_THREADS = 64;
 
-__global__ void __launch_bounds__(128) k_parse(PassArgs a) {
+__global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
+    extern __shared__ __align__(16) uint8_t s_ring[];
     const uint32_t n = ncand(a);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t st = a.status[i];
-    if (st != ST_OK && st != ST_CHECK) return;
-    const Cand c = a.cand[i];
-    if (c.flags & 2) return;   // frame belongs to the neighbouring shard (kept only as an end marker)
+    uint8_t st = ST_DROP;
+    Cand c;
+    c.bs = 0; c.assign = 0; c.flags = 0; c.off = 0; c.hdr_len = 0; c.bps = 0;
+    if (i < n) { st = a.status[i]; c = a.cand[i]; }
+    bool live = (st == ST_OK || st == ST_CHECK) && !(c.flags & 2);   // flag 2: frame of the neighbouring shard (end marker only)
     const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
     const uint64_t frame_bit0 = c.off * 8;
-    const uint64_t end_bit = (c.off + a.flen[i]) * 8;
-    BitReader br;
-    br.set_limit(a.in, a.in_len);
-    br.init(a.in, frame_bit0 + 8ull * c.hdr_len);
+    const uint64_t end_bit = live ? (c.off + a.flen[i]) * 8 : 0;
+    RingBits br;
+    if (live) br.init(smem_u32(s_ring) + threadIdx.x * RB_STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
     bool bad = false, unparse = false;
     uint32_t max_order = 0, any_wide = 0;
-    for (uint32_t ch = 0; ch < channels && !bad && !unparse; ch++) {
-        uint32_t bps = c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1u : 0u);
-        SubInfo si;
-        si.bit_offset = (uint32_t)(br.pos(a.in) - frame_bit0);
-        uint32_t x = br.get(8);
-        if (x & 0x80) { bad = true; break; }
-        uint32_t type = (x >> 1) & 0x3f, w = 0;
-        if (x & 1) { w = br.unary(64) + 1; if (w >= bps) { unparse = true; break; } bps -= w; }
-        si.wasted = (uint8_t)w; si.flags = 0; si.order = 0;
-        uint32_t order = 0; bool has_resid = false;
-        if (type == 0) { si.type = 0; br.skip(bps > 32 ? 32 : bps); }
-        else if (type == 1) {
-            si.type = 1;
-            // jump over blocksize * bps raw bits
-            uint64_t p = br.pos(a.in) + (uint64_t)c.bs * bps;
-            if (p > end_bit) { bad = true; break; }
-            br.init(a.in, p);
-        } else if (type >= 8 && type <= 12) { si.type = 2; order = type - 8; has_resid = true; }
-        else if (type >= 32) { si.type = 3; order = type - 31; has_resid = true; }
-        else { unparse = true; break; }
-        if (has_resid) {
-            si.order = (uint8_t)order;
-            if (order > c.bs) { unparse = true; break; }
-            if (order > max_order) max_order = order;
-            { uint64_t p = br.pos(a.in) + (uint64_t)order * bps; if (p > end_bit) { bad = true; break; } br.init(a.in, p); }
-            if (si.type == 3) {
-                uint32_t prec = br.get(4) + 1;
-                if (prec == 16) { unparse = true; break; }
-                int32_t shift = br.gets(5);
-                if (shift < 0) { unparse = true; break; }
-                uint64_t p = br.pos(a.in) + (uint64_t)order * prec;
-                br.init(a.in, p);
-                if (bps + prec + (uint32_t)ilog2u(order) <= 32) si.flags |= 1; else any_wide = 1;
-            } else si.flags |= 1;
-            uint32_t method = br.get(2);
-            if (method > 1) { unparse = true; break; }
-            if (method) si.flags |= 2;
-            const int plen = method ? 5 : 4; const uint32_t esc = method ? 31u : 15u;
-            uint32_t po = br.get(4);
-            uint32_t psize = c.bs >> po;
-            if (po > 0 ? psize < order : c.bs < order) { unparse = true; break; }
-            for (uint32_t p = 0; p < (1u << po) && !bad; p++) {
-                uint32_t cnt = (po == 0) ? c.bs - order : (p == 0 ? psize - order : psize);
-                uint32_t k = br.get(plen);
-                if (k == esc) {
-                    uint32_t nb = br.get(5);
-                    uint64_t q = br.pos(a.in) + (uint64_t)cnt * nb;
-                    if (q > end_bit) { bad = true; break; }
-                    br.init(a.in, q);
-                } else {
-                    for (uint32_t s = 0; s < cnt; s++) {
-                        uint32_t top = br.peek32();
-                        if (top) {
-                            int adv = __clz(top) + 1 + (int)k;       // <= 62
-                            if (adv > 32) { br.skip(32); adv -= 32; }
-                            br.skip(adv);
-                        } else {
-                            br.unary(1u << 16);
-                            br.skip((int)k);
-                            if (br.pos(a.in) > end_bit) { bad = true; break; }
+    // lanes of a warp are different frames; they walk channel by channel and, inside a subframe, sample index by
+    // sample index in lockstep, so that partition boundaries (multiples of blocksize >> order) fall on the same iteration
+    const uint32_t wmax_ch = __reduce_max_sync(FULL, live ? channels : 0u);
+    const uint32_t wmax_bs = __reduce_max_sync(FULL, live ? c.bs : 0u);
+    for (uint32_t ch = 0; ch < wmax_ch; ch++) {
+        bool walk = false;            // this lane walks a Rice-coded residual in this phase
+        uint32_t order = 0, plen = 4, esc = 15, psize = 0, left = 0, k1 = 1, rawskip = 0;
+        bool first = true;
+        if (live && !bad && !unparse && ch < channels) {
+            uint32_t bps = c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1u : 0u);
+            SubInfo si;
+            si.bit_offset = (uint32_t)(br.abs_pos(a.in) - frame_bit0);
+            si.type = 0; si.order = 0; si.flags = 0;
+            uint32_t x = br.get(8);
+            uint32_t type = (x >> 1) & 0x3f, w = 0;
+            if (x & 0x80) bad = true;
+            else if ((x & 1) && (w = br.unary(64) + 1) >= bps) unparse = true;
+            else {
+                bps -= w;
+                si.wasted = (uint8_t)w;
+                bool has_resid = false;
+                if (type == 0) br.advance(bps);
+                else if (type == 1) {
+                    si.type = 1;
+                    if (br.abs_pos(a.in) + (uint64_t)c.bs * bps > end_bit) bad = true; else br.advance(c.bs * bps);
+                } else if (type >= 8 && type <= 12) { si.type = 2; order = type - 8; has_resid = true; }
+                else if (type >= 32) { si.type = 3; order = type - 31; has_resid = true; }
+                else unparse = true;
+                if (has_resid) {
+                    si.order = (uint8_t)order;
+                    if (order > c.bs) unparse = true;
+                    else if (br.abs_pos(a.in) + (uint64_t)order * bps > end_bit) bad = true;
+                    else {
+                        if (order > max_order) max_order = order;
+                        br.advance(order * bps);
+                        if (si.type == 3) {
+                            uint32_t prec = br.get(4) + 1;
+                            int32_t shift = br.gets(5);
+                            if (prec == 16 || shift < 0) unparse = true;
+                            else {
+                                br.advance(order * prec);
+                                if (bps + prec + (uint32_t)ilog2u(order) <= 32) si.flags |= 1; else any_wide = 1;
+                            }
+                        } else si.flags |= 1;
+                        if (!unparse) {
+                            uint32_t method = br.get(2);
+                            if (method > 1) unparse = true;
+                            else {
+                                if (method) { si.flags |= 2; plen = 5; esc = 31; }
+                                uint32_t po = br.get(4);
+                                psize = po ? c.bs >> po : c.bs;
+                                if (psize < order) unparse = true;
+                                // the residual of the LAST subframe need not be walked when the frame span is already
+                                // CRC-validated: nothing starts after it
+                                else walk = !(st == ST_OK && ch + 1 == channels);
+                            }
                         }
                     }
-                    if (br.pos(a.in) > end_bit) { bad = true; break; }
+                }
+            }
+            if (!bad && !unparse) a.sub[(uint64_t)i * MAX_CH + ch] = si;
+            else walk = false;
+        }
+        if (!__any_sync(FULL, walk)) continue;
+        for (uint32_t s = 0; s < wmax_bs; s++) {
+            if (walk && s >= order && s < c.bs) {
+                if (left == 0) {   // partition boundary (s is a multiple of psize, or s == order)
+                    do {               // twice only when partition 0 holds zero samples (its parameter is still coded)
+                        left = psize - (s == order && first ? order : 0);
+                        first = false;
+                        uint32_t k = br.get(plen);
+                        rawskip = 0;
+                        if (k == esc) {
+                            uint32_t nb = br.get(5);
+                            if (br.abs_pos(a.in) + (uint64_t)left * nb > end_bit) { bad = true; walk = false; left = 1; }
+                            else { br.advance(left * nb); rawskip = 1; }
+                        }
+                        k1 = k + 1;
+                    } while (left == 0);
+                }
+                left--;
+                if (!rawskip && walk) {
+                    uint32_t wd = br.window();
+                    if (wd) br.advance(__clz(wd) + k1);
+                    else {
+                        br.unary(1u << 16);
+                        br.advance(k1 - 1);
+                        if (br.abs_pos(a.in) > end_bit) { bad = true; walk = false; }
+                    }
                 }
             }
         }
-        a.sub[(uint64_t)i * MAX_CH + ch] = si;
+        if (walk && br.abs_pos(a.in) > end_bit) bad = true;
     }
-    if (!bad && !unparse) {
-        uint64_t p = (br.pos(a.in) + 7) & ~7ull;
-        if (st == ST_OK) {
-            if (p + 16 != end_bit) bad = true;     // parse disagrees with the CRC-validated span
-        } else {  // ST_CHECK: validate the way the reference does: CRC-16 over the bytes the parse consumed
-            if (p + 16 > end_bit) bad = true;
-            else {
-                const uint8_t* q = a.in + c.off;
-                uint32_t nbytes = (uint32_t)(p / 8 - c.off), crc = 0;
-                for (uint32_t b = 0; b < nbytes; b++) crc = crc16_update_bitwise(crc, q[b]);
-                uint32_t want = (uint32_t)q[nbytes] << 8 | q[nbytes + 1];
-                a.flen[i] = nbytes + 2;
-                st = (crc == want) ? ST_OK : ST_CRC;
-            }
+    if (!live) return;
+    if (!bad && !unparse && st == ST_CHECK) {
+        uint64_t p = (br.abs_pos(a.in) + 7) & ~7ull;
+        // validate the way the reference does: CRC-16 over the bytes the parse consumed
+        if (p + 16 > end_bit) bad = true;
+        else {
+            const uint8_t* q = a.in + c.off;
+            uint32_t nbytes = (uint32_t)(p / 8 - c.off), crc = 0;
+            for (uint32_t b = 0; b < nbytes; b++) crc = crc16_update_bitwise(crc, q[b]);
+            uint32_t want = (uint32_t)q[nbytes] << 8 | q[nbytes + 1];
+            a.flen[i] = nbytes + 2;
+            st = (crc == want) ? ST_OK : ST_CRC;
         }
     }
     if (unparse) st = ST_UNPARSEABLE;
@@ -740,7 +840,7 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
     k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
-    k_parse<<<blocks_for(nb, 128), 128, 0, S(stream)>>>(a); g_launches++;
+    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * RB_STRIDE, S(stream)>>>(a); g_launches++;
 }
 void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream) {
     k_prefix<<<1, 1024, 0, S(stream)>>>(a, bytes_per_sample); g_launches++;
