@@ -106,7 +106,7 @@ void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream);
-void launch_decode(const PassArgs& a, uint32_t nacc_bound, uint32_t channels, uint32_t bytes_per_sample, uint32_t max_order, void* stream);
+void launch_decode(const PassArgs& a, uint32_t nacc_bound, uint32_t channels, uint32_t bytes_per_sample, uint32_t max_order, bool wide, void* stream);
 int kernel_launch_count();   // kernels launched so far by this process (bench "gpu_launches")
 
 } // namespace bnf

@@ -342,7 +342,7 @@ static int run_back(bnflac* h, uint8_t* d_out, uint64_t cap) {
     if (h->totals.pcm_bytes > cap) return BNFLAC_ERR_CAPACITY;
     h->args.out = d_out; h->args.out_cap = cap;
     if (h->totals.n_accepted)
-        launch_decode(h->args, h->totals.n_accepted, h->info.channels, h->info.bytes_per_sample, h->totals.max_order, h->stream);
+        launch_decode(h->args, h->totals.n_accepted, h->info.channels, h->info.bytes_per_sample, h->totals.max_order, h->totals.any_wide != 0, h->stream);
     CK(cudaEventRecord(h->ev[5], h->stream));
     CK(cudaGetLastError());
     return 0;

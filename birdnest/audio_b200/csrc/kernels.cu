@@ -380,54 +380,60 @@ struct BitReader {
 
 // ------------------------------------------------------------------------------------------------ ring bit reader
 // Every lane walks its own serial bitstream.  The bytes are staged through shared memory by per-lane cp.async
-// (LDGSTS, 16 B each) into a private 4-block ring, two blocks ahead of the read position, so the serial parse never
-// waits on HBM: a block boundary is crossed once per RB_BLOCK bytes and the block needed next was requested one
-// full block earlier.  Reads are position based: two LDS + byte swaps + one funnel shift give a 32-bit window.
-constexpr int RB_BLOCK = 64;                    // bytes per ring block
-constexpr int RB_NBLK = 4;
-constexpr int RB_BYTES = RB_BLOCK * RB_NBLK;    // 256 B of ring per lane
-constexpr int RB_STRIDE = RB_BYTES + 16;        // lane stride (16 B skew spreads lanes over banks, keeps 16 B alignment)
-
+// (LDGSTS, 16 B each) into a private ring that runs several blocks ahead of the read position, so the serial parse
+// never waits on HBM.  Reads are position based: two LDS + byte swaps + one funnel shift give a 32-bit window.
+// Refill is CHECKPOINTED: all lanes of a warp top up their rings at the same loop iterations (every CK samples), so the
+// divergent "my ring ran low" branch is not taken on almost every iteration by some lane.  Between checkpoints a lane
+// may consume at most CK*32 bits + one window, which the ring always holds ahead (see checkpoint()).
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
 __device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 
+template <int NBLK>                              // ring = NBLK blocks of 16 bytes per lane (NBLK a power of two)
 struct RingBits {
+    static constexpr int BLK = 16;
+    static constexpr int RB_BYTES = BLK * NBLK;
+    static constexpr int STRIDE = RB_BYTES + 16;           // lane stride: 16 B skew spreads lanes over banks, keeps 16 B alignment
+    // bytes guaranteed readable ahead of pos right after checkpoint(): blocks up to (curblk_prev + NBLK - 1) are complete
     uint32_t sring;        // shared-space address of this lane's ring
     uint32_t pos;          // bit position relative to g0
-    uint32_t cur;          // block the read position is in (blocks cur, cur+1 resident, cur+2 in flight)
-    const uint8_t* g0;     // global address of ring word 0 (RB_BLOCK aligned)
+    uint32_t filled;       // blocks [.., filled) have been requested
+    const uint8_t* g0;     // global address of ring byte 0 (16 B aligned)
     const uint8_t* gend;   // end of the padded input: blocks past it are zero-filled
 
     __device__ __forceinline__ void fetch(uint32_t b) {
-        const uint8_t* src = g0 + (uint64_t)b * RB_BLOCK;
-        const uint32_t dst = sring + (b & (RB_NBLK - 1)) * RB_BLOCK;
-#pragma unroll
-        for (int k = 0; k < RB_BLOCK / 16; k++) {
-            const uint8_t* s = src + 16 * k;
-            uint32_t n = (s + 16 <= gend) ? 16u : 0u;
-            if (!n) s = gend - 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16 * k), "l"(s), "r"(n) : "memory");
-        }
+        const uint8_t* s = g0 + (uint64_t)b * BLK;
+        uint32_t n = (s + 16 <= gend) ? 16u : 0u;
+        if (!n) s = gend - 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + (b & (NBLK - 1)) * BLK), "l"(s), "r"(n) : "memory");
     }
     __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-    __device__ __forceinline__ void wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-    __device__ __forceinline__ void refill_from(uint32_t blk) {   // make blocks blk, blk+1 resident and blk+2 in flight
-        if (blk == cur + 1) { fetch(blk + 2); commit(); }
-        else { fetch(blk); fetch(blk + 1); commit(); fetch(blk + 2); commit(); }
-        wait1();
-        cur = blk;
+    __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ void request() {     // request every block the ring has room for (never the slot being read)
+        const uint32_t curblk = pos / (BLK * 8);
+        if (filled < curblk) filled = curblk;       // jumped over unrequested blocks
+        const uint32_t lim = curblk + NBLK;
+        if (filled < lim) {
+#pragma unroll 1
+            do { fetch(filled); filled++; } while (filled < lim);
+            commit();
+        }
     }
-    // in: base of the (256 B aligned) device input; abs_bit: absolute bit position in it
+    // Periodic top-up, executed by all lanes at the same iteration: first make what was requested one period ago
+    // visible, then request more.  Requests therefore have a whole period to land.
+    __device__ __forceinline__ void checkpoint() { wait_all(); request(); }
+    // Synchronous variant for rare big moves (VERBATIM skip, long unary runs, init).
+    __device__ __forceinline__ void ensure_now() { request(); wait_all(); }
     __device__ __forceinline__ void init(uint32_t sring_, const uint8_t* in, uint64_t in_len, uint64_t abs_bit) {
         sring = sring_;
-        const uint64_t byte = abs_bit >> 3, b0 = byte & ~(uint64_t)(RB_BLOCK - 1);
+        const uint64_t b0 = (abs_bit >> 3) & ~(uint64_t)(BLK - 1);
         g0 = in + b0; gend = in + (in_len & ~15ull);
         pos = (uint32_t)(abs_bit - b0 * 8);
-        cur = 0xFFFFFFF0u;
-        refill_from(0);
+        filled = 0;
+        ensure_now();
     }
     __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
     __device__ __forceinline__ uint32_t window() const {      // next 32 bits, MSB first
@@ -435,28 +441,37 @@ struct RingBits {
         const uint32_t a = lds32(sring + bo), b = lds32(sring + ((bo + 4) & (RB_BYTES - 4)));
         return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), pos & 31);
     }
-    __device__ __forceinline__ void advance(uint32_t n) {
-        pos += n;
-        const uint32_t blk = pos / (RB_BLOCK * 8);
-        if (blk != cur) refill_from(blk);
-    }
-    __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); advance(n); return v; }          // n <= 32
-    __device__ __forceinline__ int32_t gets(uint32_t n) { int32_t v = n ? sar_c((int32_t)window(), 32 - n) : 0; advance(n); return v; }
-    __device__ __forceinline__ uint32_t unary(uint32_t limit) {
+    __device__ __forceinline__ void skip(uint32_t n) { pos += n; }                        // n <= 32, covered by the checkpoint budget
+    __device__ __forceinline__ void jump(uint32_t n) { pos += n; ensure_now(); }          // any n
+    __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); pos += n; return v; }          // n <= 32
+    __device__ __forceinline__ int32_t gets(uint32_t n) { int32_t v = n ? sar_c((int32_t)window(), 32 - n) : 0; pos += n; return v; }
+    // unary run that did not terminate inside one window (rare): walks 32 zero bits at a time with synchronous refills
+    __device__ __forceinline__ uint32_t unary_slow(uint32_t limit) {
         uint32_t q = 0;
+#pragma unroll 1
         for (;;) {
+            ensure_now();
             uint32_t w = window();
-            if (w) { uint32_t z = __clz(w); advance(z + 1); return q + z; }
-            q += 32; advance(32);
-            if (q > limit) return q;
+            if (w) { uint32_t z = __clz(w); pos += z + 1; ensure_now(); return q + z; }
+            q += 32; pos += 32;
+            if (q > limit) { ensure_now(); return q; }
         }
     }
+    __device__ __forceinline__ uint32_t unary(uint32_t limit) {
+        uint32_t w = window();
+        if (w) { uint32_t z = __clz(w); pos += z + 1; return z; }
+        return unary_slow(limit);
+    }
 };
+// budget: between two checkpoints a lane may advance by at most (NBLK*16 - 16 - 8 - 16) bytes:
+//   ring - (partially consumed current block) - (window over-read) - (blocks requested this checkpoint are not yet waited for)
+// NBLK = 8: 128 B ring, blocks requested one checkpoint ago are complete -> >= 64 B ahead; CK = 8 samples * 4 B + slack fits.
 
 // ------------------------------------------------------------------------------------------------ K2 parse
 // One thread per frame: walks the subframes, records where each starts and what it is, skips the residual.
 __device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
 constexpr int PARSE_THREADS = 64;
+using ParseBits = RingBits<16>;   // 256 B ring: a Rice codeword walked here may be up to 62 bits
 
 __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     extern __shared__ __align__(16) uint8_t s_ring[];
@@ -470,8 +485,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
     const uint64_t frame_bit0 = c.off * 8;
     const uint64_t end_bit = live ? (c.off + a.flen[i]) * 8 : 0;
-    RingBits br;
-    if (live) br.init(smem_u32(s_ring) + threadIdx.x * RB_STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
+    ParseBits br;
+    if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
     bool bad = false, unparse = false;
     uint32_t max_order = 0, any_wide = 0;
     // lanes of a warp are different frames; they walk channel by channel and, inside a subframe, sample index by
@@ -495,10 +510,10 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                 bps -= w;
                 si.wasted = (uint8_t)w;
                 bool has_resid = false;
-                if (type == 0) br.advance(bps);
+                if (type == 0) br.skip(bps);
                 else if (type == 1) {
                     si.type = 1;
-                    if (br.abs_pos(a.in) + (uint64_t)c.bs * bps > end_bit) bad = true; else br.advance(c.bs * bps);
+                    if (br.abs_pos(a.in) + (uint64_t)c.bs * bps > end_bit) bad = true; else br.jump(c.bs * bps);
                 } else if (type >= 8 && type <= 12) { si.type = 2; order = type - 8; has_resid = true; }
                 else if (type >= 32) { si.type = 3; order = type - 31; has_resid = true; }
                 else unparse = true;
@@ -508,13 +523,13 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                     else if (br.abs_pos(a.in) + (uint64_t)order * bps > end_bit) bad = true;
                     else {
                         if (order > max_order) max_order = order;
-                        br.advance(order * bps);
+                        br.jump(order * bps);
                         if (si.type == 3) {
                             uint32_t prec = br.get(4) + 1;
                             int32_t shift = br.gets(5);
                             if (prec == 16 || shift < 0) unparse = true;
                             else {
-                                br.advance(order * prec);
+                                br.jump(order * prec);
                                 if (bps + prec + (uint32_t)ilog2u(order) <= 32) si.flags |= 1; else any_wide = 1;
                             }
                         } else si.flags |= 1;
@@ -539,6 +554,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         }
         if (!__any_sync(FULL, walk)) continue;
         for (uint32_t s = 0; s < wmax_bs; s++) {
+            if ((s & 7) == 0 && walk) br.checkpoint();
             if (walk && s >= order && s < c.bs) {
                 if (left == 0) {   // partition boundary (s is a multiple of psize, or s == order)
                     do {               // twice only when partition 0 holds zero samples (its parameter is still coded)
@@ -549,7 +565,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                         if (k == esc) {
                             uint32_t nb = br.get(5);
                             if (br.abs_pos(a.in) + (uint64_t)left * nb > end_bit) { bad = true; walk = false; left = 1; }
-                            else { br.advance(left * nb); rawskip = 1; }
+                            else { br.jump(left * nb); rawskip = 1; }
                         }
                         k1 = k + 1;
                     } while (left == 0);
@@ -557,10 +573,10 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                 left--;
                 if (!rawskip && walk) {
                     uint32_t wd = br.window();
-                    if (wd) br.advance(__clz(wd) + k1);
+                    if (wd) br.skip(__clz(wd) + k1);
                     else {
-                        br.unary(1u << 16);
-                        br.advance(k1 - 1);
+                        br.unary_slow(1u << 16);
+                        br.jump(k1 - 1);
                         if (br.abs_pos(a.in) > end_bit) { bad = true; walk = false; }
                     }
                 }
@@ -637,93 +653,20 @@ __global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_
 }
 
 // ------------------------------------------------------------------------------------------------ K3-5 decode
+// One thread per (frame, channel).  Threads of a CTA advance sample index by sample index in lockstep; each keeps its
+// bit position, Rice state, quantised LPC coefficients and the last ORD samples in registers (the history is a
+// register ring: the sample loop is unrolled ORD times so every tap has a fixed register).  Stereo decorrelation is a
+// warp shuffle between the two channel lanes; samples are staged interleaved in shared memory and written out packed.
 constexpr int DEC_THREADS = 128;
-constexpr int DEC_T = 64;       // samples per channel staged per tile
+using DecBits = RingBits<8>;                     // 128 B ring per lane
 
-template <int ORD>
-struct SubDec {
-    BitReader br;
-    int32_t coef[ORD];
-    int32_t hist[ORD];          // hist[0] = most recent sample (before the wasted-bits shift)
-    uint32_t part_left, part_size;
-    int32_t cval;
-    int type, order, bps, wasted, shift, idx, k, plen, rawbits;
-    bool narrow, esc;
-
-    __device__ __forceinline__ void read_residual_header(uint32_t bs) {
-        uint32_t method = br.get(2);
-        plen = method ? 5 : 4;
-        uint32_t po = br.get(4);
-        part_size = bs >> po;
-        part_left = (po == 0 ? bs : part_size) - (uint32_t)order;
-        next_partition_params();
-    }
-    __device__ __forceinline__ void next_partition_params() {
-        uint32_t kk = br.get(plen);
-        esc = kk == (plen == 5 ? 31u : 15u);
-        k = (int)kk;
-        if (esc) rawbits = (int)br.get(5);
-    }
-    __device__ __forceinline__ void read_predictor(uint32_t bs) {
-        if (type == 3) {
-            int prec = (int)br.get(4) + 1;
-            shift = br.gets(5);
-            narrow = (bps + prec + ilog2u((uint32_t)order)) <= 32;
-#pragma unroll
-            for (int j = 0; j < ORD; j++) if (j < order) coef[j] = br.gets(prec);
-        } else {
-            shift = 0; narrow = true;
-            // FIXED predictors as LPC coefficient sets
-            const int o = order;
-            if (ORD >= 1 && o >= 1) coef[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
-            if (ORD >= 2 && o >= 2) coef[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
-            if (ORD >= 3 && o >= 3) coef[2] = o == 3 ? 1 : 4;
-            if (ORD >= 4 && o >= 4) coef[3] = -1;
-        }
-        read_residual_header(bs);
-    }
-    __device__ __forceinline__ void init(const uint8_t* in, uint64_t in_len, const Cand& c, const SubInfo& si, uint32_t ch) {
-        br.set_limit(in, in_len);
-        br.init(in, c.off * 8 + si.bit_offset);
-        uint32_t x = br.get(8);
-        if (x & 1) br.unary(64);
-        type = si.type; order = si.order; wasted = si.wasted;
-        bps = (int)c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1 : 0) - wasted;
-        idx = 0; shift = 0; narrow = true; esc = false; k = 0; rawbits = 0; plen = 4; part_left = 0; part_size = 0; cval = 0;
-#pragma unroll
-        for (int j = 0; j < ORD; j++) { coef[j] = 0; hist[j] = 0; }
-        if (type == 0) cval = br.gets(bps);
-        else if (type >= 2 && order == 0) read_predictor(c.bs);
-    }
-    __device__ __forceinline__ int32_t next(uint32_t bs) {
-        int32_t s;
-        if (type == 0) s = cval;
-        else if (type == 1 || idx < order) {
-            s = br.gets(bps);
-            if (type != 1 && idx == order - 1) read_predictor(bs);
-        } else {
-            while (part_left == 0) { part_left = part_size; next_partition_params(); }
-            part_left--;
-            int32_t r;
-            if (esc) r = br.gets(rawbits);
-            else {
-                uint32_t q = br.unary(1u << 24);
-                uint32_t u = (q << k) | br.get(k);
-                r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-            }
-            int64_t sum = 0;
-#pragma unroll
-            for (int j = 0; j < ORD; j++) sum += (int64_t)coef[j] * hist[j];
-            if (narrow) sum = (int64_t)(int32_t)sum;      // libFLAC 1.2.1 accumulates in 32 bits here
-            s = (int32_t)((uint32_t)r + (uint32_t)(int32_t)(sum >> shift));
-        }
-#pragma unroll
-        for (int j = ORD - 1; j > 0; j--) hist[j] = hist[j - 1];
-        if (ORD > 0) hist[0] = s;
-        idx++;
-        return (int32_t)((uint32_t)s << wasted);
-    }
+template <int ORD> struct DecCfg {
+    static constexpr int T = 64;                          // samples per channel staged per tile
+    static constexpr int U = (ORD >= 16) ? 8 : 4;         // sample-loop unroll; the history shifts by U registers every U samples
+    static constexpr int CK = 8;                          // samples between ring checkpoints
 };
+
+enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 
 // bytes [0, nbytes) of the interleaved packed PCM of `ts` (flat int32 samples, B bytes each) -> dst, cooperatively by a warp
 __device__ __forceinline__ uint32_t sample_byte(const int32_t* ts, uint32_t b, uint32_t B) {
@@ -757,60 +700,185 @@ __device__ void store_packed(uint8_t* __restrict__ dst, uint32_t nbytes, const i
     if (tb + lane < nbytes) dst[tb + lane] = (uint8_t)sample_byte(ts, tb + lane, B);
 }
 
-template <int ORD>
+template <int ORD, bool WIDE>
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(PassArgs a, uint32_t C, uint32_t B) {
-    extern __shared__ int32_t s_tile[];
+    constexpr int T = DecCfg<ORD>::T, U = DecCfg<ORD>::U, CK = DecCfg<ORD>::CK;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ uint32_t s_bs[DEC_THREADS];
     __shared__ uint64_t s_po[DEC_THREADS];
     __shared__ uint32_t s_maxbs;
+    int32_t* s_tile = reinterpret_cast<int32_t*>(s_dyn + DEC_THREADS * DecBits::STRIDE);
     const uint32_t F = DEC_THREADS / C;
-    const uint32_t stride = DEC_T * C + C;
+    const uint32_t stride = T * C + C;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_acc = a.totals->n_accepted;
     const uint32_t fl = tid / C, ch = tid - fl * C;
+    // idle threads (C does not divide the CTA size) write to a scratch word behind the tiles
+    const uint32_t my_base = smem_u32(fl < F ? s_tile + fl * stride + ch : s_tile + F * stride);
+    const uint32_t c4 = fl < F ? C * 4 : 0;
     for (uint32_t g = blockIdx.x; (uint64_t)g * F < n_acc; g += gridDim.x) {
-        const uint32_t k = g * F + fl;
-        const bool active = fl < F && k < n_acc;
+        const uint32_t kf = g * F + fl;
+        const bool active = fl < F && kf < n_acc;
         if (tid == 0) s_maxbs = 0;
         __syncthreads();
-        SubDec<ORD> dec;
-        uint32_t bs = 0, assign = 0; bool ok = false;
+        // ---- per-subframe state (registers)
+        DecBits br;
+        int32_t coef[ORD], hist[ORD];          // hist[0] = most recent sample (before the wasted-bits shift)
+#pragma unroll
+        for (int j = 0; j < ORD; j++) { coef[j] = 0; hist[j] = 0; }
+        uint32_t bs = 0, assign = 0, order = 0, wasted = 0, shift = 0, bps = 0;
+        uint32_t psize = 0, plen = 4, fastleft = 0, rawleft = 0, rawbits = 0, k = 0;
+        int32_t cval = 0;
+        int mode = M_IDLE;
+        bool narrow = true, first_part = true;
         if (active) {
-            const uint32_t i = a.acc_idx[k];
+            const uint32_t i = a.acc_idx[kf];
             const Cand c = a.cand[i];
             bs = c.bs; assign = c.assign;
-            ok = a.status[i] == ST_OK;
+            bool ok = a.status[i] == ST_OK;
             const uint64_t po = a.pcm_off[i];
             if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
             if (ch == 0) { s_bs[fl] = bs; s_po[fl] = po; }
-            if (ok) dec.init(a.in, a.in_len, c, a.sub[(uint64_t)i * MAX_CH + ch], ch);
             atomicMax(&s_maxbs, bs);
+            if (ok) {
+                const SubInfo si = a.sub[(uint64_t)i * MAX_CH + ch];
+                br.init(smem_u32(s_dyn) + tid * DecBits::STRIDE, a.in, a.in_len, c.off * 8 + si.bit_offset);
+                uint32_t x = br.get(8);
+                if (x & 1) br.unary(64);
+                order = si.order; wasted = si.wasted;
+                bps = (uint32_t)c.bps + (((assign == 8 && ch == 1) || (assign == 9 && ch == 0) || (assign == 10 && ch == 1)) ? 1u : 0u) - wasted;
+                if (si.type == 0) { mode = M_CONST; cval = br.gets(bps); }
+                else if (si.type == 1) mode = M_VERBATIM;
+                else {
+                    mode = M_PRED;
+                    // warm-up samples are parked in this thread's tile slots 0..order-1 (order <= 32 <= T) and picked up
+                    // again, in order, by the sample loop
+#pragma unroll 1
+                    for (uint32_t j = 0; j < order; j++) { sts32(my_base + j * c4, (uint32_t)br.gets(bps)); if ((j & 7) == 7) br.ensure_now(); }
+                    br.ensure_now();
+                    if (si.type == 3) {
+                        const uint32_t prec = br.get(4) + 1;
+                        shift = (uint32_t)br.gets(5);
+                        narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
+#pragma unroll
+                        for (int j = 0; j < ORD; j++) if (j < (int)order) { coef[j] = br.gets(prec); if ((j & 7) == 7) br.ensure_now(); }
+                        br.ensure_now();
+                    } else {   // FIXED predictors as LPC coefficient sets, 32-bit wrap-around arithmetic
+                        const int o = (int)order;
+                        if (ORD >= 1 && o >= 1) coef[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
+                        if (ORD >= 2 && o >= 2) coef[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
+                        if (ORD >= 3 && o >= 3) coef[2] = o == 3 ? 1 : 4;
+                        if (ORD >= 4 && o >= 4) coef[3] = -1;
+                    }
+                    const uint32_t method = br.get(2);
+                    plen = method ? 5 : 4;
+                    const uint32_t porder = br.get(4);
+                    psize = porder ? bs >> porder : bs;
+                }
+            }
         } else if (fl < F && ch == 0) s_bs[fl] = 0;
         __syncthreads();
         const uint32_t maxbs = s_maxbs;
-        int32_t* my = s_tile + fl * stride + ch;
-        for (uint32_t i0 = 0; i0 < maxbs; i0 += DEC_T) {
+        const bool reads = mode >= M_VERBATIM;
+        for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
 #pragma unroll 1
-            for (uint32_t t = 0; t < DEC_T; t++) {
-                int32_t v = 0;
-                if (ok && i0 + t < bs) v = dec.next(bs);
-                if (C == 2) {
-                    int32_t o = __shfl_xor_sync(FULL, v, 1);
-                    if (assign == 8) { if (ch == 1) v = (int32_t)((uint32_t)o - (uint32_t)v); }
-                    else if (assign == 9) { if (ch == 0) v = (int32_t)((uint32_t)v + (uint32_t)o); }
-                    else if (assign == 10) {
-                        int32_t mid = ch == 0 ? v : o, side = ch == 0 ? o : v;
-                        uint32_t m2 = ((uint32_t)mid << 1) | ((uint32_t)side & 1u);
-                        v = ch == 0 ? ((int32_t)(m2 + (uint32_t)side) >> 1) : ((int32_t)(m2 - (uint32_t)side) >> 1);
+            for (uint32_t t0 = 0; t0 < (uint32_t)T; t0 += U) {
+                const uint32_t my_row = my_base + t0 * c4;
+                if ((t0 % CK) == 0 && reads) br.checkpoint();
+                int32_t nw[U];
+#pragma unroll
+                for (int j = 0; j < U; j++) {
+                    const uint32_t idx = i0 + t0 + j;
+                    int32_t s = 0;
+                    bool pred = false;
+                    int32_t r = 0;
+                    if (fastleft) {          // the common case: next Rice codeword of the current partition
+                        fastleft--;
+                        pred = true;
+                        const uint32_t w = br.window();
+                        const uint32_t z = __clz(w);
+                        if (z + 1 + k <= 32) {
+                            const uint32_t u = (z << k) | shr_c(shl_c(w, z + 1), 32 - k);
+                            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                            br.skip(z + 1 + k);
+                        } else {                 // codeword longer than one window (rare): resynchronise the ring afterwards
+                            const uint32_t q = br.unary(1u << 24);
+                            const uint32_t u = (q << k) | br.get(k);
+                            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                            br.ensure_now();
+                        }
+                    } else if (idx < bs && mode != M_IDLE) {
+                        if (mode == M_CONST) s = cval;
+                        else if (mode == M_VERBATIM) s = br.gets(bps);
+                        else if (idx < order) s = (int32_t)lds32(my_row + (uint32_t)j * c4);      // parked warm-up sample
+                        else {
+                            pred = true;
+                            if (rawleft == 0) {                  // partition boundary
+                                uint32_t cnt;
+#pragma unroll 1
+                                do {                             // twice only if partition 0 holds zero samples
+                                    cnt = psize - (first_part ? order : 0);
+                                    first_part = false;
+                                    k = br.get(plen);
+                                    if (k == (plen == 5 ? 31u : 15u)) { rawbits = br.get(5); rawleft = cnt; fastleft = 0; }
+                                    else { fastleft = cnt; rawleft = 0; }
+                                } while (cnt == 0);
+                            }
+                            if (rawleft) { rawleft--; r = br.gets(rawbits); }
+                            else {
+                                fastleft--;
+                                const uint32_t q = br.unary(1u << 24);
+                                const uint32_t u = (q << k) | br.get(k);
+                                r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                                br.ensure_now();
+                            }
+                        }
                     }
+                    if (pred) {
+                        if (WIDE) {
+                            int64_t sum = 0;
+#pragma unroll
+                            for (int m = 0; m < ORD; m++) {
+                                const int32_t h = (m < j) ? nw[j - 1 - m < 0 ? 0 : j - 1 - m] : hist[m - j < 0 ? 0 : m - j];
+                                asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(sum) : "r"(coef[m]), "r"(h));
+                            }
+                            if (narrow) sum = (int64_t)(int32_t)sum;      // libFLAC 1.2.1 accumulates in 32 bits here
+                            s = (int32_t)((uint32_t)r + (uint32_t)(int32_t)(sum >> shift));
+                        } else {
+                            uint32_t sum = 0;
+#pragma unroll
+                            for (int m = 0; m < ORD; m++) {
+                                const int32_t h = (m < j) ? nw[j - 1 - m < 0 ? 0 : j - 1 - m] : hist[m - j < 0 ? 0 : m - j];
+                                sum += (uint32_t)coef[m] * (uint32_t)h;
+                            }
+                            s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
+                        }
+                    }
+                    nw[j] = s;
+                    int32_t v = (int32_t)((uint32_t)s << wasted);
+                    if (C == 2) {
+                        const int32_t o = __shfl_xor_sync(FULL, v, 1);
+                        if (assign == 8) { if (ch == 1) v = (int32_t)((uint32_t)o - (uint32_t)v); }
+                        else if (assign == 9) { if (ch == 0) v = (int32_t)((uint32_t)v + (uint32_t)o); }
+                        else if (assign == 10) {
+                            const int32_t mid = ch == 0 ? v : o, side = ch == 0 ? o : v;
+                            const uint32_t m2 = ((uint32_t)mid << 1) | ((uint32_t)side & 1u);
+                            v = ch == 0 ? ((int32_t)(m2 + (uint32_t)side) >> 1) : ((int32_t)(m2 - (uint32_t)side) >> 1);
+                        }
+                    }
+                    sts32(my_row + (uint32_t)j * c4, (uint32_t)v);
                 }
-                if (fl < F) my[t * C] = v;
+                // slide the history window by U samples
+#pragma unroll
+                for (int m = ORD - 1; m >= U; m--) hist[m] = hist[m - U];
+#pragma unroll
+                for (int m = 0; m < U && m < ORD; m++) hist[m] = nw[U - 1 - m];
             }
             __syncthreads();
             for (uint32_t f = warp; f < F; f += DEC_THREADS / 32) {
                 const uint32_t fbs = s_bs[f];
                 if (i0 >= fbs) continue;
-                const uint32_t nt = min((uint32_t)DEC_T, fbs - i0);
+                const uint32_t nt = min((uint32_t)T, fbs - i0);
                 store_packed(a.out + s_po[f] + (uint64_t)i0 * C * B, nt * C * B, s_tile + f * stride, B, lane);
             }
             __syncthreads();
@@ -840,20 +908,37 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
     k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
-    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * RB_STRIDE, S(stream)>>>(a); g_launches++;
+    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a); g_launches++;
 }
 void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream) {
     k_prefix<<<1, 1024, 0, S(stream)>>>(a, bytes_per_sample); g_launches++;
 }
-void launch_decode(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, void* stream) {
+template <int ORD, bool WIDE>
+static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
     const uint32_t F = DEC_THREADS / C;
-    uint32_t grid = blocks_for(nacc, F); if (grid > 148 * 16) grid = 148 * 16;
-    size_t smem = (size_t)F * (DEC_T * C + C) * sizeof(int32_t);
-    if (max_order <= 4) k_decode<4><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
-    else if (max_order <= 8) k_decode<8><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
-    else if (max_order <= 12) k_decode<12><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
-    else k_decode<32><<<grid, DEC_THREADS, smem, S(stream)>>>(a, C, B);
+    uint32_t grid = blocks_for(nacc, F);
+    if (grid > 148 * 32) grid = 148 * 32;
+    const size_t smem = (size_t)DEC_THREADS * DecBits::STRIDE + ((size_t)F * (DecCfg<ORD>::T * C + C) + 4) * sizeof(int32_t);
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(k_decode<ORD, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_done = true; }
+    k_decode<ORD, WIDE><<<grid, DEC_THREADS, smem, st>>>(a, C, B);
     g_launches++;
+}
+void launch_decode(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, bool wide, void* stream) {
+    cudaStream_t st = S(stream);
+    if (wide) {
+        if (max_order <= 4) launch_decode_t<4, true>(a, nacc, C, B, st);
+        else if (max_order <= 8) launch_decode_t<8, true>(a, nacc, C, B, st);
+        else if (max_order <= 12) launch_decode_t<12, true>(a, nacc, C, B, st);
+        else if (max_order <= 16) launch_decode_t<16, true>(a, nacc, C, B, st);
+        else launch_decode_t<32, true>(a, nacc, C, B, st);
+    } else {
+        if (max_order <= 4) launch_decode_t<4, false>(a, nacc, C, B, st);
+        else if (max_order <= 8) launch_decode_t<8, false>(a, nacc, C, B, st);
+        else if (max_order <= 12) launch_decode_t<12, false>(a, nacc, C, B, st);
+        else if (max_order <= 16) launch_decode_t<16, false>(a, nacc, C, B, st);
+        else launch_decode_t<32, false>(a, nacc, C, B, st);
+    }
 }
 
 } // namespace bnf
