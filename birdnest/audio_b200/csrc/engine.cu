@@ -396,7 +396,17 @@ static int fetch_diag(bnflac* h) {
         f.channels = (uint8_t)(cand[i].assign < 8 ? cand[i].assign + 1 : 2); f.bits_per_sample = cand[i].bps; f.assignment = cand[i].assign;
         f.status = st[i] == ST_OK ? BNFLAC_FRAME_OK : BNFLAC_FRAME_CRC_MISMATCH;
         f.number = cand[i].number; f.pcm_offset = po[i];
-        if (f.offset != expect) h->errors.push_back(0);           // LOST_SYNC: bytes skipped before this frame
+        if (f.offset != expect) {
+            // bytes were skipped before this frame.  The reference reports BAD_HEADER first when the skipped bytes begin
+            // with a sync code whose header did not validate, then LOST_SYNC (observed on the DLL, tests/golden faults)
+            uint8_t two[2] = {0, 0};
+            if (expect + 2 <= h->len) {
+                if (h->host_ptr) memcpy(two, h->host_ptr + expect, 2);
+                else cudaMemcpy(two, h->d_ext + expect, 2, cudaMemcpyDeviceToHost);
+            }
+            if (two[0] == 0xFF && (two[1] & 0xFC) == 0xF8) h->errors.push_back(1);
+            h->errors.push_back(0);
+        }
         if (st[i] == ST_CRC) h->errors.push_back(2);              // FRAME_CRC_MISMATCH
         expect = f.offset + f.length;
         h->frames.push_back(f);

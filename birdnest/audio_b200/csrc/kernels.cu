@@ -296,17 +296,19 @@ __global__ void __launch_bounds__(256) k_link(PassArgs a) {
         j++;
     }
     if (st != ST_OK) {
-        // CRC failed: if a later candidate continues the numbering, this is a damaged frame (delivered zero-filled)
+        // CRC failed over every plausible span.  If a later candidate continues the numbering, this frame is damaged
+        // (the reference delivers it zero-filled).  Otherwise its successor's header is what is damaged (or this is the
+        // last frame before trailing bytes): K2 validates it the way the reference does, by parsing to its end.
         uint32_t k = i + 1;
+        bool found = false;
         for (;; k++) {
             const bool at_seg_end = !(k < n && a.cand[k].seg == ci.seg);
-            if (at_seg_end) {
-                // last frame of the segment (or everything after is unrelated): K2 decides by parsing
-                if (seg_end - ci.off <= (uint64_t)max_frame + 65536) { st = ST_CHECK; nx = k; fend = seg_end; }
-                break;
-            }
-            if (a.cand[k].off - ci.off > max_frame) break;
-            if (continuous(ci, a.cand[k])) { st = ST_CRC; nx = k; fend = a.cand[k].off; break; }
+            if (at_seg_end || a.cand[k].off - ci.off > max_frame) break;
+            if (continuous(ci, a.cand[k])) { st = ST_CRC; nx = k; fend = a.cand[k].off; found = true; break; }
+        }
+        if (!found) {
+            st = ST_CHECK; nx = k;
+            fend = seg_end - ci.off > (uint64_t)max_frame ? ci.off + max_frame : seg_end;
         }
     }
     a.status[i] = st;

@@ -1,0 +1,23 @@
+"""Frame-range sharding plan: FLAC frames are independent and self-positioned, so a stream is split into
+`count` byte ranges of its frame data; a shard owns the frames whose sync code lies inside its range, decodes them with
+no data-path collective, and the host concatenates the PCM slices in shard order.
+
+The same arithmetic lives in csrc/engine.cu (compute_shard): keep the two in step.
+"""
+from typing import List, Sequence, Tuple
+
+
+def shard_ranges(stream_len: int, first_frame_offset: int, count: int) -> List[Tuple[int, int]]:
+    """[own_begin, own_end) of every shard, in stream order."""
+    d = stream_len - first_frame_offset
+    out = []
+    for i in range(count):
+        lo = first_frame_offset + d * i // count
+        hi = stream_len if i + 1 == count else first_frame_offset + d * (i + 1) // count
+        out.append((lo, hi))
+    return out
+
+
+def owned_frames(frame_offsets: Sequence[int], lo: int, hi: int) -> List[int]:
+    """Indices of the frames whose first byte is in [lo, hi).  frame_offsets may carry a trailing end-of-stream offset."""
+    return [i for i, o in enumerate(frame_offsets) if lo <= o < hi and (i + 1 < len(frame_offsets))]

@@ -350,8 +350,8 @@ static int64_t decode_span(const uint8_t* d, size_t len, const fo_streaminfo* si
         fhdr_t h;
         int rc = parse_frame_header(d, len, pos, si, &h);
         if (rc < 0) break; /* truncated: end of stream */
-        if (rc == 1) { ERR(FO_ERR_BAD_HEADER); in_sync = 0; pos += 2; continue; }
-        if (rc == 3) { ERR(FO_ERR_UNPARSEABLE); in_sync = 0; pos += 2; continue; }
+        if (rc == 1) { ERR(FO_ERR_BAD_HEADER); in_sync = 1; pos += 2; continue; }   /* libFLAC reports LOST_SYNC again when it then has to skip bytes */
+        if (rc == 3) { ERR(FO_ERR_UNPARSEABLE); in_sync = 1; pos += 2; continue; }
         if (work_reserve(&w, h.blocksize)) { work_free(&w); return -100; }
         br_t b = { d, len, (uint64_t)(pos + h.header_len) * 8, 0 };
         int bad = 0;

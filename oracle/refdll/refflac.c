@@ -31,6 +31,7 @@ static i32 sys_close(int fd) { return sc3(6, fd, 0, 0); }
 struct mm { u32 addr, len, prot, flags, fd, off; };
 static void* xmmap(u32 addr, u32 len, u32 prot, u32 flags) { struct mm m = {addr, len, prot, flags, (u32)-1, 0}; return (void*)sc3(90, (i32)&m, 0, 0); }
 struct ts { i32 sec, nsec; };
+static u64 udiv64(u64 n, u32 d) { u64 q = 0, r = 0; for (int i = 63; i >= 0; i--) { r = (r << 1) | ((n >> i) & 1); if (r >= d) { r -= d; q |= 1ull << i; } } return q; }
 static u64 now_ns(void) { struct ts t; sc3(265, 1, (i32)&t, 0); return (u64)(u32)t.sec * 1000000000ull + (u32)t.nsec; }
 
 /* ------------------------------------------------------------------ tiny libc */
@@ -258,7 +259,7 @@ static int cmain(int argc, char** argv) {
         out_buf = xmmap(0, out_cap, 3, 0x22); if ((i32)out_buf < 0 && (i32)out_buf > -4096) die("cannot map output");
         if (bench) {
             u32 iters = argc > 4 ? atou(argv[4]) : 3;
-            for (u32 i = 0; i < iters; i++) { u64 t0 = now_ns(); decode_once(); u64 t1 = now_ns(); put("ms="); putu((u32)((t1 - t0) / 1000)); put("us frames="); putu(n_frames); put(" bytes="); putu(out_len); put("\n"); }
+            for (u32 i = 0; i < iters; i++) { u64 t0 = now_ns(); decode_once(); u64 t1 = now_ns(); put("ms="); putu((u32)udiv64(t1 - t0, 1000)); put("us frames="); putu(n_frames); put(" bytes="); putu(out_len); put("\n"); }
             return 0;
         }
         decode_once();

@@ -1,0 +1,81 @@
+"""CPU suite: the C-ABI library loads, exports exactly what include/bnflac.h declares, and its host-side logic
+(metadata parse, error vocabulary, no-device behaviour) works without a GPU.  No compute calls here."""
+import ctypes as C
+import io
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def test_header_symbols_are_exported_and_bound():
+    from birdnest.audio_b200 import _abi
+    hdr = open(os.path.join(ROOT, "include", "bnflac.h")).read()
+    declared = set(re.findall(r"\b(bnflac_[a-z_0-9]+)\s*\(", hdr)) - {"bnflac_read_cb"}
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _abi.lib_path()], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert declared <= exported, declared - exported
+    assert declared == set(_abi._PROTOS), declared ^ set(_abi._PROTOS)
+    L = _abi.lib()
+    assert L.bnflac_abi_version() == 1
+    assert L.bnflac_strerror(-4).decode().startswith("no CUDA device")
+    assert [L.bnflac_state_name(i).decode() for i in (2, 3, 4, 7)] == ["SearchForFrameSync", "ReadFrame", "EndOfStream", "Aborted"]
+    assert [L.bnflac_frame_status_name(i).decode() for i in range(5)] == ["Ok", "LostSync", "BadHeader", "FrameCrcMismatch", "UnparsableStream"]
+
+
+def test_no_torch_types_in_the_abi():
+    hdr = open(os.path.join(ROOT, "include", "bnflac.h")).read()
+    assert "torch" not in hdr and "at::" not in hdr and 'extern "C"' in hdr
+
+
+def test_struct_layouts_match_the_header():
+    from birdnest.audio_b200 import _abi
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "bnflac.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(bnflac_opts), sizeof(bnflac_info_t), sizeof(bnflac_frame_t), sizeof(bnflac_subframe_t),
+        sizeof(bnflac_timing), sizeof(bnflac_clip_result), offsetof(bnflac_info_t, md5), offsetof(bnflac_frame_t, pcm_offset)); return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])   # the header is plain C
+        got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")], text=True).split()]
+    want = [C.sizeof(_abi.Opts), C.sizeof(_abi.Info), C.sizeof(_abi.FrameRec), C.sizeof(_abi.SubframeRec), C.sizeof(_abi.Timing),
+            C.sizeof(_abi.ClipResult), _abi.Info.md5.offset, _abi.FrameRec.pcm_offset.offset]
+    assert got == want
+
+
+def test_open_rejects_non_flac_before_touching_a_device():
+    from birdnest.audio_b200 import _abi
+    for blob, code in ((b"RIFF0000WAVEfmt ", _abi.ERR_NOT_FLAC), (b"fLaC\x00\x00\x00\x22" + b"\x00" * 10, _abi.ERR_TRUNCATED), (b"fL", _abi.ERR_TRUNCATED)):
+        with pytest.raises(_abi.BnflacError) as e:
+            _abi.open_memory(blob)
+        assert e.value.code == code
+
+
+def test_valid_stream_without_device_fails_loudly(streams):
+    from birdnest.audio_b200 import _abi
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_abi.BnflacError) as e:
+        _abi.open_memory(streams("cfg1_16bit_stereo_lpc8").flac)
+    assert e.value.code == _abi.ERR_NO_DEVICE      # there is no CPU fallback to fall into
+
+
+def test_flacdecoder_mirror_error_texts(streams):
+    """FLACDecoder ctor failure texts (FLACDecoder.cs:66-70,98-105) and the closed/NotImplemented surface."""
+    from birdnest.audio_b200 import FLACDecoder, FLACPacketQueue, EmptyStubLogger, ApplicationException
+    with pytest.raises(ApplicationException) as e:
+        FLACDecoder(io.BytesIO(b"this is not flac at all" * 10), FLACPacketQueue(), EmptyStubLogger())
+    assert str(e.value) == "FLAC: Could not Could not process until end of metadata - EndOfStream!"
+
+
+def test_library_has_no_oracle_or_cpu_decode_symbols():
+    """The product must not link the oracle (a CPU fallback would void the parity claims)."""
+    from birdnest.audio_b200 import _abi
+    out = subprocess.check_output(["nm", "-D", _abi.lib_path()], text=True)
+    assert "fo_decode" not in out and "fo_read_streaminfo" not in out and "bnc_encode" not in out
