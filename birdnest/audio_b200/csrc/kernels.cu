@@ -15,6 +15,7 @@
 // FLACDecoder.cs:215) and the interleave loops FLACDecoder.cs:552-576 / FLACFileReader.cs:214-243.
 #include "bnflac_dev.h"
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace bnf {
 
@@ -326,91 +327,42 @@ __global__ void __launch_bounds__(256) k_cover(PassArgs a) {
     for (uint32_t j = i + 1; j < nx && j < n; j++) a.status[j] = ST_DROP;
 }
 
-// ------------------------------------------------------------------------------------------------ bit reader
-struct BitReader {
-    const uint32_t* wp;   // next 32-bit word to load
-    const uint32_t* wend; // first word past the (padded) input: loads beyond it read as zero
-    uint64_t buf;         // MSB-aligned window, at least 32 valid bits after every operation
-    int cnt;              // valid bits in buf
-
-    __device__ __forceinline__ uint32_t load() {
-        uint32_t w = wp < wend ? __ldg(wp) : 0u;
-        wp++;
-        return __byte_perm(w, 0, 0x0123);
-    }
-    __device__ __forceinline__ void set_limit(const uint8_t* base, uint64_t in_len) {
-        wend = reinterpret_cast<const uint32_t*>(base) + ((in_len + 3) >> 2);
-    }
-    __device__ __forceinline__ void init(const uint8_t* base, uint64_t bitpos) {
-        wp = reinterpret_cast<const uint32_t*>(base) + (bitpos >> 5);
-        uint32_t w0 = load(), w1 = load();
-        buf = ((uint64_t)w0 << 32) | w1;
-        cnt = 64;
-        int s = (int)(bitpos & 31);
-        if (s) skip(s);
-    }
-    __device__ __forceinline__ void skip(int n) {   // 0 <= n <= 32
-        buf <<= n;
-        cnt -= n;
-        if (cnt < 32) { buf |= (uint64_t)load() << (32 - cnt); cnt += 32; }
-    }
-    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
-    __device__ __forceinline__ uint32_t get(int n) {   // 0 <= n <= 32
-        uint32_t v = n ? (uint32_t)(buf >> (64 - n)) : 0u;
-        skip(n);
-        return v;
-    }
-    __device__ __forceinline__ int32_t gets(int n) {
-        int32_t v = n ? (int32_t)((int64_t)buf >> (64 - n)) : 0;
-        skip(n);
-        return v;
-    }
-    __device__ __forceinline__ uint64_t pos(const uint8_t* base) const {
-        return (uint64_t)(wp - reinterpret_cast<const uint32_t*>(base)) * 32 - (uint64_t)cnt;
-    }
-    // zeros before the terminating 1; `limit` bounds a runaway on damaged data
-    __device__ __forceinline__ uint32_t unary(uint32_t limit) {
-        uint32_t q = 0;
-        for (;;) {
-            uint32_t top = peek32();
-            if (top) { int z = __clz(top); skip(z + 1); return q + (uint32_t)z; }
-            q += 32; skip(32);
-            if (q > limit) return q;
-        }
-    }
-};
-
 // ------------------------------------------------------------------------------------------------ ring bit reader
 // Every lane walks its own serial bitstream.  The bytes are staged through shared memory by per-lane cp.async
-// (LDGSTS, 16 B each) into a private ring that runs several blocks ahead of the read position, so the serial parse
-// never waits on HBM.  Reads are position based: two LDS + byte swaps + one funnel shift give a 32-bit window.
-// Refill is CHECKPOINTED: all lanes of a warp top up their rings at the same loop iterations (every CK samples), so the
-// divergent "my ring ran low" branch is not taken on almost every iteration by some lane.  Between checkpoints a lane
-// may consume at most CK*32 bits + one window, which the ring always holds ahead (see checkpoint()).
+// (LDGSTS, 16 B each) into a private 128-byte ring that runs several blocks ahead of the read position, so the serial
+// walk never waits on HBM.  Reads are position based: two LDS + byte swaps + one funnel shift give a 32-bit window; block
+// 0 of the ring is duplicated behind block 7, so the second word of a window never needs a wrap-around address.
+// Refill is CHECKPOINTED: all lanes of a warp top up their rings at the same loop iterations (every 8 samples): first
+// wait for what was requested one period ago, then request more.  Budget: blocks up to (block of pos at the previous
+// checkpoint) + 7 have landed, i.e. >= 113 bytes past that position; a period may therefore advance by A bytes with
+// 2A + 8 <= 113 (this period's reads reach pos_prev + 2A + 8).  The walkers keep A <= 42: eight samples of at most 32
+// bits each plus partition parameters; anything longer takes a synchronous path (ensure_now).
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
 __device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }   // index of the leading one; 0xffffffff for 0
+__device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
 
-template <int NBLK>                              // ring = NBLK blocks of 16 bytes per lane (NBLK a power of two)
 struct RingBits {
-    static constexpr int BLK = 16;
-    static constexpr int RB_BYTES = BLK * NBLK;
-    static constexpr int STRIDE = RB_BYTES + 16;           // lane stride: 16 B skew spreads lanes over banks, keeps 16 B alignment
-    // bytes guaranteed readable ahead of pos right after checkpoint(): blocks up to (curblk_prev + NBLK - 1) are complete
+    static constexpr int NBLK = 8, BLK = 16, RB_BYTES = NBLK * BLK;
+    static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
     uint32_t sring;        // shared-space address of this lane's ring
     uint32_t pos;          // bit position relative to g0
     uint32_t filled;       // blocks [.., filled) have been requested
+    uint32_t navail;       // whole 16-byte blocks readable from g0 (blocks past the padded input read as zero)
     const uint8_t* g0;     // global address of ring byte 0 (16 B aligned)
-    const uint8_t* gend;   // end of the padded input: blocks past it are zero-filled
 
     __device__ __forceinline__ void fetch(uint32_t b) {
-        const uint8_t* s = g0 + (uint64_t)b * BLK;
-        uint32_t n = (s + 16 <= gend) ? 16u : 0u;
-        if (!n) s = gend - 16;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + (b & (NBLK - 1)) * BLK), "l"(s), "r"(n) : "memory");
+        const uint32_t n = b < navail ? 16u : 0u;
+        const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
+        const uint32_t slot = b & (NBLK - 1);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + slot * BLK), "l"(s), "r"(n) : "memory");
+        if (slot == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + RB_BYTES), "l"(s), "r"(n) : "memory");
     }
     __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
     __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -424,31 +376,32 @@ struct RingBits {
             commit();
         }
     }
-    // Periodic top-up, executed by all lanes at the same iteration: first make what was requested one period ago
-    // visible, then request more.  Requests therefore have a whole period to land.
     __device__ __forceinline__ void checkpoint() { wait_all(); request(); }
-    // Synchronous variant for rare big moves (VERBATIM skip, long unary runs, init).
-    __device__ __forceinline__ void ensure_now() { request(); wait_all(); }
+    __device__ __forceinline__ void ensure_now() { request(); wait_all(); }     // synchronous: rare big moves, init
     __device__ __forceinline__ void init(uint32_t sring_, const uint8_t* in, uint64_t in_len, uint64_t abs_bit) {
         sring = sring_;
         const uint64_t b0 = (abs_bit >> 3) & ~(uint64_t)(BLK - 1);
-        g0 = in + b0; gend = in + (in_len & ~15ull);
+        g0 = in + b0;
+        const uint64_t nb = in_len > b0 ? (in_len - b0) >> 4 : 0;
+        navail = (uint32_t)(nb > 0xffffffffull ? 0xffffffffull : nb);
         pos = (uint32_t)(abs_bit - b0 * 8);
         filled = 0;
         ensure_now();
     }
+    __device__ __forceinline__ void init_idle(uint32_t sring_, const uint8_t* in) { sring = sring_; g0 = in; navail = 0; pos = 0; filled = NBLK; }
     __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
-    __device__ __forceinline__ uint32_t window() const {      // next 32 bits, MSB first
-        const uint32_t bo = (pos >> 3) & (RB_BYTES - 4);
-        const uint32_t a = lds32(sring + bo), b = lds32(sring + ((bo + 4) & (RB_BYTES - 4)));
-        return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), pos & 31);
+    __device__ __forceinline__ uint32_t window_at(uint32_t p) const {      // 32 bits starting at bit p, MSB first
+        const uint32_t bo = (p >> 3) & (RB_BYTES - 4);
+        const uint32_t a = lds32(sring + bo), b = lds32(sring + bo + 4);
+        return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), p);
     }
+    __device__ __forceinline__ uint32_t window() const { return window_at(pos); }
     __device__ __forceinline__ void skip(uint32_t n) { pos += n; }                        // n <= 32, covered by the checkpoint budget
     __device__ __forceinline__ void jump(uint32_t n) { pos += n; ensure_now(); }          // any n
     __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); pos += n; return v; }          // n <= 32
     __device__ __forceinline__ int32_t gets(uint32_t n) { int32_t v = n ? sar_c((int32_t)window(), 32 - n) : 0; pos += n; return v; }
     // unary run that did not terminate inside one window (rare): walks 32 zero bits at a time with synchronous refills
-    __device__ __forceinline__ uint32_t unary_slow(uint32_t limit) {
+    __device__ __noinline__ uint32_t unary_slow(uint32_t limit) {
         uint32_t q = 0;
 #pragma unroll 1
         for (;;) {
@@ -464,16 +417,58 @@ struct RingBits {
         if (w) { uint32_t z = __clz(w); pos += z + 1; return z; }
         return unary_slow(limit);
     }
+    // one Rice codeword with parameter k, any length; leaves the ring synchronised when the codeword was long
+    __device__ __forceinline__ int32_t rice_careful(uint32_t k) {
+        const uint32_t w = window();
+        const uint32_t f = bfind(w);
+        uint32_t u;
+        if ((int32_t)(f - k) >= 0) { u = (31u - f) << k | (shr_c(w, f - k) & ((1u << k) - 1u)); pos += k + 32u - f; }
+        else { const uint32_t q = unary(1u << 24); ensure_now(); u = (q << k) | get(k); ensure_now(); }
+        return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+    }
+    // skip one Rice codeword; returns false when the unary run is implausibly long (damaged data)
+    __device__ __forceinline__ bool rice_skip_careful(uint32_t k) {
+        const uint32_t w = window();
+        const uint32_t f = bfind(w);
+        if ((int32_t)(f - k) >= 0) { pos += k + 32u - f; return true; }
+        const uint32_t q = unary(1u << 16);
+        jump(k);
+        return q <= (1u << 16);
+    }
 };
-// budget: between two checkpoints a lane may advance by at most (NBLK*16 - 16 - 8 - 16) bytes:
-//   ring - (partially consumed current block) - (window over-read) - (blocks requested this checkpoint are not yet waited for)
-// NBLK = 8: 128 B ring, blocks requested one checkpoint ago are complete -> >= 64 B ahead; CK = 8 samples * 4 B + slack fits.
 
 // ------------------------------------------------------------------------------------------------ K2 parse
-// One thread per frame: walks the subframes, records where each starts and what it is, skips the residual.
-__device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
+// One lane per frame: walks the subframes, records where each starts and what it is, skips the residual.  Lanes of a warp
+// advance channel by channel and, inside a subframe, in groups of 8 sample indices in lockstep.  A group takes the
+// branch-free fast path (window, bfind, add; an overflow flag instead of a branch) when every walking lane has at least
+// 8 codewords left in its partition; otherwise the careful per-sample path.  The residual of the LAST subframe of a
+// CRC-validated frame is not walked: nothing starts after it.
 constexpr int PARSE_THREADS = 64;
-using ParseBits = RingBits<16>;   // 256 B ring: a Rice codeword walked here may be up to 62 bits
+
+struct ParseSub {            // per-lane state of the residual being skipped
+    uint32_t order, psize, plen, left, k, kp32;
+    bool first, raw;
+};
+
+// next partition parameter(s); a zero-sample partition 0 (order == partition size) is followed immediately by partition 1
+__device__ __forceinline__ bool parse_param(RingBits& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
+#pragma unroll 1
+    for (int guard = 0; guard < 2; guard++) {
+        const uint32_t cnt = p.psize - (p.first ? p.order : 0);
+        p.first = false;
+        const uint32_t k = br.get(p.plen);
+        p.raw = false;
+        if (k == (p.plen == 5 ? 31u : 15u)) {
+            const uint32_t nb = br.get(5);
+            if (br.abs_pos(in) + (uint64_t)cnt * nb > end_bit) return false;
+            br.jump(cnt * nb);
+            p.raw = true;
+        }
+        p.k = k; p.kp32 = k + 32u; p.left = cnt;
+        if (cnt) break;
+    }
+    return p.left != 0;
+}
 
 __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     extern __shared__ __align__(16) uint8_t s_ring[];
@@ -487,32 +482,33 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
     const uint64_t frame_bit0 = c.off * 8;
     const uint64_t end_bit = live ? (c.off + a.flen[i]) * 8 : 0;
-    ParseBits br;
-    if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
+    RingBits br;
+    if (live) br.init(smem_u32(s_ring) + threadIdx.x * RingBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
+    else br.init_idle(smem_u32(s_ring) + threadIdx.x * RingBits::STRIDE, a.in);
     bool bad = false, unparse = false;
     uint32_t max_order = 0, any_wide = 0;
-    // lanes of a warp are different frames; they walk channel by channel and, inside a subframe, sample index by
-    // sample index in lockstep, so that partition boundaries (multiples of blocksize >> order) fall on the same iteration
     const uint32_t wmax_ch = __reduce_max_sync(FULL, live ? channels : 0u);
     const uint32_t wmax_bs = __reduce_max_sync(FULL, live ? c.bs : 0u);
     for (uint32_t ch = 0; ch < wmax_ch; ch++) {
         bool walk = false;            // this lane walks a Rice-coded residual in this phase
-        uint32_t order = 0, plen = 4, esc = 15, psize = 0, left = 0, k1 = 1, rawskip = 0;
-        bool first = true;
+        ParseSub ps;
+        ps.order = 0; ps.psize = 0; ps.plen = 4; ps.left = 0; ps.k = 0; ps.kp32 = 32; ps.first = true; ps.raw = false;
         if (live && !bad && !unparse && ch < channels) {
             uint32_t bps = c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1u : 0u);
             SubInfo si;
             si.bit_offset = (uint32_t)(br.abs_pos(a.in) - frame_bit0);
-            si.type = 0; si.order = 0; si.flags = 0;
+            si.type = 0; si.order = 0; si.flags = 0; si.wasted = 0;
             uint32_t x = br.get(8);
             uint32_t type = (x >> 1) & 0x3f, w = 0;
             if (x & 0x80) bad = true;
             else if ((x & 1) && (w = br.unary(64) + 1) >= bps) unparse = true;
             else {
+                br.ensure_now();
                 bps -= w;
                 si.wasted = (uint8_t)w;
                 bool has_resid = false;
-                if (type == 0) br.skip(bps);
+                uint32_t order = 0;
+                if (type == 0) br.jump(bps);
                 else if (type == 1) {
                     si.type = 1;
                     if (br.abs_pos(a.in) + (uint64_t)c.bs * bps > end_bit) bad = true; else br.jump(c.bs * bps);
@@ -539,13 +535,13 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                             uint32_t method = br.get(2);
                             if (method > 1) unparse = true;
                             else {
-                                if (method) { si.flags |= 2; plen = 5; esc = 31; }
+                                if (method) { si.flags |= 2; ps.plen = 5; }
                                 uint32_t po = br.get(4);
-                                psize = po ? c.bs >> po : c.bs;
-                                if (psize < order) unparse = true;
-                                // the residual of the LAST subframe need not be walked when the frame span is already
-                                // CRC-validated: nothing starts after it
+                                ps.psize = po ? c.bs >> po : c.bs;
+                                ps.order = order;
+                                if (ps.psize == 0 || ps.psize < order) unparse = true;
                                 else walk = !(st == ST_OK && ch + 1 == channels);
+                                br.ensure_now();
                             }
                         }
                     }
@@ -555,36 +551,49 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
             else walk = false;
         }
         if (!__any_sync(FULL, walk)) continue;
-        for (uint32_t s = 0; s < wmax_bs; s++) {
-            if ((s & 7) == 0 && walk) br.checkpoint();
-            if (walk && s >= order && s < c.bs) {
-                if (left == 0) {   // partition boundary (s is a multiple of psize, or s == order)
-                    do {               // twice only when partition 0 holds zero samples (its parameter is still coded)
-                        left = psize - (s == order && first ? order : 0);
-                        first = false;
-                        uint32_t k = br.get(plen);
-                        rawskip = 0;
-                        if (k == esc) {
-                            uint32_t nb = br.get(5);
-                            if (br.abs_pos(a.in) + (uint64_t)left * nb > end_bit) { bad = true; walk = false; left = 1; }
-                            else { br.jump(left * nb); rawskip = 1; }
-                        }
-                        k1 = k + 1;
-                    } while (left == 0);
+#pragma unroll 1
+        for (uint32_t s0 = 0; s0 < wmax_bs; s0 += 8) {
+            if (walk) br.checkpoint();
+            if (walk && ps.left == 0 && s0 >= ps.order && s0 < c.bs) {
+                if (!parse_param(br, ps, a.in, end_bit)) { bad = true; walk = false; }
+            }
+            const bool fast_ok = !walk || ps.left >= 8;
+            if (__all_sync(FULL, fast_ok)) {
+                uint32_t pos = br.pos;
+                const uint32_t k = ps.k, kp32 = ps.kp32;
+                bool ovf = false;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t f = bfind(br.window_at(pos));
+                    ovf |= (int32_t)(f - k) < 0;
+                    pos += kp32 - f;
                 }
-                left--;
-                if (!rawskip && walk) {
-                    uint32_t wd = br.window();
-                    if (wd) br.skip(__clz(wd) + k1);
-                    else {
-                        br.unary_slow(1u << 16);
-                        br.jump(k1 - 1);
-                        if (br.abs_pos(a.in) > end_bit) { bad = true; walk = false; }
+                if (walk) {
+                    ps.left -= 8;
+                    if (!ps.raw) {
+                        if (!ovf) br.pos = pos;
+                        else {
+#pragma unroll 1
+                            for (int j = 0; j < 8; j++) if (!br.rice_skip_careful(k)) { bad = true; walk = false; break; }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t j = 0; j < 8; j++) {
+                    const uint32_t s = s0 + j;
+                    if (walk && s >= ps.order && s < c.bs) {
+                        if (ps.left == 0 && !parse_param(br, ps, a.in, end_bit)) { bad = true; walk = false; }
+                        else {
+                            ps.left--;
+                            if (!ps.raw && !br.rice_skip_careful(ps.k)) { bad = true; walk = false; }
+                        }
                     }
                 }
             }
+            if (walk && s0 + 8 >= c.bs) { walk = false; if (br.abs_pos(a.in) > end_bit) bad = true; }
+            else if (walk && br.abs_pos(a.in) > end_bit) { bad = true; walk = false; }
         }
-        if (walk && br.abs_pos(a.in) > end_bit) bad = true;
     }
     if (!live) return;
     if (!bad && !unparse && st == ST_CHECK) {
@@ -655,236 +664,330 @@ __global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_
 }
 
 // ------------------------------------------------------------------------------------------------ K3-5 decode
-// One thread per (frame, channel).  Threads of a CTA advance sample index by sample index in lockstep; each keeps its
-// bit position, Rice state, quantised LPC coefficients and the last ORD samples in registers (the history is a
-// register ring: the sample loop is unrolled ORD times so every tap has a fixed register).  Stereo decorrelation is a
-// warp shuffle between the two channel lanes; samples are staged interleaved in shared memory and written out packed.
-constexpr int DEC_THREADS = 128;
-using DecBits = RingBits<8>;                     // 128 B ring per lane
-
-template <int ORD> struct DecCfg {
-    static constexpr int T = 64;                          // samples per channel staged per tile
-    static constexpr int U = (ORD >= 16) ? 8 : 4;         // sample-loop unroll; the history shifts by U registers every U samples
-    static constexpr int CK = 8;                          // samples between ring checkpoints
-};
-
+// One lane per (frame, channel); a warp (= one CTA) owns 32/C frames and works tile by tile (T samples per channel):
+//   Rice phase     each lane decodes its next T residuals into its own column of the shared-memory tile.  Groups of 8
+//                  codewords take a branch-free path (window, bfind, shift, one IMAD, zig-zag; an overflow flag instead
+//                  of a branch) whenever every lane has 8 codewords left in its partition; warm-up samples, partition
+//                  tails, escape partitions and VERBATIM subframes take the careful per-sample path.
+//   restore phase  each lane runs the FIXED/LPC recurrence over its column in place.  Coefficients and the last ORD
+//                  samples stay in registers; the loop is unrolled ORD times so every tap has a fixed register.
+//                  16-bit streams accumulate in 32-bit IMADs.  Streams that need libFLAC's 64-bit accumulator use the FP64
+//                  pipe instead: every product and partial sum is an integer below 2^53, so DFMA is exact, the
+//                  quantisation shift is folded into the coefficients (a power of two), floor() is one round-down add of
+//                  1.5*2^52, and the FP64 pipe runs beside the integer pipes the Rice phase of the other warps keeps busy.
+//   pack phase     the warp re-reads the tile row-wise (interleaved order), applies left/side, side/right, mid/side
+//                  decorrelation to stereo pairs and writes packed little-endian 8/16/24-bit PCM, 4 samples per lane.
+// Tile layout: sample t of lane l at word t*S + l, S = 32 + pad chosen so that both the column accesses of the first two
+// phases and the vector row reads of the pack phase are bank-conflict free.
 enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 
-// bytes [0, nbytes) of the interleaved packed PCM of `ts` (flat int32 samples, B bytes each) -> dst, cooperatively by a warp
-__device__ __forceinline__ uint32_t sample_byte(const int32_t* ts, uint32_t b, uint32_t B) {
-    uint32_t q = b / B, r = b - q * B;
-    return ((uint32_t)ts[q] >> (8 * r)) & 0xFFu;
-}
-__device__ void store_packed(uint8_t* __restrict__ dst, uint32_t nbytes, const int32_t* __restrict__ ts, uint32_t B, int lane) {
-    uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
-    if (head > nbytes) head = nbytes;
-    if ((uint32_t)lane < head) dst[lane] = (uint8_t)sample_byte(ts, lane, B);
-    const uint32_t nw = (nbytes - head) >> 2;
-    uint32_t* __restrict__ dw = reinterpret_cast<uint32_t*>(dst + head);
-    for (uint32_t j = lane; j < nw; j += 32) {
-        const uint32_t b0 = head + 4 * j;
-        uint32_t w;
-        if (B == 3) {
-            uint32_t q = (b0 * 0xAAABu) >> 17, r = b0 - 3 * q;
-            uint32_t s0 = (uint32_t)ts[q], s1 = (uint32_t)ts[q + 1];
-            w = r == 0 ? __byte_perm(s0, s1, 0x4210) : r == 1 ? __byte_perm(s0, s1, 0x5421) : __byte_perm(s0, s1, 0x6542);
-        } else if (B == 2 && !(b0 & 1)) {
-            uint32_t q = b0 >> 1;
-            w = __byte_perm((uint32_t)ts[q], (uint32_t)ts[q + 1], 0x5410);
-        } else if (B == 1) {
-            w = __byte_perm(__byte_perm((uint32_t)ts[b0], (uint32_t)ts[b0 + 1], 0x0040), __byte_perm((uint32_t)ts[b0 + 2], (uint32_t)ts[b0 + 3], 0x0040), 0x5410);
-        } else {
-            w = sample_byte(ts, b0, B) | sample_byte(ts, b0 + 1, B) << 8 | sample_byte(ts, b0 + 2, B) << 16 | sample_byte(ts, b0 + 3, B) << 24;
-        }
-        dw[j] = w;
+template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : 48; };
+constexpr int DEC_MAX_S = 36;
+
+struct RiceSt {
+    uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
+    bool first;
+};
+
+__device__ __forceinline__ void rice_param(RingBits& br, RiceSt& rs) {
+#pragma unroll 1
+    for (int guard = 0; guard < 2; guard++) {
+        const uint32_t cnt = rs.psize - (rs.first ? rs.order : 0);
+        rs.first = false;
+        const uint32_t k = br.get(rs.plen);
+        if (k == (rs.plen == 5 ? 31u : 15u)) { rs.rawbits = br.get(5); rs.rawleft = cnt; rs.fastleft = 0; }
+        else { rs.fastleft = cnt; rs.rawleft = 0; rs.k = k; rs.kp32 = k + 32u; rs.negP = 0u - (1u << k); rs.c30 = 30u << k; }
+        if (cnt) break;
     }
-    const uint32_t tb = head + 4 * nw;
-    if (tb + lane < nbytes) dst[tb + lane] = (uint8_t)sample_byte(ts, tb + lane, B);
+}
+
+// ---- restore: one block of ORD samples of this lane's column, in place
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_i32(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
+                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
+    int32_t nw[ORD];
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        uint32_t sum = 0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) {
+            const int32_t hv = (m < j) ? nw[(j - 1 - m) < 0 ? 0 : (j - 1 - m)] : h[(m - j) < 0 ? 0 : (m - j)];
+            sum += (uint32_t)cf[m] * (uint32_t)hv;
+        }
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
+        if (FIRST) { if (j < (int)order) s = r; }
+        nw[j] = s;
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+#pragma unroll
+    for (int m = 0; m < ORD; m++) h[m] = nw[ORD - 1 - m];
+}
+
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, const double (&cf)[ORD], double (&h)[ORD],
+                                                  uint32_t order, uint32_t sh_n, uint32_t wasted) {
+    double nw[ORD];
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) {
+            const double hv = (m < j) ? nw[(j - 1 - m) < 0 ? 0 : (j - 1 - m)] : h[(m - j) < 0 ? 0 : (m - j)];
+            if (ORD > 16 && (m & 1)) acc1 = fma(cf[m], hv, acc1);
+            else acc0 = fma(cf[m], hv, acc0);
+        }
+        if (ORD > 16) acc0 += acc1;                                       // exact: integers (scaled by 2^-shift) below 2^53
+        const double y = __dadd_rd(acc0, 6755399441055744.0);            // + 1.5*2^52, rounded down: low word = floor(acc) mod 2^32
+        int32_t p = __double2loint(y);
+        if (EXTRA) p >>= sh_n;
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
+        if (FIRST) { if (j < (int)order) s = r; }
+        nw[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+#pragma unroll
+    for (int m = 0; m < ORD; m++) h[m] = nw[ORD - 1 - m];
+}
+
+template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
+__device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const TT (&cf)[ORD], TT (&h)[ORD], uint32_t order, uint32_t shift, uint32_t wasted) {
+    if constexpr (WIDE) restore_block_f64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+    else restore_block_i32<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+}
+
+// ---- pack: 4 consecutive samples (interleaved order) of one frame per lane
+__device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32_t C, uint32_t B, uint32_t F, uint32_t i0, uint32_t T,
+                                          uint32_t ftab, uint8_t* __restrict__ out, uint32_t lane) {
+    const uint32_t upf = (T * C) >> 2;                 // units of 4 samples per frame-tile (T is a multiple of 4)
+    const uint32_t total = F * upf;
+    const uint32_t rcp_upf = 65536u / upf + 1u;        // g / upf for g < 2^12 (checked on the host side of the launch)
+    const uint32_t rcp_c = 65536u / C + 1u;
+    for (uint32_t g = lane; g < total; g += 32) {
+        const uint32_t f = (g * rcp_upf) >> 16, u = g - f * upf;
+        const uint32_t bs = lds32(ftab + 4 * f);
+        if (i0 >= bs) continue;
+        const uint32_t nt = min(T, bs - i0), nsamp = nt * C, q0 = 4 * u;
+        if (q0 >= nsamp) continue;
+        const uint32_t assign = lds32(ftab + 128 + 4 * f);
+        const uint2 pol = lds64(ftab + 256 + 8 * f);
+        uint8_t* dst = out + (((uint64_t)pol.y << 32) | pol.x) + ((uint64_t)i0 * C + q0) * B;
+        uint32_t v0, v1, v2, v3;
+        const uint32_t fbase = tile_base + 4 * f * C;
+        if (C == 2) {
+            const uint32_t t = q0 >> 1;
+            uint2 p0 = lds64(fbase + 4 * t * S), p1 = lds64(fbase + 4 * (t + 1) * S);   // row t+1 exists in the tile even past nt
+            if (assign == 8) { p0.y = p0.x - p0.y; p1.y = p1.x - p1.y; }
+            else if (assign == 9) { p0.x = p0.x + p0.y; p1.x = p1.x + p1.y; }
+            else if (assign == 10) {
+                uint32_t m = (p0.x << 1) | (p0.y & 1u), s = p0.y;
+                p0.x = (uint32_t)((int32_t)(m + s) >> 1); p0.y = (uint32_t)((int32_t)(m - s) >> 1);
+                m = (p1.x << 1) | (p1.y & 1u); s = p1.y;
+                p1.x = (uint32_t)((int32_t)(m + s) >> 1); p1.y = (uint32_t)((int32_t)(m - s) >> 1);
+            }
+            v0 = p0.x; v1 = p0.y; v2 = p1.x; v3 = p1.y;
+        } else if (C == 1) {
+            v0 = lds32(fbase + 4 * q0 * S); v1 = lds32(fbase + 4 * (q0 + 1) * S); v2 = lds32(fbase + 4 * (q0 + 2) * S); v3 = lds32(fbase + 4 * (q0 + 3) * S);
+        } else if ((C & 3) == 0) {
+            const uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
+            const uint4 p = lds128(fbase + 4 * (t * S + c));
+            v0 = p.x; v1 = p.y; v2 = p.z; v3 = p.w;
+        } else {
+            uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
+            uint32_t ad = fbase + 4 * (t * S + c);
+            const uint32_t wrap = 4 * (S - C);
+            v0 = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; }
+            v1 = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; }
+            v2 = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; }
+            v3 = lds32(ad);
+        }
+        if (q0 + 4 <= nsamp && (((uintptr_t)dst) & 3u) == 0) {
+            uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+            if (B == 3) {
+                dw[0] = __byte_perm(v0, v1, 0x4210); dw[1] = __byte_perm(v1, v2, 0x5421); dw[2] = __byte_perm(v2, v3, 0x6542);
+            } else if (B == 2) {
+                dw[0] = __byte_perm(v0, v1, 0x5410); dw[1] = __byte_perm(v2, v3, 0x5410);
+            } else {
+                dw[0] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+            }
+        } else {
+            const uint32_t nv = min(4u, nsamp - q0);
+            const uint32_t vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (uint32_t e = 0; e < 4; e++)
+                if (e < nv) for (uint32_t b = 0; b < B; b++) dst[e * B + b] = (uint8_t)(vv[e] >> (8 * b));
+        }
+    }
 }
 
 template <int ORD, bool WIDE>
-__global__ void __launch_bounds__(DEC_THREADS) k_decode(PassArgs a, uint32_t C, uint32_t B) {
-    constexpr int T = DecCfg<ORD>::T, U = DecCfg<ORD>::U, CK = DecCfg<ORD>::CK;
+__global__ void __launch_bounds__(32) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
+    constexpr int T = DecCfg<ORD>::T;
     extern __shared__ __align__(16) uint8_t s_dyn[];
-    __shared__ uint32_t s_bs[DEC_THREADS];
-    __shared__ uint64_t s_po[DEC_THREADS];
-    __shared__ uint32_t s_maxbs;
-    int32_t* s_tile = reinterpret_cast<int32_t*>(s_dyn + DEC_THREADS * DecBits::STRIDE);
-    const uint32_t F = DEC_THREADS / C;
-    const uint32_t stride = T * C + C;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t ring_base = smem_u32(s_dyn);
+    const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
+    const uint32_t ftab = tile_base + T * DEC_MAX_S * 4;       // bs[32] | assign[32] | pcm offset[32] (u64)
+    const uint32_t F = 32 / C;
     const uint32_t n_acc = a.totals->n_accepted;
-    const uint32_t fl = tid / C, ch = tid - fl * C;
-    // idle threads (C does not divide the CTA size) write to a scratch word behind the tiles
-    const uint32_t my_base = smem_u32(fl < F ? s_tile + fl * stride + ch : s_tile + F * stride);
-    const uint32_t c4 = fl < F ? C * 4 : 0;
-    for (uint32_t g = blockIdx.x; (uint64_t)g * F < n_acc; g += gridDim.x) {
-        const uint32_t kf = g * F + fl;
-        const bool active = fl < F && kf < n_acc;
-        if (tid == 0) s_maxbs = 0;
-        __syncthreads();
-        // ---- per-subframe state (registers)
-        DecBits br;
-        int32_t coef[ORD], hist[ORD];          // hist[0] = most recent sample (before the wasted-bits shift)
+    const uint32_t fl = lane / C, ch = lane - fl * C;
+    const uint32_t kf = blockIdx.x * F + fl;
+    const bool active = fl < F && kf < n_acc;
+    const uint32_t rs4 = S * 4;
+    const uint32_t col = tile_base + lane * 4;
+
+    // ---- per-subframe state (registers)
+    RingBits br;
+    br.init_idle(ring_base + lane * RingBits::STRIDE, a.in);
+    typename std::conditional<WIDE, double, int32_t>::type cf[ORD], hist[ORD];
 #pragma unroll
-        for (int j = 0; j < ORD; j++) { coef[j] = 0; hist[j] = 0; }
-        uint32_t bs = 0, assign = 0, order = 0, wasted = 0, shift = 0, bps = 0;
-        uint32_t psize = 0, plen = 4, fastleft = 0, rawleft = 0, rawbits = 0, k = 0;
+    for (int j = 0; j < ORD; j++) { cf[j] = 0; hist[j] = 0; }
+    RiceSt rs;
+    rs.fastleft = 0; rs.rawleft = 0; rs.rawbits = 0; rs.k = 0; rs.kp32 = 32; rs.negP = ~0u; rs.c30 = 30; rs.psize = 0; rs.plen = 4; rs.order = 0; rs.first = true;
+    uint32_t bs = 0, assign = 0, wasted = 0, shift = 0, bps = 0;
+    int mode = M_IDLE;
+    if (fl < F && ch == 0) { sts32(ftab + 4 * fl, 0); sts32(ftab + 128 + 4 * fl, 0); }
+    if (active) {
+        const uint32_t i = a.acc_idx[kf];
+        const Cand c = a.cand[i];
+        bs = c.bs; assign = c.assign;
+        bool ok = a.status[i] == ST_OK;
+        const uint64_t po = a.pcm_off[i];
+        if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
+        if (ch == 0) { sts32(ftab + 4 * fl, bs); sts32(ftab + 128 + 4 * fl, assign); sts32(ftab + 256 + 8 * fl, (uint32_t)po); sts32(ftab + 260 + 8 * fl, (uint32_t)(po >> 32)); }
         int32_t cval = 0;
-        int mode = M_IDLE;
-        bool narrow = true, first_part = true;
-        if (active) {
-            const uint32_t i = a.acc_idx[kf];
-            const Cand c = a.cand[i];
-            bs = c.bs; assign = c.assign;
-            bool ok = a.status[i] == ST_OK;
-            const uint64_t po = a.pcm_off[i];
-            if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
-            if (ch == 0) { s_bs[fl] = bs; s_po[fl] = po; }
-            atomicMax(&s_maxbs, bs);
-            if (ok) {
-                const SubInfo si = a.sub[(uint64_t)i * MAX_CH + ch];
-                br.init(smem_u32(s_dyn) + tid * DecBits::STRIDE, a.in, a.in_len, c.off * 8 + si.bit_offset);
-                uint32_t x = br.get(8);
-                if (x & 1) br.unary(64);
-                order = si.order; wasted = si.wasted;
-                bps = (uint32_t)c.bps + (((assign == 8 && ch == 1) || (assign == 9 && ch == 0) || (assign == 10 && ch == 1)) ? 1u : 0u) - wasted;
-                if (si.type == 0) { mode = M_CONST; cval = br.gets(bps); }
-                else if (si.type == 1) mode = M_VERBATIM;
-                else {
-                    mode = M_PRED;
-                    // warm-up samples are parked in this thread's tile slots 0..order-1 (order <= 32 <= T) and picked up
-                    // again, in order, by the sample loop
+        mode = M_CONST;                              // damaged frames (CRC mismatch) are delivered zero-filled
+        if (ok) {
+            const SubInfo si = a.sub[(uint64_t)i * MAX_CH + ch];
+            br.init(ring_base + lane * RingBits::STRIDE, a.in, a.in_len, c.off * 8 + si.bit_offset);
+            uint32_t x = br.get(8);
+            if (x & 1) { br.unary(64); br.ensure_now(); }
+            const uint32_t order = si.order;
+            wasted = si.wasted;
+            bps = (uint32_t)c.bps + (((assign == 8 && ch == 1) || (assign == 9 && ch == 0) || (assign == 10 && ch == 1)) ? 1u : 0u) - wasted;
+            if (si.type == 0) cval = br.gets(bps);
+            else if (si.type == 1) mode = M_VERBATIM;
+            else {
+                mode = M_PRED;
+                rs.order = order;
+                // warm-up samples are parked in this lane's tile rows 0..order-1 (order <= 32 <= T)
 #pragma unroll 1
-                    for (uint32_t j = 0; j < order; j++) { sts32(my_base + j * c4, (uint32_t)br.gets(bps)); if ((j & 7) == 7) br.ensure_now(); }
+                for (uint32_t j = 0; j < order; j++) { sts32(col + j * rs4, (uint32_t)br.gets(bps)); if ((j & 7) == 7) br.ensure_now(); }
+                br.ensure_now();
+                bool narrow = true;
+                if (si.type == 3) {
+                    const uint32_t prec = br.get(4) + 1;
+                    shift = (uint32_t)br.gets(5);
+                    narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
+                    // libFLAC 1.2.1 width rule: narrow subframes accumulate in 32 bits (wrap), the others in 64
+                    const double scale = (WIDE && !narrow) ? __hiloint2double((int)((1023u - shift) << 20), 0) : 1.0;
+#pragma unroll
+                    for (int j = 0; j < ORD; j++) if (j < (int)order) {
+                        const int32_t q = br.gets(prec);
+                        if (WIDE) cf[j] = (double)q * scale; else cf[j] = q;
+                        if ((j & 7) == 7) br.ensure_now();
+                    }
                     br.ensure_now();
-                    if (si.type == 3) {
-                        const uint32_t prec = br.get(4) + 1;
-                        shift = (uint32_t)br.gets(5);
-                        narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
-#pragma unroll
-                        for (int j = 0; j < ORD; j++) if (j < (int)order) { coef[j] = br.gets(prec); if ((j & 7) == 7) br.ensure_now(); }
-                        br.ensure_now();
-                    } else {   // FIXED predictors as LPC coefficient sets, 32-bit wrap-around arithmetic
-                        const int o = (int)order;
-                        if (ORD >= 1 && o >= 1) coef[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
-                        if (ORD >= 2 && o >= 2) coef[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
-                        if (ORD >= 3 && o >= 3) coef[2] = o == 3 ? 1 : 4;
-                        if (ORD >= 4 && o >= 4) coef[3] = -1;
-                    }
-                    const uint32_t method = br.get(2);
-                    plen = method ? 5 : 4;
-                    const uint32_t porder = br.get(4);
-                    psize = porder ? bs >> porder : bs;
+                    if (WIDE && !narrow) shift = 0;          // folded into the coefficients
+                } else {   // FIXED predictors as coefficient sets, 32-bit wrap-around arithmetic
+                    const int o = (int)order;
+                    if (ORD >= 1 && o >= 1) cf[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
+                    if (ORD >= 2 && o >= 2) cf[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
+                    if (ORD >= 3 && o >= 3) cf[2] = o == 3 ? 1 : 4;
+                    if (ORD >= 4 && o >= 4) cf[3] = -1;
                 }
+                const uint32_t method = br.get(2);
+                rs.plen = method ? 5 : 4;
+                const uint32_t porder = br.get(4);
+                rs.psize = porder ? bs >> porder : bs;
+                br.ensure_now();
             }
-        } else if (fl < F && ch == 0) s_bs[fl] = 0;
-        __syncthreads();
-        const uint32_t maxbs = s_maxbs;
-        const bool reads = mode >= M_VERBATIM;
-        for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
-#pragma unroll 1
-            for (uint32_t t0 = 0; t0 < (uint32_t)T; t0 += U) {
-                const uint32_t my_row = my_base + t0 * c4;
-                if ((t0 % CK) == 0 && reads) br.checkpoint();
-                int32_t nw[U];
-#pragma unroll
-                for (int j = 0; j < U; j++) {
-                    const uint32_t idx = i0 + t0 + j;
-                    int32_t s = 0;
-                    bool pred = false;
-                    int32_t r = 0;
-                    if (fastleft) {          // the common case: next Rice codeword of the current partition
-                        fastleft--;
-                        pred = true;
-                        const uint32_t w = br.window();
-                        const uint32_t z = __clz(w);
-                        if (z + 1 + k <= 32) {
-                            const uint32_t u = (z << k) | shr_c(shl_c(w, z + 1), 32 - k);
-                            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                            br.skip(z + 1 + k);
-                        } else {                 // codeword longer than one window (rare): resynchronise the ring afterwards
-                            const uint32_t q = br.unary(1u << 24);
-                            const uint32_t u = (q << k) | br.get(k);
-                            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                            br.ensure_now();
-                        }
-                    } else if (idx < bs && mode != M_IDLE) {
-                        if (mode == M_CONST) s = cval;
-                        else if (mode == M_VERBATIM) s = br.gets(bps);
-                        else if (idx < order) s = (int32_t)lds32(my_row + (uint32_t)j * c4);      // parked warm-up sample
-                        else {
-                            pred = true;
-                            if (rawleft == 0) {                  // partition boundary
-                                uint32_t cnt;
-#pragma unroll 1
-                                do {                             // twice only if partition 0 holds zero samples
-                                    cnt = psize - (first_part ? order : 0);
-                                    first_part = false;
-                                    k = br.get(plen);
-                                    if (k == (plen == 5 ? 31u : 15u)) { rawbits = br.get(5); rawleft = cnt; fastleft = 0; }
-                                    else { fastleft = cnt; rawleft = 0; }
-                                } while (cnt == 0);
-                            }
-                            if (rawleft) { rawleft--; r = br.gets(rawbits); }
-                            else {
-                                fastleft--;
-                                const uint32_t q = br.unary(1u << 24);
-                                const uint32_t u = (q << k) | br.get(k);
-                                r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                                br.ensure_now();
-                            }
-                        }
-                    }
-                    if (pred) {
-                        if (WIDE) {
-                            int64_t sum = 0;
-#pragma unroll
-                            for (int m = 0; m < ORD; m++) {
-                                const int32_t h = (m < j) ? nw[j - 1 - m < 0 ? 0 : j - 1 - m] : hist[m - j < 0 ? 0 : m - j];
-                                asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(sum) : "r"(coef[m]), "r"(h));
-                            }
-                            if (narrow) sum = (int64_t)(int32_t)sum;      // libFLAC 1.2.1 accumulates in 32 bits here
-                            s = (int32_t)((uint32_t)r + (uint32_t)(int32_t)(sum >> shift));
-                        } else {
-                            uint32_t sum = 0;
-#pragma unroll
-                            for (int m = 0; m < ORD; m++) {
-                                const int32_t h = (m < j) ? nw[j - 1 - m < 0 ? 0 : j - 1 - m] : hist[m - j < 0 ? 0 : m - j];
-                                sum += (uint32_t)coef[m] * (uint32_t)h;
-                            }
-                            s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
-                        }
-                    }
-                    nw[j] = s;
-                    int32_t v = (int32_t)((uint32_t)s << wasted);
-                    if (C == 2) {
-                        const int32_t o = __shfl_xor_sync(FULL, v, 1);
-                        if (assign == 8) { if (ch == 1) v = (int32_t)((uint32_t)o - (uint32_t)v); }
-                        else if (assign == 9) { if (ch == 0) v = (int32_t)((uint32_t)v + (uint32_t)o); }
-                        else if (assign == 10) {
-                            const int32_t mid = ch == 0 ? v : o, side = ch == 0 ? o : v;
-                            const uint32_t m2 = ((uint32_t)mid << 1) | ((uint32_t)side & 1u);
-                            v = ch == 0 ? ((int32_t)(m2 + (uint32_t)side) >> 1) : ((int32_t)(m2 - (uint32_t)side) >> 1);
-                        }
-                    }
-                    sts32(my_row + (uint32_t)j * c4, (uint32_t)v);
-                }
-                // slide the history window by U samples
-#pragma unroll
-                for (int m = ORD - 1; m >= U; m--) hist[m] = hist[m - U];
-#pragma unroll
-                for (int m = 0; m < U && m < ORD; m++) hist[m] = nw[U - 1 - m];
-            }
-            __syncthreads();
-            for (uint32_t f = warp; f < F; f += DEC_THREADS / 32) {
-                const uint32_t fbs = s_bs[f];
-                if (i0 >= fbs) continue;
-                const uint32_t nt = min((uint32_t)T, fbs - i0);
-                store_packed(a.out + s_po[f] + (uint64_t)i0 * C * B, nt * C * B, s_tile + f * stride, B, lane);
-            }
-            __syncthreads();
         }
+        if (mode == M_CONST) {                        // column holds the final value once and for all (restore leaves it unchanged)
+            const uint32_t v = (uint32_t)cval << wasted;
+            wasted = 0;
+#pragma unroll 1
+            for (uint32_t t = 0; t < (uint32_t)T; t++) sts32(col + t * rs4, v);
+        }
+    }
+    __syncwarp();
+    const uint32_t maxbs = __reduce_max_sync(FULL, bs);
+    const bool reads = mode >= M_VERBATIM;
+    const bool extra = __any_sync(FULL, wasted != 0 || (WIDE && shift != 0));
+    const uint32_t order = rs.order;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
+        // ---- Rice phase
+#pragma unroll 1
+        for (uint32_t t0 = 0; t0 < (uint32_t)T; t0 += 8) {
+            const uint32_t idx0 = i0 + t0;
+            const uint32_t row = col + t0 * rs4;
+            if (reads) br.checkpoint();
+            const bool inert = mode <= M_CONST || idx0 >= bs;
+            if (mode == M_PRED && !inert && rs.fastleft == 0 && rs.rawleft == 0 && idx0 >= order) rice_param(br, rs);
+            const bool fast_ok = inert || (mode == M_PRED && rs.fastleft >= 8);
+            if (__all_sync(FULL, fast_ok)) {
+                uint32_t pos = br.pos;
+                const uint32_t k = rs.k, kp32 = rs.kp32, negP = rs.negP, c30 = rs.c30;
+                bool ovf = false;
+                int32_t r[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t w = br.window_at(pos);
+                    const uint32_t f = bfind(w);
+                    const uint32_t d = f - k;
+                    ovf |= (int32_t)d < 0;
+                    const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
+                    r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                    pos += kp32 - f;
+                }
+                if (!inert) {
+                    rs.fastleft -= 8;
+                    if (!ovf) {
+                        br.pos = pos;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)r[j]);
+                    } else {             // a codeword longer than one window (rare): redo the group carefully
+#pragma unroll 1
+                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.rice_careful(k));
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t j = 0; j < 8; j++) {
+                    const uint32_t idx = idx0 + j;
+                    if (mode <= M_CONST || idx >= bs) continue;
+                    int32_t v;
+                    if (mode == M_VERBATIM) v = br.gets(bps);
+                    else {
+                        if (idx < order) continue;               // parked warm-up sample
+                        if (rs.fastleft == 0 && rs.rawleft == 0) rice_param(br, rs);
+                        if (rs.rawleft) { rs.rawleft--; v = br.gets(rs.rawbits); }
+                        else { rs.fastleft--; v = br.rice_careful(rs.k); }
+                    }
+                    sts32(row + j * rs4, (uint32_t)v);
+                }
+            }
+        }
+        // ---- restore phase (own column only: no warp synchronisation needed before it)
+        if (i0 == 0) {
+            if (extra) restore_block<ORD, WIDE, true, true>(col, rs4, cf, hist, order, shift, wasted);
+            else restore_block<ORD, WIDE, true, false>(col, rs4, cf, hist, order, shift, wasted);
+        }
+        if (extra) {
+#pragma unroll 1
+            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, true>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
+        } else {
+#pragma unroll 1
+            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, false>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
+        }
+        __syncwarp();
+        // ---- pack phase
+        pack_tile(tile_base, S, C, B, F, i0, T, ftab, a.out, lane);
+        __syncwarp();
     }
 }
 
@@ -910,20 +1013,38 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
     k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
-    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a); g_launches++;
+    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * RingBits::STRIDE, S(stream)>>>(a); g_launches++;
 }
 void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream) {
     k_prefix<<<1, 1024, 0, S(stream)>>>(a, bytes_per_sample); g_launches++;
 }
 template <int ORD, bool WIDE>
 static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
-    const uint32_t F = DEC_THREADS / C;
-    uint32_t grid = blocks_for(nacc, F);
-    if (grid > 148 * 32) grid = 148 * 32;
-    const size_t smem = (size_t)DEC_THREADS * DecBits::STRIDE + ((size_t)F * (DecCfg<ORD>::T * C + C) + 4) * sizeof(int32_t);
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_decode<ORD, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_done = true; }
-    k_decode<ORD, WIDE><<<grid, DEC_THREADS, smem, st>>>(a, C, B);
+    constexpr int T = DecCfg<ORD>::T;
+    const uint32_t F = 32 / C;
+    const uint32_t S = 32 + ((C & 3) == 0 ? 4 : (C & 1) == 0 ? 2 : 1);
+    const uint32_t grid = blocks_for(nacc, F);
+    size_t smem = (size_t)32 * RingBits::STRIDE + (size_t)T * DEC_MAX_S * 4 + 512;
+    static int max_resident = 0, n_sm = 0;
+    if (!max_resident) {
+        cudaFuncSetAttribute(k_decode<ORD, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE>, 32, smem);
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (max_resident < 1) max_resident = 1;
+        if (n_sm < 1) n_sm = 148;
+    }
+    // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  Cap the residency
+    // (by asking for more shared memory) so that the waves are equally full instead of a full one plus a nearly empty one.
+    const uint64_t per_wave = (uint64_t)n_sm * max_resident;
+    const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
+    uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
+    if (resident < 1) resident = 1;
+    if (resident < (uint32_t)max_resident) {
+        size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
+        if (want > 200 * 1024) want = 200 * 1024;
+        if (want > smem) smem = want;
+    }
+    k_decode<ORD, WIDE><<<grid, 32, smem, st>>>(a, C, B, S);
     g_launches++;
 }
 void launch_decode(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, bool wide, void* stream) {
