@@ -401,7 +401,7 @@ struct RingBits {
     __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); pos += n; return v; }          // n <= 32
     __device__ __forceinline__ int32_t gets(uint32_t n) { int32_t v = n ? sar_c((int32_t)window(), 32 - n) : 0; pos += n; return v; }
     // unary run that did not terminate inside one window (rare): walks 32 zero bits at a time with synchronous refills
-    __device__ __noinline__ uint32_t unary_slow(uint32_t limit) {
+    __device__ __forceinline__ uint32_t unary_slow(uint32_t limit) {
         uint32_t q = 0;
 #pragma unroll 1
         for (;;) {
@@ -682,7 +682,6 @@ __global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_
 enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 
 template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : 48; };
-constexpr int DEC_MAX_S = 36;
 
 struct RiceSt {
     uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
@@ -759,82 +758,115 @@ __device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const
     else restore_block_i32<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
 }
 
-// ---- pack: 4 consecutive samples (interleaved order) of one frame per lane
+// ---- pack: 16 consecutive samples (interleaved order) of one frame per lane -> B 16-byte stores
+__device__ __forceinline__ void pack4(uint32_t* dw, uint32_t B, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    if (B == 3) { dw[0] = __byte_perm(v0, v1, 0x4210); dw[1] = __byte_perm(v1, v2, 0x5421); dw[2] = __byte_perm(v2, v3, 0x6542); }
+    else if (B == 2) { dw[0] = __byte_perm(v0, v1, 0x5410); dw[1] = __byte_perm(v2, v3, 0x5410); }
+    else dw[0] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+}
+// stereo decorrelation of one (ch0, ch1) pair.  mid/side: with m' = 2M + (S&1), L = (m'+S)>>1 = R + S and
+// R = (m'-S)>>1 = M - (S>>1) (identical in every bit that reaches the output, also when the int32 arithmetic wraps).
+__device__ __forceinline__ void decorr(uint32_t assign, uint32_t& x, uint32_t& y) {
+    if (assign == 10) { const uint32_t r = x - (uint32_t)((int32_t)y >> 1); x = r + y; y = r; }
+    else if (assign == 8) y = x - y;
+    else if (assign == 9) x = x + y;
+}
+
 __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32_t C, uint32_t B, uint32_t F, uint32_t i0, uint32_t T,
                                           uint32_t ftab, uint8_t* __restrict__ out, uint32_t lane) {
-    const uint32_t upf = (T * C) >> 2;                 // units of 4 samples per frame-tile (T is a multiple of 4)
+    const uint32_t upf = (T * C) >> 4;                 // units of 16 samples per frame-tile (T is a multiple of 16)
     const uint32_t total = F * upf;
-    const uint32_t rcp_upf = 65536u / upf + 1u;        // g / upf for g < 2^12 (checked on the host side of the launch)
+    const uint32_t rcp_upf = 65536u / upf + 1u;        // g / upf for g < 2^9
     const uint32_t rcp_c = 65536u / C + 1u;
     for (uint32_t g = lane; g < total; g += 32) {
         const uint32_t f = (g * rcp_upf) >> 16, u = g - f * upf;
         const uint32_t bs = lds32(ftab + 4 * f);
         if (i0 >= bs) continue;
-        const uint32_t nt = min(T, bs - i0), nsamp = nt * C, q0 = 4 * u;
+        const uint32_t nt = min(T, bs - i0), nsamp = nt * C, q0 = 16 * u;
         if (q0 >= nsamp) continue;
         const uint32_t assign = lds32(ftab + 128 + 4 * f);
         const uint2 pol = lds64(ftab + 256 + 8 * f);
         uint8_t* dst = out + (((uint64_t)pol.y << 32) | pol.x) + ((uint64_t)i0 * C + q0) * B;
-        uint32_t v0, v1, v2, v3;
+        uint32_t v[16];
         const uint32_t fbase = tile_base + 4 * f * C;
         if (C == 2) {
-            const uint32_t t = q0 >> 1;
-            uint2 p0 = lds64(fbase + 4 * t * S), p1 = lds64(fbase + 4 * (t + 1) * S);   // row t+1 exists in the tile even past nt
-            if (assign == 8) { p0.y = p0.x - p0.y; p1.y = p1.x - p1.y; }
-            else if (assign == 9) { p0.x = p0.x + p0.y; p1.x = p1.x + p1.y; }
-            else if (assign == 10) {
-                uint32_t m = (p0.x << 1) | (p0.y & 1u), s = p0.y;
-                p0.x = (uint32_t)((int32_t)(m + s) >> 1); p0.y = (uint32_t)((int32_t)(m - s) >> 1);
-                m = (p1.x << 1) | (p1.y & 1u); s = p1.y;
-                p1.x = (uint32_t)((int32_t)(m + s) >> 1); p1.y = (uint32_t)((int32_t)(m - s) >> 1);
+            const uint32_t ad = fbase + 4 * (q0 >> 1) * S;
+#pragma unroll
+            for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
+            if (assign >= 8) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) decorr(assign, v[2 * e], v[2 * e + 1]);
             }
-            v0 = p0.x; v1 = p0.y; v2 = p1.x; v3 = p1.y;
         } else if (C == 1) {
-            v0 = lds32(fbase + 4 * q0 * S); v1 = lds32(fbase + 4 * (q0 + 1) * S); v2 = lds32(fbase + 4 * (q0 + 2) * S); v3 = lds32(fbase + 4 * (q0 + 3) * S);
-        } else if ((C & 3) == 0) {
-            const uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
-            const uint4 p = lds128(fbase + 4 * (t * S + c));
-            v0 = p.x; v1 = p.y; v2 = p.z; v3 = p.w;
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] = lds32(fbase + 4 * (q0 + e) * S);
+        } else if (C == 4) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * ((q0 >> 2) + e) * S); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
+        } else if (C == 8) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * ((q0 >> 3) + (e >> 1)) * S + 16 * (e & 1)); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
         } else {
             uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
             uint32_t ad = fbase + 4 * (t * S + c);
             const uint32_t wrap = 4 * (S - C);
-            v0 = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; }
-            v1 = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; }
-            v2 = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; }
-            v3 = lds32(ad);
+#pragma unroll
+            for (int e = 0; e < 16; e++) { v[e] = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; } }
         }
-        if (q0 + 4 <= nsamp && (((uintptr_t)dst) & 3u) == 0) {
-            uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+        if (q0 + 16 <= nsamp && (((uintptr_t)dst) & 15u) == 0) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
             if (B == 3) {
-                dw[0] = __byte_perm(v0, v1, 0x4210); dw[1] = __byte_perm(v1, v2, 0x5421); dw[2] = __byte_perm(v2, v3, 0x6542);
+#pragma unroll
+                for (int e = 0; e < 3; e++) {       // 16 samples x 3 bytes = 12 words: word j holds bytes 4j..4j+3
+                    uint32_t w[4];
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const int j = 4 * e + x, q = (4 * j) / 3, r = (4 * j) % 3;
+                        w[x] = r == 0 ? __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x4210) : r == 1 ? __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x5421) : __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x6542);
+                    }
+                    d4[e] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             } else if (B == 2) {
-                dw[0] = __byte_perm(v0, v1, 0x5410); dw[1] = __byte_perm(v2, v3, 0x5410);
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    d4[e] = make_uint4(__byte_perm(v[8 * e], v[8 * e + 1], 0x5410), __byte_perm(v[8 * e + 2], v[8 * e + 3], 0x5410),
+                                       __byte_perm(v[8 * e + 4], v[8 * e + 5], 0x5410), __byte_perm(v[8 * e + 6], v[8 * e + 7], 0x5410));
             } else {
-                dw[0] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+                uint32_t w[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) w[x] = __byte_perm(__byte_perm(v[4 * x], v[4 * x + 1], 0x0040), __byte_perm(v[4 * x + 2], v[4 * x + 3], 0x0040), 0x5410);
+                d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         } else {
-            const uint32_t nv = min(4u, nsamp - q0);
-            const uint32_t vv[4] = {v0, v1, v2, v3};
+            const uint32_t nv = min(16u, nsamp - q0);
 #pragma unroll
-            for (uint32_t e = 0; e < 4; e++)
-                if (e < nv) for (uint32_t b = 0; b < B; b++) dst[e * B + b] = (uint8_t)(vv[e] >> (8 * b));
+            for (uint32_t e = 0; e < 16; e += 4) {
+                if (e + 4 <= nv && (((uintptr_t)dst) & 3u) == 0) pack4(reinterpret_cast<uint32_t*>(dst + e * B), B, v[e], v[e + 1], v[e + 2], v[e + 3]);
+                else {
+#pragma unroll
+                    for (uint32_t x = 0; x < 4; x++)
+                        if (e + x < nv) for (uint32_t b = 0; b < B; b++) dst[(e + x) * B + b] = (uint8_t)(v[e + x] >> (8 * b));
+                }
+            }
         }
     }
 }
 
+constexpr int DEC_WARPS = 2;                  // independent warps per CTA (no CTA-wide barrier anywhere)
+__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
+
 template <int ORD, bool WIDE>
-__global__ void __launch_bounds__(32) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
+__global__ void __launch_bounds__(32 * DEC_WARPS, ORD <= 12 ? 9 : 1) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
     constexpr int T = DecCfg<ORD>::T;
     extern __shared__ __align__(16) uint8_t s_dyn[];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t ring_base = smem_u32(s_dyn);
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t ring_base = smem_u32(s_dyn) + wib * dec_warp_smem(T, S);
     const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
-    const uint32_t ftab = tile_base + T * DEC_MAX_S * 4;       // bs[32] | assign[32] | pcm offset[32] (u64)
+    const uint32_t ftab = tile_base + T * S * 4;               // bs[32] | assign[32] | pcm offset[32] (u64)
     const uint32_t F = 32 / C;
     const uint32_t n_acc = a.totals->n_accepted;
     const uint32_t fl = lane / C, ch = lane - fl * C;
-    const uint32_t kf = blockIdx.x * F + fl;
+    const uint32_t kf = (blockIdx.x * DEC_WARPS + wib) * F + fl;
     const bool active = fl < F && kf < n_acc;
     const uint32_t rs4 = S * 4;
     const uint32_t col = tile_base + lane * 4;
@@ -1023,18 +1055,19 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     constexpr int T = DecCfg<ORD>::T;
     const uint32_t F = 32 / C;
     const uint32_t S = 32 + ((C & 3) == 0 ? 4 : (C & 1) == 0 ? 2 : 1);
-    const uint32_t grid = blocks_for(nacc, F);
-    size_t smem = (size_t)32 * RingBits::STRIDE + (size_t)T * DEC_MAX_S * 4 + 512;
-    static int max_resident = 0, n_sm = 0;
-    if (!max_resident) {
+    const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
+    size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S);
+    static int n_sm = 0;
+    if (!n_sm) {
         cudaFuncSetAttribute(k_decode<ORD, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE>, 32, smem);
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (max_resident < 1) max_resident = 1;
         if (n_sm < 1) n_sm = 148;
     }
+    int max_resident = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE>, 32 * DEC_WARPS, smem);
+    if (max_resident < 1) max_resident = 1;
     // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  Cap the residency
-    // (by asking for more shared memory) so that the waves are equally full instead of a full one plus a nearly empty one.
+    // (by asking for more shared memory) so that the waves are equally full instead of full ones plus a nearly empty one.
     const uint64_t per_wave = (uint64_t)n_sm * max_resident;
     const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
     uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
@@ -1044,7 +1077,7 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
         if (want > 200 * 1024) want = 200 * 1024;
         if (want > smem) smem = want;
     }
-    k_decode<ORD, WIDE><<<grid, 32, smem, st>>>(a, C, B, S);
+    k_decode<ORD, WIDE><<<grid, 32 * DEC_WARPS, smem, st>>>(a, C, B, S);
     g_launches++;
 }
 void launch_decode(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, bool wide, void* stream) {
