@@ -13,8 +13,7 @@
 
 namespace bnf {
 
-constexpr int SCAN_CHUNK = 32768;      // bytes per scan CTA
-constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_CHUNK = 32768;      // bytes per scan work unit; chunk k of a segment covers [max(begin, A + k*32768), A + (k+1)*32768), A = begin & ~15
 constexpr int SCAN_SCAP = 4096;        // max frame candidates per chunk (min frame is 10 bytes -> 3277)
 constexpr int MAX_CH = 8;
 
@@ -33,7 +32,8 @@ struct SegInfo {
     uint64_t own_begin, own_end;  // frames whose sync lies in [own_begin, own_end) belong to this shard
     uint32_t bps, channels, sample_rate, min_bs, max_bs;
     uint32_t max_frame_bytes;     // upper bound used when extending a CRC span over false syncs
-    uint32_t pad[2];
+    uint32_t first_chunk;         // index of the segment's first scan chunk
+    uint32_t pad;
 };
 
 struct Chunk {
@@ -84,6 +84,8 @@ struct PassArgs {
     uint32_t* chunk_count;
     uint32_t* chunk_scan;
     uint32_t* counters;     // [0] total candidates appended, [1] overflow flags
+    uint16_t* crc_tmp;      // CRC-16 from each candidate to the next one / the end of its chunk (chunk order)
+    uint16_t* chunk_head;   // CRC-16 of the bytes in front of a chunk's first candidate (of the whole chunk if it has none)
     uint16_t* seg_crc;
     uint32_t* next;
     uint32_t* flen;

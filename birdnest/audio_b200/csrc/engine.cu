@@ -165,7 +165,7 @@ struct bnflac {
     bool uploaded = false;
 
     // device state
-    DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next,
+    DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_crc_tmp, d_chunk_head,
         d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out;
     uint32_t nchunks = 0, cand_cap = 0;
     bool tables_ready = false;
@@ -184,7 +184,7 @@ struct bnflac {
 
     ~bnflac() {
         cudaSetDevice(device);
-        DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc,
+        DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_crc_tmp, &d_chunk_head,
                          &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out};
         for (DevBuf* b : all) b->release();
         pcm_host.release();
@@ -252,7 +252,12 @@ static int ensure_tables(bnflac* h) {
     seg.bps = h->info.bits_per_sample; seg.channels = h->info.channels; seg.sample_rate = h->info.sample_rate;
     seg.min_bs = h->info.min_blocksize; seg.max_bs = h->info.max_blocksize; seg.max_frame_bytes = frame_bound(h->info);
     std::vector<Chunk> chunks;
-    for (uint64_t p = seg.begin; p < seg.end; p += SCAN_CHUNK) chunks.push_back(Chunk{p, (uint32_t)std::min<uint64_t>(SCAN_CHUNK, seg.end - p), 0});
+    seg.first_chunk = 0;
+    for (uint64_t p = seg.begin; p < seg.end;) {          // chunk boundaries at multiples of 32 KiB from the segment's aligned base
+        const uint64_t stop = std::min<uint64_t>(seg.end, ((p & ~15ull) - ((p & ~15ull) - (seg.begin & ~15ull)) % SCAN_CHUNK) + SCAN_CHUNK);
+        chunks.push_back(Chunk{p, (uint32_t)(stop - p), 0});
+        p = stop;
+    }
     h->nchunks = (uint32_t)chunks.size();
     int rc;
     if ((rc = h->d_segs.reserve(sizeof seg))) return rc;
@@ -260,6 +265,7 @@ static int ensure_tables(bnflac* h) {
     if ((rc = h->d_chunk_base.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_chunk_count.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_chunk_scan.reserve(4ull * (h->nchunks + 1)))) return rc;
+    if ((rc = h->d_chunk_head.reserve(2ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_counters.reserve(64))) return rc;
     if ((rc = h->d_totals.reserve(sizeof(Totals)))) return rc;
     CK(cudaMemcpyAsync(h->d_segs.p, &seg, sizeof seg, cudaMemcpyHostToDevice, h->stream));
@@ -271,6 +277,7 @@ static int ensure_tables(bnflac* h) {
     h->args.chunks = h->d_chunks.as<Chunk>(); h->args.nchunks = h->nchunks;
     h->args.chunk_base = h->d_chunk_base.as<uint32_t>(); h->args.chunk_count = h->d_chunk_count.as<uint32_t>();
     h->args.chunk_scan = h->d_chunk_scan.as<uint32_t>(); h->args.counters = h->d_counters.as<uint32_t>();
+    h->args.chunk_head = h->d_chunk_head.as<uint16_t>();
     h->args.totals = h->d_totals.as<Totals>();
     h->tables_ready = true;
     return 0;
@@ -281,6 +288,7 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
     if ((rc = h->d_cand_tmp.reserve(sizeof(Cand) * (size_t)cap))) return rc;
     if ((rc = h->d_cand.reserve(sizeof(Cand) * (size_t)cap))) return rc;
     if ((rc = h->d_seg_crc.reserve(2ull * cap))) return rc;
+    if ((rc = h->d_crc_tmp.reserve(2ull * cap))) return rc;
     if ((rc = h->d_next.reserve(4ull * cap))) return rc;
     if ((rc = h->d_flen.reserve(4ull * cap))) return rc;
     if ((rc = h->d_status.reserve(cap))) return rc;
@@ -289,7 +297,7 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
     if ((rc = h->d_acc_idx.reserve(4ull * cap))) return rc;
     h->cand_cap = cap;
     h->args.cand_tmp = h->d_cand_tmp.as<Cand>(); h->args.cand = h->d_cand.as<Cand>(); h->args.cand_cap = cap;
-    h->args.seg_crc = h->d_seg_crc.as<uint16_t>(); h->args.next = h->d_next.as<uint32_t>(); h->args.flen = h->d_flen.as<uint32_t>();
+    h->args.seg_crc = h->d_seg_crc.as<uint16_t>(); h->args.crc_tmp = h->d_crc_tmp.as<uint16_t>(); h->args.next = h->d_next.as<uint32_t>(); h->args.flen = h->d_flen.as<uint32_t>();
     h->args.status = h->d_status.as<uint8_t>(); h->args.sub = h->d_sub.as<SubInfo>(); h->args.pcm_off = h->d_pcm_off.as<uint64_t>();
     h->args.acc_idx = h->d_acc_idx.as<uint32_t>();
     return 0;

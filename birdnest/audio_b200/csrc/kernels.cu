@@ -59,6 +59,19 @@ __device__ uint32_t gf_xpow8(uint32_t nbytes) {
     return result;
 }
 
+// ------------------------------------------------------------------------------------------------ shared-memory / bit helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
+__device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+__device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }   // index of the leading one; 0xffffffff for 0
+__device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
+
+
 // ------------------------------------------------------------------------------------------------ frame header
 struct Hdr {
     uint64_t number;
@@ -66,15 +79,18 @@ struct Hdr {
     uint32_t hdr_len, bps, assign, variable, channels;
 };
 
-// Frame header syntax + CRC-8.  p must have 17 readable bytes.
-__device__ bool parse_header(const uint8_t* __restrict__ p, const SegInfo& s, Hdr& h) {
-    if (p[0] != 0xFF || (p[1] & 0xFE) != 0xF8) return false;
-    uint32_t b2 = p[2], b3 = p[3];
+// Frame header syntax + CRC-8.  at(i) returns byte i of the candidate; 17 bytes must be readable.
+template <class F>
+__device__ __forceinline__ bool parse_header_t(F at, const SegInfo& s, Hdr& h) {
+    if (at(0) != 0xFF || (at(1) & 0xFE) != 0xF8) return false;
+    uint32_t b2 = at(2), b3 = at(3);
     uint32_t bsc = b2 >> 4, src = b2 & 15, ca = b3 >> 4, ssc = (b3 >> 1) & 7;
     if ((b3 & 1) || bsc == 0 || src == 15 || ca > 10 || ssc == 3 || ssc == 7) return false;
-    h.variable = p[1] & 1;
+    h.variable = at(1) & 1;
+    uint32_t c = crc8_update(crc8_update(crc8_update(crc8_update(0, 0xFF), at(1)), b2), b3);
     uint32_t q = 4;
-    uint32_t x = p[q++];
+    uint32_t x = at(q++);
+    c = crc8_update(c, x);
     uint64_t num;
     if (x < 0x80) num = x;
     else {
@@ -82,7 +98,8 @@ __device__ bool parse_header(const uint8_t* __restrict__ p, const SegInfo& s, Hd
         if (n == 1 || n > 7 || (!h.variable && n == 7)) return false;
         num = (n == 7) ? 0 : (x & ((1u << (7 - n)) - 1));
         for (int i = 1; i < n; i++) {
-            uint32_t y = p[q++];
+            uint32_t y = at(q++);
+            c = crc8_update(c, y);
             if ((y >> 6) != 2) return false;
             num = (num << 6) | (y & 0x3f);
         }
@@ -91,8 +108,8 @@ __device__ bool parse_header(const uint8_t* __restrict__ p, const SegInfo& s, Hd
     uint32_t bs;
     if (bsc == 1) bs = 192;
     else if (bsc <= 5) bs = 576u << (bsc - 2);
-    else if (bsc == 6) { bs = p[q] + 1u; q += 1; }
-    else if (bsc == 7) { bs = ((uint32_t)p[q] << 8 | p[q + 1]) + 1u; q += 2; }
+    else if (bsc == 6) { uint32_t v = at(q++); c = crc8_update(c, v); bs = v + 1u; }
+    else if (bsc == 7) { uint32_t v0 = at(q++), v1 = at(q++); c = crc8_update(crc8_update(c, v0), v1); bs = (v0 << 8 | v1) + 1u; }
     else bs = 256u << (bsc - 8);
     uint32_t sr;
     switch (src) {
@@ -100,101 +117,273 @@ __device__ bool parse_header(const uint8_t* __restrict__ p, const SegInfo& s, Hd
     case 1: sr = 88200; break; case 2: sr = 176400; break; case 3: sr = 192000; break; case 4: sr = 8000; break;
     case 5: sr = 16000; break; case 6: sr = 22050; break; case 7: sr = 24000; break; case 8: sr = 32000; break;
     case 9: sr = 44100; break; case 10: sr = 48000; break; case 11: sr = 96000; break;
-    case 12: sr = p[q] * 1000u; q += 1; break;
-    case 13: sr = (uint32_t)p[q] << 8 | p[q + 1]; q += 2; break;
-    default: sr = ((uint32_t)p[q] << 8 | p[q + 1]) * 10u; q += 2; break;
+    case 12: { uint32_t v = at(q++); c = crc8_update(c, v); sr = v * 1000u; break; }
+    default: { uint32_t v0 = at(q++), v1 = at(q++); c = crc8_update(crc8_update(c, v0), v1); sr = (v0 << 8 | v1) * (src == 13 ? 1u : 10u); break; }
     }
-    uint32_t c = 0;
-    for (uint32_t i = 0; i < q; i++) c = crc8_update(c, p[i]);
-    if (c != p[q]) return false;
+    if (c != at(q)) return false;
     q++;
     h.bs = bs; h.sample_rate = sr; h.hdr_len = q; h.assign = ca;
     h.channels = ca < 8 ? ca + 1 : 2;
-    static const uint8_t sst[8] = {0, 8, 12, 0, 16, 20, 24, 0};
-    h.bps = ssc == 0 ? s.bps : sst[ssc];
+    h.bps = ssc == 0 ? s.bps : ssc == 1 ? 8u : ssc == 2 ? 12u : ssc == 4 ? 16u : ssc == 5 ? 20u : 24u;
     // the engine decodes streams whose frames agree with STREAMINFO (every real encoder; per-frame channel/bps
     // changes are treated as false syncs)
     if (h.channels != s.channels || h.bps != s.bps) return false;
     return true;
 }
 
-// ------------------------------------------------------------------------------------------------ K1a scan
-__device__ __forceinline__ uint32_t bytemask4(uint32_t eq) {   // 0xFF/0x00 per byte -> 4-bit mask
-    uint32_t x = (eq & 0x80808080u) >> 7;
-    return (x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xFu;
+// ------------------------------------------------------------------------------------------------ K1 scan + CRC-16
+// One streaming pass over the compressed bytes does both jobs of K1: it finds the frame-sync candidates (0xFFF8/0xFFF9 +
+// header syntax + CRC-8) and it computes the CRC-16 of every stretch of bytes between consecutive candidates, which is
+// what the link step needs to tell frames from false syncs.
+//   * persistent CTAs (one per SM, 512 threads); a CTA takes 32 KiB chunks, double-buffered through shared memory with
+//     coalesced 16-byte cp.async (units XOR-swizzled so that the per-thread reads below are conflict free);
+//   * every thread owns one 64-byte piece: it scans it for sync codes (cheap "has a 0xFF byte" filter, exact header parse
+//     on hits) and computes its CRC-16 with slicing-by-4.  The four 256-entry tables are replicated 32 times (one copy
+//     per bank, 128 KiB) so that the data-dependent lookups of a warp never conflict;
+//   * CRC is linear over GF(2): the CRC of a stretch is the XOR of (piece CRC * x^(8*distance to the stretch end)).  Each
+//     piece multiplies by a table entry x^(512*d) and is XOR-reduced into its stretch; one more factor x^(8*b) per stretch
+//     and the partial pieces at the stretch boundaries finish it.
+// Output: the chunk's ordered candidate list, the CRC of the bytes from each candidate to the next candidate or the end
+// of the chunk, and the CRC of the bytes before the chunk's first candidate; k_crc_spans joins them across chunks.
+constexpr int SC_THREADS = 512;
+constexpr int SC_PIECE = 64;
+static_assert(SC_THREADS * SC_PIECE == SCAN_CHUNK, "one 64-byte piece per thread");
+constexpr uint32_t SC_OFF_DATA = 4u * 256u * 32u * 4u;                          // after the replicated tables
+constexpr uint32_t SC_OFF_X64 = SC_OFF_DATA + 2u * SCAN_CHUNK;                  // x^(512 d), d < 512
+constexpr uint32_t SC_OFF_X1 = SC_OFF_X64 + 512u * 4u;                          // x^(8 b), b < 64
+constexpr uint32_t SC_OFF_XINV = SC_OFF_X1 + 64u * 4u;                          // x^(-8 b), b <= 64
+constexpr uint32_t SC_OFF_LIST = SC_OFF_XINV + 68u * 4u;                        // candidate offsets in the chunk (u16)
+constexpr uint32_t SC_OFF_ACC = SC_OFF_LIST + SCAN_SCAP * 2u;                   // per-stretch accumulators
+constexpr uint32_t SC_OFF_MISC = SC_OFF_ACC + (SCAN_SCAP + 1u) * 4u + 12u;
+constexpr uint32_t SC_SMEM = SC_OFF_MISC + 128u;
+
+__device__ __forceinline__ uint32_t sc_swz(uint32_t unit) { return (unit ^ ((unit >> 3) & 7u)) << 4; }
+__device__ __forceinline__ uint32_t bswap16(uint32_t v) { return __byte_perm(v, 0, 0x4401); }
+__device__ uint32_t gf_pow(uint32_t base, uint32_t e) {
+    uint32_t r = 1;
+    while (e) { if (e & 1u) r = gf_mul(r, base); base = gf_mul(base, base); e >>= 1; }
+    return r;
+}
+// CRC-16 of 16 little-endian words (slicing-by-4, per-bank table copies), returned in the usual (not swapped) form
+__device__ __forceinline__ uint32_t sc_crc64(const uint32_t (&w)[16], uint32_t tl) {
+    uint32_t cs = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t x = w[k] ^ cs;
+        const uint32_t t3 = lds32(tl + ((x << 7) & 0x7F80u) + 3u * 32768u);
+        const uint32_t t2 = lds32(tl + ((x >> 1) & 0x7F80u) + 2u * 32768u);
+        const uint32_t t1 = lds32(tl + ((x >> 9) & 0x7F80u) + 1u * 32768u);
+        const uint32_t t0 = lds32(tl + ((x >> 17) & 0x7F80u));
+        cs = t3 ^ t2 ^ t1 ^ t0;
+    }
+    return bswap16(cs);
+}
+// keep bytes [from, to) of the piece, zero the rest
+__device__ __forceinline__ void sc_keep(uint32_t (&w)[16], uint32_t from, uint32_t to) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t b0 = 4 * k;
+        uint32_t m = 0xFFFFFFFFu;
+        if (b0 + 4 <= from || b0 >= to) m = 0;
+        else {
+            if (b0 < from) m &= 0xFFFFFFFFu << (8 * (from - b0));
+            if (b0 + 4 > to) m &= 0xFFFFFFFFu >> (8 * (b0 + 4 - to));
+        }
+        w[k] &= m;
+    }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(PassArgs a) {
-    __shared__ uint32_t s_list[SCAN_SCAP];
-    __shared__ uint32_t s_sorted[SCAN_SCAP];
-    __shared__ uint32_t s_n, s_base;
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (uint32_t chunk = blockIdx.x; chunk < a.nchunks; chunk += gridDim.x) {
-        const Chunk c = a.chunks[chunk];
-        const SegInfo seg = a.segs[c.seg];
-        if (tid == 0) s_n = 0;
+__global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
+    extern __shared__ __align__(128) uint8_t s_sc[];
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_sc);
+    uint32_t* s_x64 = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_X64);
+    uint32_t* s_x1 = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_X1);
+    uint32_t* s_xinv = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_XINV);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_sc + SC_OFF_LIST);
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_ACC);
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_MISC);     // [0..15] warp counts, [17] global base
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t data_base = smem_u32(s_sc + SC_OFF_DATA);
+
+    // ---- tables (once per CTA)
+    for (uint32_t e = tid; e < 1024; e += SC_THREADS) {          // W_j[v] = v * x^(16+8j) mod P, stored byte-swapped
+        const uint32_t j = e >> 8, v = e & 255;
+        uint32_t c = v << 8;
+        for (uint32_t k = 0; k < 8 * (j + 1); k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
+        const uint32_t sw = bswap16(c);
+        for (uint32_t r = 0; r < 32; r++) s_tab[(j * 256 + v) * 32 + r] = sw;
+    }
+    s_x64[tid] = gf_xpow8(64u * tid);
+    if (tid < 64) s_x1[tid] = gf_xpow8(tid);
+    if (tid <= 64) s_xinv[tid] = gf_pow(0xC002u, 8u * tid);      // x^-1 = x^15 + x^14 + x  (x * that = P + 1)
+    for (uint32_t e = tid; e <= SCAN_SCAP; e += SC_THREADS) s_acc[e] = 0;
+    __syncthreads();
+    const uint32_t tl = smem_u32(s_tab) + lane * 4;             // this lane's copy of the tables
+
+    auto prefetch = [&](const Chunk& c, uint32_t buf) {
+        const uint64_t ab = c.begin & ~15ull;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t u = tid + SC_THREADS * k;
+            const uint64_t g = ab + 16ull * u;
+            const uint32_t n = g + 16 <= a.in_len ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(data_base + buf * SCAN_CHUNK + sc_swz(u)), "l"(a.in + (n ? g : 0)), "r"(n) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // descriptors run two chunks ahead of the data so that no global round trip is exposed inside the loop
+    uint32_t buf = 0, n_prev = 0;
+    Chunk c_cur{}, c_next{};
+    SegInfo seg{}, seg_next{};
+    if (blockIdx.x < a.nchunks) { c_cur = a.chunks[blockIdx.x]; seg = a.segs[c_cur.seg]; prefetch(c_cur, 0); }
+    if (blockIdx.x + gridDim.x < a.nchunks) { c_next = a.chunks[blockIdx.x + gridDim.x]; seg_next = a.segs[c_next.seg]; }
+    for (uint32_t chunk = blockIdx.x; chunk < a.nchunks; chunk += gridDim.x, buf ^= 1) {
+        const Chunk c = c_cur;
+        const uint64_t ab = c.begin & ~15ull;
+        const uint32_t lo = (uint32_t)(c.begin - ab), hi = lo + c.len;          // valid bytes of the chunk, buffer-relative
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        const uint64_t abeg = c.begin & ~15ull;
-        const uint32_t nunits = (uint32_t)((c.begin + c.len - abeg + 15) >> 4);
-        const uint32_t nloop = (nunits + 31) & ~31u;
-        for (uint32_t u = tid; u < nloop; u += SCAN_THREADS) {
-            const bool valid = u < nunits;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (valid) v = __ldg(reinterpret_cast<const uint4*>(a.in + abeg) + u);
-            uint32_t nextb = __shfl_down_sync(FULL, v.x & 0xFFu, 1);
-            if (valid && (lane == 31 || u + 1 >= nunits)) nextb = a.in[abeg + 16ull * (u + 1)];   // padded input: always readable
-            uint32_t ff = bytemask4(__vcmpeq4(v.x, 0xFFFFFFFFu)) | bytemask4(__vcmpeq4(v.y, 0xFFFFFFFFu)) << 4 |
-                          bytemask4(__vcmpeq4(v.z, 0xFFFFFFFFu)) << 8 | bytemask4(__vcmpeq4(v.w, 0xFFFFFFFFu)) << 12;
-            if (ff) {
-                const uint32_t m = 0xFEFEFEFEu, k = 0xF8F8F8F8u;
-                uint32_t f8 = bytemask4(__vcmpeq4(v.x & m, k)) | bytemask4(__vcmpeq4(v.y & m, k)) << 4 |
-                              bytemask4(__vcmpeq4(v.z & m, k)) << 8 | bytemask4(__vcmpeq4(v.w & m, k)) << 12;
-                if ((nextb & 0xFE) == 0xF8) f8 |= 1u << 16;
-                uint32_t hits = ff & (f8 >> 1);
-                while (hits) {
-                    int p = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    uint64_t o = abeg + 16ull * u + p;
-                    if (o < c.begin || o >= c.begin + c.len) continue;
+        const bool have_next = chunk + gridDim.x < a.nchunks;
+        if (have_next) prefetch(c_next, buf ^ 1);
+        Chunk c_nn{}; SegInfo seg_nn{};
+        if (chunk + 2 * gridDim.x < a.nchunks) { c_nn = a.chunks[chunk + 2 * gridDim.x]; seg_nn = a.segs[c_nn.seg]; }
+        const uint32_t dbase = data_base + buf * SCAN_CHUNK;
+        const uint32_t p0 = tid * SC_PIECE;                                    // first byte of this thread's piece
+        // byte i of the buffer (bytes past the buffer come from global memory: only headers that straddle the chunk end)
+        auto byte_at = [&](uint32_t o) -> uint32_t {
+            if (o < (uint32_t)SCAN_CHUNK) { const uint32_t wd = lds32(dbase + sc_swz(o >> 4) + (o & 12u)); return (wd >> (8 * (o & 3u))) & 0xFFu; }
+            const uint64_t g = ab + o;
+            return g < a.in_len ? a.in[g] : 0u;
+        };
+
+        // ---- load the piece, zero what lies outside [lo, hi)
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint4 v = lds128(dbase + sc_swz(4 * tid + k)); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+        if (p0 < lo || p0 + SC_PIECE > hi) sc_keep(w, lo > p0 ? lo - p0 : 0u, hi > p0 ? (hi - p0 < 64u ? hi - p0 : 64u) : 0u);
+        // ---- sync scan: byte == 0xFF followed by (byte & 0xFE) == 0xF8
+        uint64_t cm = 0;                                                       // candidate start bytes inside the piece
+        {
+            uint32_t nextb = __shfl_down_sync(FULL, w[0] & 0xFFu, 1);
+            if (lane == 31) nextb = (w[15] >> 24) == 0xFFu ? byte_at(p0 + SC_PIECE) : 0u;   // (a zeroed next byte cannot complete a sync code)
+            uint32_t wm = 0;                                                   // words that may hold a 0xFF byte
+#pragma unroll
+            for (int k = 0; k < 16; k++) { const uint32_t t = ~w[k]; if ((t - 0x01010101u) & w[k] & 0x80808080u) wm |= 1u << k; }
+#pragma unroll 1
+            while (wm) {                                                       // rare: re-read the word pair from shared memory
+                const uint32_t k = (uint32_t)__ffs(wm) - 1u;
+                wm &= wm - 1;
+                const uint32_t ow = p0 + 4 * k;                                // buffer offset of the word
+                const uint32_t wk = lds32(dbase + sc_swz(ow >> 4) + (ow & 12u));
+                const uint32_t nx = k < 15 ? (lds32(dbase + sc_swz((ow + 4) >> 4) + ((ow + 4) & 12u)) & 0xFFu) : nextb;
+                const uint64_t pair = (uint64_t)wk | ((uint64_t)nx << 32);
+#pragma unroll 1
+                for (uint32_t byte = 0; byte < 4; byte++) {
+                    const uint32_t two = (uint32_t)(pair >> (8 * byte)) & 0xFFFFu;              // this byte and the next
+                    if ((two & 0xFEFFu) != 0xF8FFu) continue;
+                    const uint32_t bo = 4 * k + byte;                          // byte offset inside the piece
+                    const uint32_t o = p0 + bo;
+                    if (o < lo || o >= hi) continue;
                     Hdr h;
-                    if (!parse_header(a.in + o, seg, h)) continue;
-                    if (o + h.hdr_len + 2 > seg.end) continue;
-                    uint32_t slot = atomicAdd(&s_n, 1u);
-                    if (slot < SCAN_SCAP) s_list[slot] = (uint32_t)(o - c.begin);
+                    if (!parse_header_t([&](uint32_t i) { return byte_at(o + i); }, seg, h)) continue;
+                    if (ab + o + h.hdr_len + 2 > seg.end) continue;
+                    cm |= 1ull << bo;
                 }
             }
         }
+        // ---- order the candidates: exclusive prefix of the per-piece counts
+        const uint32_t cnt = (uint32_t)__popcll(cm);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
+        if (lane == 31) s_misc[warp] = inc;
+        // the accumulators of the previous chunk are cleared here (its outputs were written before the barrier at the loop top)
+        for (uint32_t e = tid; e <= n_prev && e <= SCAN_SCAP; e += SC_THREADS) s_acc[e] = 0;
         __syncthreads();
-        uint32_t n = s_n;
-        if (n > SCAN_SCAP) { n = SCAN_SCAP; if (tid == 0) atomicOr(&a.counters[1], 1u); }
-        // order the chunk's list by offset (n is ~chunk/frame size; rank sort)
-        for (uint32_t e = tid; e < n; e += SCAN_THREADS) {
-            uint32_t key = s_list[e], rank = 0;
-            for (uint32_t j = 0; j < n; j++) rank += (s_list[j] < key);
-            s_sorted[rank] = key;
+        uint32_t base = inc - cnt, total = 0;
+#pragma unroll
+        for (uint32_t wv = 0; wv < SC_THREADS / 32; wv++) { const uint32_t x = s_misc[wv]; if (wv < warp) base += x; total += x; }
+        const bool overflow = total > SCAN_SCAP;
+        const uint32_t n = overflow ? 0 : total;
+        n_prev = n;
+        if (!overflow) { uint64_t m = cm; uint32_t j = base; while (m) { const uint32_t bo = (uint32_t)(__ffsll((long long)m) - 1); m &= m - 1; s_list[j++] = (uint16_t)(p0 + bo); } }
+        uint32_t gb = 0;
+        if (tid == 0) {                                // the result is not needed before the output step below
+            if (overflow) atomicOr(&a.counters[1], 1u);
+            else if (n) gb = atomicAdd(&a.counters[0], n);
+        }
+        __syncthreads();
+        // ---- piece CRC with the bytes before the piece's last boundary zeroed: what remains is the head of the stretch
+        //      that starts there
+        const bool end_in = hi > p0 && hi < p0 + SC_PIECE;                    // the end of the valid bytes falls inside the piece
+        const bool head_ok = p0 < hi && !end_in;                             // (a piece that holds the end has no stretch running past it)
+        if (cm) sc_keep(w, 63u - (uint32_t)__clzll((long long)cm), 64u);
+        const uint32_t pc = sc_crc64(w, tl);
+        // ---- into the stretch: stretch s ends at candidate s (or at hi); this piece's head belongs to stretch base+cnt
+        const uint32_t sidx = base + cnt;
+        uint32_t term = 0;
+        if (head_ok && !overflow) {
+            const uint32_t e = sidx < n ? s_list[sidx] : hi;
+            term = gf_mul(pc, s_x64[(e >> 6) - 1 - tid]);                     // the stretch ends in piece e >> 6 >= tid + 1
+        }
+        {
+            const uint32_t s0 = __shfl_sync(FULL, sidx, 0);
+            if (__all_sync(FULL, sidx == s0)) { const uint32_t r = __reduce_xor_sync(FULL, term); if (lane == 0 && r) atomicXor(&s_acc[s0], r); }
+            else if (term) atomicXor(&s_acc[sidx], term);
+        }
+        __syncthreads();
+        for (uint32_t sx = tid; sx <= n; sx += SC_THREADS) { const uint32_t e = sx < n ? s_list[sx] : hi; s_acc[sx] = gf_mul(s_acc[sx], s_x1[e & 63u]); }
+        __syncthreads();
+        // ---- partial pieces in front of each boundary (candidates, end of the valid bytes).  CRC of bytes [prev, bo) =
+        //      CRC of the piece with everything else zeroed, times x^(-8 (64 - bo)) (trailing zeros undone)
+        if ((cm || end_in) && !overflow) {
+            uint64_t m = cm;
+            if (end_in) m |= 1ull << (hi - p0);
+            uint32_t prev = lo > p0 ? lo - p0 : 0u, j = base;
+#pragma unroll 1
+            while (m) {
+                const uint32_t bo = (uint32_t)(__ffsll((long long)m) - 1);
+                m &= m - 1;
+                if (bo > prev) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { const uint4 v = lds128(dbase + sc_swz(4 * tid + k)); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+                    sc_keep(w, prev, bo);
+                    const uint32_t v = gf_mul(sc_crc64(w, tl), s_xinv[64u - bo]);
+                    if (v) atomicXor(&s_acc[j], v);
+                }
+                j++; prev = bo;
+            }
         }
         if (tid == 0) {
-            uint32_t base = atomicAdd(&a.counters[0], n);
-            if (base + n > a.cand_cap) { atomicOr(&a.counters[1], 2u); n = base < a.cand_cap ? a.cand_cap - base : 0; }
-            s_base = base; s_n = n;
-            a.chunk_base[chunk] = base;
-            a.chunk_count[chunk] = n;
+            s_misc[17] = gb;
+            a.chunk_base[chunk] = gb;
+            a.chunk_count[chunk] = (gb + n > a.cand_cap) ? (gb < a.cand_cap ? a.cand_cap - gb : 0) : n;
+            if (gb + n > a.cand_cap) atomicOr(&a.counters[1], 2u);
         }
         __syncthreads();
-        n = s_n;
-        for (uint32_t e = tid; e < n; e += SCAN_THREADS) {
-            uint64_t o = c.begin + s_sorted[e];
-            Hdr h;
-            parse_header(a.in + o, seg, h);
-            Cand cd;
-            cd.off = o; cd.number = h.number; cd.bs = h.bs; cd.seg = c.seg;
-            cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
-            cd.flags = (uint8_t)(h.variable | ((o < seg.own_begin || o >= seg.own_end) ? 2u : 0u));
-            cd.sample_rate = h.sample_rate;
-            a.cand_tmp[s_base + e] = cd;
+        // ---- outputs (the barrier at the top of the next iteration orders them before the buffers are reused)
+        if (tid == 0) a.chunk_head[chunk] = (uint16_t)s_acc[0];
+        {
+            const uint32_t gbase = s_misc[17];
+            for (uint32_t e = tid; e < n; e += SC_THREADS) {
+                if (gbase + e >= a.cand_cap) break;
+                const uint32_t o = s_list[e];
+                Hdr h;
+                parse_header_t([&](uint32_t i) { return byte_at(o + i); }, seg, h);
+                const uint64_t go = ab + o;
+                Cand cd;
+                cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = c.seg;
+                cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
+                cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
+                cd.sample_rate = h.sample_rate;
+                a.cand_tmp[gbase + e] = cd;
+                a.crc_tmp[gbase + e] = (uint16_t)s_acc[e + 1];
+            }
         }
-        __syncthreads();
+        c_cur = c_next; seg = seg_next; c_next = c_nn; seg_next = seg_nn;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // single-CTA exclusive scan of chunk_count -> chunk_scan
@@ -222,7 +411,7 @@ __global__ void __launch_bounds__(256) k_gather(PassArgs a) {
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t chunk = warp; chunk < a.nchunks; chunk += nwarps) {
         uint32_t n = a.chunk_count[chunk], src = a.chunk_base[chunk], dst = a.chunk_scan[chunk];
-        for (uint32_t r = lane; r < n; r += 32) a.cand[dst + r] = a.cand_tmp[src + r];
+        for (uint32_t r = lane; r < n; r += 32) { a.cand[dst + r] = a.cand_tmp[src + r]; a.seg_crc[dst + r] = a.crc_tmp[src + r]; }
     }
 }
 
@@ -234,39 +423,29 @@ __device__ __forceinline__ uint64_t span_end(const PassArgs& a, uint32_t i, uint
     return a.segs[ci.seg].end;
 }
 
+// Joins the chunk-local CRCs into the CRC-16 of every span between consecutive candidates: the stretch from the candidate
+// to the end of its chunk, whole chunks in between, and the bytes in front of the next candidate in its chunk.
 __global__ void __launch_bounds__(256) k_crc(PassArgs a) {
-    __shared__ uint16_t s_tab[256];
-    {
-        uint32_t d = (uint32_t)threadIdx.x << 8;
-#pragma unroll
-        for (int k = 0; k < 8; k++) d = (d & 0x8000) ? ((d << 1) ^ 0x8005) & 0xFFFF : (d << 1) & 0xFFFF;
-        s_tab[threadIdx.x] = (uint16_t)d;
-    }
-    __syncthreads();
     const uint32_t n = ncand(a);
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = warp; i < n; i += nwarps) {
-        const Cand ci = a.cand[i];
-        const uint64_t e = span_end(a, i, n, ci);
-        const int64_t L = (int64_t)(e - ci.off);
-        const int64_t m = (L + 31) >> 5;
-        // zero bytes in front of a message do not change its CRC: lane pieces are laid out from the END so that all
-        // (virtual) pieces have the same length m and one factor x^(8m) serves the whole combine tree
-        int64_t pb = L - (int64_t)(32 - lane) * m, pe = pb + m;
-        if (pb < 0) pb = 0;
-        uint32_t crc = 0;
-        const uint8_t* p = a.in + ci.off;
-        for (int64_t b = pb; b < pe; b++) crc = ((crc << 8) ^ s_tab[(crc >> 8) ^ p[b]]) & 0xFFFF;
-        uint32_t f = gf_xpow8((uint32_t)m);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_down_sync(FULL, crc, d);
-            crc = gf_mul(crc, f) ^ o;
-            f = gf_mul(f, f);
-        }
-        if (lane == 0) a.seg_crc[i] = (uint16_t)crc;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Cand ci = a.cand[i];
+    const SegInfo& sg = a.segs[ci.seg];
+    const uint64_t e = span_end(a, i, n, ci);
+    const uint64_t ab0 = sg.begin & ~15ull;
+    uint32_t c = sg.first_chunk + (uint32_t)((ci.off - ab0) >> 15);
+    uint32_t crc = a.seg_crc[i];
+    const Chunk c0 = a.chunks[c];
+    uint64_t cend = c0.begin + c0.len;
+    while (e > cend) {                      // the span runs past this chunk: append the next chunk's leading stretch
+        c++;
+        const Chunk ck = a.chunks[c];
+        const uint64_t kend = ck.begin + ck.len;
+        const uint64_t upto = e < kend ? e : kend;        // chunk c holds no candidate before `upto`: chunk_head covers [begin, upto)
+        crc = gf_mul(crc, gf_xpow8((uint32_t)(upto - ck.begin))) ^ a.chunk_head[c];
+        cend = kend;
     }
+    a.seg_crc[i] = (uint16_t)crc;
 }
 
 // ------------------------------------------------------------------------------------------------ K1d link / validate
@@ -337,17 +516,6 @@ __global__ void __launch_bounds__(256) k_cover(PassArgs a) {
 // checkpoint) + 7 have landed, i.e. >= 113 bytes past that position; a period may therefore advance by A bytes with
 // 2A + 8 <= 113 (this period's reads reach pos_prev + 2A + 8).  The walkers keep A <= 42: eight samples of at most 32
 // bits each plus partition parameters; anything longer takes a synchronous path (ensure_now).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
-__device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
-__device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
-__device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }   // index of the leading one; 0xffffffff for 0
-__device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
-
 struct RingBits {
     static constexpr int NBLK = 8, BLK = 16, RB_BYTES = NBLK * BLK;
     static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
@@ -856,7 +1024,7 @@ constexpr int DEC_WARPS = 2;                  // independent warps per CTA (no C
 __host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
 
 template <int ORD, bool WIDE>
-__global__ void __launch_bounds__(32 * DEC_WARPS, ORD <= 12 ? 9 : 1) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
+__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? 112 : 255) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
     constexpr int T = DecCfg<ORD>::T;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1028,17 +1196,22 @@ static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
 static inline uint32_t blocks_for(uint64_t n, uint32_t per) { uint64_t b = (n + per - 1) / per; return (uint32_t)(b ? b : 1); }
 
 void launch_scan(const PassArgs& a, void* stream) {
-    uint32_t grid = a.nchunks < 148u * 8 ? a.nchunks : 148u * 8;
+    static int n_sm = 0;
+    if (!n_sm) {
+        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm < 1) n_sm = 148;
+    }
+    uint32_t grid = a.nchunks < (uint32_t)n_sm ? a.nchunks : (uint32_t)n_sm;
     if (!grid) grid = 1;
-    k_scan<<<grid, SCAN_THREADS, 0, S(stream)>>>(a); g_launches++;
+    k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); g_launches++;
 }
 void launch_order(const PassArgs& a, void* stream) {
     k_chunk_scan<<<1, 1024, 0, S(stream)>>>(a); g_launches++;
     k_gather<<<148 * 2, 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_crc(const PassArgs& a, uint32_t nb, void* stream) {
-    uint32_t grid = blocks_for(nb, 8); if (grid > 148 * 8) grid = 148 * 8;
-    k_crc<<<grid, 256, 0, S(stream)>>>(a); g_launches++;
+    k_crc<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
     k_link<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
