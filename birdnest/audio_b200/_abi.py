@@ -84,6 +84,7 @@ _PROTOS = {
     "bnflac_abi_version": (C.c_int, []),
     "bnflac_device_count": (C.c_int, []),
     "bnflac_kernel_launches": (C.c_uint64, []),
+    "bnflac_trim_pools": (None, []),
 }
 
 
@@ -271,3 +272,28 @@ def open_callbacks(read_fn, device=-1) -> Handle:
     h = C.c_void_p()
     _check(lib().bnflac_open_callbacks(cb, None, C.byref(o), C.byref(h)), "bnflac_open_callbacks")
     return Handle(h.value)
+
+
+def decode_batch(clips, device=-1, dst=None, dst_is_device=False):
+    """bnflac_decode_batch: many independent clips in one pipeline pass per (channels, bits) group (BASELINE cfg4).
+    clips: sequence of bytes-like.  Returns (pcm, results) with pcm = bytes (dst=None), or the byte count written
+    into `dst` (a writable host buffer / torch tensor; a device pointer or CUDA tensor with dst_is_device=True)."""
+    n = len(clips)
+    spans = (Span * max(1, n))()
+    keep = []
+    for i, c in enumerate(clips):
+        keep.append(c)
+        spans[i].data = _addr(c)
+        spans[i].len = c.numel() * c.element_size() if hasattr(c, "numel") else len(c)
+    res = (ClipResult * max(1, n))()
+    o = _opts(device)
+    w = C.c_uint64()
+    if dst is None:
+        _check(lib().bnflac_decode_batch(spans, n, C.byref(o), None, 0, 0, res, C.byref(w)), "bnflac_decode_batch(size)")
+        out = bytearray(int(w.value))
+        if w.value:
+            _check(lib().bnflac_decode_batch(spans, n, C.byref(o), _addr(out), len(out), 0, res, C.byref(w)), "bnflac_decode_batch")
+        return bytes(out[:w.value]), [ClipResult.from_buffer_copy(res[i]) for i in range(n)]
+    cap = dst.numel() * dst.element_size() if hasattr(dst, "numel") else len(dst)
+    _check(lib().bnflac_decode_batch(spans, n, C.byref(o), _addr(dst), cap, 1 if dst_is_device else 0, res, C.byref(w)), "bnflac_decode_batch")
+    return int(w.value), [ClipResult.from_buffer_copy(res[i]) for i in range(n)]

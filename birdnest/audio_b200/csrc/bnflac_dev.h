@@ -108,6 +108,9 @@ void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream);
+void launch_clear(const PassArgs& a, void* stream);                                   // counters + totals = 0
+void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream);  // <= 32 words to mapped host memory
+void launch_seg_summary(const PassArgs& a, uint32_t ncand_bound, uint64_t* seg_pcm, uint32_t* seg_flags, void* stream);
 void launch_decode(const PassArgs& a, uint32_t nacc_bound, uint32_t channels, uint32_t bytes_per_sample, uint32_t max_order, bool wide, void* stream);
 int kernel_launch_count();   // kernels launched so far by this process (bench "gpu_launches")
 

@@ -8,12 +8,15 @@
 #include "bnflac_dev.h"
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 using namespace bnf;
@@ -24,19 +27,64 @@ static thread_local std::string g_cuda_err;
 // ------------------------------------------------------------------------------------------------ small helpers
 namespace {
 
+// Process-wide cache of device and pinned-host blocks (the only global mutable state, mutex-guarded).  cudaMalloc /
+// cudaFree / cudaHostAlloc cost milliseconds per gigabyte and cudaFree synchronises the device, which would serialise
+// the pipelined host decode; handles therefore take their buffers from here and give them back on close.
+struct BlockPool {
+    struct Blk { void* p; size_t n; int dev; };     // dev < 0: pinned host block
+    std::mutex m;
+    std::vector<Blk> free_;
+    static constexpr size_t MAX_CACHED = 2048;
+    void* take(size_t n, int dev, size_t* got) {
+        std::lock_guard<std::mutex> g(m);
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].dev == dev && free_[i].n >= n && free_[i].n <= 2 * n + (1u << 20) && (best == (size_t)-1 || free_[i].n < free_[best].n)) best = i;
+        if (best == (size_t)-1) return nullptr;
+        void* p = free_[best].p; *got = free_[best].n;
+        free_[best] = free_.back(); free_.pop_back();
+        return p;
+    }
+    static void destroy(const Blk& b) {
+        if (b.dev < 0) cudaFreeHost(b.p);
+        else { int cur = 0; cudaGetDevice(&cur); if (cur != b.dev) cudaSetDevice(b.dev); cudaFree(b.p); if (cur != b.dev) cudaSetDevice(cur); }
+    }
+    void give(void* p, size_t n, int dev) {
+        Blk drop{nullptr, 0, 0};
+        {
+            std::lock_guard<std::mutex> g(m);
+            free_.push_back(Blk{p, n, dev});
+            if (free_.size() > MAX_CACHED) {       // drop the smallest block
+                size_t k = 0;
+                for (size_t i = 1; i < free_.size(); i++) if (free_[i].n < free_[k].n) k = i;
+                drop = free_[k]; free_[k] = free_.back(); free_.pop_back();
+            }
+        }
+        if (drop.p) destroy(drop);
+    }
+    void trim() {
+        std::vector<Blk> all;
+        { std::lock_guard<std::mutex> g(m); all.swap(free_); }
+        for (const Blk& b : all) destroy(b);
+    }
+};
+BlockPool g_pool;
+
 struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
+    void* p = nullptr; size_t cap = 0; int dev = 0;
     int reserve(size_t n) {
         if (n <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
+        release();
+        cudaGetDevice(&dev);
+        size_t want = ((n + n / 8 + 256) + 255) & ~(size_t)255;
+        if ((p = g_pool.take(want, dev, &cap))) return 0;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); p = nullptr; return BNFLAC_ERR_MEMORY; }
+        if (e != cudaSuccess) { cudaGetLastError(); g_pool.trim(); e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); p = nullptr; return BNFLAC_ERR_MEMORY; }
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) g_pool.give(p, cap, dev); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -44,14 +92,15 @@ struct PinBuf {
     void* p = nullptr; size_t cap = 0;
     int reserve(size_t n) {
         if (n <= cap) return 0;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaHostAlloc(&p, n + 64, cudaHostAllocDefault);
-        if (e != cudaSuccess) { g_cuda_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); p = nullptr; return BNFLAC_ERR_MEMORY; }
-        cap = n + 64;
+        release();
+        size_t want = ((n + 64) + 4095) & ~(size_t)4095;
+        if ((p = g_pool.take(want, -1, &cap))) return 0;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) { g_cuda_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); p = nullptr; return BNFLAC_ERR_MEMORY; }
+        cap = want;
         return 0;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() { if (p) g_pool.give(p, cap, -1); p = nullptr; cap = 0; }
 };
 
 // RFC 1321, used only by the optional BNFLAC_OPT_VERIFY_MD5 host check
@@ -148,6 +197,15 @@ uint32_t frame_bound(const bnflac_info_t& si) {
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ the handle
+// One `bnflac` is one pipeline pass over one device-resident run of bytes: a whole stream, one frame-range shard of it,
+// or (batch) the clips of one format group laid back to back.  A handle that decodes a large host-resident stream to
+// host memory owns `kids`: sub-shards of its own range that are uploaded, decoded and downloaded on their own streams
+// so that the PCIe transfers of one overlap the kernels of another (decode_host_pipelined).
+struct SegDesc {            // host description of one segment of a pass, in coordinates of the uploaded bytes
+    uint64_t begin, end, own_begin, own_end;
+    uint32_t sample_rate, min_bs, max_bs, max_frame_bytes;
+};
+
 struct bnflac {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = false;
@@ -162,18 +220,26 @@ struct bnflac {
     size_t len = 0;
     uint64_t slice_begin = 0, slice_end = 0;   // byte range of the whole stream this handle (shard) keeps on the device
     uint64_t own_begin = 0, own_end = 0;
+    uint64_t sub_begin = 0, sub_end = 0;       // (kid) explicit sub-range of the parent's own range; 0,0 = none
     bool uploaded = false;
+    std::vector<SegDesc> batch_segs;           // batch passes: segments given explicitly (coordinates of d_in)
 
     // device state
     DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_crc_tmp, d_chunk_head,
-        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out;
-    uint32_t nchunks = 0, cand_cap = 0;
+        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags;
+    uint32_t nchunks = 0, cand_cap = 0, nsegs = 0;
     bool tables_ready = false;
     PassArgs args{};
     Totals totals{};
     uint32_t ncand = 0;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};             // 0..5 stage boundaries, 6/7 pipelined start/end, 8 upload done
+    cudaStream_t up_stream = nullptr;    // (pipelined parent) all sub-shard uploads, in order
     bnflac_timing timing{};
+
+    PinBuf mailbox;                     // mapped pinned words the kernels publish counters / totals into
+    // pipelined host decode
+    std::vector<bnflac*> kids;
+    uint64_t pcm_base = 0;              // (kid) where this sub-shard's PCM starts in the parent's output
 
     // results
     std::vector<bnflac_frame_t> frames; std::vector<bnflac_subframe_t> subs; std::vector<uint32_t> errors;
@@ -183,19 +249,22 @@ struct bnflac {
     PinBuf pcm_host; uint64_t pcm_len = 0, read_pos = 0; bool decoded = false;
 
     ~bnflac() {
+        for (bnflac* k : kids) delete k;
         cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
         DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_crc_tmp, &d_chunk_head,
-                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out};
+                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags};
         for (DevBuf* b : all) b->release();
-        pcm_host.release();
+        pcm_host.release(); mailbox.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (up_stream) cudaStreamDestroy(up_stream);
     }
 };
 
 static int setup_device(bnflac* h) {
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { g_cuda_err = "no CUDA device"; return BNFLAC_ERR_NO_DEVICE; }
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); g_cuda_err = "no CUDA device"; return BNFLAC_ERR_NO_DEVICE; }
     if (h->opts.device >= 0) h->device = h->opts.device; else if (cudaGetDevice(&h->device) != cudaSuccess) h->device = 0;
     if (h->device >= n) return BNFLAC_ERR_ARG;
     CK(cudaSetDevice(h->device));
@@ -208,10 +277,12 @@ static int setup_device(bnflac* h) {
 static void compute_shard(bnflac* h) {
     const uint64_t first = h->info.first_frame_offset, D = h->len - first;
     uint32_t n = h->opts.shard_count ? h->opts.shard_count : 1, i = std::min(h->opts.shard_index, n - 1);
-    h->own_begin = first + D * i / n;
-    h->own_end = (i + 1 == n) ? h->len : first + D * (i + 1) / n;
-    h->slice_begin = h->own_begin & ~15ull;
-    h->slice_end = (i + 1 == n) ? h->len : std::min<uint64_t>(h->len, h->own_end + frame_bound(h->info) + 32);
+    uint64_t b = first + D * i / n;
+    uint64_t e = (i + 1 == n) ? h->len : first + D * (i + 1) / n;
+    if (h->sub_end > h->sub_begin) { b = h->sub_begin; e = h->sub_end; }      // sub-shard of the own range
+    h->own_begin = b; h->own_end = e;
+    h->slice_begin = b & ~15ull;
+    h->slice_end = (e >= h->len) ? h->len : std::min<uint64_t>(h->len, e + frame_bound(h->info) + 32);
 }
 
 static int common_open(bnflac* h, const uint8_t* header, size_t header_len) {
@@ -234,7 +305,7 @@ static int ensure_input(bnflac* h) {
     if (h->uploaded) return 0;
     if (h->d_ext) { h->uploaded = true; return 0; }
     const size_t n = (size_t)(h->slice_end - h->slice_begin);
-    int rc = h->d_in.reserve(n + 128); if (rc) return rc;
+    int rc = h->d_in.reserve(n + 128); if (rc) return rc;       // (no-op when already reserved)
     CK(cudaMemcpyAsync(h->d_in.p, h->host_ptr + h->slice_begin, n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync((uint8_t*)h->d_in.p + n, 0, 128, h->stream));
     h->uploaded = true;
@@ -243,24 +314,39 @@ static int ensure_input(bnflac* h) {
 
 static int ensure_tables(bnflac* h) {
     if (h->tables_ready) return 0;
-    // `in` addresses are relative to the start of what is on the device
-    const uint64_t base = h->d_ext ? 0 : h->slice_begin;
-    SegInfo seg{};
-    seg.begin = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset) - base;
-    seg.end = h->slice_end - base;
-    seg.own_begin = h->own_begin - base; seg.own_end = h->own_end - base;
-    seg.bps = h->info.bits_per_sample; seg.channels = h->info.channels; seg.sample_rate = h->info.sample_rate;
-    seg.min_bs = h->info.min_blocksize; seg.max_bs = h->info.max_blocksize; seg.max_frame_bytes = frame_bound(h->info);
+    std::vector<SegDesc> descs;
+    uint64_t in_len;
+    if (!h->batch_segs.empty()) { descs = h->batch_segs; in_len = h->len; }
+    else {
+        // `in` addresses are relative to the start of what is on the device
+        const uint64_t base = h->d_ext ? 0 : h->slice_begin;
+        SegDesc d{};
+        d.begin = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset) - base;
+        d.end = h->slice_end - base;
+        d.own_begin = h->own_begin - base; d.own_end = h->own_end - base;
+        d.sample_rate = h->info.sample_rate; d.min_bs = h->info.min_blocksize; d.max_bs = h->info.max_blocksize; d.max_frame_bytes = frame_bound(h->info);
+        descs.push_back(d);
+        in_len = h->d_ext ? h->len : (h->slice_end - h->slice_begin);
+    }
+    std::vector<SegInfo> segs(descs.size());
     std::vector<Chunk> chunks;
-    seg.first_chunk = 0;
-    for (uint64_t p = seg.begin; p < seg.end;) {          // chunk boundaries at multiples of 32 KiB from the segment's aligned base
-        const uint64_t stop = std::min<uint64_t>(seg.end, ((p & ~15ull) - ((p & ~15ull) - (seg.begin & ~15ull)) % SCAN_CHUNK) + SCAN_CHUNK);
-        chunks.push_back(Chunk{p, (uint32_t)(stop - p), 0});
-        p = stop;
+    for (size_t k = 0; k < descs.size(); k++) {
+        const SegDesc& d = descs[k];
+        SegInfo& seg = segs[k];
+        seg.begin = d.begin; seg.end = d.end; seg.own_begin = d.own_begin; seg.own_end = d.own_end;
+        seg.bps = h->info.bits_per_sample; seg.channels = h->info.channels; seg.sample_rate = d.sample_rate;
+        seg.min_bs = d.min_bs; seg.max_bs = d.max_bs; seg.max_frame_bytes = d.max_frame_bytes;
+        seg.first_chunk = (uint32_t)chunks.size(); seg.pad = 0;
+        for (uint64_t p = seg.begin; p < seg.end;) {          // chunk boundaries at multiples of SCAN_CHUNK from the segment's aligned base
+            const uint64_t stop = std::min<uint64_t>(seg.end, ((p & ~15ull) - ((p & ~15ull) - (seg.begin & ~15ull)) % SCAN_CHUNK) + SCAN_CHUNK);
+            chunks.push_back(Chunk{p, (uint32_t)(stop - p), (uint32_t)k});
+            p = stop;
+        }
     }
     h->nchunks = (uint32_t)chunks.size();
+    h->nsegs = (uint32_t)segs.size();
     int rc;
-    if ((rc = h->d_segs.reserve(sizeof seg))) return rc;
+    if ((rc = h->d_segs.reserve(sizeof(SegInfo) * segs.size()))) return rc;
     if ((rc = h->d_chunks.reserve(sizeof(Chunk) * std::max<size_t>(1, chunks.size())))) return rc;
     if ((rc = h->d_chunk_base.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_chunk_count.reserve(4ull * (h->nchunks + 1)))) return rc;
@@ -268,12 +354,13 @@ static int ensure_tables(bnflac* h) {
     if ((rc = h->d_chunk_head.reserve(2ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_counters.reserve(64))) return rc;
     if ((rc = h->d_totals.reserve(sizeof(Totals)))) return rc;
-    CK(cudaMemcpyAsync(h->d_segs.p, &seg, sizeof seg, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = h->mailbox.reserve(256))) return rc;
+    CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), sizeof(SegInfo) * segs.size(), cudaMemcpyHostToDevice, h->stream));
     if (!chunks.empty()) CK(cudaMemcpyAsync(h->d_chunks.p, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // chunks is a local
+    CK(cudaStreamSynchronize(h->stream));   // segs / chunks are locals
     h->args.in = h->d_ext ? h->d_ext : h->d_in.as<uint8_t>();
-    h->args.in_len = (h->d_ext ? h->len : (h->slice_end - h->slice_begin)) + 64;
-    h->args.segs = h->d_segs.as<SegInfo>(); h->args.nsegs = 1;
+    h->args.in_len = in_len + 64;
+    h->args.segs = h->d_segs.as<SegInfo>(); h->args.nsegs = h->nsegs;
     h->args.chunks = h->d_chunks.as<Chunk>(); h->args.nchunks = h->nchunks;
     h->args.chunk_base = h->d_chunk_base.as<uint32_t>(); h->args.chunk_count = h->d_chunk_count.as<uint32_t>();
     h->args.chunk_scan = h->d_chunk_scan.as<uint32_t>(); h->args.counters = h->d_counters.as<uint32_t>();
@@ -311,17 +398,17 @@ static int run_front(bnflac* h) {
     if ((rc = ensure_input(h))) return rc;
     if ((rc = ensure_tables(h))) return rc;
     if (!h->cand_cap) {
-        uint64_t est = (h->slice_end - h->slice_begin) / 512 + 4096;
+        const uint64_t nbytes = h->batch_segs.empty() ? (h->slice_end - h->slice_begin) : h->len;
+        uint64_t est = nbytes / 512 + 4096;
         if ((rc = reserve_cand(h, (uint32_t)std::min<uint64_t>(est, 0x7fffffff)))) return rc;
     }
     for (int attempt = 0;; attempt++) {
-        CK(cudaMemsetAsync(h->d_counters.p, 0, 64, h->stream));
-        CK(cudaMemsetAsync(h->d_totals.p, 0, sizeof(Totals), h->stream));
+        launch_clear(h->args, h->stream);
         launch_scan(h->args, h->stream);
-        uint32_t counters[2];
-        CK(cudaMemcpyAsync(counters, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        volatile uint32_t* counters = (volatile uint32_t*)h->mailbox.p;
+        launch_publish(h->d_counters.p, h->mailbox.p, 2, h->stream);
         CK(cudaStreamSynchronize(h->stream));
-        if (counters[1] & 1u) return BNFLAC_ERR_UNSUPPORTED;       // > SCAN_SCAP frame headers inside 32 KiB
+        if (counters[1] & 1u) return BNFLAC_ERR_UNSUPPORTED;       // > SCAN_SCAP frame headers inside one scan chunk
         if (counters[0] > h->cand_cap) {
             if (attempt > 2) return BNFLAC_ERR_MEMORY;
             if ((rc = reserve_cand(h, counters[0] + counters[0] / 8 + 1024))) return rc;
@@ -339,9 +426,11 @@ static int run_front(bnflac* h) {
     launch_parse(h->args, h->ncand, h->stream);
     launch_prefix(h->args, h->info.bytes_per_sample, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
-    CK(cudaMemcpyAsync(&h->totals, h->d_totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, h->stream));
+    static_assert(sizeof(Totals) % 4 == 0 && sizeof(Totals) / 4 <= 32 - 16, "totals fit the mailbox");
+    launch_publish(h->d_totals.p, (uint8_t*)h->mailbox.p + 64, sizeof(Totals) / 4, h->stream);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    memcpy(&h->totals, (const uint8_t*)h->mailbox.p + 64, sizeof(Totals));
     h->diag_valid = false;
     return 0;
 }
@@ -380,8 +469,142 @@ static int decode_to_device(bnflac* h, void* d_dst, size_t cap, void** d_out, ui
     return 0;
 }
 
-static int fetch_diag(bnflac* h) {
-    if (h->diag_valid) return 0;
+// ---- host-destination decode: one pass, or a software pipeline of sub-shards for large host-resident streams
+// Sub-shard schedule of the pipelined host decode: the first sub-shard is small so that the download engine starts
+// early, sizes then double up to a cap (large sub-shards keep the kernels efficient and the per-pass host work small).
+static size_t env_mb(const char* name, long dflt) { const char* e = getenv(name); long mb = e ? atol(e) : dflt; if (mb < 1) mb = 1; return (size_t)mb << 20; }
+static size_t pipe_shard_bytes() { return env_mb("BNFLAC_PIPE_MB", 256); }                                   // cap (MiB of compressed bytes)
+static size_t pipe_first_bytes() { return std::min(env_mb("BNFLAC_PIPE_FIRST_MB", 16), pipe_shard_bytes()); }
+static std::vector<uint64_t> pipe_cuts(uint64_t b, uint64_t e) {       // boundaries b = c0 < c1 < ... < cK = e; K = 1: not worth pipelining
+    std::vector<uint64_t> cuts{b};
+    const uint64_t first = pipe_first_bytes(), cap = pipe_shard_bytes();
+    if (e - b >= 3 * first) {
+        uint64_t pos = b, sz = first;
+        while (e - pos > sz + sz / 2 && cuts.size() < 256) { pos += sz; cuts.push_back(pos); sz = std::min<uint64_t>(2 * sz, cap); }
+    }
+    cuts.push_back(e);
+    return cuts;
+}
+
+static int decode_host_single(bnflac* h, uint8_t* dst, size_t cap, uint64_t* written) {
+    int rc = run_front(h); if (rc) return rc;
+    if (h->totals.pcm_bytes > cap) return BNFLAC_ERR_CAPACITY;
+    if ((rc = h->d_out.reserve((size_t)h->totals.pcm_bytes + 64))) return rc;
+    if ((rc = run_back(h, h->d_out.as<uint8_t>(), h->d_out.cap))) return rc;
+    if (h->totals.pcm_bytes) CK(cudaMemcpyAsync(dst, h->d_out.p, (size_t)h->totals.pcm_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = finish_timing(h))) return rc;
+    *written = h->totals.pcm_bytes;
+    return 0;
+}
+
+// Sub-shards k = 0..K-1 of the handle's range, each on its own stream: all uploads are queued first (the copy engine
+// runs them back to back), then for each sub-shard in order: front kernels, host learns its PCM size (and thereby
+// where the next one starts), decode kernel, download.  The host-side waits inside run_front block only the issuing
+// thread: the other streams' copies and kernels keep running, so the H2D engine, the SMs and the D2H engine overlap.
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static int decode_host_pipelined(bnflac* h, const std::vector<uint64_t>& cuts, uint8_t* dst, size_t cap, uint64_t* written) {
+    int rc = 0;
+    const uint32_t K = (uint32_t)cuts.size() - 1;
+    CK(cudaSetDevice(h->device));
+    const bool trace = getenv("BNFLAC_TRACE") != nullptr;
+    const double t_begin = now_ms();
+    double t_kids = 0, t_tables = 0, t_upq = 0, t_loop = 0;
+    bool same = h->kids.size() == K;
+    for (uint32_t i = 0; same && i < K; i++) same = h->kids[i]->sub_begin == cuts[i] && h->kids[i]->sub_end == cuts[i + 1];
+    if (!same) {
+        for (bnflac* k : h->kids) delete k;
+        h->kids.clear();
+        for (uint32_t i = 0; i < K; i++) {
+            bnflac* c = new (std::nothrow) bnflac; if (!c) return BNFLAC_ERR_MEMORY;
+            h->kids.push_back(c);
+            c->opts = h->opts; c->opts.stream = nullptr; c->opts.device = h->device; c->opts.flags &= ~BNFLAC_OPT_VERIFY_MD5;
+            c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = cuts[i]; c->sub_end = cuts[i + 1];
+            compute_shard(c);
+            c->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
+            if ((rc = setup_device(c))) return rc;
+        }
+    }
+    auto drain = [&]() { if (h->up_stream) cudaStreamSynchronize(h->up_stream); for (bnflac* c : h->kids) if (c->stream) cudaStreamSynchronize(c->stream); };
+    t_kids = now_ms();
+    // tables first: their (small) uploads must not queue behind the bulk uploads on the copy engine
+    for (bnflac* c : h->kids) {
+        if (!c->tables_ready && ((rc = c->d_in.reserve((size_t)(c->slice_end - c->slice_begin) + 128)) || (rc = ensure_tables(c)))) { drain(); return rc; }
+        if (!c->cand_cap && (rc = reserve_cand(c, (uint32_t)((c->slice_end - c->slice_begin) / 512 + 4096)))) { drain(); return rc; }
+    }
+    t_tables = now_ms();
+    // All uploads go through ONE stream, in sub-shard order.  Spread over the sub-shards' own streams the copy engines
+    // would serve them concurrently, every upload would finish late and no download could start early.
+    if (!h->up_stream) CK(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    cudaEventRecord(h->kids.front()->ev[6], h->up_stream);
+    for (bnflac* c : h->kids) {
+        if (c != h->kids.front()) cudaEventRecord(c->ev[6], h->up_stream);
+        if (!c->uploaded) {
+            const size_t n = (size_t)(c->slice_end - c->slice_begin);
+            if (cudaMemcpyAsync(c->d_in.p, c->host_ptr + c->slice_begin, n, cudaMemcpyHostToDevice, h->up_stream) != cudaSuccess ||
+                cudaMemsetAsync((uint8_t*)c->d_in.p + n, 0, 128, h->up_stream) != cudaSuccess) { drain(); cudaStreamSynchronize(h->up_stream); g_cuda_err = "pipelined upload"; return BNFLAC_ERR_CUDA; }
+            c->uploaded = true;
+        }
+        cudaEventRecord(c->ev[8], h->up_stream);
+        cudaStreamWaitEvent(c->stream, c->ev[8], 0);
+    }
+    t_upq = now_ms();
+    uint64_t off = 0;
+    for (bnflac* c : h->kids) {
+        if ((rc = run_front(c))) break;
+        c->pcm_base = off;
+        if (off + c->totals.pcm_bytes > cap) { rc = BNFLAC_ERR_CAPACITY; break; }
+        if ((rc = c->d_out.reserve((size_t)c->totals.pcm_bytes + 64))) break;
+        if ((rc = run_back(c, c->d_out.as<uint8_t>(), c->d_out.cap))) break;
+        if (c->totals.pcm_bytes && cudaMemcpyAsync(dst + off, c->d_out.p, (size_t)c->totals.pcm_bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = BNFLAC_ERR_CUDA; g_cuda_err = "cudaMemcpyAsync (D2H)"; break; }
+        cudaEventRecord(c->ev[7], c->stream);
+        off += c->totals.pcm_bytes;
+    }
+    t_loop = now_ms();
+    drain();
+    if (trace) fprintf(stderr, "[bnflac] pipelined K=%u: kids %.2f ms, tables %.2f, upload queue %.2f, issue loop %.2f, drain %.2f\n", K,
+                       t_kids - t_begin, t_tables - t_kids, t_upq - t_tables, t_loop - t_upq, now_ms() - t_loop);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    bnflac_timing t{};
+    for (bnflac* c : h->kids) {
+        if ((rc = finish_timing(c))) return rc;
+        t.scan += c->timing.scan; t.crc += c->timing.crc; t.link += c->timing.link; t.parse += c->timing.parse; t.decode += c->timing.decode;
+        t.launches += c->timing.launches;
+    }
+    if (trace) {
+        for (bnflac* c : h->kids) {
+            float a = 0, b = 0, d = 0, e = 0;
+            cudaEventElapsedTime(&a, h->kids.front()->ev[6], c->ev[6]); cudaEventElapsedTime(&b, h->kids.front()->ev[6], c->ev[0]);
+            cudaEventElapsedTime(&d, h->kids.front()->ev[6], c->ev[5]); cudaEventElapsedTime(&e, h->kids.front()->ev[6], c->ev[7]);
+            fprintf(stderr, "[bnflac]   sub-shard %3.0f MiB: upload %6.2f..%6.2f  kernels ..%6.2f  download ..%6.2f ms (%.0f MiB)\n",
+                    (c->own_end - c->own_begin) / 1048576.0, a, b, d, e, c->totals.pcm_bytes / 1048576.0);
+        }
+    }
+    float wall = 0;
+    cudaEventElapsedTime(&wall, h->kids.front()->ev[6], h->kids.back()->ev[7]);
+    t.total = wall;                     // first upload queued .. last download finished
+    h->timing = t;
+    h->diag_valid = false;
+    *written = off;
+    return 0;
+}
+
+static int decode_host(bnflac* h, uint8_t* dst, size_t cap, uint64_t* written) {
+    if (h->host_ptr && !h->d_ext && h->batch_segs.empty()) {
+        const std::vector<uint64_t> cuts = pipe_cuts(std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end);
+        if (cuts.size() > 2) return decode_host_pipelined(h, cuts, dst, cap, written);
+    }
+    for (bnflac* k : h->kids) delete k;
+    h->kids.clear();
+    return decode_host_single(h, dst, cap, written);
+}
+
+// Builds the host-side frame / subframe / error tables of one pass.  `expect` is where the next frame should start
+// (carried across the sub-shards of a pipelined decode so that the events are those of an unsharded decode).
+static int collect_diag(bnflac* h, uint64_t& expect, uint64_t pcm_base, const uint8_t* host_ptr, uint64_t stream_len,
+                        std::vector<bnflac_frame_t>& frames, std::vector<bnflac_subframe_t>& subs, std::vector<uint32_t>& errors) {
     CK(cudaSetDevice(h->device));
     const uint32_t n = h->ncand;
     std::vector<Cand> cand(n); std::vector<uint8_t> st(n); std::vector<uint32_t> fl(n); std::vector<uint64_t> po(n); std::vector<SubInfo> sub((size_t)n * MAX_CH);
@@ -392,39 +615,158 @@ static int fetch_diag(bnflac* h) {
         CK(cudaMemcpy(po.data(), h->d_pcm_off.p, 8ull * n, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(sub.data(), h->d_sub.p, sizeof(SubInfo) * MAX_CH * (size_t)n, cudaMemcpyDeviceToHost));
     }
-    h->frames.clear(); h->subs.clear(); h->errors.clear();
     const uint64_t base = h->d_ext ? 0 : h->slice_begin;
-    uint64_t expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
     for (uint32_t i = 0; i < n; i++) {
         if (cand[i].flags & 2) continue;
-        if (st[i] == ST_UNPARSEABLE) { h->errors.push_back(3); continue; }
+        if (st[i] == ST_UNPARSEABLE) { errors.push_back(3); continue; }
         if (st[i] != ST_OK && st[i] != ST_CRC) continue;
         bnflac_frame_t f{};
         f.offset = cand[i].off + base; f.length = fl[i]; f.blocksize = cand[i].bs;
         f.channels = (uint8_t)(cand[i].assign < 8 ? cand[i].assign + 1 : 2); f.bits_per_sample = cand[i].bps; f.assignment = cand[i].assign;
         f.status = st[i] == ST_OK ? BNFLAC_FRAME_OK : BNFLAC_FRAME_CRC_MISMATCH;
-        f.number = cand[i].number; f.pcm_offset = po[i];
+        f.number = cand[i].number; f.pcm_offset = po[i] + pcm_base;
         if (f.offset != expect) {
             // bytes were skipped before this frame.  The reference reports BAD_HEADER first when the skipped bytes begin
             // with a sync code whose header did not validate, then LOST_SYNC (observed on the DLL, tests/golden faults)
             uint8_t two[2] = {0, 0};
-            if (expect + 2 <= h->len) {
-                if (h->host_ptr) memcpy(two, h->host_ptr + expect, 2);
+            if (expect + 2 <= stream_len) {
+                if (host_ptr) memcpy(two, host_ptr + expect, 2);
                 else cudaMemcpy(two, h->d_ext + expect, 2, cudaMemcpyDeviceToHost);
             }
-            if (two[0] == 0xFF && (two[1] & 0xFC) == 0xF8) h->errors.push_back(1);
-            h->errors.push_back(0);
+            if (two[0] == 0xFF && (two[1] & 0xFC) == 0xF8) errors.push_back(1);
+            errors.push_back(0);
         }
-        if (st[i] == ST_CRC) h->errors.push_back(2);              // FRAME_CRC_MISMATCH
+        if (st[i] == ST_CRC) errors.push_back(2);              // FRAME_CRC_MISMATCH
         expect = f.offset + f.length;
-        h->frames.push_back(f);
+        frames.push_back(f);
         for (int c = 0; c < MAX_CH; c++) {
             bnflac_subframe_t s{};
             if (c < f.channels && st[i] == ST_OK) { const SubInfo& si = sub[(size_t)i * MAX_CH + c]; s.bit_offset = si.bit_offset; s.type = si.type; s.order = si.order; s.wasted = si.wasted; s.flags = si.flags; }
-            h->subs.push_back(s);
+            subs.push_back(s);
         }
     }
+    return 0;
+}
+
+static int fetch_diag(bnflac* h) {
+    if (h->diag_valid) return 0;
+    h->frames.clear(); h->subs.clear(); h->errors.clear();
+    uint64_t expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
+    int rc;
+    if (!h->kids.empty()) {
+        for (bnflac* c : h->kids)
+            if ((rc = collect_diag(c, expect, c->pcm_base, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
+    } else if ((rc = collect_diag(h, expect, 0, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
     h->diag_valid = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ batch of clips
+namespace {
+struct ClipMeta { bnflac_info_t info; int rc; size_t group; uint64_t seg_begin; };
+
+// copies the clips of one group into a pinned staging buffer with several host threads (memcpy of gigabytes on one
+// thread would dominate the batch)
+void parallel_gather(uint8_t* dst, const std::vector<std::pair<const uint8_t*, size_t>>& src, const std::vector<uint64_t>& at) {
+    const size_t n = src.size();
+    size_t total = 0; for (auto& s : src) total += s.second;
+    unsigned nt = (unsigned)std::min<size_t>(std::max<size_t>(1, total >> 24), std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())));
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) memcpy(dst + at[i], src[i].first, src[i].second); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&, t]() { for (size_t i = t; i < n; i += nt) memcpy(dst + at[i], src[i].first, src[i].second); });
+    for (auto& x : th) x.join();
+}
+} // namespace
+
+static int decode_batch_impl(const bnflac_span* clips, size_t n, const bnflac_opts* opts_in, uint8_t* dst, size_t cap, int dst_is_device,
+                             bnflac_clip_result* results, uint64_t* written) {
+    bnflac_opts opts = default_opts(opts_in);
+    std::vector<ClipMeta> meta(n);
+    struct Group { uint32_t ch, bps; std::vector<size_t> clips; };
+    std::vector<Group> groups;
+    for (size_t i = 0; i < n; i++) {
+        ClipMeta& m = meta[i];
+        m.rc = (clips[i].data && clips[i].len) ? parse_metadata(clips[i].data, clips[i].len, &m.info) : BNFLAC_ERR_ARG;
+        if (!m.rc && (m.info.channels > 8 || m.info.bits_per_sample > 24 || m.info.bits_per_sample < 4)) m.rc = BNFLAC_ERR_UNSUPPORTED;
+        if (results) { memset(&results[i], 0, sizeof results[i]); results[i].status = m.rc ? 4u : 0u; }
+        if (m.rc) continue;
+        size_t g = 0;
+        for (; g < groups.size(); g++) if (groups[g].ch == m.info.channels && groups[g].bps == m.info.bits_per_sample) break;
+        if (g == groups.size()) groups.push_back(Group{m.info.channels, m.info.bits_per_sample, {}});
+        groups[g].clips.push_back(i);
+        m.group = g;
+    }
+    uint64_t out_off = 0;
+    int rc = 0;
+    for (Group& G : groups) {
+        bnflac h;
+        h.opts = opts; h.info = meta[G.clips[0]].info;
+        // layout of the group's bytes on the device: each clip's frame data (metadata stripped) at a 16-byte aligned offset
+        std::vector<std::pair<const uint8_t*, size_t>> src; std::vector<uint64_t> at;
+        uint64_t pos = 0;
+        for (size_t ci : G.clips) {
+            const ClipMeta& m = meta[ci];
+            const uint64_t first = m.info.first_frame_offset, nbytes = clips[ci].len - first;
+            SegDesc d{};
+            d.begin = pos; d.end = pos + nbytes; d.own_begin = d.begin; d.own_end = d.end;
+            d.sample_rate = m.info.sample_rate; d.min_bs = m.info.min_blocksize; d.max_bs = m.info.max_blocksize; d.max_frame_bytes = frame_bound(m.info);
+            h.batch_segs.push_back(d);
+            src.emplace_back(clips[ci].data + first, (size_t)nbytes); at.push_back(pos);
+            pos = (pos + nbytes + 15) & ~15ull;
+        }
+        h.len = pos;
+        if ((rc = setup_device(&h))) return rc;
+        PinBuf stage;
+        if ((rc = stage.reserve((size_t)pos + 64))) return rc;
+        parallel_gather((uint8_t*)stage.p, src, at);
+        if ((rc = h.d_in.reserve((size_t)pos + 128))) { stage.release(); return rc; }
+        if (cudaMemcpyAsync(h.d_in.p, stage.p, (size_t)pos, cudaMemcpyHostToDevice, h.stream) != cudaSuccess ||
+            cudaMemsetAsync((uint8_t*)h.d_in.p + pos, 0, 128, h.stream) != cudaSuccess) { stage.release(); g_cuda_err = "batch upload"; return BNFLAC_ERR_CUDA; }
+        h.uploaded = true;
+        rc = run_front(&h);
+        stage.release();                            // run_front synchronised the stream: the upload is done
+        if (rc) return rc;
+        const uint32_t ns = (uint32_t)h.batch_segs.size();
+        if ((rc = h.d_seg_pcm.reserve(8ull * ns)) || (rc = h.d_seg_flags.reserve(4ull * ns))) return rc;
+        CK(cudaMemsetAsync(h.d_seg_pcm.p, 0xFF, 8ull * ns, h.stream));
+        CK(cudaMemsetAsync(h.d_seg_flags.p, 0, 4ull * ns, h.stream));
+        if (h.ncand) launch_seg_summary(h.args, h.ncand, h.d_seg_pcm.as<uint64_t>(), h.d_seg_flags.as<uint32_t>(), h.stream);
+        std::vector<uint64_t> seg_pcm(ns); std::vector<uint32_t> seg_flags(ns);
+        CK(cudaMemcpyAsync(seg_pcm.data(), h.d_seg_pcm.p, 8ull * ns, cudaMemcpyDeviceToHost, h.stream));
+        CK(cudaMemcpyAsync(seg_flags.data(), h.d_seg_flags.p, 4ull * ns, cudaMemcpyDeviceToHost, h.stream));
+        CK(cudaStreamSynchronize(h.stream));
+        // a segment without any candidate never wrote its slot: it starts where the next one does
+        uint64_t nextb = h.totals.pcm_bytes;
+        for (uint32_t k = ns; k-- > 0;) { if (seg_pcm[k] == ~0ull) seg_pcm[k] = nextb; nextb = seg_pcm[k]; }
+        if (results) {
+            for (uint32_t k = 0; k < ns; k++) {
+                const size_t ci = G.clips[k];
+                const ClipMeta& m = meta[ci];
+                bnflac_clip_result& r = results[ci];
+                r.pcm_offset = out_off + seg_pcm[k];
+                r.pcm_bytes = (k + 1 < ns ? seg_pcm[k + 1] : h.totals.pcm_bytes) - seg_pcm[k];
+                r.sample_rate = m.info.sample_rate; r.channels = m.info.channels; r.bits_per_sample = m.info.bits_per_sample;
+                r.total_samples = m.info.total_samples;
+                r.status = seg_flags[k];
+                if (m.info.total_samples && r.pcm_bytes != m.info.pcm_bytes) r.status |= 2u;     // frames lost or extra
+            }
+        }
+        if (dst) {
+            if (out_off + h.totals.pcm_bytes > cap) return BNFLAC_ERR_CAPACITY;
+            if (dst_is_device) {
+                if ((rc = run_back(&h, dst + out_off, cap - out_off))) return rc;
+            } else {
+                if ((rc = h.d_out.reserve((size_t)h.totals.pcm_bytes + 64))) return rc;
+                if ((rc = run_back(&h, h.d_out.as<uint8_t>(), h.d_out.cap))) return rc;
+                if (h.totals.pcm_bytes) CK(cudaMemcpyAsync(dst + out_off, h.d_out.p, (size_t)h.totals.pcm_bytes, cudaMemcpyDeviceToHost, h.stream));
+            }
+            CK(cudaStreamSynchronize(h.stream));
+            CK(cudaGetLastError());
+        }
+        out_off += h.totals.pcm_bytes;
+    }
+    if (written) *written = out_off;
     return 0;
 }
 
@@ -432,9 +774,10 @@ static int fetch_diag(bnflac* h) {
 extern "C" {
 
 int bnflac_abi_version(void) { return BNFLAC_ABI_VERSION; }
-int bnflac_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int bnflac_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 const char* bnflac_last_cuda_error(void) { return g_cuda_err.c_str(); }
 uint64_t bnflac_kernel_launches(void) { return (uint64_t)kernel_launch_count(); }
+void bnflac_trim_pools(void) { g_pool.trim(); }
 
 const char* bnflac_strerror(int err) {
     switch (err) {
@@ -514,11 +857,18 @@ void bnflac_close(bnflac_t* h) { delete h; }
 
 int bnflac_decode_device(bnflac_t* h, void* d_dst, size_t cap, void** d_out, uint64_t* written) {
     if (!h) return BNFLAC_ERR_ARG;
+    for (bnflac* k : h->kids) delete k;
+    h->kids.clear();
     return decode_to_device(h, d_dst, cap, d_out, written);
 }
 
 int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes) {
     if (!h || !bytes) return BNFLAC_ERR_ARG;
+    if (h->info.total_samples && (h->opts.shard_count <= 1)) {
+        // STREAMINFO states it; a damaged stream may decode to less, never to more than its frame count allows.  Large
+        // host streams take the pipelined path, where the exact figure is only known at the end.
+        if (h->host_ptr && !h->d_ext && pipe_cuts(std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end).size() > 2) { *bytes = h->info.pcm_bytes; return 0; }
+    }
     int rc = run_front(h); if (rc) return rc;
     *bytes = h->totals.pcm_bytes;
     return 0;
@@ -526,19 +876,14 @@ int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes) {
 
 int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written) {
     if (!h || !dst) return BNFLAC_ERR_ARG;
-    int rc = run_front(h); if (rc) return rc;
-    if (h->totals.pcm_bytes > cap) return BNFLAC_ERR_CAPACITY;
-    if ((rc = h->d_out.reserve((size_t)h->totals.pcm_bytes + 64))) return rc;
-    if ((rc = run_back(h, h->d_out.as<uint8_t>(), h->d_out.cap))) return rc;
-    CK(cudaMemcpyAsync(dst, h->d_out.p, (size_t)h->totals.pcm_bytes, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if ((rc = finish_timing(h))) return rc;
-    if (written) *written = h->totals.pcm_bytes;
+    uint64_t w = 0;
+    int rc = decode_host(h, dst, cap, &w); if (rc) return rc;
+    if (written) *written = w;
     h->state = BNFLAC_STATE_END_OF_STREAM;
     if (h->opts.flags & BNFLAC_OPT_VERIFY_MD5) {
         static const uint8_t zero[16] = {0};
         if (memcmp(h->info.md5, zero, 16) && (h->opts.shard_count <= 1)) {
-            Md5 m; m.update(dst, (size_t)h->totals.pcm_bytes); uint8_t d[16]; m.final(d);
+            Md5 m; m.update(dst, (size_t)w); uint8_t d[16]; m.final(d);
             if (memcmp(d, h->info.md5, 16)) return BNFLAC_ERR_STATE;
         }
     }
@@ -548,14 +893,23 @@ int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written) 
 int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count) {
     if (!h || (!dst && count)) return BNFLAC_ERR_ARG;
     if (!h->decoded) {
-        int rc = run_front(h); if (rc) return rc;
-        if ((rc = h->d_out.reserve((size_t)h->totals.pcm_bytes + 64))) return rc;
-        if ((rc = h->pcm_host.reserve((size_t)h->totals.pcm_bytes))) return rc;
-        if ((rc = run_back(h, h->d_out.as<uint8_t>(), h->d_out.cap))) return rc;
-        CK(cudaMemcpyAsync(h->pcm_host.p, h->d_out.p, (size_t)h->totals.pcm_bytes, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        if ((rc = finish_timing(h))) return rc;
-        h->pcm_len = h->totals.pcm_bytes; h->read_pos = 0; h->decoded = true;
+        // the whole (shard of the) stream is decoded at the first Read into pinned host memory; later Reads are memcpy.
+        // Capacity: what STREAMINFO promises, or (unknown length / damaged stream) what the frame scan finds.
+        CK(cudaSetDevice(h->device));
+        uint64_t need = 0; int rc;
+        if ((rc = bnflac_decoded_size(h, &need))) return rc;
+        if ((rc = h->pcm_host.reserve((size_t)need + 64))) return rc;
+        uint64_t w = 0;
+        rc = decode_host(h, (uint8_t*)h->pcm_host.p, h->pcm_host.cap, &w);
+        if (rc == BNFLAC_ERR_CAPACITY) {           // STREAMINFO understated the stream: size it by scanning
+            for (bnflac* k : h->kids) delete k;
+            h->kids.clear();
+            if ((rc = run_front(h))) return rc;
+            if ((rc = h->pcm_host.reserve((size_t)h->totals.pcm_bytes + 64))) return rc;
+            rc = decode_host_single(h, (uint8_t*)h->pcm_host.p, h->pcm_host.cap, &w);
+        }
+        if (rc) return rc;
+        h->pcm_len = w; h->read_pos = 0; h->decoded = true;
         h->state = BNFLAC_STATE_READ_FRAME;
     }
     uint64_t left = h->pcm_len - h->read_pos;
@@ -568,8 +922,10 @@ int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count) {
 
 int bnflac_decode_batch(const bnflac_span* clips, size_t n, const bnflac_opts* opts, uint8_t* dst, size_t cap, int dst_is_device,
                         bnflac_clip_result* results, uint64_t* written) {
-    (void)clips; (void)n; (void)opts; (void)dst; (void)cap; (void)dst_is_device; (void)results; (void)written;
-    return BNFLAC_ERR_UNSUPPORTED;
+    if ((!clips && n) || (!dst && cap)) return BNFLAC_ERR_ARG;
+    if (written) *written = 0;
+    if (!n) return 0;
+    return decode_batch_impl(clips, n, opts, dst, cap, dst_is_device, results, written);
 }
 
 int bnflac_frames(bnflac_t* h, const bnflac_frame_t** frames, size_t* n) {

@@ -831,6 +831,30 @@ __global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_
     if (tid == 0) { uint32_t m = 0; for (int w = 0; w < 32; w++) m = max(m, s_maxbs[w]); a.totals->max_bs = m; }
 }
 
+// start-of-pass reset and end-of-stage hand-off to the host.  The host learns the candidate count and the totals through
+// a few words of MAPPED pinned memory written by k_publish, not through cudaMemcpy: a small copy would queue on the copy
+// engines behind the multi-megabyte uploads/downloads of the other sub-shards of a pipelined decode and stall the pass.
+__global__ void k_clear(uint32_t* counters, Totals* totals) {
+    if (threadIdx.x < 16) counters[threadIdx.x] = 0;
+    if (threadIdx.x < sizeof(Totals) / 4) reinterpret_cast<uint32_t*>(totals)[threadIdx.x] = 0;
+}
+__global__ void k_publish(const uint32_t* src, uint32_t* dst_mapped, uint32_t nwords) {
+    if (threadIdx.x < nwords) dst_mapped[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+// per-segment (clip) summary for batched passes: where the segment's PCM starts and whether any of its frames is damaged
+__global__ void __launch_bounds__(256) k_seg_summary(PassArgs a, uint64_t* seg_pcm, uint32_t* seg_flags) {
+    const uint32_t n = ncand(a);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t sg = a.cand[i].seg;
+    if (i == 0 || a.cand[i - 1].seg != sg) seg_pcm[sg] = a.pcm_off[i];
+    const uint8_t st = a.status[i];
+    if (st == ST_CRC) atomicOr(&seg_flags[sg], 1u);
+    else if (st == ST_UNPARSEABLE) atomicOr(&seg_flags[sg], 8u);
+}
+
 // ------------------------------------------------------------------------------------------------ K3-5 decode
 // One lane per (frame, channel); a warp (= one CTA) owns 32/C frames and works tile by tile (T samples per channel):
 //   Rice phase     each lane decodes its next T residuals into its own column of the shared-memory tile.  Groups of 8
@@ -1222,6 +1246,13 @@ void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
 }
 void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream) {
     k_prefix<<<1, 1024, 0, S(stream)>>>(a, bytes_per_sample); g_launches++;
+}
+void launch_clear(const PassArgs& a, void* stream) { k_clear<<<1, 32, 0, S(stream)>>>(a.counters, a.totals); g_launches++; }
+void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream) {
+    k_publish<<<1, 32, 0, S(stream)>>>((const uint32_t*)src, (uint32_t*)dst_mapped, nwords); g_launches++;
+}
+void launch_seg_summary(const PassArgs& a, uint32_t nb, uint64_t* seg_pcm, uint32_t* seg_flags, void* stream) {
+    k_seg_summary<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a, seg_pcm, seg_flags); g_launches++;
 }
 template <int ORD, bool WIDE>
 static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {

@@ -147,6 +147,9 @@ int bnflac_abi_version(void);
 int bnflac_device_count(void);
 /* kernels launched by this process so far (bench.py's gpu_launches is a difference of two reads) */
 uint64_t bnflac_kernel_launches(void);
+/* Device and pinned-host blocks are cached process-wide between handles (cudaMalloc/cudaFree cost milliseconds per
+ * gigabyte and cudaFree stalls the device); this returns every cached block to the driver. */
+void bnflac_trim_pools(void);
 
 #ifdef __cplusplus
 }
