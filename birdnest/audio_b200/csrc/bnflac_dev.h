@@ -6,6 +6,7 @@
 //   SegInfo[] : one per segment (= one FLAC stream or one shard of it)
 //   Chunk[]   : scan work units (<= SCAN_CHUNK bytes of one segment), built on the host
 //   Cand[]    : frame table, sorted by byte offset (K1 output)
+//   pref[]    : per scan tile, 32 tile-prefix CRC residues (K1 output, 64 B per 8 KiB of input)
 //   per-candidate arrays: seg_crc, next, flen, status, pcm_off, acc_idx, sub_bitoff[8]
 //   out       : interleaved little-endian packed PCM, frames back to back in stream order
 #pragma once
@@ -13,8 +14,7 @@
 
 namespace bnf {
 
-constexpr int SCAN_CHUNK = 32768;      // bytes per scan work unit; chunk k of a segment covers [max(begin, A + k*32768), A + (k+1)*32768), A = begin & ~15
-constexpr int SCAN_SCAP = 4096;        // max frame candidates per chunk (min frame is 10 bytes -> 3277)
+constexpr int SCAN_CHUNK = 8192;       // bytes per scan tile (one warp); tile k of a segment covers [max(begin, A + k*8192), A + (k+1)*8192), A = begin & ~15
 constexpr int MAX_CH = 8;
 
 // per-candidate status
@@ -84,9 +84,8 @@ struct PassArgs {
     uint32_t* chunk_count;
     uint32_t* chunk_scan;
     uint32_t* counters;     // [0] total candidates appended, [1] overflow flags
-    uint16_t* crc_tmp;      // CRC-16 from each candidate to the next one / the end of its chunk (chunk order)
-    uint16_t* chunk_head;   // CRC-16 of the bytes in front of a chunk's first candidate (of the whole chunk if it has none)
-    uint16_t* seg_crc;
+    uint16_t* pref;         // [tile][32] CRC-16 residue of the bytes from the start of the tile to the end of each 256-byte piece
+    uint16_t* seg_crc;      // CRC-16 residue of each span between consecutive candidates (0 <=> the span is a frame whose CRC matches)
     uint32_t* next;
     uint32_t* flen;
     uint8_t* status;

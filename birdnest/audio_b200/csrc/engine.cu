@@ -225,7 +225,7 @@ struct bnflac {
     std::vector<SegDesc> batch_segs;           // batch passes: segments given explicitly (coordinates of d_in)
 
     // device state
-    DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_crc_tmp, d_chunk_head,
+    DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_pref,
         d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags;
     uint32_t nchunks = 0, cand_cap = 0, nsegs = 0;
     bool tables_ready = false;
@@ -252,7 +252,7 @@ struct bnflac {
         for (bnflac* k : kids) delete k;
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
-        DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_crc_tmp, &d_chunk_head,
+        DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref,
                          &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags};
         for (DevBuf* b : all) b->release();
         pcm_host.release(); mailbox.release();
@@ -351,7 +351,7 @@ static int ensure_tables(bnflac* h) {
     if ((rc = h->d_chunk_base.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_chunk_count.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_chunk_scan.reserve(4ull * (h->nchunks + 1)))) return rc;
-    if ((rc = h->d_chunk_head.reserve(2ull * (h->nchunks + 1)))) return rc;
+    if ((rc = h->d_pref.reserve(64ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_counters.reserve(64))) return rc;
     if ((rc = h->d_totals.reserve(sizeof(Totals)))) return rc;
     if ((rc = h->mailbox.reserve(256))) return rc;
@@ -364,7 +364,7 @@ static int ensure_tables(bnflac* h) {
     h->args.chunks = h->d_chunks.as<Chunk>(); h->args.nchunks = h->nchunks;
     h->args.chunk_base = h->d_chunk_base.as<uint32_t>(); h->args.chunk_count = h->d_chunk_count.as<uint32_t>();
     h->args.chunk_scan = h->d_chunk_scan.as<uint32_t>(); h->args.counters = h->d_counters.as<uint32_t>();
-    h->args.chunk_head = h->d_chunk_head.as<uint16_t>();
+    h->args.pref = h->d_pref.as<uint16_t>();
     h->args.totals = h->d_totals.as<Totals>();
     h->tables_ready = true;
     return 0;
@@ -375,7 +375,6 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
     if ((rc = h->d_cand_tmp.reserve(sizeof(Cand) * (size_t)cap))) return rc;
     if ((rc = h->d_cand.reserve(sizeof(Cand) * (size_t)cap))) return rc;
     if ((rc = h->d_seg_crc.reserve(2ull * cap))) return rc;
-    if ((rc = h->d_crc_tmp.reserve(2ull * cap))) return rc;
     if ((rc = h->d_next.reserve(4ull * cap))) return rc;
     if ((rc = h->d_flen.reserve(4ull * cap))) return rc;
     if ((rc = h->d_status.reserve(cap))) return rc;
@@ -384,7 +383,7 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
     if ((rc = h->d_acc_idx.reserve(4ull * cap))) return rc;
     h->cand_cap = cap;
     h->args.cand_tmp = h->d_cand_tmp.as<Cand>(); h->args.cand = h->d_cand.as<Cand>(); h->args.cand_cap = cap;
-    h->args.seg_crc = h->d_seg_crc.as<uint16_t>(); h->args.crc_tmp = h->d_crc_tmp.as<uint16_t>(); h->args.next = h->d_next.as<uint32_t>(); h->args.flen = h->d_flen.as<uint32_t>();
+    h->args.seg_crc = h->d_seg_crc.as<uint16_t>(); h->args.next = h->d_next.as<uint32_t>(); h->args.flen = h->d_flen.as<uint32_t>();
     h->args.status = h->d_status.as<uint8_t>(); h->args.sub = h->d_sub.as<SubInfo>(); h->args.pcm_off = h->d_pcm_off.as<uint64_t>();
     h->args.acc_idx = h->d_acc_idx.as<uint32_t>();
     return 0;
@@ -408,7 +407,6 @@ static int run_front(bnflac* h) {
         volatile uint32_t* counters = (volatile uint32_t*)h->mailbox.p;
         launch_publish(h->d_counters.p, h->mailbox.p, 2, h->stream);
         CK(cudaStreamSynchronize(h->stream));
-        if (counters[1] & 1u) return BNFLAC_ERR_UNSUPPORTED;       // > SCAN_SCAP frame headers inside one scan chunk
         if (counters[0] > h->cand_cap) {
             if (attempt > 2) return BNFLAC_ERR_MEMORY;
             if ((rc = reserve_cand(h, counters[0] + counters[0] / 8 + 1024))) return rc;

@@ -37,28 +37,6 @@ __device__ __forceinline__ uint32_t crc16_update_bitwise(uint32_t c, uint32_t by
     for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
     return c;
 }
-// product of two residues modulo x^16 + x^15 + x^2 + 1
-__device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
-    uint32_t r = 0;
-#pragma unroll
-    for (int i = 15; i >= 0; --i) {
-        r <<= 1;
-        if (r & 0x10000u) r ^= 0x18005u;
-        if ((b >> i) & 1u) r ^= a;
-    }
-    return r & 0xFFFFu;
-}
-// x^(8*nbytes) mod P : appending nbytes bytes to a message multiplies its CRC by this
-__device__ uint32_t gf_xpow8(uint32_t nbytes) {
-    uint32_t result = 1, base = 0x100;
-    while (nbytes) {
-        if (nbytes & 1u) result = gf_mul(result, base);
-        base = gf_mul(base, base);
-        nbytes >>= 1;
-    }
-    return result;
-}
-
 // ------------------------------------------------------------------------------------------------ shared-memory / bit helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
@@ -131,259 +109,236 @@ __device__ __forceinline__ bool parse_header_t(F at, const SegInfo& s, Hdr& h) {
     return true;
 }
 
-// ------------------------------------------------------------------------------------------------ K1 scan + CRC-16
-// One streaming pass over the compressed bytes does both jobs of K1: it finds the frame-sync candidates (0xFFF8/0xFFF9 +
-// header syntax + CRC-8) and it computes the CRC-16 of every stretch of bytes between consecutive candidates, which is
-// what the link step needs to tell frames from false syncs.
-//   * persistent CTAs (one per SM, 512 threads); a CTA takes 32 KiB chunks, double-buffered through shared memory with
-//     coalesced 16-byte cp.async (units XOR-swizzled so that the per-thread reads below are conflict free);
-//   * every thread owns one 64-byte piece: it scans it for sync codes (cheap "has a 0xFF byte" filter, exact header parse
-//     on hits) and computes its CRC-16 with slicing-by-4.  The four 256-entry tables are replicated 32 times (one copy
-//     per bank, 128 KiB) so that the data-dependent lookups of a warp never conflict;
-//   * CRC is linear over GF(2): the CRC of a stretch is the XOR of (piece CRC * x^(8*distance to the stretch end)).  Each
-//     piece multiplies by a table entry x^(512*d) and is XOR-reduced into its stretch; one more factor x^(8*b) per stretch
-//     and the partial pieces at the stretch boundaries finish it.
-// Output: the chunk's ordered candidate list, the CRC of the bytes from each candidate to the next candidate or the end
-// of the chunk, and the CRC of the bytes before the chunk's first candidate; k_crc_spans joins them across chunks.
-constexpr int SC_THREADS = 512;
-constexpr int SC_PIECE = 64;
-static_assert(SC_THREADS * SC_PIECE == SCAN_CHUNK, "one 64-byte piece per thread");
-constexpr uint32_t SC_OFF_DATA = 4u * 256u * 32u * 4u;                          // after the replicated tables
-constexpr uint32_t SC_OFF_X64 = SC_OFF_DATA + 2u * SCAN_CHUNK;                  // x^(512 d), d < 512
-constexpr uint32_t SC_OFF_X1 = SC_OFF_X64 + 512u * 4u;                          // x^(8 b), b < 64
-constexpr uint32_t SC_OFF_XINV = SC_OFF_X1 + 64u * 4u;                          // x^(-8 b), b <= 64
-constexpr uint32_t SC_OFF_LIST = SC_OFF_XINV + 68u * 4u;                        // candidate offsets in the chunk (u16)
-constexpr uint32_t SC_OFF_ACC = SC_OFF_LIST + SCAN_SCAP * 2u;                   // per-stretch accumulators
-constexpr uint32_t SC_OFF_MISC = SC_OFF_ACC + (SCAN_SCAP + 1u) * 4u + 12u;
-constexpr uint32_t SC_SMEM = SC_OFF_MISC + 128u;
-
-__device__ __forceinline__ uint32_t sc_swz(uint32_t unit) { return (unit ^ ((unit >> 3) & 7u)) << 4; }
-__device__ __forceinline__ uint32_t bswap16(uint32_t v) { return __byte_perm(v, 0, 0x4401); }
-__device__ uint32_t gf_pow(uint32_t base, uint32_t e) {
-    uint32_t r = 1;
-    while (e) { if (e & 1u) r = gf_mul(r, base); base = gf_mul(base, base); e >>= 1; }
+// ------------------------------------------------------------------------------------------------ CRC-16 without tables
+// FLAC's frame CRC polynomial factors: x^16 + x^15 + x^2 + 1 = (x + 1)(x^15 + x + 1).  A frame is intact iff its bytes,
+// read as one polynomial F over GF(2), are divisible by both factors (F = M*x^16 + crc(M), and x is invertible):
+//   F mod (x + 1)          is the parity of all the bits;
+//   F mod Q, Q = x^15+x+1  is a trinomial residue: x^15 == x + 1, hence (Frobenius) x^(15*2^j) == x^(2^j) + 1 and in
+//                          particular x^480 == x^32 + 1 -- a 32-bit word that lies 15 words above the end of a message
+//                          can be XORed into the words 1 and 0 positions further down.  Folding a message down to its
+//                          last 15 words therefore costs ONE three-input XOR per word and no table.
+// Everything the pipeline keeps is a 16-bit "residue" r = parity << 15 | (F mod Q); r == 0 <=> CRC-16 matches.
+// Residues combine like CRCs: res(A || B) = res(A) * x^(8 |B|) + res(B), the parity bit unaffected by the shift.
+constexpr uint32_t QPOLY = 0x8003u;
+__host__ __device__ constexpr uint32_t q_reduce(uint32_t v) { return (v & 0x7FFFu) ^ (v >> 15) ^ ((v >> 15) << 1); }   // one round: v < 2^29 -> < 2^15 if v < 2^23
+__host__ __device__ constexpr uint32_t q_mul(uint32_t a, uint32_t b) {                  // a, b < 2^15
+    uint32_t r = 0;
+    for (int i = 14; i >= 0; --i) {
+        r <<= 1;
+        if (r & 0x8000u) r ^= QPOLY;
+        if ((b >> i) & 1u) r ^= a;
+    }
     return r;
 }
-// CRC-16 of 16 little-endian words (slicing-by-4, per-bank table copies), returned in the usual (not swapped) form
-__device__ __forceinline__ uint32_t sc_crc64(const uint32_t (&w)[16], uint32_t tl) {
-    uint32_t cs = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint32_t x = w[k] ^ cs;
-        const uint32_t t3 = lds32(tl + ((x << 7) & 0x7F80u) + 3u * 32768u);
-        const uint32_t t2 = lds32(tl + ((x >> 1) & 0x7F80u) + 2u * 32768u);
-        const uint32_t t1 = lds32(tl + ((x >> 9) & 0x7F80u) + 1u * 32768u);
-        const uint32_t t0 = lds32(tl + ((x >> 17) & 0x7F80u));
-        cs = t3 ^ t2 ^ t1 ^ t0;
+__host__ __device__ constexpr uint32_t q_xpow8(uint64_t nbytes) {                       // x^(8 nbytes) mod Q
+    uint32_t result = 1, base = 0x100;
+    while (nbytes) {
+        if (nbytes & 1u) result = q_mul(result, base);
+        base = q_mul(base, base);
+        nbytes >>= 1;
     }
-    return bswap16(cs);
+    return result;
 }
-// keep bytes [from, to) of the piece, zero the rest
-__device__ __forceinline__ void sc_keep(uint32_t (&w)[16], uint32_t from, uint32_t to) {
+// residue of A || B from res(A), |B| in bytes and res(B)
+__device__ __forceinline__ uint32_t res_append(uint32_t ra, uint64_t nbytes_b, uint32_t rb) {
+    return ((ra ^ rb) & 0x8000u) | (q_mul(ra & 0x7FFFu, q_xpow8(nbytes_b)) ^ (rb & 0x7FFFu));
+}
+// residue of up to a few hundred bytes read from global memory (frame-table join only; never on the streaming path)
+__device__ uint32_t res_bytes(const uint8_t* p, uint32_t n) {
+    uint32_t q = 0, par = 0;
+    for (uint32_t i = 0; i < n; i++) { const uint32_t b = p[i]; par ^= b; q = q_reduce((q << 8) ^ b); }
+    return ((__popc(par) & 1u) << 15) | q;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 scan + CRC-16
+// One streaming pass over the compressed bytes does both jobs of K1: it finds the frame-sync candidates (0xFFF8/0xFFF9 +
+// header syntax + CRC-8) and it leaves behind what is needed to get the CRC-16 residue of ANY byte range in O(1):
+// the residue of the bytes from the start of each 8 KiB tile to the end of each 256-byte piece of it.
+//   * persistent, warp-autonomous: a warp owns a tile at a time (no CTA-wide barrier anywhere), double-buffered through
+//     shared memory with coalesced 16-byte cp.async (units XOR-swizzled so that the per-lane reads are conflict free);
+//   * a lane owns one 256-byte piece.  Per 32-bit word: one LDS.128 per four words, a four-instruction sync filter
+//     (byte == 0xFF followed by a byte >= 0xF8), one XOR for the parity and one three-input XOR for the fold described
+//     above; then 15 Horner steps with x^32 == x^4 + x^2 bring the piece down to 15 bits;
+//   * a Kogge-Stone scan across the lanes with the constants x^(2048 d) mod Q (all of degree <= 8, so a multiplication
+//     is a few shifts and one reduction round) turns piece residues into tile-prefix residues;
+//   * lanes whose filter fired (about one per tile) re-read their words, check the sync codes exactly and validate the
+//     header (syntax, UTF-8 number, CRC-8, agreement with STREAMINFO); the tile's candidates are appended in order.
+// k_crc turns prefix residues into the residue of every span between consecutive candidates.
+constexpr int SC_WARPS = 8;
+constexpr int SC_THREADS = 32 * SC_WARPS;
+constexpr int SC_PIECE = SCAN_CHUNK / 32;                  // bytes per lane and tile
+constexpr int SC_PWORDS = SC_PIECE / 4;
+constexpr int SC_STAGES = 2;
+constexpr uint32_t SC_SMEM = SC_WARPS * SC_STAGES * SCAN_CHUNK;
+static_assert(SC_PIECE == 256 && SCAN_CHUNK == 8192, "scan constants below are for 256-byte pieces of 8 KiB tiles");
+// x^(8 * SC_PIECE * d) mod Q for d = 1, 2, 4, 8, 16 and x^(8 * SCAN_CHUNK) mod Q
+constexpr uint32_t SC_XD1 = q_xpow8(256), SC_XD2 = q_xpow8(512), SC_XD4 = q_xpow8(1024), SC_XD8 = q_xpow8(2048), SC_XD16 = q_xpow8(4096);
+static_assert(SC_XD1 == 0x114 && SC_XD2 == 0x116 && SC_XD4 == 0x112 && SC_XD8 == 0x102 && SC_XD16 == 0x2 && q_xpow8(8192) == 0x4, "sparse multipliers");
+
+__device__ __forceinline__ uint32_t sc_swz(uint32_t unit) { return (unit ^ ((unit >> 4) & 7u)) << 4; }    // 16-byte unit -> byte offset in the tile buffer
+template <uint32_t C> __device__ __forceinline__ uint32_t q_mulc(uint32_t q) {           // q * C mod Q for a constant C of degree <= 8
+    uint32_t v = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint32_t b0 = 4 * k;
-        uint32_t m = 0xFFFFFFFFu;
-        if (b0 + 4 <= from || b0 >= to) m = 0;
-        else {
-            if (b0 < from) m &= 0xFFFFFFFFu << (8 * (from - b0));
-            if (b0 + 4 > to) m &= 0xFFFFFFFFu >> (8 * (b0 + 4 - to));
-        }
-        w[k] &= m;
-    }
+    for (int t = 0; t <= 8; t++) if ((C >> t) & 1u) v ^= q << t;
+    return q_reduce(v);
 }
 
 __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
     extern __shared__ __align__(128) uint8_t s_sc[];
-    uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_sc);
-    uint32_t* s_x64 = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_X64);
-    uint32_t* s_x1 = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_X1);
-    uint32_t* s_xinv = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_XINV);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_sc + SC_OFF_LIST);
-    uint32_t* s_acc = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_ACC);
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_sc + SC_OFF_MISC);     // [0..15] warp counts, [17] global base
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t data_base = smem_u32(s_sc + SC_OFF_DATA);
-
-    // ---- tables (once per CTA)
-    for (uint32_t e = tid; e < 1024; e += SC_THREADS) {          // W_j[v] = v * x^(16+8j) mod P, stored byte-swapped
-        const uint32_t j = e >> 8, v = e & 255;
-        uint32_t c = v << 8;
-        for (uint32_t k = 0; k < 8 * (j + 1); k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
-        const uint32_t sw = bswap16(c);
-        for (uint32_t r = 0; r < 32; r++) s_tab[(j * 256 + v) * 32 + r] = sw;
-    }
-    s_x64[tid] = gf_xpow8(64u * tid);
-    if (tid < 64) s_x1[tid] = gf_xpow8(tid);
-    if (tid <= 64) s_xinv[tid] = gf_pow(0xC002u, 8u * tid);      // x^-1 = x^15 + x^14 + x  (x * that = P + 1)
-    for (uint32_t e = tid; e <= SCAN_SCAP; e += SC_THREADS) s_acc[e] = 0;
-    __syncthreads();
-    const uint32_t tl = smem_u32(s_tab) + lane * 4;             // this lane's copy of the tables
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = smem_u32(s_sc) + warp * (SC_STAGES * SCAN_CHUNK);
+    const uint32_t gw = blockIdx.x * SC_WARPS + warp, nwarps = gridDim.x * SC_WARPS;
 
     auto prefetch = [&](const Chunk& c, uint32_t buf) {
         const uint64_t ab = c.begin & ~15ull;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t u = tid + SC_THREADS * k;
+        for (int k = 0; k < SCAN_CHUNK / 512; k++) {
+            const uint32_t u = lane + 32u * k;
             const uint64_t g = ab + 16ull * u;
             const uint32_t n = g + 16 <= a.in_len ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(data_base + buf * SCAN_CHUNK + sc_swz(u)), "l"(a.in + (n ? g : 0)), "r"(n) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wbase + buf * SCAN_CHUNK + sc_swz(u)), "l"(a.in + (n ? g : 0)), "r"(n) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    // descriptors run two chunks ahead of the data so that no global round trip is exposed inside the loop
-    uint32_t buf = 0, n_prev = 0;
+    // descriptors run two tiles ahead of the data so that no global round trip is exposed inside the loop
+    uint32_t buf = 0;
     Chunk c_cur{}, c_next{};
-    SegInfo seg{}, seg_next{};
-    if (blockIdx.x < a.nchunks) { c_cur = a.chunks[blockIdx.x]; seg = a.segs[c_cur.seg]; prefetch(c_cur, 0); }
-    if (blockIdx.x + gridDim.x < a.nchunks) { c_next = a.chunks[blockIdx.x + gridDim.x]; seg_next = a.segs[c_next.seg]; }
-    for (uint32_t chunk = blockIdx.x; chunk < a.nchunks; chunk += gridDim.x, buf ^= 1) {
+    if (gw < a.nchunks) { c_cur = a.chunks[gw]; prefetch(c_cur, 0); }
+    if (gw + nwarps < a.nchunks) c_next = a.chunks[gw + nwarps];
+    for (uint32_t chunk = gw; chunk < a.nchunks; chunk += nwarps, buf ^= 1) {
         const Chunk c = c_cur;
         const uint64_t ab = c.begin & ~15ull;
-        const uint32_t lo = (uint32_t)(c.begin - ab), hi = lo + c.len;          // valid bytes of the chunk, buffer-relative
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        const bool have_next = chunk + gridDim.x < a.nchunks;
-        if (have_next) prefetch(c_next, buf ^ 1);
-        Chunk c_nn{}; SegInfo seg_nn{};
-        if (chunk + 2 * gridDim.x < a.nchunks) { c_nn = a.chunks[chunk + 2 * gridDim.x]; seg_nn = a.segs[c_nn.seg]; }
-        const uint32_t dbase = data_base + buf * SCAN_CHUNK;
-        const uint32_t p0 = tid * SC_PIECE;                                    // first byte of this thread's piece
-        // byte i of the buffer (bytes past the buffer come from global memory: only headers that straddle the chunk end)
-        auto byte_at = [&](uint32_t o) -> uint32_t {
-            if (o < (uint32_t)SCAN_CHUNK) { const uint32_t wd = lds32(dbase + sc_swz(o >> 4) + (o & 12u)); return (wd >> (8 * (o & 3u))) & 0xFFu; }
-            const uint64_t g = ab + o;
-            return g < a.in_len ? a.in[g] : 0u;
-        };
+        const uint32_t lo = (uint32_t)(c.begin - ab), hi = lo + c.len;          // valid bytes of the tile, buffer-relative
+        if (chunk + nwarps < a.nchunks) { prefetch(c_next, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        Chunk c_nn{};
+        if (chunk + 2 * nwarps < a.nchunks) c_nn = a.chunks[chunk + 2 * nwarps];
+        const uint32_t dbase = wbase + buf * SCAN_CHUNK;
+        const uint32_t p0 = lane * SC_PIECE;                                   // first byte of this lane's piece
+        const bool edge = p0 < lo || p0 + SC_PIECE > hi;                       // some bytes of the piece lie outside the tile's valid range
 
-        // ---- load the piece, zero what lies outside [lo, hi)
-        uint32_t w[16];
+        // ---- streaming part: parity, fold, sync filter
+        uint32_t f[16];
+        uint32_t par = 0, hits = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const uint4 v = lds128(dbase + sc_swz(4 * tid + k)); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
-        if (p0 < lo || p0 + SC_PIECE > hi) sc_keep(w, lo > p0 ? lo - p0 : 0u, hi > p0 ? (hi - p0 < 64u ? hi - p0 : 64u) : 0u);
-        // ---- sync scan: byte == 0xFF followed by (byte & 0xFE) == 0xF8
-        uint64_t cm = 0;                                                       // candidate start bytes inside the piece
-        {
-            uint32_t nextb = __shfl_down_sync(FULL, w[0] & 0xFFu, 1);
-            if (lane == 31) nextb = (w[15] >> 24) == 0xFFu ? byte_at(p0 + SC_PIECE) : 0u;   // (a zeroed next byte cannot complete a sync code)
-            uint32_t wm = 0;                                                   // words that may hold a 0xFF byte
+        for (int g = 0; g < SC_PWORDS / 16; g++) {
+            uint32_t m[17];
 #pragma unroll
-            for (int k = 0; k < 16; k++) { const uint32_t t = ~w[k]; if ((t - 0x01010101u) & w[k] & 0x80808080u) wm |= 1u << k; }
-#pragma unroll 1
-            while (wm) {                                                       // rare: re-read the word pair from shared memory
-                const uint32_t k = (uint32_t)__ffs(wm) - 1u;
-                wm &= wm - 1;
-                const uint32_t ow = p0 + 4 * k;                                // buffer offset of the word
-                const uint32_t wk = lds32(dbase + sc_swz(ow >> 4) + (ow & 12u));
-                const uint32_t nx = k < 15 ? (lds32(dbase + sc_swz((ow + 4) >> 4) + ((ow + 4) & 12u)) & 0xFFu) : nextb;
-                const uint64_t pair = (uint64_t)wk | ((uint64_t)nx << 32);
-#pragma unroll 1
-                for (uint32_t byte = 0; byte < 4; byte++) {
-                    const uint32_t two = (uint32_t)(pair >> (8 * byte)) & 0xFFFFu;              // this byte and the next
-                    if ((two & 0xFEFFu) != 0xF8FFu) continue;
-                    const uint32_t bo = 4 * k + byte;                          // byte offset inside the piece
-                    const uint32_t o = p0 + bo;
-                    if (o < lo || o >= hi) continue;
-                    Hdr h;
-                    if (!parse_header_t([&](uint32_t i) { return byte_at(o + i); }, seg, h)) continue;
-                    if (ab + o + h.hdr_len + 2 > seg.end) continue;
-                    cm |= 1ull << bo;
+            for (int k = 0; k < 4; k++) { const uint4 v = lds128(dbase + sc_swz(16 * lane + 4 * g + k)); m[4 * k] = v.x; m[4 * k + 1] = v.y; m[4 * k + 2] = v.z; m[4 * k + 3] = v.w; }
+            // the word after the group (the byte after the tile is not in the buffer: assume a sync continuation there)
+            const uint32_t un = 16 * lane + 4 * g + 4;
+            m[16] = un < (uint32_t)(SCAN_CHUNK / 16) ? lds32(dbase + sc_swz(un)) : 0xFFFFFFFFu;
+            if (edge) {
+#pragma unroll
+                for (int k = 0; k < 17; k++) {
+                    const uint32_t b0 = p0 + 64 * g + 4 * k;
+                    uint32_t msk = 0xFFFFFFFFu;
+                    if (b0 + 4 <= lo || b0 >= hi) msk = 0;
+                    else {
+                        if (b0 < lo) msk &= 0xFFFFFFFFu << (8 * (lo - b0));
+                        if (b0 + 4 > hi) msk &= 0xFFFFFFFFu >> (8 * (b0 + 4 - hi));
+                    }
+                    if (k < 16 || un < (uint32_t)(SCAN_CHUNK / 16)) m[k] &= msk;
                 }
             }
-        }
-        // ---- order the candidates: exclusive prefix of the per-piece counts
-        const uint32_t cnt = (uint32_t)__popcll(cm);
-        uint32_t inc = cnt;
+            uint32_t acc = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
-        if (lane == 31) s_misc[warp] = inc;
-        // the accumulators of the previous chunk are cleared here (its outputs were written before the barrier at the loop top)
-        for (uint32_t e = tid; e <= n_prev && e <= SCAN_SCAP; e += SC_THREADS) s_acc[e] = 0;
-        __syncthreads();
-        uint32_t base = inc - cnt, total = 0;
+            for (int k = 0; k < 16; k++) {
+                const int j = 16 * g + k;
+                const uint32_t w = m[k];
+                // sync filter: byte == 0xFF and next byte >= 0xF8  <=>  (w & (next | 0x07..)) has a 0xFF byte
+                const uint32_t z = w & (__funnelshift_r(w, m[k + 1], 8) | 0x07070707u);
+                acc |= (0xFEFEFEFEu - z) & z;                                 // bit 7 of a byte survives only if that byte (or a lower one) is 0xFF
+                par ^= w;
+                uint32_t v = w;
+                if (j >= 15) v ^= f[(j - 15) & 15];
+                if (j >= 14 && j <= SC_PWORDS - 2) v ^= f[(j - 14) & 15];
+                f[j & 15] = v;
+            }
+            if (acc & 0x80808080u) hits |= 1u << g;
+        }
+        // ---- the last 15 words -> 15 bits (Horner, x^32 == x^4 + x^2), then the prefix over the lanes
+        uint32_t q = 0;
 #pragma unroll
-        for (uint32_t wv = 0; wv < SC_THREADS / 32; wv++) { const uint32_t x = s_misc[wv]; if (wv < warp) base += x; total += x; }
-        const bool overflow = total > SCAN_SCAP;
-        const uint32_t n = overflow ? 0 : total;
-        n_prev = n;
-        if (!overflow) { uint64_t m = cm; uint32_t j = base; while (m) { const uint32_t bo = (uint32_t)(__ffsll((long long)m) - 1); m &= m - 1; s_list[j++] = (uint16_t)(p0 + bo); } }
-        uint32_t gb = 0;
-        if (tid == 0) {                                // the result is not needed before the output step below
-            if (overflow) atomicOr(&a.counters[1], 1u);
-            else if (n) gb = atomicAdd(&a.counters[0], n);
-        }
-        __syncthreads();
-        // ---- piece CRC with the bytes before the piece's last boundary zeroed: what remains is the head of the stretch
-        //      that starts there
-        const bool end_in = hi > p0 && hi < p0 + SC_PIECE;                    // the end of the valid bytes falls inside the piece
-        const bool head_ok = p0 < hi && !end_in;                             // (a piece that holds the end has no stretch running past it)
-        if (cm) sc_keep(w, 63u - (uint32_t)__clzll((long long)cm), 64u);
-        const uint32_t pc = sc_crc64(w, tl);
-        // ---- into the stretch: stretch s ends at candidate s (or at hi); this piece's head belongs to stretch base+cnt
-        const uint32_t sidx = base + cnt;
-        uint32_t term = 0;
-        if (head_ok && !overflow) {
-            const uint32_t e = sidx < n ? s_list[sidx] : hi;
-            term = gf_mul(pc, s_x64[(e >> 6) - 1 - tid]);                     // the stretch ends in piece e >> 6 >= tid + 1
-        }
+        for (int j = SC_PWORDS - 15; j < SC_PWORDS; j++) q = q_reduce((q << 4) ^ (q << 2) ^ __byte_perm(f[j & 15], 0, 0x0123));
+        q = q_reduce(q);
         {
-            const uint32_t s0 = __shfl_sync(FULL, sidx, 0);
-            if (__all_sync(FULL, sidx == s0)) { const uint32_t r = __reduce_xor_sync(FULL, term); if (lane == 0 && r) atomicXor(&s_acc[s0], r); }
-            else if (term) atomicXor(&s_acc[sidx], term);
+            uint32_t t;
+            t = __shfl_up_sync(FULL, q, 1);  if (lane >= 1)  q ^= q_mulc<SC_XD1>(t);
+            t = __shfl_up_sync(FULL, q, 2);  if (lane >= 2)  q ^= q_mulc<SC_XD2>(t);
+            t = __shfl_up_sync(FULL, q, 4);  if (lane >= 4)  q ^= q_mulc<SC_XD4>(t);
+            t = __shfl_up_sync(FULL, q, 8);  if (lane >= 8)  q ^= q_mulc<SC_XD8>(t);
+            t = __shfl_up_sync(FULL, q, 16); if (lane >= 16) q ^= q_mulc<SC_XD16>(t);
         }
-        __syncthreads();
-        for (uint32_t sx = tid; sx <= n; sx += SC_THREADS) { const uint32_t e = sx < n ? s_list[sx] : hi; s_acc[sx] = gf_mul(s_acc[sx], s_x1[e & 63u]); }
-        __syncthreads();
-        // ---- partial pieces in front of each boundary (candidates, end of the valid bytes).  CRC of bytes [prev, bo) =
-        //      CRC of the piece with everything else zeroed, times x^(-8 (64 - bo)) (trailing zeros undone)
-        if ((cm || end_in) && !overflow) {
-            uint64_t m = cm;
-            if (end_in) m |= 1ull << (hi - p0);
-            uint32_t prev = lo > p0 ? lo - p0 : 0u, j = base;
+        const uint32_t pbits = __ballot_sync(FULL, __popc(par) & 1u);
+        const uint32_t ppar = __popc(pbits & (0xFFFFFFFFu >> (31 - lane))) & 1u;
+        a.pref[(uint64_t)chunk * 32 + lane] = (uint16_t)((ppar << 15) | q);
+
+        // ---- candidates (rare): exact sync check + header validation, appended in order
+        uint32_t n_tile = 0, gbase = 0;
+        if (__any_sync(FULL, hits != 0)) {
+            const SegInfo seg = a.segs[c.seg];
+            // byte o of the tile buffer; bytes past the buffer come from global memory (headers that straddle the tile end)
+            auto byte_at = [&](uint32_t o) -> uint32_t {
+                if (o < (uint32_t)SCAN_CHUNK) { const uint32_t wd = lds32(dbase + sc_swz(o >> 4) + (o & 12u)); return (wd >> (8 * (o & 3u))) & 0xFFu; }
+                const uint64_t g = ab + o;
+                return g < a.in_len ? a.in[g] : 0u;
+            };
+            auto walk = [&](bool emit, uint32_t slot) -> uint32_t {
+                uint32_t cnt = 0;
 #pragma unroll 1
-            while (m) {
-                const uint32_t bo = (uint32_t)(__ffsll((long long)m) - 1);
-                m &= m - 1;
-                if (bo > prev) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { const uint4 v = lds128(dbase + sc_swz(4 * tid + k)); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
-                    sc_keep(w, prev, bo);
-                    const uint32_t v = gf_mul(sc_crc64(w, tl), s_xinv[64u - bo]);
-                    if (v) atomicXor(&s_acc[j], v);
+                for (uint32_t g = 0; g < (uint32_t)(SC_PWORDS / 16); g++) {
+                    if (!((hits >> g) & 1u)) continue;
+#pragma unroll 1
+                    for (uint32_t k = 0; k < 16; k++) {
+                        const uint32_t ow = p0 + 64 * g + 4 * k;               // buffer offset of the word
+                        const uint32_t wk = lds32(dbase + sc_swz(ow >> 4) + (ow & 12u));
+                        if (!((0xFEFEFEFEu - wk) & wk & 0x80808080u)) continue;   // no 0xFF byte in this word
+                        const uint64_t pair = (uint64_t)wk | ((uint64_t)byte_at(ow + 4) << 32);
+#pragma unroll 1
+                        for (uint32_t byte = 0; byte < 4; byte++) {
+                            const uint32_t two = (uint32_t)(pair >> (8 * byte)) & 0xFFFFu;          // this byte and the next
+                            if ((two & 0xFEFFu) != 0xF8FFu) continue;
+                            const uint32_t o = ow + byte;
+                            if (o < lo || o >= hi) continue;
+                            Hdr h;
+                            if (!parse_header_t([&](uint32_t i) { return byte_at(o + i); }, seg, h)) continue;
+                            const uint64_t go = ab + o;
+                            if (go + h.hdr_len + 2 > seg.end) continue;
+                            if (emit && slot + cnt < a.cand_cap) {
+                                Cand cd;
+                                cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = c.seg;
+                                cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
+                                cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
+                                cd.sample_rate = h.sample_rate;
+                                a.cand_tmp[slot + cnt] = cd;
+                            }
+                            cnt++;
+                        }
+                    }
                 }
-                j++; prev = bo;
+                return cnt;
+            };
+            const uint32_t cnt = hits ? walk(false, 0) : 0u;
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
+            n_tile = __shfl_sync(FULL, inc, 31);
+            if (n_tile) {
+                if (lane == 0) gbase = atomicAdd(&a.counters[0], n_tile);
+                gbase = __shfl_sync(FULL, gbase, 0);
+                if (cnt) walk(true, gbase + inc - cnt);
             }
         }
-        if (tid == 0) {
-            s_misc[17] = gb;
-            a.chunk_base[chunk] = gb;
-            a.chunk_count[chunk] = (gb + n > a.cand_cap) ? (gb < a.cand_cap ? a.cand_cap - gb : 0) : n;
-            if (gb + n > a.cand_cap) atomicOr(&a.counters[1], 2u);
+        if (lane == 0) {
+            a.chunk_base[chunk] = gbase;
+            a.chunk_count[chunk] = (gbase + n_tile > a.cand_cap) ? (gbase < a.cand_cap ? a.cand_cap - gbase : 0) : n_tile;
         }
-        __syncthreads();
-        // ---- outputs (the barrier at the top of the next iteration orders them before the buffers are reused)
-        if (tid == 0) a.chunk_head[chunk] = (uint16_t)s_acc[0];
-        {
-            const uint32_t gbase = s_misc[17];
-            for (uint32_t e = tid; e < n; e += SC_THREADS) {
-                if (gbase + e >= a.cand_cap) break;
-                const uint32_t o = s_list[e];
-                Hdr h;
-                parse_header_t([&](uint32_t i) { return byte_at(o + i); }, seg, h);
-                const uint64_t go = ab + o;
-                Cand cd;
-                cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = c.seg;
-                cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
-                cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
-                cd.sample_rate = h.sample_rate;
-                a.cand_tmp[gbase + e] = cd;
-                a.crc_tmp[gbase + e] = (uint16_t)s_acc[e + 1];
-            }
-        }
-        c_cur = c_next; seg = seg_next; c_next = c_nn; seg_next = seg_nn;
+        __syncwarp();                      // every lane is done with this buffer before the next iteration refills it
+        c_cur = c_next; c_next = c_nn;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // single-CTA exclusive scan of chunk_count -> chunk_scan
@@ -407,11 +362,12 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(PassArgs a) {
 
 // move each chunk's (already sorted) list to its place in the global frame table
 __global__ void __launch_bounds__(256) k_gather(PassArgs a) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t chunk = warp; chunk < a.nchunks; chunk += nwarps) {
-        uint32_t n = a.chunk_count[chunk], src = a.chunk_base[chunk], dst = a.chunk_scan[chunk];
-        for (uint32_t r = lane; r < n; r += 32) { a.cand[dst + r] = a.cand_tmp[src + r]; a.seg_crc[dst + r] = a.crc_tmp[src + r]; }
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t chunk = i0; chunk < a.nchunks; chunk += stride) {
+        const uint32_t n = a.chunk_count[chunk];
+        if (!n) continue;
+        const uint32_t src = a.chunk_base[chunk], dst = a.chunk_scan[chunk];
+        for (uint32_t r = 0; r < n; r++) a.cand[dst + r] = a.cand_tmp[src + r];
     }
 }
 
@@ -423,29 +379,48 @@ __device__ __forceinline__ uint64_t span_end(const PassArgs& a, uint32_t i, uint
     return a.segs[ci.seg].end;
 }
 
-// Joins the chunk-local CRCs into the CRC-16 of every span between consecutive candidates: the stretch from the candidate
-// to the end of its chunk, whole chunks in between, and the bytes in front of the next candidate in its chunk.
+// residue of the bytes from the start of p's tile up to p (exclusive).  `as_end`: p closes a range, so a p on a tile
+// boundary belongs to the tile before it.  Also returns the tile index and p's offset in it.
+__device__ uint32_t tile_prefix(const PassArgs& a, const SegInfo& sg, uint64_t p, bool as_end, uint32_t& tile, uint32_t& off) {
+    const uint64_t ab0 = sg.begin & ~15ull;
+    const uint64_t rel = p - ab0 - (as_end ? 1u : 0u);
+    tile = sg.first_chunk + (uint32_t)(rel / SCAN_CHUNK);
+    const uint64_t tstart = ab0 + (rel / SCAN_CHUNK) * SCAN_CHUNK;
+    off = (uint32_t)(p - tstart);                                            // 0 .. SCAN_CHUNK (SCAN_CHUNK only as_end)
+    const uint32_t l = off / SC_PIECE, o = off % SC_PIECE;
+    uint32_t r = l ? a.pref[(uint64_t)tile * 32 + l - 1] : 0u;
+    if (o) {
+        uint64_t from = tstart + (uint64_t)l * SC_PIECE;
+        if (from < sg.begin) from = sg.begin;                                // bytes in front of the segment count as zero
+        r = res_append(r, o, from < p ? res_bytes(a.in + from, (uint32_t)(p - from)) : 0u);
+    }
+    return r;
+}
+
+// The residue of every span between consecutive candidates, from the tile-prefix residues k_scan left behind:
+// res[a, e) = G(e) - G(a) x^(8 (e - a)) inside one tile; across tiles the tail of the first tile, whole tiles in between
+// (each one multiplication by x^(8 * 8192) == x^2) and the head of the last.
 __global__ void __launch_bounds__(256) k_crc(PassArgs a) {
     const uint32_t n = ncand(a);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Cand ci = a.cand[i];
-    const SegInfo& sg = a.segs[ci.seg];
+    const SegInfo sg = a.segs[ci.seg];
     const uint64_t e = span_end(a, i, n, ci);
-    const uint64_t ab0 = sg.begin & ~15ull;
-    uint32_t c = sg.first_chunk + (uint32_t)((ci.off - ab0) >> 15);
-    uint32_t crc = a.seg_crc[i];
-    const Chunk c0 = a.chunks[c];
-    uint64_t cend = c0.begin + c0.len;
-    while (e > cend) {                      // the span runs past this chunk: append the next chunk's leading stretch
-        c++;
-        const Chunk ck = a.chunks[c];
-        const uint64_t kend = ck.begin + ck.len;
-        const uint64_t upto = e < kend ? e : kend;        // chunk c holds no candidate before `upto`: chunk_head covers [begin, upto)
-        crc = gf_mul(crc, gf_xpow8((uint32_t)(upto - ck.begin))) ^ a.chunk_head[c];
-        cend = kend;
+    uint32_t ta, oa, te, oe;
+    const uint32_t ga = tile_prefix(a, sg, ci.off, false, ta, oa);
+    const uint32_t ge = tile_prefix(a, sg, e, true, te, oe);
+    uint32_t r;
+    if (ta == te) r = res_append(ga, oe - oa, ge);                           // GF(2): subtraction is XOR
+    else {
+        r = res_append(ga, SCAN_CHUNK - oa, a.pref[(uint64_t)ta * 32 + 31]);
+        for (uint32_t t = ta + 1; t < te; t++) {
+            const uint32_t w = a.pref[(uint64_t)t * 32 + 31];
+            r = ((r ^ w) & 0x8000u) | (q_mulc<0x4>(r & 0x7FFFu) ^ (w & 0x7FFFu));
+        }
+        r = res_append(r, oe, ge);
     }
-    a.seg_crc[i] = (uint16_t)crc;
+    a.seg_crc[i] = (uint16_t)r;
 }
 
 // ------------------------------------------------------------------------------------------------ K1d link / validate
@@ -472,7 +447,7 @@ __global__ void __launch_bounds__(256) k_link(PassArgs a) {
         if (at_seg_end || e - ci.off > max_frame) break;
         // extend the span over candidate j (a false sync inside this frame)
         const uint64_t e2 = (j + 1 < n && a.cand[j + 1].seg == ci.seg) ? a.cand[j + 1].off : seg_end;
-        crc = gf_mul(crc, gf_xpow8((uint32_t)(e2 - e))) ^ a.seg_crc[j];
+        crc = res_append(crc, e2 - e, a.seg_crc[j]);
         j++;
     }
     if (st != ST_OK) {
@@ -1226,13 +1201,14 @@ void launch_scan(const PassArgs& a, void* stream) {
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm < 1) n_sm = 148;
     }
-    uint32_t grid = a.nchunks < (uint32_t)n_sm ? a.nchunks : (uint32_t)n_sm;
+    uint32_t grid = (a.nchunks + SC_WARPS - 1) / SC_WARPS;
+    if (grid > (uint32_t)n_sm) grid = (uint32_t)n_sm;
     if (!grid) grid = 1;
     k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); g_launches++;
 }
 void launch_order(const PassArgs& a, void* stream) {
     k_chunk_scan<<<1, 1024, 0, S(stream)>>>(a); g_launches++;
-    k_gather<<<148 * 2, 256, 0, S(stream)>>>(a); g_launches++;
+    k_gather<<<148 * 4, 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_crc(const PassArgs& a, uint32_t nb, void* stream) {
     k_crc<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
