@@ -83,7 +83,7 @@ struct PassArgs {
     uint32_t* chunk_base;
     uint32_t* chunk_count;
     uint32_t* chunk_scan;
-    uint32_t* counters;     // [0] total candidates appended, [1] overflow flags
+    uint32_t* counters;     // [0] total candidates appended, [1] overflow flags, [16..271] k_order's per-CTA totals
     uint16_t* pref;         // [tile][32] CRC-16 residue of the bytes from the start of the tile to the end of each 256-byte piece
     uint16_t* seg_crc;      // CRC-16 residue of each span between consecutive candidates (0 <=> the span is a frame whose CRC matches)
     uint32_t* next;
@@ -102,7 +102,7 @@ struct PassArgs {
 
 // launchers (kernels.cu); all asynchronous on `stream`
 void launch_scan(const PassArgs& a, void* stream);
-void launch_order(const PassArgs& a, void* stream);
+void launch_order(const PassArgs& a, uint32_t* blk_tot, void* stream);
 void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);

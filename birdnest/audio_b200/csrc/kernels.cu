@@ -1,8 +1,8 @@
 // kernels.cu -- sm_100a kernels of the bnflac decode pipeline (no tensor cores: nothing here is a contraction).
 //
 //   K1  k_scan      frame-sync scan (0xFFF8/0xFFF9) + header syntax + CRC-8  -> per-chunk sorted candidate lists
-//       k_chunk_scan / k_gather   order the per-chunk lists into one frame table
-//       k_crc       CRC-16 of every inter-candidate span (warp per span, GF(2) combine of lane pieces)
+//       k_order     orders the per-tile candidate lists into one frame table (prefix of tile counts + gather)
+//       k_crc       CRC-16 residue of every inter-candidate span, joined from the tile-prefix residues k_scan leaves
 //       k_link      span validation (CRC residue 0 + frame/sample-number continuity), false-sync elimination
 //   K2  k_parse     subframe header parse (CONSTANT / VERBATIM / FIXED 0-4 / LPC 1-32, wasted bits) and residual
 //                   skip: finds where every subframe starts, so K3-5 can run one thread per (frame, channel)
@@ -139,14 +139,26 @@ __host__ __device__ constexpr uint32_t q_xpow8(uint64_t nbytes) {               
     }
     return result;
 }
+// x^(8 n) mod Q for n <= 256 (the distances inside one 256-byte piece), built at compile time
+struct XPow8Table { uint16_t v[257]; };
+constexpr XPow8Table make_xpow8_table() { XPow8Table t{}; for (int i = 0; i <= 256; i++) t.v[i] = (uint16_t)q_xpow8((uint64_t)i); return t; }
+__constant__ XPow8Table c_xpow8 = make_xpow8_table();
+__device__ __forceinline__ uint32_t q_xpow8_dev(uint64_t nbytes) { return nbytes <= 256 ? (uint32_t)c_xpow8.v[nbytes] : q_xpow8(nbytes); }
 // residue of A || B from res(A), |B| in bytes and res(B)
 __device__ __forceinline__ uint32_t res_append(uint32_t ra, uint64_t nbytes_b, uint32_t rb) {
-    return ((ra ^ rb) & 0x8000u) | (q_mul(ra & 0x7FFFu, q_xpow8(nbytes_b)) ^ (rb & 0x7FFFu));
+    return ((ra ^ rb) & 0x8000u) | (q_mul(ra & 0x7FFFu, q_xpow8_dev(nbytes_b)) ^ (rb & 0x7FFFu));
 }
 // residue of up to a few hundred bytes read from global memory (frame-table join only; never on the streaming path)
 __device__ uint32_t res_bytes(const uint8_t* p, uint32_t n) {
-    uint32_t q = 0, par = 0;
-    for (uint32_t i = 0; i < n; i++) { const uint32_t b = p[i]; par ^= b; q = q_reduce((q << 8) ^ b); }
+    uint32_t q = 0, par = 0, i = 0;
+    for (; i < n && ((uintptr_t)(p + i) & 15u); i++) { const uint32_t b = p[i]; par ^= b; q = q_reduce((q << 8) ^ b); }
+    for (; i + 16 <= n; i += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { par ^= w[k]; q = q_reduce(q_reduce((q << 4) ^ (q << 2) ^ __byte_perm(w[k], 0, 0x0123))); }
+    }
+    for (; i < n; i++) { const uint32_t b = p[i]; par ^= b; q = q_reduce((q << 8) ^ b); }
     return ((__popc(par) & 1u) << 15) | q;
 }
 
@@ -164,7 +176,7 @@ __device__ uint32_t res_bytes(const uint8_t* p, uint32_t n) {
 //   * lanes whose filter fired (about one per tile) re-read their words, check the sync codes exactly and validate the
 //     header (syntax, UTF-8 number, CRC-8, agreement with STREAMINFO); the tile's candidates are appended in order.
 // k_crc turns prefix residues into the residue of every span between consecutive candidates.
-constexpr int SC_WARPS = 8;
+constexpr int SC_WARPS = 12;
 constexpr int SC_THREADS = 32 * SC_WARPS;
 constexpr int SC_PIECE = SCAN_CHUNK / 32;                  // bytes per lane and tile
 constexpr int SC_PWORDS = SC_PIECE / 4;
@@ -183,29 +195,89 @@ template <uint32_t C> __device__ __forceinline__ uint32_t q_mulc(uint32_t q) {  
     return q_reduce(v);
 }
 
+// byte o of a tile buffer; bytes past the buffer come from global memory (headers that straddle the tile end)
+struct TileBytes {
+    uint32_t dbase; uint64_t ab; const uint8_t* in; uint64_t in_len;
+    __device__ __forceinline__ uint32_t operator()(uint32_t o) const {
+        if (o < (uint32_t)SCAN_CHUNK) { const uint32_t wd = lds32(dbase + sc_swz(o >> 4) + (o & 12u)); return (wd >> (8 * (o & 3u))) & 0xFFu; }
+        const uint64_t g = ab + o;
+        return g < in_len ? in[g] : 0u;
+    }
+};
+
+// Exact check of the sync codes in the flagged 16-byte units of one lane's piece + header validation; counts the frame
+// candidates and, with `emit`, writes them to cand_tmp[slot ...] in stream order.  One copy of this code serves both
+// passes (count, then emit once the tile's place in the table is known); it runs for about one lane in every few tiles.
+__device__ __noinline__ uint32_t sc_walk(const PassArgs& a, const TileBytes tb, const SegInfo& seg, uint32_t seg_id, uint32_t p0, uint32_t lo, uint32_t hi,
+                                         uint32_t hits, bool emit, uint32_t slot) {
+    uint32_t cnt = 0;
+#pragma unroll 1
+    while (hits) {
+        const uint32_t u = (uint32_t)__ffs(hits) - 1u;
+        hits &= hits - 1;
+#pragma unroll 1
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t ow = p0 + 16 * u + 4 * k;                   // buffer offset of the word
+            const uint32_t wk = lds32(tb.dbase + sc_swz(ow >> 4) + (ow & 12u));
+            if (!((0xFEFEFEFEu - wk) & wk & 0x80808080u)) continue;    // no 0xFF byte in this word
+            const uint64_t pair = (uint64_t)wk | ((uint64_t)tb(ow + 4) << 32);
+#pragma unroll 1
+            for (uint32_t byte = 0; byte < 4; byte++) {
+                const uint32_t two = (uint32_t)(pair >> (8 * byte)) & 0xFFFFu;              // this byte and the next
+                if ((two & 0xFEFFu) != 0xF8FFu) continue;
+                const uint32_t o = ow + byte;
+                if (o < lo || o >= hi) continue;
+                Hdr h;
+                if (!parse_header_t([&](uint32_t i) { return tb(o + i); }, seg, h)) continue;
+                const uint64_t go = tb.ab + o;
+                if (go + h.hdr_len + 2 > seg.end) continue;
+                if (emit && slot + cnt < a.cand_cap) {
+                    Cand cd;
+                    cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = seg_id;
+                    cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
+                    cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
+                    cd.sample_rate = h.sample_rate;
+                    a.cand_tmp[slot + cnt] = cd;
+                }
+                cnt++;
+            }
+        }
+    }
+    return cnt;
+}
+
 __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
     extern __shared__ __align__(128) uint8_t s_sc[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t wbase = smem_u32(s_sc) + warp * (SC_STAGES * SCAN_CHUNK);
     const uint32_t gw = blockIdx.x * SC_WARPS + warp, nwarps = gridDim.x * SC_WARPS;
-
+    const uint32_t my_swz = sc_swz(lane);                                       // unit lane + 32 k sits at my_swz ^ (k << 5) + 512 k
     auto prefetch = [&](const Chunk& c, uint32_t buf) {
         const uint64_t ab = c.begin & ~15ull;
+        const uint32_t sdst = wbase + buf * SCAN_CHUNK;
+        const uint8_t* src = a.in + ab + 16u * lane;
+        if (ab + SCAN_CHUNK <= a.in_len) {
 #pragma unroll
-        for (int k = 0; k < SCAN_CHUNK / 512; k++) {
-            const uint32_t u = lane + 32u * k;
-            const uint64_t g = ab + 16ull * u;
-            const uint32_t n = g + 16 <= a.in_len ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wbase + buf * SCAN_CHUNK + sc_swz(u)), "l"(a.in + (n ? g : 0)), "r"(n) : "memory");
+            for (int k = 0; k < SCAN_CHUNK / 512; k++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + sc_swz(lane + 32u * k)), "l"(src + 512 * k) : "memory");
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < SCAN_CHUNK / 512; k++) {
+                const uint64_t g = ab + 16ull * (lane + 32u * k);
+                const uint32_t n = g + 16 <= a.in_len ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + sc_swz(lane + 32u * k)), "l"(a.in + (n ? g : 0)), "r"(n) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    (void)my_swz;
 
     // descriptors run two tiles ahead of the data so that no global round trip is exposed inside the loop
     uint32_t buf = 0;
     Chunk c_cur{}, c_next{};
     if (gw < a.nchunks) { c_cur = a.chunks[gw]; prefetch(c_cur, 0); }
     if (gw + nwarps < a.nchunks) c_next = a.chunks[gw + nwarps];
+#pragma unroll 1
     for (uint32_t chunk = gw; chunk < a.nchunks; chunk += nwarps, buf ^= 1) {
         const Chunk c = c_cur;
         const uint64_t ab = c.begin & ~15ull;
@@ -217,7 +289,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
         if (chunk + 2 * nwarps < a.nchunks) c_nn = a.chunks[chunk + 2 * nwarps];
         const uint32_t dbase = wbase + buf * SCAN_CHUNK;
         const uint32_t p0 = lane * SC_PIECE;                                   // first byte of this lane's piece
-        const bool edge = p0 < lo || p0 + SC_PIECE > hi;                       // some bytes of the piece lie outside the tile's valid range
+        if (lo > 0 || hi < (uint32_t)SCAN_CHUNK) {
+            // first / last tile of a segment: bytes outside [lo, hi) belong to something else and count as zero
+#pragma unroll 1
+            for (uint32_t wi = lane; wi < (uint32_t)(SCAN_CHUNK / 4); wi += 32) {
+                const uint32_t b0 = 4 * wi;
+                if (b0 >= lo && b0 + 4 <= hi) continue;
+                uint32_t msk = 0;
+                if (b0 + 4 > lo && b0 < hi) {
+                    msk = 0xFFFFFFFFu;
+                    if (b0 < lo) msk &= 0xFFFFFFFFu << (8 * (lo - b0));
+                    if (b0 + 4 > hi) msk &= 0xFFFFFFFFu >> (8 * (b0 + 4 - hi));
+                }
+                const uint32_t ad = dbase + sc_swz(b0 >> 4) + (b0 & 12u);
+                sts32(ad, lds32(ad) & msk);
+            }
+            __syncwarp();
+        }
 
         // ---- streaming part: parity, fold, sync filter
         uint32_t f[16];
@@ -229,35 +317,25 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
             for (int k = 0; k < 4; k++) { const uint4 v = lds128(dbase + sc_swz(16 * lane + 4 * g + k)); m[4 * k] = v.x; m[4 * k + 1] = v.y; m[4 * k + 2] = v.z; m[4 * k + 3] = v.w; }
             // the word after the group (the byte after the tile is not in the buffer: assume a sync continuation there)
             const uint32_t un = 16 * lane + 4 * g + 4;
-            m[16] = un < (uint32_t)(SCAN_CHUNK / 16) ? lds32(dbase + sc_swz(un)) : 0xFFFFFFFFu;
-            if (edge) {
+            m[16] = un < (uint32_t)(SCAN_CHUNK / 16) ? lds32(dbase + sc_swz(un)) : 0xF8F8F8F8u;
 #pragma unroll
-                for (int k = 0; k < 17; k++) {
-                    const uint32_t b0 = p0 + 64 * g + 4 * k;
-                    uint32_t msk = 0xFFFFFFFFu;
-                    if (b0 + 4 <= lo || b0 >= hi) msk = 0;
-                    else {
-                        if (b0 < lo) msk &= 0xFFFFFFFFu << (8 * (lo - b0));
-                        if (b0 + 4 > hi) msk &= 0xFFFFFFFFu >> (8 * (b0 + 4 - hi));
-                    }
-                    if (k < 16 || un < (uint32_t)(SCAN_CHUNK / 16)) m[k] &= msk;
+            for (int k4 = 0; k4 < 4; k4++) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int k = 4 * k4 + kk, j = 16 * g + k;
+                    const uint32_t w = m[k];
+                    // sync filter: byte in {0xFE, 0xFF} followed by a byte in {0xF8, 0xF9}  <=>  z has a byte >= 0xFE
+                    const uint32_t z = w & (__funnelshift_r(w, m[k + 1], 8) ^ 0x07070707u);
+                    acc |= (0xFDFDFDFDu - z) & z;                             // bit 7 of a byte survives only if that byte (or a lower one) is >= 0xFE
+                    par ^= w;
+                    uint32_t v = w;
+                    if (j >= 15) v ^= f[(j - 15) & 15];
+                    if (j >= 14 && j <= SC_PWORDS - 2) v ^= f[(j - 14) & 15];
+                    f[j & 15] = v;
                 }
+                if (acc & 0x80808080u) hits |= 1u << (4 * g + k4);
             }
-            uint32_t acc = 0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const int j = 16 * g + k;
-                const uint32_t w = m[k];
-                // sync filter: byte == 0xFF and next byte >= 0xF8  <=>  (w & (next | 0x07..)) has a 0xFF byte
-                const uint32_t z = w & (__funnelshift_r(w, m[k + 1], 8) | 0x07070707u);
-                acc |= (0xFEFEFEFEu - z) & z;                                 // bit 7 of a byte survives only if that byte (or a lower one) is 0xFF
-                par ^= w;
-                uint32_t v = w;
-                if (j >= 15) v ^= f[(j - 15) & 15];
-                if (j >= 14 && j <= SC_PWORDS - 2) v ^= f[(j - 14) & 15];
-                f[j & 15] = v;
-            }
-            if (acc & 0x80808080u) hits |= 1u << g;
         }
         // ---- the last 15 words -> 15 bits (Horner, x^32 == x^4 + x^2), then the prefix over the lanes
         uint32_t q = 0;
@@ -280,56 +358,16 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
         uint32_t n_tile = 0, gbase = 0;
         if (__any_sync(FULL, hits != 0)) {
             const SegInfo seg = a.segs[c.seg];
-            // byte o of the tile buffer; bytes past the buffer come from global memory (headers that straddle the tile end)
-            auto byte_at = [&](uint32_t o) -> uint32_t {
-                if (o < (uint32_t)SCAN_CHUNK) { const uint32_t wd = lds32(dbase + sc_swz(o >> 4) + (o & 12u)); return (wd >> (8 * (o & 3u))) & 0xFFu; }
-                const uint64_t g = ab + o;
-                return g < a.in_len ? a.in[g] : 0u;
-            };
-            auto walk = [&](bool emit, uint32_t slot) -> uint32_t {
-                uint32_t cnt = 0;
-#pragma unroll 1
-                for (uint32_t g = 0; g < (uint32_t)(SC_PWORDS / 16); g++) {
-                    if (!((hits >> g) & 1u)) continue;
-#pragma unroll 1
-                    for (uint32_t k = 0; k < 16; k++) {
-                        const uint32_t ow = p0 + 64 * g + 4 * k;               // buffer offset of the word
-                        const uint32_t wk = lds32(dbase + sc_swz(ow >> 4) + (ow & 12u));
-                        if (!((0xFEFEFEFEu - wk) & wk & 0x80808080u)) continue;   // no 0xFF byte in this word
-                        const uint64_t pair = (uint64_t)wk | ((uint64_t)byte_at(ow + 4) << 32);
-#pragma unroll 1
-                        for (uint32_t byte = 0; byte < 4; byte++) {
-                            const uint32_t two = (uint32_t)(pair >> (8 * byte)) & 0xFFFFu;          // this byte and the next
-                            if ((two & 0xFEFFu) != 0xF8FFu) continue;
-                            const uint32_t o = ow + byte;
-                            if (o < lo || o >= hi) continue;
-                            Hdr h;
-                            if (!parse_header_t([&](uint32_t i) { return byte_at(o + i); }, seg, h)) continue;
-                            const uint64_t go = ab + o;
-                            if (go + h.hdr_len + 2 > seg.end) continue;
-                            if (emit && slot + cnt < a.cand_cap) {
-                                Cand cd;
-                                cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = c.seg;
-                                cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
-                                cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
-                                cd.sample_rate = h.sample_rate;
-                                a.cand_tmp[slot + cnt] = cd;
-                            }
-                            cnt++;
-                        }
-                    }
-                }
-                return cnt;
-            };
-            const uint32_t cnt = hits ? walk(false, 0) : 0u;
-            uint32_t inc = cnt;
+            const TileBytes tb{dbase, ab, a.in, a.in_len};
+            const uint32_t cnt = hits ? sc_walk(a, tb, seg, c.seg, p0, lo, hi, hits, false, 0) : 0u;
+            if (__any_sync(FULL, cnt != 0)) {
+                uint32_t inc = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
-            n_tile = __shfl_sync(FULL, inc, 31);
-            if (n_tile) {
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
+                n_tile = __shfl_sync(FULL, inc, 31);
                 if (lane == 0) gbase = atomicAdd(&a.counters[0], n_tile);
                 gbase = __shfl_sync(FULL, gbase, 0);
-                if (cnt) walk(true, gbase + inc - cnt);
+                if (cnt) sc_walk(a, tb, seg, c.seg, p0, lo, hi, hits, true, gbase + inc - cnt);
             }
         }
         if (lane == 0) {
@@ -341,33 +379,58 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
     }
 }
 
-// single-CTA exclusive scan of chunk_count -> chunk_scan
-__global__ void __launch_bounds__(1024) k_chunk_scan(PassArgs a) {
-    __shared__ uint32_t s_part[1024];
-    const uint32_t tid = threadIdx.x, n = a.nchunks;
-    const uint32_t per = (n + 1023) / 1024;
-    uint32_t b = tid * per, e = min(b + per, n), sum = 0;
-    for (uint32_t i = b; i < e; i++) sum += a.chunk_count[i];
-    s_part[tid] = sum;
+// Orders the frame table: exclusive prefix of the per-tile candidate counts, then every tile's (already sorted) list
+// moves to its place.  One launch: each CTA scans a contiguous run of tiles with coalesced loads, publishes its total,
+// waits for the totals of the CTAs before it (the grid is at most one CTA per SM, so all of them are resident) and
+// copies its candidates.
+constexpr int ORD_THREADS = 1024;
+__global__ void __launch_bounds__(ORD_THREADS) k_order(PassArgs a, uint32_t per_cta, volatile uint32_t* blk_tot) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry, s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t t0 = blockIdx.x * per_cta, t1 = min(t0 + per_cta, a.nchunks);
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        uint32_t v = tid >= d ? s_part[tid - d] : 0;
+    // pass 1: local exclusive prefix (relative to the CTA's first tile) into chunk_scan
+    for (uint32_t b = t0; b < t1; b += ORD_THREADS) {
+        const uint32_t i = b + tid;
+        const uint32_t c = i < t1 ? a.chunk_count[i] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
+        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        s_part[tid] += v;
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, wi, d); if (lane >= (uint32_t)d) wi += o; }
+            s_warp[lane] = wi - w;                                   // exclusive over warps
+            if (lane == 31) s_base = wi;                             // total of this batch
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (i < t1) a.chunk_scan[i] = carry + s_warp[warp] + inc - c;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + s_base;
         __syncthreads();
     }
-    uint32_t run = s_part[tid] - sum;
-    for (uint32_t i = b; i < e; i++) { a.chunk_scan[i] = run; run += a.chunk_count[i]; }
-}
-
-// move each chunk's (already sorted) list to its place in the global frame table
-__global__ void __launch_bounds__(256) k_gather(PassArgs a) {
-    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t chunk = i0; chunk < a.nchunks; chunk += stride) {
-        const uint32_t n = a.chunk_count[chunk];
-        if (!n) continue;
-        const uint32_t src = a.chunk_base[chunk], dst = a.chunk_scan[chunk];
-        for (uint32_t r = 0; r < n; r++) a.cand[dst + r] = a.cand_tmp[src + r];
+    // publish the CTA total (+1 so that 0 means "not yet"), then sum the totals of the CTAs in front
+    if (tid == 0) { __threadfence(); blk_tot[blockIdx.x] = s_carry + 1u; }
+    uint32_t before = 0;
+    if (warp == 0) {
+        for (uint32_t b = lane; b < blockIdx.x; b += 32) { uint32_t v; while ((v = blk_tot[b]) == 0u) { } before += v - 1u; }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) before += __shfl_xor_sync(FULL, before, d);
+        if (lane == 0) s_base = before;
+    }
+    __syncthreads();
+    before = s_base;
+    // pass 2: final offsets + gather
+    for (uint32_t i = t0 + tid; i < t1; i += ORD_THREADS) {
+        const uint32_t dst = a.chunk_scan[i] + before;
+        a.chunk_scan[i] = dst;
+        const uint32_t n = a.chunk_count[i];
+        if (n) { const uint32_t src = a.chunk_base[i]; for (uint32_t r = 0; r < n; r++) a.cand[dst + r] = a.cand_tmp[src + r]; }
     }
 }
 
@@ -810,7 +873,7 @@ __global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_
 // a few words of MAPPED pinned memory written by k_publish, not through cudaMemcpy: a small copy would queue on the copy
 // engines behind the multi-megabyte uploads/downloads of the other sub-shards of a pipelined decode and stall the pass.
 __global__ void k_clear(uint32_t* counters, Totals* totals) {
-    if (threadIdx.x < 16) counters[threadIdx.x] = 0;
+    for (uint32_t i = threadIdx.x; i < 16 + 256; i += blockDim.x) counters[i] = 0;      // [0..15] counters, [16..271] k_order CTA totals
     if (threadIdx.x < sizeof(Totals) / 4) reinterpret_cast<uint32_t*>(totals)[threadIdx.x] = 0;
 }
 __global__ void k_publish(const uint32_t* src, uint32_t* dst_mapped, uint32_t nwords) {
@@ -1206,9 +1269,14 @@ void launch_scan(const PassArgs& a, void* stream) {
     if (!grid) grid = 1;
     k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); g_launches++;
 }
-void launch_order(const PassArgs& a, void* stream) {
-    k_chunk_scan<<<1, 1024, 0, S(stream)>>>(a); g_launches++;
-    k_gather<<<148 * 4, 256, 0, S(stream)>>>(a); g_launches++;
+void launch_order(const PassArgs& a, uint32_t* blk_tot, void* stream) {     // blk_tot: >= 256 words, zeroed by launch_clear
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; if (n_sm > 256) n_sm = 256; }
+    uint32_t per = (a.nchunks + n_sm - 1) / n_sm;
+    per = (per + ORD_THREADS - 1) / ORD_THREADS * ORD_THREADS;
+    if (!per) per = ORD_THREADS;
+    const uint32_t grid = a.nchunks ? (a.nchunks + per - 1) / per : 1;
+    k_order<<<grid, ORD_THREADS, 0, S(stream)>>>(a, per, blk_tot); g_launches++;
 }
 void launch_crc(const PassArgs& a, uint32_t nb, void* stream) {
     k_crc<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
