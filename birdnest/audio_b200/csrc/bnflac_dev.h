@@ -16,6 +16,9 @@ namespace bnf {
 
 constexpr int SCAN_CHUNK = 8192;       // bytes per scan tile (one warp); tile k of a segment covers [max(begin, A + k*8192), A + (k+1)*8192), A = begin & ~15
 constexpr int MAX_CH = 8;
+// layout of PassArgs::counters (words): [0] candidates appended, [1] overflow flags, then the per-CTA totals of the two
+// look-back kernels (at most 256 CTAs each)
+constexpr int CNT_ORDER = 16, CNT_PFX_CNT = CNT_ORDER + 256, CNT_PFX_BYTES = CNT_PFX_CNT + 256, CNT_WORDS = CNT_PFX_BYTES + 512;
 
 // per-candidate status
 enum : uint8_t {
@@ -83,7 +86,7 @@ struct PassArgs {
     uint32_t* chunk_base;
     uint32_t* chunk_count;
     uint32_t* chunk_scan;
-    uint32_t* counters;     // [0] total candidates appended, [1] overflow flags, [16..271] k_order's per-CTA totals
+    uint32_t* counters;     // CNT_WORDS words, see above
     uint16_t* pref;         // [tile][32] CRC-16 residue of the bytes from the start of the tile to the end of each 256-byte piece
     uint16_t* seg_crc;      // CRC-16 residue of each span between consecutive candidates (0 <=> the span is a frame whose CRC matches)
     uint32_t* next;
@@ -102,11 +105,11 @@ struct PassArgs {
 
 // launchers (kernels.cu); all asynchronous on `stream`
 void launch_scan(const PassArgs& a, void* stream);
-void launch_order(const PassArgs& a, uint32_t* blk_tot, void* stream);
+void launch_order(const PassArgs& a, void* stream);
 void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
-void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream);
+void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream);
 void launch_clear(const PassArgs& a, void* stream);                                   // counters + totals = 0
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream);  // <= 32 words to mapped host memory
 void launch_seg_summary(const PassArgs& a, uint32_t ncand_bound, uint64_t* seg_pcm, uint32_t* seg_flags, void* stream);

@@ -352,7 +352,7 @@ static int ensure_tables(bnflac* h) {
     if ((rc = h->d_chunk_count.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_chunk_scan.reserve(4ull * (h->nchunks + 1)))) return rc;
     if ((rc = h->d_pref.reserve(64ull * (h->nchunks + 1)))) return rc;
-    if ((rc = h->d_counters.reserve(4 * (16 + 256)))) return rc;
+    if ((rc = h->d_counters.reserve(4 * CNT_WORDS))) return rc;
     if ((rc = h->d_totals.reserve(sizeof(Totals)))) return rc;
     if ((rc = h->mailbox.reserve(256))) return rc;
     CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), sizeof(SegInfo) * segs.size(), cudaMemcpyHostToDevice, h->stream));
@@ -416,13 +416,13 @@ static int run_front(bnflac* h) {
         break;
     }
     CK(cudaEventRecord(h->ev[1], h->stream));
-    launch_order(h->args, h->d_counters.as<uint32_t>() + 16, h->stream);
+    launch_order(h->args, h->stream);
     launch_crc(h->args, h->ncand, h->stream);
     CK(cudaEventRecord(h->ev[2], h->stream));
     launch_link(h->args, h->ncand, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
     launch_parse(h->args, h->ncand, h->stream);
-    launch_prefix(h->args, h->info.bytes_per_sample, h->stream);
+    launch_prefix(h->args, h->ncand, h->info.bytes_per_sample, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
     static_assert(sizeof(Totals) % 4 == 0 && sizeof(Totals) / 4 <= 32 - 16, "totals fit the mailbox");
     launch_publish(h->d_totals.p, (uint8_t*)h->mailbox.p + 64, sizeof(Totals) / 4, h->stream);

@@ -16,6 +16,7 @@
 #include "bnflac_dev.h"
 #include <cuda_runtime.h>
 #include <type_traits>
+#include <cstdlib>
 
 namespace bnf {
 
@@ -825,55 +826,76 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ prefix
-__global__ void __launch_bounds__(1024) k_prefix(PassArgs a, uint32_t bytes_per_sample) {
-    __shared__ uint64_t s_bytes[1024];
-    __shared__ uint32_t s_cnt[1024];
-    __shared__ uint32_t s_maxbs[32];
-    const uint32_t tid = threadIdx.x, n = ncand(a);
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t b = min(tid * per, n), e = min(b + per, n);
-    uint64_t bytes = 0; uint32_t cnt = 0, maxbs = 0;
-    for (uint32_t i = b; i < e; i++) {
-        uint8_t st = a.status[i];
-        const Cand& c = a.cand[i];
-        if ((st == ST_OK || st == ST_CRC) && !(c.flags & 2)) {
-            uint32_t ch = c.assign < 8 ? c.assign + 1u : 2u;
-            bytes += (uint64_t)c.bs * ch * bytes_per_sample; cnt++;
-            maxbs = max(maxbs, c.bs);
-        }
+// Accepted-frame compaction + PCM byte offsets.  Same shape as k_order: every CTA reduces a contiguous run of the frame
+// table, publishes (bytes, count), sums what the CTAs in front published, then scans its run and writes the offsets.
+__device__ __forceinline__ bool frame_delivered(const PassArgs& a, uint32_t i, uint32_t& bs, uint32_t& ch) {
+    const uint8_t st = a.status[i];
+    const Cand& c = a.cand[i];
+    bs = c.bs; ch = c.assign < 8 ? c.assign + 1u : 2u;
+    return (st == ST_OK || st == ST_CRC) && !(c.flags & 2);
+}
+__global__ void __launch_bounds__(ORD_THREADS) k_prefix(PassArgs a, uint32_t bytes_per_sample, uint32_t per_cta, volatile uint32_t* blk_cnt, volatile unsigned long long* blk_bytes) {
+    __shared__ unsigned long long s_wb[32];
+    __shared__ uint32_t s_wc[32];
+    __shared__ unsigned long long s_cb, s_tb;
+    __shared__ uint32_t s_cc, s_tc;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = ncand(a);
+    const uint32_t t0 = min(blockIdx.x * per_cta, n), t1 = min(t0 + per_cta, n);
+    // pass 1: totals of this CTA's run
+    unsigned long long bytes = 0; uint32_t cnt = 0, maxbs = 0;
+    for (uint32_t i = t0 + tid; i < t1; i += ORD_THREADS) {
+        uint32_t bs, ch;
+        if (frame_delivered(a, i, bs, ch)) { bytes += (unsigned long long)bs * ch * bytes_per_sample; cnt++; maxbs = max(maxbs, bs); }
     }
-    s_bytes[tid] = bytes; s_cnt[tid] = cnt;
-    maxbs = __reduce_max_sync(FULL, maxbs);
-    if ((tid & 31) == 0) s_maxbs[tid >> 5] = maxbs;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { bytes += __shfl_xor_sync(FULL, bytes, d); cnt += __shfl_xor_sync(FULL, cnt, d); maxbs = max(maxbs, __shfl_xor_sync(FULL, maxbs, d)); }
+    if (lane == 0) { s_wb[warp] = bytes; s_wc[warp] = cnt; if (maxbs) atomicMax(&a.totals->max_bs, maxbs); }
     __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        uint64_t vb = tid >= d ? s_bytes[tid - d] : 0; uint32_t vc = tid >= d ? s_cnt[tid - d] : 0;
+    if (warp == 0) {
+        bytes = s_wb[lane]; cnt = s_wc[lane];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { bytes += __shfl_xor_sync(FULL, bytes, d); cnt += __shfl_xor_sync(FULL, cnt, d); }
+        if (lane == 0) { s_tb = bytes; s_tc = cnt; blk_bytes[blockIdx.x] = bytes; __threadfence(); blk_cnt[blockIdx.x] = cnt + 1u; }
+        unsigned long long bb = 0; uint32_t bc = 0;
+        for (uint32_t b = lane; b < blockIdx.x; b += 32) { uint32_t v; while ((v = blk_cnt[b]) == 0u) { } __threadfence(); bc += v - 1u; bb += blk_bytes[b]; }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { bb += __shfl_xor_sync(FULL, bb, d); bc += __shfl_xor_sync(FULL, bc, d); }
+        if (lane == 0) { s_cb = bb; s_cc = bc; }
+    }
+    __syncthreads();
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        a.totals->pcm_bytes = s_cb + s_tb; a.totals->n_accepted = s_cc + s_tc; a.totals->n_cand = n; a.totals->overflow = a.counters[1];
+    }
+    // pass 2: offsets
+    for (uint32_t b = t0; b < t1; b += ORD_THREADS) {
+        const uint32_t i = b + tid;
+        uint32_t bs = 0, ch = 0;
+        const bool ok = i < t1 && frame_delivered(a, i, bs, ch);
+        const unsigned long long v = ok ? (unsigned long long)bs * ch * bytes_per_sample : 0ull;
+        unsigned long long ib = v; uint32_t ic = ok ? 1u : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long ob = __shfl_up_sync(FULL, ib, d); const uint32_t oc = __shfl_up_sync(FULL, ic, d); if (lane >= (uint32_t)d) { ib += ob; ic += oc; } }
+        __syncthreads();                               // (s_wb / s_wc of the previous batch have been read)
+        if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
         __syncthreads();
-        s_bytes[tid] += vb; s_cnt[tid] += vc;
+        unsigned long long wb = 0; uint32_t wc = 0;
+        for (uint32_t w = 0; w < warp; w++) { wb += s_wb[w]; wc += s_wc[w]; }
+        const unsigned long long cb = s_cb; const uint32_t cc = s_cc;
+        if (i < t1) {
+            a.pcm_off[i] = cb + wb + ib - v;
+            if (ok) a.acc_idx[cc + wc + ic - 1u] = i;
+        }
+        __syncthreads();
+        if (tid == ORD_THREADS - 1) { s_cb = cb + wb + ib; s_cc = cc + wc + ic; }
         __syncthreads();
     }
-    uint64_t rb = s_bytes[tid] - bytes; uint32_t rc = s_cnt[tid] - cnt;
-    for (uint32_t i = b; i < e; i++) {
-        uint8_t st = a.status[i];
-        const Cand& c = a.cand[i];
-        if ((st == ST_OK || st == ST_CRC) && !(c.flags & 2)) {
-            uint32_t ch = c.assign < 8 ? c.assign + 1u : 2u;
-            a.pcm_off[i] = rb; a.acc_idx[rc] = i;
-            rb += (uint64_t)c.bs * ch * bytes_per_sample; rc++;
-        } else a.pcm_off[i] = rb;
-    }
-    if (tid == 1023) {
-        a.totals->pcm_bytes = s_bytes[1023]; a.totals->n_accepted = s_cnt[1023]; a.totals->n_cand = n;
-        a.totals->overflow = a.counters[1];
-    }
-    if (tid == 0) { uint32_t m = 0; for (int w = 0; w < 32; w++) m = max(m, s_maxbs[w]); a.totals->max_bs = m; }
 }
 
 // start-of-pass reset and end-of-stage hand-off to the host.  The host learns the candidate count and the totals through
 // a few words of MAPPED pinned memory written by k_publish, not through cudaMemcpy: a small copy would queue on the copy
 // engines behind the multi-megabyte uploads/downloads of the other sub-shards of a pipelined decode and stall the pass.
-__global__ void k_clear(uint32_t* counters, Totals* totals) {
-    for (uint32_t i = threadIdx.x; i < 16 + 256; i += blockDim.x) counters[i] = 0;      // [0..15] counters, [16..271] k_order CTA totals
+__global__ void __launch_bounds__(256) k_clear(uint32_t* counters, Totals* totals) {
+    for (uint32_t i = threadIdx.x; i < CNT_WORDS; i += blockDim.x) counters[i] = 0;     // counters, k_order / k_prefix CTA totals
     if (threadIdx.x < sizeof(Totals) / 4) reinterpret_cast<uint32_t*>(totals)[threadIdx.x] = 0;
 }
 __global__ void k_publish(const uint32_t* src, uint32_t* dst_mapped, uint32_t nwords) {
@@ -911,7 +933,13 @@ __global__ void __launch_bounds__(256) k_seg_summary(PassArgs a, uint64_t* seg_p
 // phases and the vector row reads of the pack phase are bank-conflict free.
 enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 
-template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : 48; };
+#ifndef DEC_MAXNREG
+#define DEC_MAXNREG 112
+#endif
+#ifndef DEC_TILE
+#define DEC_TILE 48
+#endif
+template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : DEC_TILE; };
 
 struct RiceSt {
     uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
@@ -931,40 +959,35 @@ __device__ __forceinline__ void rice_param(RingBits& br, RiceSt& rs) {
 }
 
 // ---- restore: one block of ORD samples of this lane's column, in place
+// `h` is a ring: before a block that starts at sample t0, h[j] holds sample t0 - ORD + j; step j reads every tap from a
+// fixed register and then overwrites h[j] (whose old value, the oldest sample, was used for the last time in that step).
 template <int ORD, bool FIRST, bool EXTRA>
 __device__ __forceinline__ void restore_block_i32(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
                                                   uint32_t order, uint32_t shift, uint32_t wasted) {
-    int32_t nw[ORD];
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
         const int32_t r = (int32_t)lds32(addr + j * rs4);
         uint32_t sum = 0;
 #pragma unroll
-        for (int m = ORD - 1; m >= 0; m--) {
-            const int32_t hv = (m < j) ? nw[(j - 1 - m) < 0 ? 0 : (j - 1 - m)] : h[(m - j) < 0 ? 0 : (m - j)];
-            sum += (uint32_t)cf[m] * (uint32_t)hv;
-        }
+        for (int m = ORD - 1; m >= 0; m--) sum += (uint32_t)cf[m] * (uint32_t)h[(j - 1 - m + 2 * ORD) % ORD];
         int32_t s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
         if (FIRST) { if (j < (int)order) s = r; }
-        nw[j] = s;
+        h[j] = s;
         if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
         else sts32(addr + j * rs4, (uint32_t)s);
     }
-#pragma unroll
-    for (int m = 0; m < ORD; m++) h[m] = nw[ORD - 1 - m];
 }
 
 template <int ORD, bool FIRST, bool EXTRA>
 __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, const double (&cf)[ORD], double (&h)[ORD],
                                                   uint32_t order, uint32_t sh_n, uint32_t wasted) {
-    double nw[ORD];
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
         const int32_t r = (int32_t)lds32(addr + j * rs4);
         double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
         for (int m = ORD - 1; m >= 0; m--) {
-            const double hv = (m < j) ? nw[(j - 1 - m) < 0 ? 0 : (j - 1 - m)] : h[(m - j) < 0 ? 0 : (m - j)];
+            const double hv = h[(j - 1 - m + 2 * ORD) % ORD];
             if (ORD > 16 && (m & 1)) acc1 = fma(cf[m], hv, acc1);
             else acc0 = fma(cf[m], hv, acc0);
         }
@@ -974,12 +997,10 @@ __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, c
         if (EXTRA) p >>= sh_n;
         int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
         if (FIRST) { if (j < (int)order) s = r; }
-        nw[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
+        h[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
         if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
         else sts32(addr + j * rs4, (uint32_t)s);
     }
-#pragma unroll
-    for (int m = 0; m < ORD; m++) h[m] = nw[ORD - 1 - m];
 }
 
 template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
@@ -1086,7 +1107,7 @@ constexpr int DEC_WARPS = 2;                  // independent warps per CTA (no C
 __host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
 
 template <int ORD, bool WIDE>
-__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? 112 : 255) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
+__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : 255) k_decode(PassArgs a, uint32_t C, uint32_t B, uint32_t S) {
     constexpr int T = DecCfg<ORD>::T;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1269,9 +1290,14 @@ void launch_scan(const PassArgs& a, void* stream) {
     if (!grid) grid = 1;
     k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); g_launches++;
 }
-void launch_order(const PassArgs& a, uint32_t* blk_tot, void* stream) {     // blk_tot: >= 256 words, zeroed by launch_clear
+static int sm_count() {
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; if (n_sm > 256) n_sm = 256; }
+    return n_sm;
+}
+void launch_order(const PassArgs& a, void* stream) {
+    const int n_sm = sm_count();
+    uint32_t* blk_tot = a.counters + CNT_ORDER;
     uint32_t per = (a.nchunks + n_sm - 1) / n_sm;
     per = (per + ORD_THREADS - 1) / ORD_THREADS * ORD_THREADS;
     if (!per) per = ORD_THREADS;
@@ -1288,10 +1314,15 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
     k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * RingBits::STRIDE, S(stream)>>>(a); g_launches++;
 }
-void launch_prefix(const PassArgs& a, uint32_t bytes_per_sample, void* stream) {
-    k_prefix<<<1, 1024, 0, S(stream)>>>(a, bytes_per_sample); g_launches++;
+void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream) {
+    const int n_sm = sm_count();
+    uint32_t per = (ncand_bound + n_sm - 1) / n_sm;
+    per = (per + ORD_THREADS - 1) / ORD_THREADS * ORD_THREADS;
+    if (!per) per = ORD_THREADS;
+    const uint32_t grid = ncand_bound ? (ncand_bound + per - 1) / per : 1;
+    k_prefix<<<grid, ORD_THREADS, 0, S(stream)>>>(a, bytes_per_sample, per, a.counters + CNT_PFX_CNT, reinterpret_cast<unsigned long long*>(a.counters + CNT_PFX_BYTES)); g_launches++;
 }
-void launch_clear(const PassArgs& a, void* stream) { k_clear<<<1, 32, 0, S(stream)>>>(a.counters, a.totals); g_launches++; }
+void launch_clear(const PassArgs& a, void* stream) { k_clear<<<1, 256, 0, S(stream)>>>(a.counters, a.totals); g_launches++; }
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream) {
     k_publish<<<1, 32, 0, S(stream)>>>((const uint32_t*)src, (uint32_t*)dst_mapped, nwords); g_launches++;
 }
@@ -1320,7 +1351,8 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
     uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
     if (resident < 1) resident = 1;
-    if (resident < (uint32_t)max_resident) {
+    static const bool balance = !(getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '0');
+    if (balance && resident < (uint32_t)max_resident) {
         size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
         if (want > 200 * 1024) want = 200 * 1024;
         if (want > smem) smem = want;
