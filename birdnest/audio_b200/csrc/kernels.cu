@@ -603,6 +603,22 @@ struct RingBits {
         return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), p);
     }
     __device__ __forceinline__ uint32_t window() const { return window_at(pos); }
+    // Register-cached window for the branch-free groups: w0:w1 are the two big-endian words under the read position, w2
+    // (still little-endian) the word after them.  A codeword advances the position by at most 32 bits, so at most one
+    // word is crossed per step; the word that will be needed after the NEXT crossing is loaded on every step, which
+    // takes the shared-memory latency off the position -> window -> length -> position dependency chain.
+    struct Win3 { uint32_t w0, w1, w2; };
+    __device__ __forceinline__ Win3 win_init(uint32_t p) const {
+        const uint32_t ad = sring + ((p >> 3) & (RB_BYTES - 4));
+        Win3 w; w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = lds32(ad + 8);
+        return w;
+    }
+    __device__ __forceinline__ static uint32_t win_peek(const Win3& w, uint32_t p) { return __funnelshift_l(w.w1, w.w0, p); }
+    __device__ __forceinline__ void win_advance(Win3& w, uint32_t p, uint32_t np) const {
+        const uint32_t nw = lds32(sring + (((np >> 3) + 8) & (RB_BYTES - 4)));
+        if ((p ^ np) & 32u) { w.w0 = w.w1; w.w1 = __byte_perm(w.w2, 0, 0x0123); }
+        w.w2 = nw;
+    }
     __device__ __forceinline__ void skip(uint32_t n) { pos += n; }                        // n <= 32, covered by the checkpoint budget
     __device__ __forceinline__ void jump(uint32_t n) { pos += n; ensure_now(); }          // any n
     __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); pos += n; return v; }          // n <= 32
@@ -769,11 +785,14 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                 uint32_t pos = br.pos;
                 const uint32_t k = ps.k, kp32 = ps.kp32;
                 bool ovf = false;
+                RingBits::Win3 wn = br.win_init(pos);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const uint32_t f = bfind(br.window_at(pos));
+                    const uint32_t f = bfind(RingBits::win_peek(wn, pos));
                     ovf |= (int32_t)(f - k) < 0;
-                    pos += kp32 - f;
+                    const uint32_t np = pos + kp32 - f;
+                    if (j < 7) br.win_advance(wn, pos, np);
+                    pos = np;
                 }
                 if (walk) {
                     ps.left -= 8;
@@ -1217,15 +1236,18 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                 const uint32_t k = rs.k, kp32 = rs.kp32, negP = rs.negP, c30 = rs.c30;
                 bool ovf = false;
                 int32_t r[8];
+                RingBits::Win3 wn = br.win_init(pos);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const uint32_t w = br.window_at(pos);
+                    const uint32_t w = RingBits::win_peek(wn, pos);
                     const uint32_t f = bfind(w);
                     const uint32_t d = f - k;
                     ovf |= (int32_t)d < 0;
+                    const uint32_t np = pos + kp32 - f;
+                    if (j < 7) br.win_advance(wn, pos, np);
+                    pos = np;
                     const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
                     r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                    pos += kp32 - f;
                 }
                 if (!inert) {
                     rs.fastleft -= 8;
@@ -1351,7 +1373,7 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
     uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
     if (resident < 1) resident = 1;
-    static const bool balance = !(getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '0');
+    static const bool balance = getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '1';
     if (balance && resident < (uint32_t)max_resident) {
         size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
         if (want > 200 * 1024) want = 200 * 1024;
