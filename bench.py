@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -154,8 +154,10 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     s = make_stream(min(args.seconds, UNIQUE_SECONDS))
     n_all = s.total_samples * s.channels
-    reps = 2
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    # calibrate so that one step is ~8 s of CPU work on every host thread (bounded sample of the 1 h workload)
+    _, _, dt1 = cpu_decode_rate(s.flac, n_all, cores, 1)
+    reps = max(2, min(200, int(8.0 / max(dt1, 1e-3))))
+    for _ in range(1 if args.warmup else 0):
         cpu_decode_rate(s.flac, n_all, cores, 1)
     rates, kind, secs = [], "port", 0.0
     for _ in range(args.steps):
@@ -303,7 +305,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": {"decode": "k_decode", "parse": "k_parse", "crc": "k_crc", "scan": "k_scan"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": units_bytes},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "bnflac_open_memory(pinned host FLAC, BORROW_INPUT) + bnflac_decode_all(pinned host PCM): pipelined sub-shards, PCIe both ways inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -311,7 +314,8 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             uniq = make_stream(min(args.seconds, UNIQUE_SECONDS)) if args.seconds > UNIQUE_SECONDS else s
             n_all = uniq.total_samples * uniq.channels
-            reps = 4
+            _, _, dt1 = cpu_decode_rate(uniq.flac, n_all, cores, 1)
+            reps = max(4, min(400, int(15.0 / max(dt1, 1e-3))))          # ~15 s of CPU work per host thread
             r, kind, dt = cpu_decode_rate(uniq.flac, n_all, cores, reps)
             line["cpu_baseline"] = {"value": r, "unit": "samples/s", "cores": cores, "kind": kind,
                                     "sample": f"{reps} x {min(args.seconds, UNIQUE_SECONDS)} s tile of the cfg2 stream on each of {cores} threads ({dt:.1f} s wall)"}
@@ -324,7 +328,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=int, default=3600, help="stream length (default: the named 1 h configuration)")

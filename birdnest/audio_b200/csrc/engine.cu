@@ -235,6 +235,7 @@ struct bnflac {
     cudaEvent_t ev[10] = {};             // 0..5 stage boundaries, 6/7 pipelined start/end, 8 upload done
     cudaStream_t up_stream = nullptr;    // (pipelined parent) all sub-shard uploads, in order
     bnflac_timing timing{};
+    int launches0 = 0;
 
     PinBuf mailbox;                     // mapped pinned words the kernels publish counters / totals into
     // pipelined host decode
@@ -393,6 +394,7 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
 static int run_front(bnflac* h) {
     int rc;
     CK(cudaSetDevice(h->device));
+    h->launches0 = kernel_launch_count();
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = ensure_input(h))) return rc;
     if ((rc = ensure_tables(h))) return rc;
@@ -448,7 +450,7 @@ static int finish_timing(bnflac* h) {
     auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, h->ev[a], h->ev[b]); return t; };
     h->timing.scan = ms(0, 1); h->timing.crc = ms(1, 2); h->timing.link = ms(2, 3); h->timing.parse = ms(3, 4);
     h->timing.decode = ms(4, 5); h->timing.total = ms(0, 5);
-    h->timing.launches = 10;
+    h->timing.launches = (uint32_t)(kernel_launch_count() - h->launches0);
     return 0;
 }
 
