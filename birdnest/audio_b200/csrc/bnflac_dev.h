@@ -18,6 +18,8 @@ constexpr int SCAN_CHUNK = 8192;       // bytes per scan tile (one warp); tile k
 constexpr int MAX_CH = 8;
 // layout of PassArgs::counters (words): [0] candidates appended, [1] overflow flags, then the per-CTA totals of the two
 // look-back kernels (at most 256 CTAs each)
+constexpr int CNT_ANOM = 2;            // candidates off the clean frame chain (k_parse -> k_resync)
+constexpr uint32_t ANOM_CAP = 8192;
 constexpr int CNT_ORDER = 16, CNT_PFX_CNT = CNT_ORDER + 256, CNT_PFX_BYTES = CNT_PFX_CNT + 256, CNT_WORDS = CNT_PFX_BYTES + 512;
 
 // per-candidate status
@@ -25,7 +27,10 @@ enum : uint8_t {
     ST_OK = 0,
     ST_LOST = 1,         // (host side only) gap before this frame
     ST_CRC = 3,          // CRC-16 mismatch: frame is delivered zero-filled (reference behaviour)
-    ST_UNPARSEABLE = 4,  // reserved field used: frame is skipped
+    ST_UNPARSEABLE = 4,  // reserved field used: frame is not delivered, the reference reports UNPARSEABLE_STREAM
+    ST_LOSTSYNC = 5,     // parse failed (pad bit, ran past any possible frame end): not delivered, the reference reports LOST_SYNC
+    ST_EOS = 7,          // parse ran off the end of the stream: the reference stops decoding here (END_OF_STREAM)
+    ST_SKIP = 6,         // never reached by the reference's cursor (it resumed past this candidate after a damaged frame)
     ST_CHECK = 0xFE,     // span check inconclusive: K2 validates by parsing
     ST_DROP = 0xFF       // false sync / covered by another frame
 };
@@ -92,6 +97,7 @@ struct PassArgs {
     uint32_t* next;
     uint32_t* flen;
     uint8_t* status;
+    uint32_t* anom;         // ANOM_CAP candidate indices that are off the clean chain (unordered)
     // K2
     SubInfo* sub;
     // prefix
@@ -109,6 +115,7 @@ void launch_order(const PassArgs& a, void* stream);
 void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
+void launch_resync(const PassArgs& a, void* stream);
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream);
 void launch_clear(const PassArgs& a, void* stream);                                   // counters + totals = 0
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream);  // <= 32 words to mapped host memory

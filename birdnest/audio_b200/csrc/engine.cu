@@ -225,7 +225,7 @@ struct bnflac {
     std::vector<SegDesc> batch_segs;           // batch passes: segments given explicitly (coordinates of d_in)
 
     // device state
-    DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_pref,
+    DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_pref, d_anom,
         d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags;
     uint32_t nchunks = 0, cand_cap = 0, nsegs = 0;
     bool tables_ready = false;
@@ -253,7 +253,7 @@ struct bnflac {
         for (bnflac* k : kids) delete k;
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
-        DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref,
+        DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref, &d_anom,
                          &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags};
         for (DevBuf* b : all) b->release();
         pcm_host.release(); mailbox.release();
@@ -356,6 +356,7 @@ static int ensure_tables(bnflac* h) {
     if ((rc = h->d_counters.reserve(4 * CNT_WORDS))) return rc;
     if ((rc = h->d_totals.reserve(sizeof(Totals)))) return rc;
     if ((rc = h->mailbox.reserve(256))) return rc;
+    if ((rc = h->d_anom.reserve(4ull * ANOM_CAP))) return rc;
     CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), sizeof(SegInfo) * segs.size(), cudaMemcpyHostToDevice, h->stream));
     if (!chunks.empty()) CK(cudaMemcpyAsync(h->d_chunks.p, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // segs / chunks are locals
@@ -366,6 +367,7 @@ static int ensure_tables(bnflac* h) {
     h->args.chunk_base = h->d_chunk_base.as<uint32_t>(); h->args.chunk_count = h->d_chunk_count.as<uint32_t>();
     h->args.chunk_scan = h->d_chunk_scan.as<uint32_t>(); h->args.counters = h->d_counters.as<uint32_t>();
     h->args.pref = h->d_pref.as<uint16_t>();
+    h->args.anom = h->d_anom.as<uint32_t>();
     h->args.totals = h->d_totals.as<Totals>();
     h->tables_ready = true;
     return 0;
@@ -424,6 +426,7 @@ static int run_front(bnflac* h) {
     launch_link(h->args, h->ncand, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
     launch_parse(h->args, h->ncand, h->stream);
+    launch_resync(h->args, h->stream);
     launch_prefix(h->args, h->ncand, h->info.bytes_per_sample, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
     static_assert(sizeof(Totals) % 4 == 0 && sizeof(Totals) / 4 <= 32 - 16, "totals fit the mailbox");
@@ -601,9 +604,68 @@ static int decode_host(bnflac* h, uint8_t* dst, size_t cap, uint64_t* written) {
     return decode_host_single(h, dst, cap, written);
 }
 
-// Builds the host-side frame / subframe / error tables of one pass.  `expect` is where the next frame should start
-// (carried across the sub-shards of a pipelined decode so that the events are those of an unsharded decode).
-static int collect_diag(bnflac* h, uint64_t& expect, uint64_t pcm_base, const uint8_t* host_ptr, uint64_t stream_len,
+// ---- diagnostics: frame / subframe tables and the error-callback events the reference would have raised
+namespace {
+// Frame header check of the reference's sync search: 0 valid, 1 BAD_HEADER (CRC-8 / syntax), 3 UNPARSEABLE
+// (reserved values), -1 truncated.  Host side, only ever run on the few bytes the decoder skipped in a damaged stream.
+int header_rc(const uint8_t* p, size_t avail) {
+    if (avail < 5) return -1;
+    bool unparse = (p[1] & 0x02) != 0;
+    const bool variable = p[1] & 1;
+    const int bsc = p[2] >> 4, src = p[2] & 15, ca = p[3] >> 4, ssc = (p[3] >> 1) & 7;
+    if ((p[3] & 1) || bsc == 0 || ca > 10 || ssc == 3 || ssc == 7) unparse = true;
+    if (src == 15) return 1;
+    size_t q = 4;
+    uint32_t x = p[q++];
+    if (x >= 0x80) {
+        int n = 0;
+        while (x & (0x80u >> n)) n++;
+        if (n == 1 || n > 7 || (!variable && n == 7)) return 1;
+        for (int i = 1; i < n; i++) { if (q >= avail) return -1; if ((p[q++] >> 6) != 2) return 1; }
+    }
+    q += (bsc == 6) ? 1 : (bsc == 7) ? 2 : 0;
+    q += (src == 12) ? 1 : (src == 13 || src == 14) ? 2 : 0;
+    if (q + 1 > avail) return -1;
+    uint32_t c = 0;
+    for (size_t i = 0; i < q; i++) { c ^= p[i]; for (int k = 0; k < 8; k++) c = (c & 0x80) ? ((c << 1) ^ 0x07) & 0xFF : (c << 1) & 0xFF; }
+    if (c != p[q]) return 1;
+    return unparse ? 3 : 0;
+}
+
+struct DiagCursor {          // the reference's sync-search state, carried across the sub-shards of a pipelined decode
+    uint64_t expect = 0;     // where its cursor stands
+    bool in_sync = true;     // LOST_SYNC is reported once per excursion
+    bool ended = false;      // a truncated header ended the stream
+    bool have_expect = true; // false: (shard > 0) start at the first frame found, whatever lies before it
+};
+} // namespace
+
+// bytes [from, to) of the stream as the reference sees them while hunting for a sync code
+static void scan_gap(bnflac* h, const uint8_t* host_ptr, uint64_t stream_len, DiagCursor& cur, uint64_t to, std::vector<uint32_t>& errors) {
+    if (cur.ended || cur.expect >= to) return;
+    const uint64_t from = cur.expect;
+    const uint64_t hi = std::min<uint64_t>(stream_len, to + 32);          // a header that starts in the gap may end after it
+    std::vector<uint8_t> tmp;
+    const uint8_t* d;
+    if (host_ptr) d = host_ptr + from;
+    else { tmp.resize((size_t)(hi - from)); cudaMemcpy(tmp.data(), h->d_ext + from, tmp.size(), cudaMemcpyDeviceToHost); d = tmp.data(); }
+    uint64_t pos = from;
+    while (pos < to && pos + 2 <= stream_len) {
+        const uint8_t* p = d + (pos - from);
+        if (!(p[0] == 0xFF && (p[1] & 0xFC) == 0xF8)) { if (cur.in_sync) { errors.push_back(0); cur.in_sync = false; } pos++; continue; }
+        const int rc = header_rc(p, (size_t)std::min<uint64_t>(hi - pos, stream_len - pos));
+        if (rc < 0) { cur.ended = true; break; }
+        if (rc == 1) { errors.push_back(1); cur.in_sync = true; pos += 2; continue; }
+        if (rc == 3) { errors.push_back(3); cur.in_sync = true; pos += 2; continue; }
+        // a valid header the engine did not consider (frame of another format, cut off by the end of the stream)
+        if (cur.in_sync) { errors.push_back(0); cur.in_sync = false; }
+        pos++;
+    }
+    cur.expect = std::max(cur.expect, to);
+}
+
+// Builds the host-side frame / subframe / error tables of one pass, replaying the reference's cursor over the frame table.
+static int collect_diag(bnflac* h, DiagCursor& cur, uint64_t pcm_base, const uint8_t* host_ptr, uint64_t stream_len,
                         std::vector<bnflac_frame_t>& frames, std::vector<bnflac_subframe_t>& subs, std::vector<uint32_t>& errors) {
     CK(cudaSetDevice(h->device));
     const uint32_t n = h->ncand;
@@ -616,28 +678,28 @@ static int collect_diag(bnflac* h, uint64_t& expect, uint64_t pcm_base, const ui
         CK(cudaMemcpy(sub.data(), h->d_sub.p, sizeof(SubInfo) * MAX_CH * (size_t)n, cudaMemcpyDeviceToHost));
     }
     const uint64_t base = h->d_ext ? 0 : h->slice_begin;
-    for (uint32_t i = 0; i < n; i++) {
+    for (uint32_t i = 0; i < n && !cur.ended; i++) {
         if (cand[i].flags & 2) continue;
-        if (st[i] == ST_UNPARSEABLE) { errors.push_back(3); continue; }
-        if (st[i] != ST_OK && st[i] != ST_CRC) continue;
+        const bool is_frame = st[i] == ST_OK || st[i] == ST_CRC;
+        if (!is_frame && st[i] != ST_LOSTSYNC && st[i] != ST_UNPARSEABLE && st[i] != ST_EOS) continue;      // covered by a frame / never reached
+        const uint64_t off = cand[i].off + base;
+        if (!cur.have_expect) { cur.expect = off; cur.have_expect = true; }
+        scan_gap(h, host_ptr, stream_len, cur, off, errors);
+        if (cur.ended) break;
+        if (st[i] == ST_EOS) { cur.ended = true; break; }         // the stream ended inside this frame
+        if (!is_frame) {                                          // the parse failed: reported, cursor resumes two bytes further
+            errors.push_back(st[i] == ST_LOSTSYNC ? 0u : 3u);
+            cur.in_sync = false;
+            cur.expect = off + 2;
+            continue;
+        }
         bnflac_frame_t f{};
-        f.offset = cand[i].off + base; f.length = fl[i]; f.blocksize = cand[i].bs;
+        f.offset = off; f.length = fl[i]; f.blocksize = cand[i].bs;
         f.channels = (uint8_t)(cand[i].assign < 8 ? cand[i].assign + 1 : 2); f.bits_per_sample = cand[i].bps; f.assignment = cand[i].assign;
         f.status = st[i] == ST_OK ? BNFLAC_FRAME_OK : BNFLAC_FRAME_CRC_MISMATCH;
         f.number = cand[i].number; f.pcm_offset = po[i] + pcm_base;
-        if (f.offset != expect) {
-            // bytes were skipped before this frame.  The reference reports BAD_HEADER first when the skipped bytes begin
-            // with a sync code whose header did not validate, then LOST_SYNC (observed on the DLL, tests/golden faults)
-            uint8_t two[2] = {0, 0};
-            if (expect + 2 <= stream_len) {
-                if (host_ptr) memcpy(two, host_ptr + expect, 2);
-                else cudaMemcpy(two, h->d_ext + expect, 2, cudaMemcpyDeviceToHost);
-            }
-            if (two[0] == 0xFF && (two[1] & 0xFC) == 0xF8) errors.push_back(1);
-            errors.push_back(0);
-        }
         if (st[i] == ST_CRC) errors.push_back(2);              // FRAME_CRC_MISMATCH
-        expect = f.offset + f.length;
+        cur.expect = f.offset + f.length; cur.in_sync = true;
         frames.push_back(f);
         for (int c = 0; c < MAX_CH; c++) {
             bnflac_subframe_t s{};
@@ -651,12 +713,15 @@ static int collect_diag(bnflac* h, uint64_t& expect, uint64_t pcm_base, const ui
 static int fetch_diag(bnflac* h) {
     if (h->diag_valid) return 0;
     h->frames.clear(); h->subs.clear(); h->errors.clear();
-    uint64_t expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
+    DiagCursor cur;
+    cur.expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
+    cur.have_expect = h->own_begin <= h->info.first_frame_offset;      // a later shard starts wherever its first frame starts
     int rc;
     if (!h->kids.empty()) {
         for (bnflac* c : h->kids)
-            if ((rc = collect_diag(c, expect, c->pcm_base, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
-    } else if ((rc = collect_diag(h, expect, 0, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
+            if ((rc = collect_diag(c, cur, c->pcm_base, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
+    } else if ((rc = collect_diag(h, cur, 0, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
+    if (h->own_end >= h->len && cur.have_expect) scan_gap(h, h->host_ptr, h->len, cur, h->len, h->errors);   // what follows the last frame
     h->diag_valid = true;
     return 0;
 }

@@ -461,30 +461,30 @@ __device__ uint32_t tile_prefix(const PassArgs& a, const SegInfo& sg, uint64_t p
     return r;
 }
 
-// The residue of every span between consecutive candidates, from the tile-prefix residues k_scan left behind:
-// res[a, e) = G(e) - G(a) x^(8 (e - a)) inside one tile; across tiles the tail of the first tile, whole tiles in between
+// The CRC-16 residue of the bytes [b, e) of a segment from the tile-prefix residues k_scan left behind:
+// res[b, e) = G(e) - G(b) x^(8 (e - b)) inside one tile; across tiles the tail of the first tile, whole tiles in between
 // (each one multiplication by x^(8 * 8192) == x^2) and the head of the last.
+__device__ uint32_t span_residue(const PassArgs& a, const SegInfo& sg, uint64_t b, uint64_t e) {
+    uint32_t ta, oa, te, oe;
+    const uint32_t ga = tile_prefix(a, sg, b, false, ta, oa);
+    const uint32_t ge = tile_prefix(a, sg, e, true, te, oe);
+    if (ta == te) return res_append(ga, oe - oa, ge);                       // GF(2): subtraction is XOR
+    uint32_t r = res_append(ga, SCAN_CHUNK - oa, a.pref[(uint64_t)ta * 32 + 31]);
+    for (uint32_t t = ta + 1; t < te; t++) {
+        const uint32_t w = a.pref[(uint64_t)t * 32 + 31];
+        r = ((r ^ w) & 0x8000u) | (q_mulc<0x4>(r & 0x7FFFu) ^ (w & 0x7FFFu));
+    }
+    return res_append(r, oe, ge);
+}
+
+// residue of every span between consecutive candidates
 __global__ void __launch_bounds__(256) k_crc(PassArgs a) {
     const uint32_t n = ncand(a);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Cand ci = a.cand[i];
     const SegInfo sg = a.segs[ci.seg];
-    const uint64_t e = span_end(a, i, n, ci);
-    uint32_t ta, oa, te, oe;
-    const uint32_t ga = tile_prefix(a, sg, ci.off, false, ta, oa);
-    const uint32_t ge = tile_prefix(a, sg, e, true, te, oe);
-    uint32_t r;
-    if (ta == te) r = res_append(ga, oe - oa, ge);                           // GF(2): subtraction is XOR
-    else {
-        r = res_append(ga, SCAN_CHUNK - oa, a.pref[(uint64_t)ta * 32 + 31]);
-        for (uint32_t t = ta + 1; t < te; t++) {
-            const uint32_t w = a.pref[(uint64_t)t * 32 + 31];
-            r = ((r ^ w) & 0x8000u) | (q_mulc<0x4>(r & 0x7FFFu) ^ (w & 0x7FFFu));
-        }
-        r = res_append(r, oe, ge);
-    }
-    a.seg_crc[i] = (uint16_t)r;
+    a.seg_crc[i] = (uint16_t)span_residue(a, sg, ci.off, span_end(a, i, n, ci));
 }
 
 // ------------------------------------------------------------------------------------------------ K1d link / validate
@@ -701,14 +701,22 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     Cand c;
     c.bs = 0; c.assign = 0; c.flags = 0; c.off = 0; c.hdr_len = 0; c.bps = 0;
     if (i < n) { st = a.status[i]; c = a.cand[i]; }
-    bool live = (st == ST_OK || st == ST_CHECK) && !(c.flags & 2);   // flag 2: frame of the neighbouring shard (end marker only)
+    // CRC-validated frames are walked up to their last subframe; frames whose CRC failed (ST_CRC: a later frame continues
+    // the numbering; ST_CHECK: nothing does) are parsed to the end the way the reference would, because what the
+    // reference does next depends on where that parse stops (flag 2: frame of the neighbouring shard, end marker only)
+    bool live = (st == ST_OK || st == ST_CHECK || st == ST_CRC) && !(c.flags & 2);
     const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
     const uint64_t frame_bit0 = c.off * 8;
-    const uint64_t end_bit = live ? (c.off + a.flen[i]) * 8 : 0;
+    uint64_t end_bit = 0, seg_end = 0;
+    if (live) {
+        const SegInfo& sg = a.segs[c.seg];
+        seg_end = sg.end;
+        end_bit = (st == ST_OK ? c.off + a.flen[i] : min(sg.end, c.off + (uint64_t)sg.max_frame_bytes)) * 8;
+    }
     RingBits br;
     if (live) br.init(smem_u32(s_ring) + threadIdx.x * RingBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
     else br.init_idle(smem_u32(s_ring) + threadIdx.x * RingBits::STRIDE, a.in);
-    bool bad = false, unparse = false;
+    bool bad = false, unparse = false, padbit = false;
     uint32_t max_order = 0, any_wide = 0;
     const uint32_t wmax_ch = __reduce_max_sync(FULL, live ? channels : 0u);
     const uint32_t wmax_bs = __reduce_max_sync(FULL, live ? c.bs : 0u);
@@ -723,7 +731,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
             si.type = 0; si.order = 0; si.flags = 0; si.wasted = 0;
             uint32_t x = br.get(8);
             uint32_t type = (x >> 1) & 0x3f, w = 0;
-            if (x & 0x80) bad = true;
+            if (x & 0x80) { bad = true; padbit = true; }          // pad bit set: the reference reports LOST_SYNC
             else if ((x & 1) && (w = br.unary(64) + 1) >= bps) unparse = true;
             else {
                 br.ensure_now();
@@ -822,25 +830,74 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         }
     }
     if (!live) return;
-    if (!bad && !unparse && st == ST_CHECK) {
-        uint64_t p = (br.abs_pos(a.in) + 7) & ~7ull;
-        // validate the way the reference does: CRC-16 over the bytes the parse consumed
-        if (p + 16 > end_bit) bad = true;
+    // Outcome, in the reference's terms (oracle/flac_oracle.c decode_span): the parse failed -> nothing is delivered and
+    // the sync search resumes two bytes after this sync code; the parse completed -> the frame is delivered (zero-filled
+    // when the CRC-16 read where the parse stopped does not match) and the search resumes after that CRC.
+    const uint8_t st_in = st;
+    if (unparse) st = ST_UNPARSEABLE;
+    else if (bad) st = (!padbit && end_bit == seg_end * 8) ? ST_EOS : ST_LOSTSYNC;   // pad bit; ran off the stream / past any possible frame end
+    else if (st_in != ST_OK) {
+        const uint64_t p = ((br.abs_pos(a.in) + 7) >> 3) + 2;           // first byte after the CRC-16 the reference would read
+        if (p > seg_end) st = ST_EOS;                                  // ran off the stream: END_OF_STREAM, frame not delivered
         else {
-            const uint8_t* q = a.in + c.off;
-            uint32_t nbytes = (uint32_t)(p / 8 - c.off), crc = 0;
-            for (uint32_t b = 0; b < nbytes; b++) crc = crc16_update_bitwise(crc, q[b]);
-            uint32_t want = (uint32_t)q[nbytes] << 8 | q[nbytes + 1];
-            a.flen[i] = nbytes + 2;
-            st = (crc == want) ? ST_OK : ST_CRC;
+            a.flen[i] = (uint32_t)(p - c.off);
+            st = span_residue(a, a.segs[c.seg], c.off, p) == 0 ? ST_OK : ST_CRC;
         }
     }
-    if (unparse) st = ST_UNPARSEABLE;
-    else if (bad) st = (st == ST_CHECK) ? ST_DROP : ST_CRC;
     a.status[i] = st;
     if (st == ST_OK) {
         if (max_order) atomicMax(&a.totals->max_order, max_order);
         if (any_wide) atomicOr(&a.totals->any_wide, 1u);
+    }
+    if (st != ST_OK || st_in != ST_OK) {                               // off the clean chain: k_resync decides what follows it
+        const uint32_t slot = atomicAdd(&a.counters[CNT_ANOM], 1u);
+        if (slot < ANOM_CAP) a.anom[slot] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ resync
+// The reference is a sequential decoder: after a damaged frame it resumes its sync search wherever its parse of the
+// damaged bits stopped, so a frame can be lost because the one before it was damaged.  Intact frames chain exactly (each
+// ends where the next starts) and need no attention; k_parse lists the few candidates that are off that chain.  One
+// thread walks that list in stream order: it computes where the reference's cursor lands after each of them and marks
+// the candidates the cursor jumps over as never reached.  Candidates inside CRC-validated frames (ST_DROP) are not
+// reconsidered.  Nothing to do (and nothing done) for intact streams.
+__global__ void __launch_bounds__(256) k_resync(PassArgs a) {
+    __shared__ uint32_t s_sorted[1024];
+    const uint32_t n = ncand(a);
+    const uint32_t m_all = a.counters[CNT_ANOM];
+    if (m_all == 0) return;
+    const uint32_t tid = threadIdx.x;
+    auto step = [&](uint32_t ai) {
+        const uint8_t st = a.status[ai];
+        if (st == ST_SKIP || st == ST_DROP) return;
+        const Cand ca = a.cand[ai];
+        if (ca.flags & 2) return;
+        const uint64_t landing = st == ST_EOS ? ~0ull : ca.off + ((st == ST_OK || st == ST_CRC) ? (uint64_t)a.flen[ai] : 2ull);
+        for (uint32_t j = ai + 1; j < n; j++) {
+            const Cand& cj = a.cand[j];
+            if (cj.seg != ca.seg) break;
+            const uint8_t sj = a.status[j];
+            if (sj == ST_DROP) continue;
+            if (cj.off >= landing) break;
+            a.status[j] = ST_SKIP;
+        }
+    };
+    if (m_all > ANOM_CAP) {                    // heavily damaged input: walk the whole table
+        if (tid == 0) for (uint32_t i = 0; i < n; i++) step(i);
+        return;
+    }
+    // rank sort of the (unordered) list, 1024 entries at a time is not needed: ranks are global
+    for (uint32_t base = 0; base < m_all; base += 1024) {
+        __syncthreads();
+        for (uint32_t e = tid; e < m_all; e += blockDim.x) {
+            const uint32_t v = a.anom[e];
+            uint32_t rank = 0;
+            for (uint32_t o = 0; o < m_all; o++) rank += a.anom[o] < v;
+            if (rank >= base && rank < base + 1024) s_sorted[rank - base] = v;
+        }
+        __syncthreads();
+        if (tid == 0) { const uint32_t cnt = min(1024u, m_all - base); for (uint32_t e = 0; e < cnt; e++) step(s_sorted[e]); }
     }
 }
 
@@ -1336,6 +1393,7 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
     k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * RingBits::STRIDE, S(stream)>>>(a); g_launches++;
 }
+void launch_resync(const PassArgs& a, void* stream) { k_resync<<<1, 256, 0, S(stream)>>>(a); g_launches++; }
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream) {
     const int n_sm = sm_count();
     uint32_t per = (ncand_bound + n_sm - 1) / n_sm;

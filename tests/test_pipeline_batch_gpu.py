@@ -68,6 +68,29 @@ def test_pipelined_decode_of_damaged_stream_reports_like_one_pass(small_pipe_sha
     assert one == want
 
 
+def test_header_and_payload_damage_across_sub_shards(small_pipe_shards, monkeypatch):
+    """Damage that makes the reference drop a frame and resynchronise (a flipped bit in a subframe header, a wiped byte):
+    the pipelined decode and the one-pass decode both match the oracle's PCM, frame list and events."""
+    import pyoracle
+    from birdnest.audio_b200 import _abi
+    s = _stream()
+    b = bytearray(s.flac)
+    n = len(b)
+    for pos, mask in ((n // 5, 0x10), (n // 2 + 3, 0xFF), (n - 40000, 0x01)):
+        b[pos] ^= mask
+    b = bytes(b)
+    want, oframes, _, oerrs = pyoracle.decode(b, want_frames=True)
+    for mb in ("1", "4096"):
+        monkeypatch.setenv("BNFLAC_PIPE_MB", mb)
+        with _abi.open_memory(b) as h:
+            out = bytearray(len(s.pcm) * s.tiles + 64)
+            k = h.decode_all(out)
+            frames, errs = h.frames(), h.errors()
+        assert bytes(out[:k]) == want, mb
+        assert [(f.offset, f.length) for f in frames] == [(o.offset, o.length) for o in oframes], mb
+        assert errs == oerrs, mb
+
+
 def test_pipelined_read_stream_semantics(small_pipe_shards):
     from birdnest.audio_b200 import _abi
     s = _stream()
