@@ -9,7 +9,7 @@ NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall -Xptxas -v
 CSRC := birdnest/audio_b200/csrc
 LIB := birdnest/audio_b200/libbnflac.so
 
-all: lib oracle corpus host
+all: lib oracle corpus host shim
 
 lib: $(LIB)
 $(LIB): $(CSRC)/kernels.cu $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
@@ -19,6 +19,12 @@ $(LIB): $(CSRC)/kernels.cu $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac
 host: birdnest/audio_b200/flacdecoder_demo
 birdnest/audio_b200/flacdecoder_demo: $(CSRC)/flac_decoder.hpp $(CSRC)/flac_decoder_demo.cpp $(LIB)
 	g++ -O2 -std=c++17 -Wall -Iinclude -o $@ $(CSRC)/flac_decoder_demo.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
+
+# the libFLAC 1.2.1 stream-decoder symbols the unmodified C# binds, replayed from a bnflac handle
+SHIM := birdnest/audio_b200/libLibFlac.so
+shim: $(SHIM)
+$(SHIM): $(CSRC)/libflac_shim.cpp include/bnflac_legacy.h include/bnflac.h $(LIB)
+	g++ -O2 -std=c++17 -Wall -fPIC -shared -Iinclude -o $@ $(CSRC)/libflac_shim.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
 
 oracle: oracle/_build/liboracle.so oracle/_build/flac_oracle
 oracle/_build/liboracle.so: oracle/flac_oracle.c oracle/flac_oracle.h
@@ -40,6 +46,6 @@ ref:
 	$(MAKE) -C oracle/refdll
 
 clean:
-	rm -rf $(LIB) oracle/_build corpus/_build birdnest/audio_b200/flacdecoder_demo
+	rm -rf $(LIB) $(SHIM) oracle/_build corpus/_build birdnest/audio_b200/flacdecoder_demo
 
-.PHONY: all lib oracle corpus ref clean host
+.PHONY: all lib oracle corpus ref clean host shim

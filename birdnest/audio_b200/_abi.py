@@ -76,6 +76,7 @@ _PROTOS = {
     "bnflac_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(FrameRec)), C.POINTER(C.c_size_t)]),
     "bnflac_subframes": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(SubframeRec)), C.POINTER(C.c_size_t)]),
     "bnflac_errors": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
+    "bnflac_error_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
     "bnflac_last_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "bnflac_strerror": (C.c_char_p, [C.c_int]),
     "bnflac_state_name": (C.c_char_p, [C.c_int]),

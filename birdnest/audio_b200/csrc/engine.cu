@@ -243,7 +243,7 @@ struct bnflac {
     uint64_t pcm_base = 0;              // (kid) where this sub-shard's PCM starts in the parent's output
 
     // results
-    std::vector<bnflac_frame_t> frames; std::vector<bnflac_subframe_t> subs; std::vector<uint32_t> errors;
+    std::vector<bnflac_frame_t> frames; std::vector<bnflac_subframe_t> subs; std::vector<uint32_t> errors, errors_at;
     bool diag_valid = false;
 
     // Stream-style read buffering
@@ -637,6 +637,9 @@ struct DiagCursor {          // the reference's sync-search state, carried acros
     bool in_sync = true;     // LOST_SYNC is reported once per excursion
     bool ended = false;      // a truncated header ended the stream
     bool have_expect = true; // false: (shard > 0) start at the first frame found, whatever lies before it
+    std::vector<uint32_t>* at = nullptr;                 // per event: how many frames had been delivered before it
+    const std::vector<bnflac_frame_t>* frames = nullptr;
+    void event(std::vector<uint32_t>& errors, uint32_t code) { errors.push_back(code); if (at) at->push_back(frames ? (uint32_t)frames->size() : 0u); }
 };
 } // namespace
 
@@ -652,13 +655,13 @@ static void scan_gap(bnflac* h, const uint8_t* host_ptr, uint64_t stream_len, Di
     uint64_t pos = from;
     while (pos < to && pos + 2 <= stream_len) {
         const uint8_t* p = d + (pos - from);
-        if (!(p[0] == 0xFF && (p[1] & 0xFC) == 0xF8)) { if (cur.in_sync) { errors.push_back(0); cur.in_sync = false; } pos++; continue; }
+        if (!(p[0] == 0xFF && (p[1] & 0xFC) == 0xF8)) { if (cur.in_sync) { cur.event(errors, 0); cur.in_sync = false; } pos++; continue; }
         const int rc = header_rc(p, (size_t)std::min<uint64_t>(hi - pos, stream_len - pos));
         if (rc < 0) { cur.ended = true; break; }
-        if (rc == 1) { errors.push_back(1); cur.in_sync = true; pos += 2; continue; }
-        if (rc == 3) { errors.push_back(3); cur.in_sync = true; pos += 2; continue; }
+        if (rc == 1) { cur.event(errors, 1); cur.in_sync = true; pos += 2; continue; }
+        if (rc == 3) { cur.event(errors, 3); cur.in_sync = true; pos += 2; continue; }
         // a valid header the engine did not consider (frame of another format, cut off by the end of the stream)
-        if (cur.in_sync) { errors.push_back(0); cur.in_sync = false; }
+        if (cur.in_sync) { cur.event(errors, 0); cur.in_sync = false; }
         pos++;
     }
     cur.expect = std::max(cur.expect, to);
@@ -688,7 +691,7 @@ static int collect_diag(bnflac* h, DiagCursor& cur, uint64_t pcm_base, const uin
         if (cur.ended) break;
         if (st[i] == ST_EOS) { cur.ended = true; break; }         // the stream ended inside this frame
         if (!is_frame) {                                          // the parse failed: reported, cursor resumes two bytes further
-            errors.push_back(st[i] == ST_LOSTSYNC ? 0u : 3u);
+            cur.event(errors, st[i] == ST_LOSTSYNC ? 0u : 3u);
             cur.in_sync = false;
             cur.expect = off + 2;
             continue;
@@ -698,7 +701,7 @@ static int collect_diag(bnflac* h, DiagCursor& cur, uint64_t pcm_base, const uin
         f.channels = (uint8_t)(cand[i].assign < 8 ? cand[i].assign + 1 : 2); f.bits_per_sample = cand[i].bps; f.assignment = cand[i].assign;
         f.status = st[i] == ST_OK ? BNFLAC_FRAME_OK : BNFLAC_FRAME_CRC_MISMATCH;
         f.number = cand[i].number; f.pcm_offset = po[i] + pcm_base;
-        if (st[i] == ST_CRC) errors.push_back(2);              // FRAME_CRC_MISMATCH
+        if (st[i] == ST_CRC) cur.event(errors, 2);              // FRAME_CRC_MISMATCH
         cur.expect = f.offset + f.length; cur.in_sync = true;
         frames.push_back(f);
         for (int c = 0; c < MAX_CH; c++) {
@@ -712,8 +715,9 @@ static int collect_diag(bnflac* h, DiagCursor& cur, uint64_t pcm_base, const uin
 
 static int fetch_diag(bnflac* h) {
     if (h->diag_valid) return 0;
-    h->frames.clear(); h->subs.clear(); h->errors.clear();
+    h->frames.clear(); h->subs.clear(); h->errors.clear(); h->errors_at.clear();
     DiagCursor cur;
+    cur.at = &h->errors_at; cur.frames = &h->frames;
     cur.expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
     cur.have_expect = h->own_begin <= h->info.first_frame_offset;      // a later shard starts wherever its first frame starts
     int rc;
@@ -1009,6 +1013,12 @@ int bnflac_errors(bnflac_t* h, const uint32_t** codes, size_t* n) {
     if (!h || !codes || !n) return BNFLAC_ERR_ARG;
     int rc = fetch_diag(h); if (rc) return rc;
     *codes = h->errors.data(); *n = h->errors.size();
+    return 0;
+}
+int bnflac_error_frames(bnflac_t* h, const uint32_t** at, size_t* n) {
+    if (!h || !at || !n) return BNFLAC_ERR_ARG;
+    int rc = fetch_diag(h); if (rc) return rc;
+    *at = h->errors_at.data(); *n = h->errors_at.size();
     return 0;
 }
 int bnflac_last_timing(bnflac_t* h, bnflac_timing* t) { if (!h || !t) return BNFLAC_ERR_ARG; *t = h->timing; return 0; }

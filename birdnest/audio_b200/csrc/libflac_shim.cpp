@@ -1,0 +1,223 @@
+// libflac_shim.cpp -- libLibFlac.so: the FLAC__stream_decoder_* symbols of include/bnflac_legacy.h over a bnflac handle.
+// A replay layer (SURVEY 8b tier A): the stream is pulled through the caller's read callback (or read from the file),
+// decoded in one go by the CUDA engine at the first process_single, and handed out frame by frame as planar int32 with
+// the error callbacks raised where the reference raises them.  No decoding happens here.
+#include <bnflac.h>
+#include <bnflac_legacy.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct FLAC__StreamDecoder {
+    int state = BNFLAC_STATE_UNINITIALIZED;
+    FLAC__StreamDecoderReadCallback read = nullptr;
+    FLAC__StreamDecoderEofCallback eof = nullptr;
+    FLAC__StreamDecoderWriteCallback write = nullptr;
+    FLAC__StreamDecoderMetadataCallback metadata = nullptr;
+    FLAC__StreamDecoderErrorCallback error = nullptr;
+    void* client = nullptr;
+    std::vector<uint8_t> bytes;            // the compressed stream
+    bool have_bytes = false, metadata_done = false, decoded = false;
+    bnflac_t* h = nullptr;
+    bnflac_info_t info{};
+    std::vector<uint8_t> pcm;
+    const bnflac_frame_t* frames = nullptr; size_t nframes = 0;
+    const uint32_t* errs = nullptr; const uint32_t* errs_at = nullptr; size_t nerrs = 0;
+    size_t next_frame = 0, next_err = 0;
+    uint64_t skip_samples = 0;             // after seek_absolute: samples of the next frame that lie before the target
+    std::vector<uint64_t> first_sample;    // per delivered frame
+    std::vector<int32_t> planes[8];
+
+    void close_engine() { if (h) bnflac_close(h); h = nullptr; frames = nullptr; nframes = 0; errs = errs_at = nullptr; nerrs = 0; decoded = false; }
+};
+
+static bool pull_stream(FLAC__StreamDecoder* d) {
+    if (d->have_bytes) return true;
+    if (!d->read) return false;
+    const size_t req = 1u << 20;          // the C# callback caps each read at its own byte[] (16 KiB, FLACDecoder.cs:336)
+    for (;;) {
+        const size_t old = d->bytes.size();
+        d->bytes.resize(old + req);
+        size_t got = req;
+        const int st = d->read(d, d->bytes.data() + old, &got, d->client);
+        if (st == 2 || got > req) { d->bytes.resize(old); d->state = BNFLAC_STATE_ABORTED; return false; }
+        d->bytes.resize(old + got);
+        if (st == 1 || got == 0) break;
+    }
+    d->have_bytes = true;
+    return true;
+}
+
+static bool do_metadata(FLAC__StreamDecoder* d) {
+    if (d->metadata_done) return true;
+    if (!pull_stream(d)) return false;
+    bnflac_opts o{}; o.struct_size = sizeof o; o.device = -1; o.flags = BNFLAC_OPT_BORROW_INPUT;
+    const int rc = bnflac_open_memory(d->bytes.data(), d->bytes.size(), &o, &d->h);
+    if (rc) { d->state = (rc == BNFLAC_ERR_MEMORY) ? BNFLAC_STATE_MEMORY_ALLOCATION_ERROR : BNFLAC_STATE_END_OF_STREAM; return false; }
+    bnflac_info(d->h, &d->info);
+    if (d->metadata) {
+        FLAC__StreamMetadata m; memset(&m, 0, sizeof m);
+        m.type = 0; m.is_last = 1; m.length = 34;
+        m.stream_info.min_blocksize = d->info.min_blocksize; m.stream_info.max_blocksize = d->info.max_blocksize;
+        m.stream_info.min_framesize = d->info.min_framesize; m.stream_info.max_framesize = d->info.max_framesize;
+        m.stream_info.sample_rate = d->info.sample_rate; m.stream_info.channels = d->info.channels; m.stream_info.bits_per_sample = d->info.bits_per_sample;
+        m.stream_info.total_samples = d->info.total_samples; memcpy(m.stream_info.md5sum, d->info.md5, 16);
+        d->metadata(d, &m, d->client);
+    }
+    d->metadata_done = true;
+    d->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
+    return true;
+}
+
+static bool do_decode(FLAC__StreamDecoder* d) {
+    if (d->decoded) return true;
+    uint64_t need = 0;
+    if (bnflac_decoded_size(d->h, &need)) { d->state = BNFLAC_STATE_ABORTED; return false; }
+    d->pcm.resize((size_t)need + 64);
+    uint64_t w = 0;
+    const int rc = bnflac_decode_all(d->h, d->pcm.data(), d->pcm.size(), &w);
+    if (rc) { d->state = (rc == BNFLAC_ERR_MEMORY) ? BNFLAC_STATE_MEMORY_ALLOCATION_ERROR : BNFLAC_STATE_ABORTED; return false; }
+    d->pcm.resize((size_t)w);
+    size_t ne2 = 0;
+    if (bnflac_frames(d->h, &d->frames, &d->nframes) || bnflac_errors(d->h, &d->errs, &d->nerrs) || bnflac_error_frames(d->h, &d->errs_at, &ne2)) { d->state = BNFLAC_STATE_ABORTED; return false; }
+    d->first_sample.assign(d->nframes + 1, 0);
+    for (size_t i = 0; i < d->nframes; i++) d->first_sample[i + 1] = d->first_sample[i] + d->frames[i].blocksize;
+    d->decoded = true;
+    return true;
+}
+
+// hands frame `i` (minus its first `skip` samples) to the write callback
+static bool deliver(FLAC__StreamDecoder* d, size_t i, uint64_t skip) {
+    const bnflac_frame_t& f = d->frames[i];
+    const uint32_t C = f.channels, B = d->info.bytes_per_sample, bs = f.blocksize;
+    const uint8_t* src = d->pcm.data() + f.pcm_offset;
+    const int sh = 32 - 8 * (int)B;
+    for (uint32_t c = 0; c < C; c++) d->planes[c].resize(bs);
+    for (uint32_t t = 0; t < bs; t++)
+        for (uint32_t c = 0; c < C; c++) {
+            const uint8_t* p = src + ((size_t)t * C + c) * B;
+            uint32_t v = 0;
+            for (uint32_t k = 0; k < B; k++) v |= (uint32_t)p[k] << (8 * k);
+            d->planes[c][t] = (int32_t)(v << sh) >> sh;                   // sign-extend the packed sample
+        }
+    FLAC__Frame fr; memset(&fr, 0, sizeof fr);
+    fr.header.blocksize = bs - (uint32_t)skip; fr.header.sample_rate = d->info.sample_rate; fr.header.channels = C;
+    fr.header.channel_assignment = f.assignment < 8 ? 0u : (uint32_t)f.assignment - 7u;
+    fr.header.bits_per_sample = f.bits_per_sample;
+    if (skip) { fr.header.number_type = 1; fr.header.number.sample_number = d->first_sample[i] + skip; }
+    else if (d->info.min_blocksize != d->info.max_blocksize && f.number == d->first_sample[i] && i) { fr.header.number_type = 1; fr.header.number.sample_number = f.number; }
+    else { fr.header.number_type = 0; fr.header.number.frame_number = (uint32_t)f.number; }
+    const int32_t* bufs[8] = {nullptr};
+    for (uint32_t c = 0; c < C; c++) bufs[c] = d->planes[c].data() + skip;
+    d->state = BNFLAC_STATE_READ_FRAME;
+    if (d->write && d->write(d, &fr, bufs, d->client) != 0) { d->state = BNFLAC_STATE_ABORTED; return false; }
+    d->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
+    return true;
+}
+
+static void raise_errors_before(FLAC__StreamDecoder* d, size_t frame_index_inclusive) {
+    // events the reference raises before (and, for a CRC mismatch, together with) the frame at this index
+    while (d->next_err < d->nerrs && d->errs_at[d->next_err] <= frame_index_inclusive) {
+        if (d->error) d->error(d, (int)d->errs[d->next_err], d->client);
+        d->next_err++;
+    }
+}
+
+extern "C" {
+
+FLAC__StreamDecoder* FLAC__stream_decoder_new(void) { return new (std::nothrow) FLAC__StreamDecoder; }
+void FLAC__stream_decoder_delete(FLAC__StreamDecoder* d) { if (d) { d->close_engine(); delete d; } }
+
+FLAC__bool FLAC__stream_decoder_finish(FLAC__StreamDecoder* d) {
+    if (!d) return 0;
+    d->close_engine();
+    d->bytes.clear(); d->have_bytes = false; d->metadata_done = false; d->next_frame = d->next_err = 0; d->skip_samples = 0;
+    d->state = BNFLAC_STATE_UNINITIALIZED;
+    return 1;
+}
+
+int FLAC__stream_decoder_init_stream(FLAC__StreamDecoder* d, FLAC__StreamDecoderReadCallback read, FLAC__StreamDecoderSeekCallback, FLAC__StreamDecoderTellCallback,
+                                     FLAC__StreamDecoderLengthCallback, FLAC__StreamDecoderEofCallback eof, FLAC__StreamDecoderWriteCallback write,
+                                     FLAC__StreamDecoderMetadataCallback metadata, FLAC__StreamDecoderErrorCallback error, void* client) {
+    if (!d || d->state != BNFLAC_STATE_UNINITIALIZED) return 5;          /* FLAC__STREAM_DECODER_INIT_STATUS_ALREADY_INITIALIZED */
+    if (!read || !write || !error) return 2;                              /* ..._INVALID_CALLBACKS */
+    d->read = read; d->eof = eof; d->write = write; d->metadata = metadata; d->error = error; d->client = client;
+    d->state = BNFLAC_STATE_SEARCH_FOR_METADATA;
+    return 0;
+}
+
+int FLAC__stream_decoder_init_file(FLAC__StreamDecoder* d, const char* filename, FLAC__StreamDecoderWriteCallback write, FLAC__StreamDecoderMetadataCallback metadata,
+                                   FLAC__StreamDecoderErrorCallback error, void* client) {
+    if (!d || d->state != BNFLAC_STATE_UNINITIALIZED) return 5;
+    if (!write || !error) return 2;
+    FILE* f = filename ? fopen(filename, "rb") : nullptr;
+    if (!f) return 4;                                                     /* ..._ERROR_OPENING_FILE */
+    fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+    d->bytes.resize(n > 0 ? (size_t)n : 0);
+    const size_t got = d->bytes.empty() ? 0 : fread(d->bytes.data(), 1, d->bytes.size(), f);
+    fclose(f);
+    d->bytes.resize(got); d->have_bytes = true;
+    d->write = write; d->metadata = metadata; d->error = error; d->client = client;
+    d->state = BNFLAC_STATE_SEARCH_FOR_METADATA;
+    return 0;
+}
+
+FLAC__bool FLAC__stream_decoder_process_until_end_of_metadata(FLAC__StreamDecoder* d) { return d && d->state != BNFLAC_STATE_UNINITIALIZED && do_metadata(d) ? 1 : 0; }
+
+FLAC__bool FLAC__stream_decoder_process_single(FLAC__StreamDecoder* d) {
+    if (!d || d->state == BNFLAC_STATE_UNINITIALIZED || d->state == BNFLAC_STATE_ABORTED) return 0;
+    if (!d->metadata_done) return do_metadata(d) ? 1 : 0;                 // libFLAC: one call consumes the metadata
+    if (d->state == BNFLAC_STATE_END_OF_STREAM) return 1;
+    if (!do_decode(d)) return 0;
+    if (d->next_frame >= d->nframes) {
+        raise_errors_before(d, d->nframes);
+        d->state = BNFLAC_STATE_END_OF_STREAM;
+        return 1;
+    }
+    const size_t i = d->next_frame++;
+    raise_errors_before(d, i);
+    const uint64_t skip = d->skip_samples; d->skip_samples = 0;
+    return deliver(d, i, skip) ? 1 : 0;
+}
+
+FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder* d) {
+    if (!d) return 0;
+    while (d->state != BNFLAC_STATE_END_OF_STREAM) if (!FLAC__stream_decoder_process_single(d)) return 0;
+    return 1;
+}
+
+// libFLAC delivers the (partial) frame that holds the target sample from inside seek_absolute; so does this
+FLAC__bool FLAC__stream_decoder_seek_absolute(FLAC__StreamDecoder* d, uint64_t sample) {
+    if (!d || d->state == BNFLAC_STATE_UNINITIALIZED) return 0;
+    if (!do_metadata(d) || !do_decode(d)) return 0;
+    const uint64_t total = d->first_sample.empty() ? 0 : d->first_sample.back();
+    if (sample >= total) { d->state = BNFLAC_STATE_SEEK_ERROR; return 0; }
+    size_t lo = 0, hi = d->nframes;                                       // last frame whose first sample <= target
+    while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (d->first_sample[mid] <= sample) lo = mid; else hi = mid; }
+    d->next_frame = lo + 1;
+    d->next_err = 0;
+    while (d->next_err < d->nerrs && d->errs_at[d->next_err] <= lo) d->next_err++;    // events of the skipped part are not replayed
+    d->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
+    return deliver(d, lo, sample - d->first_sample[lo]) ? 1 : 0;
+}
+
+FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, uint64_t* position) {
+    if (!d || !position || !d->decoded) return 0;
+    *position = d->next_frame < d->nframes ? d->frames[d->next_frame].offset : d->bytes.size();
+    return 1;
+}
+uint64_t FLAC__stream_decoder_get_total_samples(const FLAC__StreamDecoder* d) { return d && d->metadata_done ? d->info.total_samples : 0; }
+unsigned FLAC__stream_decoder_get_channels(const FLAC__StreamDecoder* d) { return d && d->metadata_done ? d->info.channels : 0; }
+unsigned FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) { return d && d->metadata_done ? d->info.bits_per_sample : 0; }
+unsigned FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return d && d->metadata_done ? d->info.sample_rate : 0; }
+int FLAC__stream_decoder_get_state(const FLAC__StreamDecoder* d) { return d ? d->state : BNFLAC_STATE_UNINITIALIZED; }
+
+FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
+    if (!d || d->state == BNFLAC_STATE_UNINITIALIZED) return 0;
+    d->next_frame = d->next_err = 0; d->skip_samples = 0;
+    d->state = d->metadata_done ? BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC : BNFLAC_STATE_SEARCH_FOR_METADATA;
+    return 1;
+}
+
+} // extern "C"

@@ -136,6 +136,9 @@ typedef struct { uint32_t bit_offset; uint8_t type, order, wasted, flags; } bnfl
 int bnflac_subframes(bnflac_t* h, const bnflac_subframe_t** sub, size_t* n);
 /* number of error-callback events the reference would have raised (ErrorCallback, FLACDecoder.cs:590-594) and their codes */
 int bnflac_errors(bnflac_t* h, const uint32_t** codes, size_t* n);
+/* for each of those events, how many frames had been delivered before it was raised (lets a frame-at-a-time host such as
+ * the libFLAC-symbol shim raise its error callbacks at the right moment) */
+int bnflac_error_frames(bnflac_t* h, const uint32_t** at, size_t* n);
 /* CUDA-event timings (ms) of the stages of the last decode on this handle */
 typedef struct { float total, scan, crc, link, parse, decode; uint32_t launches; uint32_t pad; } bnflac_timing;
 int bnflac_last_timing(bnflac_t* h, bnflac_timing* t);

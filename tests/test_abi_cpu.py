@@ -79,3 +79,39 @@ def test_library_has_no_oracle_or_cpu_decode_symbols():
     from birdnest.audio_b200 import _abi
     out = subprocess.check_output(["nm", "-D", _abi.lib_path()], text=True)
     assert "fo_decode" not in out and "fo_read_streaminfo" not in out and "bnc_encode" not in out
+
+
+def test_legacy_shim_exports_the_symbols_the_csharp_binds():
+    """include/bnflac_legacy.h == the decoder DllImports of LibFLACSharp.cs:42-85,175-185; libLibFlac.so exports every one,
+    and the struct views have the offsets the C# marshals against (LibFLACSharp.cs:216-234, 295-319)."""
+    shim = os.path.join(ROOT, "birdnest", "audio_b200", "libLibFlac.so")
+    if not os.path.exists(shim):
+        pytest.skip("libLibFlac.so not built (make shim)")
+    hdr = open(os.path.join(ROOT, "include", "bnflac_legacy.h")).read()
+    declared = set(re.findall(r"\b(FLAC__stream_decoder_[a-z_]+)\s*\(", hdr))
+    assert {"FLAC__stream_decoder_new", "FLAC__stream_decoder_init_stream", "FLAC__stream_decoder_process_until_end_of_metadata",
+            "FLAC__stream_decoder_process_single", "FLAC__stream_decoder_get_state", "FLAC__stream_decoder_finish", "FLAC__stream_decoder_delete",
+            "FLAC__stream_decoder_init_file", "FLAC__stream_decoder_get_total_samples", "FLAC__stream_decoder_seek_absolute"} <= declared
+    out = subprocess.check_output(["nm", "-D", "--defined-only", shim], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert declared <= exported, declared - exported
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "bnflac_legacy.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(FLAC__FrameHeader), offsetof(FLAC__FrameHeader, bits_per_sample), offsetof(FLAC__FrameHeader, number),
+        offsetof(FLAC__StreamMetadata, stream_info), offsetof(FLAC__StreamMetadata, stream_info.sample_rate), offsetof(FLAC__StreamMetadata, stream_info.bits_per_sample),
+        offsetof(FLAC__StreamMetadata, stream_info.total_samples), offsetof(FLAC__StreamMetadata, stream_info.md5sum)); return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")], text=True).split()]
+    assert got == [40, 16, 24, 16, 32, 40, 48, 56]
+    L = C.CDLL(shim)
+    L.FLAC__stream_decoder_new.restype = C.c_void_p
+    L.FLAC__stream_decoder_get_state.argtypes = [C.c_void_p]
+    L.FLAC__stream_decoder_delete.argtypes = [C.c_void_p]
+    dec = L.FLAC__stream_decoder_new()
+    assert L.FLAC__stream_decoder_get_state(dec) == 9      # Uninitialized (LibFLACSharp.cs:36)
+    L.FLAC__stream_decoder_delete(dec)
