@@ -555,13 +555,23 @@ __global__ void __launch_bounds__(256) k_cover(PassArgs a) {
 // checkpoint) + 7 have landed, i.e. >= 113 bytes past that position; a period may therefore advance by A bytes with
 // 2A + 8 <= 113 (this period's reads reach pos_prev + 2A + 8).  The walkers keep A <= 42: eight samples of at most 32
 // bits each plus partition parameters; anything longer takes a synchronous path (ensure_now).
-struct RingBits {
-    static constexpr int NBLK = 8, BLK = 16, RB_BYTES = NBLK * BLK;
+// DEPTH = how many of the most recent refill groups may still be in flight after a checkpoint (prefetch distance in
+// checkpoint periods).  With DEPTH = 0 a checkpoint waits for what was requested one period earlier, which exposes the
+// HBM latency whenever too few warps are resident to hide it (streams with few, large frames).  With DEPTH > 0 the
+// checkpoint only waits for older groups, provided what those covered (mark[DEPTH]) reaches past everything the coming
+// period can read; a lane that consumed unusually many bits falls back to a full wait.
+template <int NBLK_, int DEPTH>
+struct RingBitsT {
+    static constexpr int NBLK = NBLK_, BLK = 16, RB_BYTES = NBLK * BLK;
     static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
+    // bytes a refill period can advance + window look-ahead: 8 samples of <= 32 bits plus parameters per 8-sample group
+    // (longer codewords take synchronous refills); rings of 16 blocks are checkpointed every 16 samples
+    static constexpr uint32_t PERIOD_REACH = (NBLK >= 16 ? 84 : 42) + 16;
     uint32_t sring;        // shared-space address of this lane's ring
     uint32_t pos;          // bit position relative to g0
     uint32_t filled;       // blocks [.., filled) have been requested
     uint32_t navail;       // whole 16-byte blocks readable from g0 (blocks past the padded input read as zero)
+    uint32_t mark[DEPTH + 1];   // `filled` after each of the last DEPTH + 1 checkpoints (mark[0] most recent)
     const uint8_t* g0;     // global address of ring byte 0 (16 B aligned)
 
     __device__ __forceinline__ void fetch(uint32_t b) {
@@ -580,11 +590,29 @@ struct RingBits {
         if (filled < lim) {
 #pragma unroll 1
             do { fetch(filled); filled++; } while (filled < lim);
-            commit();
         }
+        commit();                                   // one group per call, possibly empty: wait_group counts calls
     }
-    __device__ __forceinline__ void checkpoint() { wait_all(); request(); }
-    __device__ __forceinline__ void ensure_now() { request(); wait_all(); }     // synchronous: rare big moves, init
+    __device__ __forceinline__ void checkpoint() {
+        if constexpr (DEPTH == 0) wait_all();
+        else {
+            if ((pos >> 3) + PERIOD_REACH <= mark[DEPTH] * (uint32_t)BLK) asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
+            else {
+                wait_all();
+#pragma unroll
+                for (int d = 0; d <= DEPTH; d++) mark[d] = filled;
+            }
+        }
+        request();
+#pragma unroll
+        for (int d = DEPTH; d > 0; d--) mark[d] = mark[d - 1];
+        mark[0] = filled;
+    }
+    __device__ __forceinline__ void ensure_now() {                               // synchronous: rare big moves, init
+        request(); wait_all();
+#pragma unroll
+        for (int d = 0; d <= DEPTH; d++) mark[d] = filled;
+    }
     __device__ __forceinline__ void init(uint32_t sring_, const uint8_t* in, uint64_t in_len, uint64_t abs_bit) {
         sring = sring_;
         const uint64_t b0 = (abs_bit >> 3) & ~(uint64_t)(BLK - 1);
@@ -595,7 +623,11 @@ struct RingBits {
         filled = 0;
         ensure_now();
     }
-    __device__ __forceinline__ void init_idle(uint32_t sring_, const uint8_t* in) { sring = sring_; g0 = in; navail = 0; pos = 0; filled = NBLK; }
+    __device__ __forceinline__ void init_idle(uint32_t sring_, const uint8_t* in) {
+        sring = sring_; g0 = in; navail = 0; pos = 0; filled = NBLK;
+#pragma unroll
+        for (int d = 0; d <= DEPTH; d++) mark[d] = NBLK;
+    }
     __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
     __device__ __forceinline__ uint32_t window_at(uint32_t p) const {      // 32 bits starting at bit p, MSB first
         const uint32_t bo = (p >> 3) & (RB_BYTES - 4);
@@ -604,20 +636,20 @@ struct RingBits {
     }
     __device__ __forceinline__ uint32_t window() const { return window_at(pos); }
     // Register-cached window for the branch-free groups: w0:w1 are the two big-endian words under the read position, w2
-    // (still little-endian) the word after them.  A codeword advances the position by at most 32 bits, so at most one
-    // word is crossed per step; the word that will be needed after the NEXT crossing is loaded on every step, which
-    // takes the shared-memory latency off the position -> window -> length -> position dependency chain.
+    // the word after them.  A codeword advances the position by at most 32 bits, so at most one word is crossed per
+    // step.  The word that a crossing shifts in (position word + 3) is loaded at the START of every step, from the
+    // position the step starts at, so the shared-memory latency is entirely off the serial
+    // position -> window -> length -> position chain (which is then SHF, FLO, IADD3, LOP3, SEL).
     struct Win3 { uint32_t w0, w1, w2; };
     __device__ __forceinline__ Win3 win_init(uint32_t p) const {
         const uint32_t ad = sring + ((p >> 3) & (RB_BYTES - 4));
-        Win3 w; w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = lds32(ad + 8);
+        Win3 w; w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = __byte_perm(lds32(ad + 8), 0, 0x0123);
         return w;
     }
+    __device__ __forceinline__ uint32_t win_next(uint32_t p) const { return __byte_perm(lds32(sring + (((p >> 3) + 12) & (RB_BYTES - 4))), 0, 0x0123); }   // word of p, + 3
     __device__ __forceinline__ static uint32_t win_peek(const Win3& w, uint32_t p) { return __funnelshift_l(w.w1, w.w0, p); }
-    __device__ __forceinline__ void win_advance(Win3& w, uint32_t p, uint32_t np) const {
-        const uint32_t nw = lds32(sring + (((np >> 3) + 8) & (RB_BYTES - 4)));
-        if ((p ^ np) & 32u) { w.w0 = w.w1; w.w1 = __byte_perm(w.w2, 0, 0x0123); }
-        w.w2 = nw;
+    __device__ __forceinline__ static void win_advance(Win3& w, uint32_t p, uint32_t np, uint32_t nxt) {
+        if ((p ^ np) & 32u) { w.w0 = w.w1; w.w1 = w.w2; w.w2 = nxt; }
     }
     __device__ __forceinline__ void skip(uint32_t n) { pos += n; }                        // n <= 32, covered by the checkpoint budget
     __device__ __forceinline__ void jump(uint32_t n) { pos += n; ensure_now(); }          // any n
@@ -660,6 +692,18 @@ struct RingBits {
     }
 };
 
+#ifndef PARSE_RING_BLOCKS
+#define PARSE_RING_BLOCKS 16
+#endif
+#ifndef PARSE_RING_DEPTH
+#define PARSE_RING_DEPTH 1
+#endif
+#ifndef DEC_RING_DEPTH
+#define DEC_RING_DEPTH 1
+#endif
+using ParseBits = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH>;   // no sample tile in k_parse: room for a longer ring and a deeper prefetch
+using RingBits = RingBitsT<8, DEC_RING_DEPTH>;                       // k_decode
+
 // ------------------------------------------------------------------------------------------------ K2 parse
 // One lane per frame: walks the subframes, records where each starts and what it is, skips the residual.  Lanes of a warp
 // advance channel by channel and, inside a subframe, in groups of 8 sample indices in lockstep.  A group takes the
@@ -674,7 +718,7 @@ struct ParseSub {            // per-lane state of the residual being skipped
 };
 
 // next partition parameter(s); a zero-sample partition 0 (order == partition size) is followed immediately by partition 1
-__device__ __forceinline__ bool parse_param(RingBits& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
+__device__ __forceinline__ bool parse_param(ParseBits& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
 #pragma unroll 1
     for (int guard = 0; guard < 2; guard++) {
         const uint32_t cnt = p.psize - (p.first ? p.order : 0);
@@ -713,9 +757,11 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         seg_end = sg.end;
         end_bit = (st == ST_OK ? c.off + a.flen[i] : min(sg.end, c.off + (uint64_t)sg.max_frame_bytes)) * 8;
     }
-    RingBits br;
-    if (live) br.init(smem_u32(s_ring) + threadIdx.x * RingBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
-    else br.init_idle(smem_u32(s_ring) + threadIdx.x * RingBits::STRIDE, a.in);
+    ParseBits br;
+    if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
+    else br.init_idle(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in);
+    // end of the frame as a ring-relative bit position (frames are far below 2^32 bits)
+    const uint32_t end_pos = live ? (uint32_t)min((uint64_t)0xFFFFFFFFu, end_bit - (uint64_t)(br.g0 - a.in) * 8) : 0xFFFFFFFFu;
     bool bad = false, unparse = false, padbit = false;
     uint32_t max_order = 0, any_wide = 0;
     const uint32_t wmax_ch = __reduce_max_sync(FULL, live ? channels : 0u);
@@ -784,7 +830,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         if (!__any_sync(FULL, walk)) continue;
 #pragma unroll 1
         for (uint32_t s0 = 0; s0 < wmax_bs; s0 += 8) {
-            if (walk) br.checkpoint();
+            if (walk && !(s0 & 8u)) br.checkpoint();              // one refill checkpoint per 16 samples (ParseBits::PERIOD_REACH)
             if (walk && ps.left == 0 && s0 >= ps.order && s0 < c.bs) {
                 if (!parse_param(br, ps, a.in, end_bit)) { bad = true; walk = false; }
             }
@@ -793,13 +839,14 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                 uint32_t pos = br.pos;
                 const uint32_t k = ps.k, kp32 = ps.kp32;
                 bool ovf = false;
-                RingBits::Win3 wn = br.win_init(pos);
+                ParseBits::Win3 wn = br.win_init(pos);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const uint32_t f = bfind(RingBits::win_peek(wn, pos));
+                    const uint32_t nxt = j < 7 ? br.win_next(pos) : 0u;
+                    const uint32_t f = bfind(ParseBits::win_peek(wn, pos));
                     ovf |= (int32_t)(f - k) < 0;
                     const uint32_t np = pos + kp32 - f;
-                    if (j < 7) br.win_advance(wn, pos, np);
+                    if (j < 7) ParseBits::win_advance(wn, pos, np, nxt);
                     pos = np;
                 }
                 if (walk) {
@@ -825,8 +872,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                     }
                 }
             }
-            if (walk && s0 + 8 >= c.bs) { walk = false; if (br.abs_pos(a.in) > end_bit) bad = true; }
-            else if (walk && br.abs_pos(a.in) > end_bit) { bad = true; walk = false; }
+            if (walk && br.pos > end_pos) { bad = true; walk = false; }     // ran past any possible end of the frame
+            if (walk && s0 + 8 >= c.bs) walk = false;
         }
     }
     if (!live) return;
@@ -1079,9 +1126,35 @@ __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, c
     }
 }
 
+// 64-bit integer accumulation (mad.wide.s32): int32 coefficients and history, half the registers of the FP64 form.
+// `wasted` carries the per-lane "narrow" flag in bit 31 (EXTRA only): narrow LPC subframes wrap at 32 bits before the shift.
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_i64(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
+                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        long long acc = 0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(cf[m]), "r"(h[(j - 1 - m + 2 * ORD) % ORD]));
+        const uint32_t lo = (uint32_t)acc, hi = (uint32_t)((unsigned long long)acc >> 32);
+        int32_t p = (int32_t)__funnelshift_r(lo, hi, shift);               // shift < 32
+        if (EXTRA) { if (wasted & 0x80000000u) p = (int32_t)lo >> shift; }
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
+        if (FIRST) { if (j < (int)order) s = r; }
+        h[j] = s;
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << (wasted & 31u));
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+}
+
+#ifndef DEC_WIDE_I64
+#define DEC_WIDE_I64 0
+#endif
 template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
 __device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const TT (&cf)[ORD], TT (&h)[ORD], uint32_t order, uint32_t shift, uint32_t wasted) {
-    if constexpr (WIDE) restore_block_f64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+    if constexpr (WIDE && DEC_WIDE_I64) restore_block_i64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+    else if constexpr (WIDE) restore_block_f64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
     else restore_block_i32<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
 }
 
@@ -1201,7 +1274,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     // ---- per-subframe state (registers)
     RingBits br;
     br.init_idle(ring_base + lane * RingBits::STRIDE, a.in);
-    typename std::conditional<WIDE, double, int32_t>::type cf[ORD], hist[ORD];
+    constexpr bool F64 = WIDE && !DEC_WIDE_I64;       // FP64-pipe accumulation (coefficients scaled by 2^-shift) vs mad.wide.s32
+    typename std::conditional<F64, double, int32_t>::type cf[ORD], hist[ORD];
 #pragma unroll
     for (int j = 0; j < ORD; j++) { cf[j] = 0; hist[j] = 0; }
     RiceSt rs;
@@ -1242,15 +1316,16 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                     shift = (uint32_t)br.gets(5);
                     narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
                     // libFLAC 1.2.1 width rule: narrow subframes accumulate in 32 bits (wrap), the others in 64
-                    const double scale = (WIDE && !narrow) ? __hiloint2double((int)((1023u - shift) << 20), 0) : 1.0;
+                    const double scale = (F64 && !narrow) ? __hiloint2double((int)((1023u - shift) << 20), 0) : 1.0;
 #pragma unroll
                     for (int j = 0; j < ORD; j++) if (j < (int)order) {
                         const int32_t q = br.gets(prec);
-                        if (WIDE) cf[j] = (double)q * scale; else cf[j] = q;
+                        if constexpr (F64) cf[j] = (double)q * scale; else cf[j] = q;
                         if ((j & 7) == 7) br.ensure_now();
                     }
                     br.ensure_now();
-                    if (WIDE && !narrow) shift = 0;          // folded into the coefficients
+                    if (F64 && !narrow) shift = 0;           // folded into the coefficients
+                    if (WIDE && !F64 && narrow && shift) wasted |= 0x80000000u;    // 32-bit wrap before the shift (restore_block_i64)
                 } else {   // FIXED predictors as coefficient sets, 32-bit wrap-around arithmetic
                     const int o = (int)order;
                     if (ORD >= 1 && o >= 1) cf[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
@@ -1275,7 +1350,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     __syncwarp();
     const uint32_t maxbs = __reduce_max_sync(FULL, bs);
     const bool reads = mode >= M_VERBATIM;
-    const bool extra = __any_sync(FULL, wasted != 0 || (WIDE && shift != 0));
+    const bool extra = __any_sync(FULL, wasted != 0 || (F64 && shift != 0));
     const uint32_t order = rs.order;
 #pragma unroll 1
     for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
@@ -1296,12 +1371,13 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                 RingBits::Win3 wn = br.win_init(pos);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
+                    const uint32_t nxt = j < 7 ? br.win_next(pos) : 0u;
                     const uint32_t w = RingBits::win_peek(wn, pos);
                     const uint32_t f = bfind(w);
                     const uint32_t d = f - k;
                     ovf |= (int32_t)d < 0;
                     const uint32_t np = pos + kp32 - f;
-                    if (j < 7) br.win_advance(wn, pos, np);
+                    if (j < 7) RingBits::win_advance(wn, pos, np, nxt);
                     pos = np;
                     const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
                     r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
@@ -1391,7 +1467,7 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
     k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
-    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * RingBits::STRIDE, S(stream)>>>(a); g_launches++;
+    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a); g_launches++;
 }
 void launch_resync(const PassArgs& a, void* stream) { k_resync<<<1, 256, 0, S(stream)>>>(a); g_launches++; }
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream) {
