@@ -59,17 +59,31 @@ struct Hdr {
 };
 
 // Frame header syntax + CRC-8.  at(i) returns byte i of the candidate; 17 bytes must be readable.
+struct Crc8Table { uint8_t v[256]; };
+constexpr Crc8Table make_crc8_table() {
+    Crc8Table t{};
+    for (int i = 0; i < 256; i++) { uint32_t c = (uint32_t)i; for (int k = 0; k < 8; k++) c = (c & 0x80) ? ((c << 1) ^ 0x07) & 0xFF : (c << 1) & 0xFF; t.v[i] = (uint8_t)c; }
+    return t;
+}
+__constant__ Crc8Table c_crc8 = make_crc8_table();
+
 template <class F>
 __device__ __forceinline__ bool parse_header_t(F at, const SegInfo& s, Hdr& h) {
-    if (at(0) != 0xFF || (at(1) & 0xFE) != 0xF8) return false;
-    uint32_t b2 = at(2), b3 = at(3);
-    uint32_t bsc = b2 >> 4, src = b2 & 15, ca = b3 >> 4, ssc = (b3 >> 1) & 7;
+    const uint32_t b1 = at(1);
+    if (at(0) != 0xFF || (b1 & 0xFE) != 0xF8) return false;
+    const uint32_t b2 = at(2), b3 = at(3);
+    const uint32_t bsc = b2 >> 4, src = b2 & 15, ca = b3 >> 4, ssc = (b3 >> 1) & 7;
     if ((b3 & 1) || bsc == 0 || src == 15 || ca > 10 || ssc == 3 || ssc == 7) return false;
-    h.variable = at(1) & 1;
-    uint32_t c = crc8_update(crc8_update(crc8_update(crc8_update(0, 0xFF), at(1)), b2), b3);
+    // the engine decodes streams whose frames agree with STREAMINFO (every real encoder; per-frame channel / bps changes
+    // are treated as false syncs).  Checked before the CRC-8: it rejects ~97 % of the random sync patterns
+    h.channels = ca < 8 ? ca + 1 : 2;
+    h.bps = ssc == 0 ? s.bps : ssc == 1 ? 8u : ssc == 2 ? 12u : ssc == 4 ? 16u : ssc == 5 ? 20u : 24u;
+    if (h.channels != s.channels || h.bps != s.bps) return false;
+    h.variable = b1 & 1;
+    uint32_t c = c_crc8.v[c_crc8.v[c_crc8.v[c_crc8.v[0xFF] ^ b1] ^ b2] ^ b3];
     uint32_t q = 4;
     uint32_t x = at(q++);
-    c = crc8_update(c, x);
+    c = c_crc8.v[c ^ x];
     uint64_t num;
     if (x < 0x80) num = x;
     else {
@@ -78,7 +92,7 @@ __device__ __forceinline__ bool parse_header_t(F at, const SegInfo& s, Hdr& h) {
         num = (n == 7) ? 0 : (x & ((1u << (7 - n)) - 1));
         for (int i = 1; i < n; i++) {
             uint32_t y = at(q++);
-            c = crc8_update(c, y);
+            c = c_crc8.v[c ^ y];
             if ((y >> 6) != 2) return false;
             num = (num << 6) | (y & 0x3f);
         }
@@ -87,8 +101,8 @@ __device__ __forceinline__ bool parse_header_t(F at, const SegInfo& s, Hdr& h) {
     uint32_t bs;
     if (bsc == 1) bs = 192;
     else if (bsc <= 5) bs = 576u << (bsc - 2);
-    else if (bsc == 6) { uint32_t v = at(q++); c = crc8_update(c, v); bs = v + 1u; }
-    else if (bsc == 7) { uint32_t v0 = at(q++), v1 = at(q++); c = crc8_update(crc8_update(c, v0), v1); bs = (v0 << 8 | v1) + 1u; }
+    else if (bsc == 6) { uint32_t v = at(q++); c = c_crc8.v[c ^ v]; bs = v + 1u; }
+    else if (bsc == 7) { uint32_t v0 = at(q++), v1 = at(q++); c = c_crc8.v[c_crc8.v[c ^ v0] ^ v1]; bs = (v0 << 8 | v1) + 1u; }
     else bs = 256u << (bsc - 8);
     uint32_t sr;
     switch (src) {
@@ -96,17 +110,12 @@ __device__ __forceinline__ bool parse_header_t(F at, const SegInfo& s, Hdr& h) {
     case 1: sr = 88200; break; case 2: sr = 176400; break; case 3: sr = 192000; break; case 4: sr = 8000; break;
     case 5: sr = 16000; break; case 6: sr = 22050; break; case 7: sr = 24000; break; case 8: sr = 32000; break;
     case 9: sr = 44100; break; case 10: sr = 48000; break; case 11: sr = 96000; break;
-    case 12: { uint32_t v = at(q++); c = crc8_update(c, v); sr = v * 1000u; break; }
-    default: { uint32_t v0 = at(q++), v1 = at(q++); c = crc8_update(crc8_update(c, v0), v1); sr = (v0 << 8 | v1) * (src == 13 ? 1u : 10u); break; }
+    case 12: { uint32_t v = at(q++); c = c_crc8.v[c ^ v]; sr = v * 1000u; break; }
+    default: { uint32_t v0 = at(q++), v1 = at(q++); c = c_crc8.v[c_crc8.v[c ^ v0] ^ v1]; sr = (v0 << 8 | v1) * (src == 13 ? 1u : 10u); break; }
     }
     if (c != at(q)) return false;
     q++;
     h.bs = bs; h.sample_rate = sr; h.hdr_len = q; h.assign = ca;
-    h.channels = ca < 8 ? ca + 1 : 2;
-    h.bps = ssc == 0 ? s.bps : ssc == 1 ? 8u : ssc == 2 ? 12u : ssc == 4 ? 16u : ssc == 5 ? 20u : 24u;
-    // the engine decodes streams whose frames agree with STREAMINFO (every real encoder; per-frame channel/bps
-    // changes are treated as false syncs)
-    if (h.channels != s.channels || h.bps != s.bps) return false;
     return true;
 }
 
@@ -177,12 +186,15 @@ __device__ uint32_t res_bytes(const uint8_t* p, uint32_t n) {
 //   * lanes whose filter fired (about one per tile) re-read their words, check the sync codes exactly and validate the
 //     header (syntax, UTF-8 number, CRC-8, agreement with STREAMINFO); the tile's candidates are appended in order.
 // k_crc turns prefix residues into the residue of every span between consecutive candidates.
-constexpr int SC_WARPS = 12;
+#ifndef SC_WARPS_N
+#define SC_WARPS_N 14
+#endif
+constexpr int SC_WARPS = SC_WARPS_N;
 constexpr int SC_THREADS = 32 * SC_WARPS;
 constexpr int SC_PIECE = SCAN_CHUNK / 32;                  // bytes per lane and tile
 constexpr int SC_PWORDS = SC_PIECE / 4;
 constexpr int SC_STAGES = 2;
-constexpr uint32_t SC_SMEM = SC_WARPS * SC_STAGES * SCAN_CHUNK;
+constexpr uint32_t SC_SMEM = SC_WARPS * SC_STAGES * SCAN_CHUNK + SC_WARPS * 128;      // tile buffers + per-warp candidate lists (SC_LIST u16)
 static_assert(SC_PIECE == 256 && SCAN_CHUNK == 8192, "scan constants below are for 256-byte pieces of 8 KiB tiles");
 // x^(8 * SC_PIECE * d) mod Q for d = 1, 2, 4, 8, 16 and x^(8 * SCAN_CHUNK) mod Q
 constexpr uint32_t SC_XD1 = q_xpow8(256), SC_XD2 = q_xpow8(512), SC_XD4 = q_xpow8(1024), SC_XD8 = q_xpow8(2048), SC_XD16 = q_xpow8(4096);
@@ -206,45 +218,52 @@ struct TileBytes {
     }
 };
 
-// Exact check of the sync codes in the flagged 16-byte units of one lane's piece + header validation; counts the frame
-// candidates and, with `emit`, writes them to cand_tmp[slot ...] in stream order.  One copy of this code serves both
-// passes (count, then emit once the tile's place in the table is known); it runs for about one lane in every few tiles.
-__device__ __noinline__ uint32_t sc_walk(const PassArgs& a, const TileBytes tb, const SegInfo& seg, uint32_t seg_id, uint32_t p0, uint32_t lo, uint32_t hi,
-                                         uint32_t hits, bool emit, uint32_t slot) {
-    uint32_t cnt = 0;
+// Exact check of the flagged 16-byte units of a tile + header validation, by the whole warp: the flagged (lane, unit)
+// pairs are visited in stream order; lanes 0..15 each look at one byte position of the unit, the (rare) lanes that see a
+// sync code validate the header, and the valid ones append the tile offset to the warp's list in order.
+// Returns the number of candidates found; at most SC_LIST are stored (the caller falls back to counting only).
+constexpr uint32_t SC_LIST = 64;
+__device__ __forceinline__ void sc_emit(const PassArgs& a, const SegInfo& seg, uint32_t seg_id, uint64_t go, const Hdr& h, uint32_t slot) {
+    if (slot >= a.cand_cap) return;
+    Cand cd;
+    cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = seg_id;
+    cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
+    cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
+    cd.sample_rate = h.sample_rate;
+    a.cand_tmp[slot] = cd;
+}
+// DIRECT: second pass for tiles with more candidates than the list holds (streams of tiny frames): the frame table slot
+// of the tile is known, every valid lane writes its entry itself.
+template <bool DIRECT>
+__device__ __forceinline__ uint32_t sc_collect(const PassArgs& a, const TileBytes tb, const SegInfo& seg, uint32_t seg_id, uint32_t lo, uint32_t hi, uint32_t hits,
+                                               uint32_t lane, uint32_t s_list, uint32_t gbase) {
+    uint32_t n = 0;
+    uint32_t lanes = __ballot_sync(FULL, hits != 0);
 #pragma unroll 1
-    while (hits) {
-        const uint32_t u = (uint32_t)__ffs(hits) - 1u;
-        hits &= hits - 1;
+    while (lanes) {
+        const uint32_t L = (uint32_t)__ffs(lanes) - 1u;
+        lanes &= lanes - 1;
+        uint32_t hl = __shfl_sync(FULL, hits, L);
 #pragma unroll 1
-        for (uint32_t k = 0; k < 4; k++) {
-            const uint32_t ow = p0 + 16 * u + 4 * k;                   // buffer offset of the word
-            const uint32_t wk = lds32(tb.dbase + sc_swz(ow >> 4) + (ow & 12u));
-            if (!((0xFEFEFEFEu - wk) & wk & 0x80808080u)) continue;    // no 0xFF byte in this word
-            const uint64_t pair = (uint64_t)wk | ((uint64_t)tb(ow + 4) << 32);
-#pragma unroll 1
-            for (uint32_t byte = 0; byte < 4; byte++) {
-                const uint32_t two = (uint32_t)(pair >> (8 * byte)) & 0xFFFFu;              // this byte and the next
-                if ((two & 0xFEFFu) != 0xF8FFu) continue;
-                const uint32_t o = ow + byte;
-                if (o < lo || o >= hi) continue;
-                Hdr h;
-                if (!parse_header_t([&](uint32_t i) { return tb(o + i); }, seg, h)) continue;
-                const uint64_t go = tb.ab + o;
-                if (go + h.hdr_len + 2 > seg.end) continue;
-                if (emit && slot + cnt < a.cand_cap) {
-                    Cand cd;
-                    cd.off = go; cd.number = h.number; cd.bs = h.bs; cd.seg = seg_id;
-                    cd.hdr_len = (uint8_t)h.hdr_len; cd.bps = (uint8_t)h.bps; cd.assign = (uint8_t)h.assign;
-                    cd.flags = (uint8_t)(h.variable | ((go < seg.own_begin || go >= seg.own_end) ? 2u : 0u));
-                    cd.sample_rate = h.sample_rate;
-                    a.cand_tmp[slot + cnt] = cd;
-                }
-                cnt++;
+        while (hl) {
+            const uint32_t u = (uint32_t)__ffs(hl) - 1u;
+            hl &= hl - 1;
+            const uint32_t o = L * SC_PIECE + 16u * u + (lane & 15u);     // tile offset this lane looks at
+            bool ok = false;
+            Hdr h;
+            if (lane < 16 && o >= lo && o < hi && tb(o) == 0xFFu && (tb(o + 1) & 0xFEu) == 0xF8u)
+                ok = parse_header_t([&](uint32_t i) { return tb(o + i); }, seg, h) && tb.ab + o + h.hdr_len + 2 <= seg.end;
+            const uint32_t m = __ballot_sync(FULL, ok);
+            if (ok) {
+                const uint32_t slot = n + __popc(m & ((1u << lane) - 1u));
+                if (DIRECT) sc_emit(a, seg, seg_id, tb.ab + o, h, gbase + slot);
+                else if (slot < SC_LIST) asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + 2u * slot), "h"((uint16_t)o) : "memory");
             }
+            n += __popc(m);
         }
     }
-    return cnt;
+    __syncwarp();
+    return n;
 }
 
 __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
@@ -289,7 +308,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
         Chunk c_nn{};
         if (chunk + 2 * nwarps < a.nchunks) c_nn = a.chunks[chunk + 2 * nwarps];
         const uint32_t dbase = wbase + buf * SCAN_CHUNK;
-        const uint32_t p0 = lane * SC_PIECE;                                   // first byte of this lane's piece
         if (lo > 0 || hi < (uint32_t)SCAN_CHUNK) {
             // first / last tile of a segment: bytes outside [lo, hi) belong to something else and count as zero
 #pragma unroll 1
@@ -355,20 +373,26 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan(PassArgs a) {
         const uint32_t ppar = __popc(pbits & (0xFFFFFFFFu >> (31 - lane))) & 1u;
         a.pref[(uint64_t)chunk * 32 + lane] = (uint16_t)((ppar << 15) | q);
 
-        // ---- candidates (rare): exact sync check + header validation, appended in order
+        // ---- candidates (rare): exact sync check + header validation by the whole warp, appended in order
         uint32_t n_tile = 0, gbase = 0;
         if (__any_sync(FULL, hits != 0)) {
             const SegInfo seg = a.segs[c.seg];
             const TileBytes tb{dbase, ab, a.in, a.in_len};
-            const uint32_t cnt = hits ? sc_walk(a, tb, seg, c.seg, p0, lo, hi, hits, false, 0) : 0u;
-            if (__any_sync(FULL, cnt != 0)) {
-                uint32_t inc = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += o; }
-                n_tile = __shfl_sync(FULL, inc, 31);
+            const uint32_t s_list = smem_u32(s_sc) + SC_WARPS * SC_STAGES * SCAN_CHUNK + warp * (2u * SC_LIST);
+            n_tile = sc_collect<false>(a, tb, seg, c.seg, lo, hi, hits, lane, s_list, 0);
+            if (n_tile) {
                 if (lane == 0) gbase = atomicAdd(&a.counters[0], n_tile);
                 gbase = __shfl_sync(FULL, gbase, 0);
-                if (cnt) sc_walk(a, tb, seg, c.seg, p0, lo, hi, hits, true, gbase + inc - cnt);
+                if (n_tile > SC_LIST) sc_collect<true>(a, tb, seg, c.seg, lo, hi, hits, lane, s_list, gbase);
+                else {
+                    for (uint32_t e = lane; e < n_tile; e += 32) {       // one candidate per lane: header fields again, table entry
+                        uint16_t o16; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(o16) : "r"(s_list + 2u * e));
+                        const uint32_t o = o16;
+                        Hdr h;
+                        parse_header_t([&](uint32_t i) { return tb(o + i); }, seg, h);
+                        sc_emit(a, seg, c.seg, ab + o, h, gbase + e);
+                    }
+                }
             }
         }
         if (lane == 0) {
