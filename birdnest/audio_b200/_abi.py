@@ -125,7 +125,7 @@ def _check(rc: int, where: str) -> None:
         raise BnflacError(rc, where)
 
 
-def _opts(device=-1, stream=0, shard_index=0, shard_count=0, flags=0) -> Opts:
+def _opts(device=-1, stream=0, shard_index=0, shard_count=0, flags=0, read_chunk_frames=0) -> Opts:
     o = Opts()
     o.struct_size = C.sizeof(Opts)
     o.device = device
@@ -133,6 +133,7 @@ def _opts(device=-1, stream=0, shard_index=0, shard_count=0, flags=0) -> Opts:
     o.shard_index = shard_index
     o.shard_count = shard_count
     o.flags = flags
+    o.read_chunk_frames = read_chunk_frames
     return o
 
 
@@ -238,8 +239,8 @@ class Handle:
         return t
 
 
-def open_memory(data, device=-1, stream=0, shard_index=0, shard_count=0, flags=0) -> Handle:
-    o = _opts(device, stream, shard_index, shard_count, flags)
+def open_memory(data, device=-1, stream=0, shard_index=0, shard_count=0, flags=0, read_chunk_frames=0) -> Handle:
+    o = _opts(device, stream, shard_index, shard_count, flags, read_chunk_frames)
     h = C.c_void_p()
     n = data.numel() * data.element_size() if hasattr(data, "numel") else len(data)
     _check(lib().bnflac_open_memory(_addr(data), n, C.byref(o), C.byref(h)), "bnflac_open_memory")

@@ -248,6 +248,8 @@ struct bnflac {
 
     // Stream-style read buffering
     PinBuf pcm_host; uint64_t pcm_len = 0, read_pos = 0; bool decoded = false;
+    // streaming Read session: sub-shards decoded ahead of the reader, see stream_read()
+    bool rd_active = false; uint32_t rd_issued = 0, rd_cur = 0; uint64_t rd_off = 0, rd_total = 0;
 
     ~bnflac() {
         for (bnflac* k : kids) delete k;
@@ -507,6 +509,26 @@ static int decode_host_single(bnflac* h, uint8_t* dst, size_t cap, uint64_t* wri
 // thread: the other streams' copies and kernels keep running, so the H2D engine, the SMs and the D2H engine overlap.
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// one child handle per sub-shard [cuts[i], cuts[i+1]) of the parent's own range (kept when the cuts did not change)
+static int make_kids(bnflac* h, const std::vector<uint64_t>& cuts) {
+    const uint32_t K = (uint32_t)cuts.size() - 1;
+    bool same = h->kids.size() == K;
+    for (uint32_t i = 0; same && i < K; i++) same = h->kids[i]->sub_begin == cuts[i] && h->kids[i]->sub_end == cuts[i + 1];
+    if (same) return 0;
+    for (bnflac* k : h->kids) delete k;
+    h->kids.clear();
+    for (uint32_t i = 0; i < K; i++) {
+        bnflac* c = new (std::nothrow) bnflac; if (!c) return BNFLAC_ERR_MEMORY;
+        h->kids.push_back(c);
+        c->opts = h->opts; c->opts.stream = nullptr; c->opts.device = h->device; c->opts.flags &= ~BNFLAC_OPT_VERIFY_MD5;
+        c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = cuts[i]; c->sub_end = cuts[i + 1];
+        compute_shard(c);
+        c->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
+        int rc = setup_device(c); if (rc) return rc;
+    }
+    return 0;
+}
+
 static int decode_host_pipelined(bnflac* h, const std::vector<uint64_t>& cuts, uint8_t* dst, size_t cap, uint64_t* written) {
     int rc = 0;
     const uint32_t K = (uint32_t)cuts.size() - 1;
@@ -514,21 +536,7 @@ static int decode_host_pipelined(bnflac* h, const std::vector<uint64_t>& cuts, u
     const bool trace = getenv("BNFLAC_TRACE") != nullptr;
     const double t_begin = now_ms();
     double t_kids = 0, t_tables = 0, t_upq = 0, t_loop = 0;
-    bool same = h->kids.size() == K;
-    for (uint32_t i = 0; same && i < K; i++) same = h->kids[i]->sub_begin == cuts[i] && h->kids[i]->sub_end == cuts[i + 1];
-    if (!same) {
-        for (bnflac* k : h->kids) delete k;
-        h->kids.clear();
-        for (uint32_t i = 0; i < K; i++) {
-            bnflac* c = new (std::nothrow) bnflac; if (!c) return BNFLAC_ERR_MEMORY;
-            h->kids.push_back(c);
-            c->opts = h->opts; c->opts.stream = nullptr; c->opts.device = h->device; c->opts.flags &= ~BNFLAC_OPT_VERIFY_MD5;
-            c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = cuts[i]; c->sub_end = cuts[i + 1];
-            compute_shard(c);
-            c->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
-            if ((rc = setup_device(c))) return rc;
-        }
-    }
+    if ((rc = make_kids(h, cuts))) return rc;
     auto drain = [&]() { if (h->up_stream) cudaStreamSynchronize(h->up_stream); for (bnflac* c : h->kids) if (c->stream) cudaStreamSynchronize(c->stream); };
     t_kids = now_ms();
     // tables first: their (small) uploads must not queue behind the bulk uploads on the copy engine
@@ -595,6 +603,7 @@ static int decode_host_pipelined(bnflac* h, const std::vector<uint64_t>& cuts, u
 }
 
 static int decode_host(bnflac* h, uint8_t* dst, size_t cap, uint64_t* written) {
+    h->rd_active = false;                     // a one-shot decode ends any streaming Read session on this handle
     if (h->host_ptr && !h->d_ext && h->batch_segs.empty()) {
         const std::vector<uint64_t> cuts = pipe_cuts(std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end);
         if (cuts.size() > 2) return decode_host_pipelined(h, cuts, dst, cap, written);
@@ -602,6 +611,81 @@ static int decode_host(bnflac* h, uint8_t* dst, size_t cap, uint64_t* written) {
     for (bnflac* k : h->kids) delete k;
     h->kids.clear();
     return decode_host_single(h, dst, cap, written);
+}
+
+// ---- streaming Read (the consumer the reference sketches in StreamingPlayer.cs:8-19,424-464: a ring of
+// small buffers refilled from FLACDecoder.Read while the previous ones play).  FLACDecoder.Read decodes one more frame
+// whenever its queue runs dry (FLACDecoder.cs:124-224); here the stream is cut into sub-shards by frame ranges -- a small
+// first one so that the first Read returns after one short upload + pass + download, then doubling -- and the
+// sub-shards after the one being read are decoded AHEAD of the reader on their own streams into their own pinned
+// buffers.  A Read only ever waits for the download event of the sub-shard it is copying from; consumed sub-shards give
+// their device and pinned blocks back to the pool (their small frame tables stay for the diagnostics).
+static size_t env_kb(const char* name, long dflt) { const char* e = getenv(name); long kb = e ? atol(e) : dflt; if (kb < 16) kb = 16; return (size_t)kb << 10; }
+static std::vector<uint64_t> read_cuts(const bnflac* h, uint64_t b, uint64_t e) {
+    uint64_t first = env_kb("BNFLAC_READ_FIRST_KB", 4096), cap = env_mb("BNFLAC_READ_MB", 64);
+    if (h->opts.read_chunk_frames) {       // caller-chosen look-ahead batch: that many frames of average compressed size
+        const uint64_t bs = h->info.max_blocksize ? h->info.max_blocksize : 4096;
+        const uint64_t nframes = h->info.total_samples ? std::max<uint64_t>(1, h->info.total_samples / bs) : 0;
+        const uint64_t per = nframes ? std::max<uint64_t>(64, (e - b) / nframes) : std::max<uint64_t>(64, frame_bound(h->info) / 2);
+        first = cap = std::max<uint64_t>(16384, per * h->opts.read_chunk_frames);
+    }
+    if (cap < first) cap = first;
+    std::vector<uint64_t> cuts{b};
+    if (e - b >= 3 * first) {
+        uint64_t pos = b, sz = first;
+        while (e - pos > sz + sz / 2 && cuts.size() < 4096) { pos += sz; cuts.push_back(pos); sz = std::min<uint64_t>(2 * sz, cap); }
+    }
+    cuts.push_back(e);
+    return cuts;
+}
+
+static constexpr uint32_t READ_LOOKAHEAD = 2;      // sub-shards in flight beyond the one being read
+
+// upload + front kernels + decode + download of sub-shard k, all asynchronous but for the two size hand-offs in run_front
+static int stream_issue(bnflac* h, uint32_t k) {
+    bnflac* c = h->kids[k];
+    int rc = run_front(c); if (rc) return rc;
+    c->pcm_base = h->rd_total;
+    h->rd_total += c->totals.pcm_bytes;
+    if ((rc = c->pcm_host.reserve((size_t)c->totals.pcm_bytes + 64))) return rc;
+    if ((rc = c->d_out.reserve((size_t)c->totals.pcm_bytes + 64))) return rc;
+    if ((rc = run_back(c, c->d_out.as<uint8_t>(), c->d_out.cap))) return rc;
+    if (c->totals.pcm_bytes) CK(cudaMemcpyAsync(c->pcm_host.p, c->d_out.p, (size_t)c->totals.pcm_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    c->pcm_len = c->totals.pcm_bytes;
+    return 0;
+}
+
+static int stream_issue_all(bnflac* h) {
+    while (h->rd_issued < h->kids.size()) { int rc = stream_issue(h, h->rd_issued); if (rc) return rc; h->rd_issued++; }
+    return 0;
+}
+
+static int64_t stream_read(bnflac* h, uint8_t* dst, size_t count) {
+    CK(cudaSetDevice(h->device));
+    const uint32_t K = (uint32_t)h->kids.size();
+    size_t done = 0;
+    int rc;
+    while (done < count && h->rd_cur < K) {
+        if (h->rd_issued <= h->rd_cur) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
+        bnflac* c = h->kids[h->rd_cur];
+        CK(cudaEventSynchronize(c->ev[7]));
+        const size_t n = (size_t)std::min<uint64_t>(c->pcm_len - h->rd_off, count - done);
+        if (n) memcpy(dst + done, (const uint8_t*)c->pcm_host.p + h->rd_off, n);
+        done += n; h->rd_off += n;
+        if (h->rd_off == c->pcm_len) {               // sub-shard consumed: its blocks go back to the pool
+            finish_timing(c);
+            h->timing.scan += c->timing.scan; h->timing.crc += c->timing.crc; h->timing.link += c->timing.link; h->timing.parse += c->timing.parse;
+            h->timing.decode += c->timing.decode; h->timing.total += c->timing.total; h->timing.launches += c->timing.launches;
+            c->pcm_host.release(); c->d_out.release();
+            if (!c->d_ext) { c->d_in.release(); c->uploaded = false; c->tables_ready = false; }
+            h->rd_cur++; h->rd_off = 0;
+        }
+    }
+    // keep the decode ahead of the reader: at most one more sub-shard per call, so no single Read pays for several
+    if (h->rd_issued < K && h->rd_issued <= h->rd_cur + READ_LOOKAHEAD) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
+    h->state = h->rd_cur == K ? BNFLAC_STATE_END_OF_STREAM : BNFLAC_STATE_READ_FRAME;
+    return (int64_t)done;
 }
 
 // ---- diagnostics: frame / subframe tables and the error-callback events the reference would have raised
@@ -721,6 +805,7 @@ static int fetch_diag(bnflac* h) {
     cur.expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
     cur.have_expect = h->own_begin <= h->info.first_frame_offset;      // a later shard starts wherever its first frame starts
     int rc;
+    if (h->rd_active && (rc = stream_issue_all(h))) return rc;       // the tables cover the whole stream, read or not
     if (!h->kids.empty()) {
         for (bnflac* c : h->kids)
             if ((rc = collect_diag(c, cur, c->pcm_base, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
@@ -961,6 +1046,17 @@ int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written) 
 
 int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count) {
     if (!h || (!dst && count)) return BNFLAC_ERR_ARG;
+    if (h->rd_active) return stream_read(h, dst, count);
+    if (!h->decoded && h->host_ptr && !h->d_ext && h->batch_segs.empty()) {
+        // large host-resident stream: decode ahead of the reader in sub-shards instead of all at once
+        const std::vector<uint64_t> cuts = read_cuts(h, std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end);
+        if (cuts.size() > 2) {
+            CK(cudaSetDevice(h->device));
+            int rc = make_kids(h, cuts); if (rc) return rc;
+            h->rd_active = true; h->rd_issued = h->rd_cur = 0; h->rd_off = h->rd_total = 0; h->timing = bnflac_timing{}; h->diag_valid = false;
+            return stream_read(h, dst, count);
+        }
+    }
     if (!h->decoded) {
         // the whole (shard of the) stream is decoded at the first Read into pinned host memory; later Reads are memcpy.
         // Capacity: what STREAMINFO promises, or (unknown length / damaged stream) what the frame scan finds.

@@ -726,7 +726,10 @@ struct RingBitsT {
 #define DEC_RING_DEPTH 1
 #endif
 using ParseBits = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH>;   // no sample tile in k_parse: room for a longer ring and a deeper prefetch
-using RingBits = RingBitsT<8, DEC_RING_DEPTH>;                       // k_decode
+#ifndef DEC_RING_BLOCKS
+#define DEC_RING_BLOCKS 8
+#endif
+using RingBits = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH>;         // k_decode (16 blocks: one refill checkpoint per 16 samples)
 
 // ------------------------------------------------------------------------------------------------ K2 parse
 // One lane per frame: walks the subframes, records where each starts and what it is, skips the residual.  Lanes of a warp
@@ -1081,7 +1084,7 @@ __global__ void __launch_bounds__(256) k_seg_summary(PassArgs a, uint64_t* seg_p
 enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 
 #ifndef DEC_MAXNREG
-#define DEC_MAXNREG 112
+#define DEC_MAXNREG 120
 #endif
 #ifndef DEC_TILE
 #define DEC_TILE 48
@@ -1276,7 +1279,10 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
     }
 }
 
-constexpr int DEC_WARPS = 2;                  // independent warps per CTA (no CTA-wide barrier anywhere)
+#ifndef DEC_WARPS_N
+#define DEC_WARPS_N 2
+#endif
+constexpr int DEC_WARPS = DEC_WARPS_N;        // independent warps per CTA (no CTA-wide barrier anywhere)
 __host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
 
 template <int ORD, bool WIDE>
@@ -1380,10 +1386,9 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
         // ---- Rice phase
 #pragma unroll 1
-        for (uint32_t t0 = 0; t0 < (uint32_t)T; t0 += 8) {
+        for (uint32_t t0 = 0, row = col; t0 < (uint32_t)T; t0 += 8, row += 8 * rs4) {      // row: loop-carried, or it is rematerialised from SR_TID every step
             const uint32_t idx0 = i0 + t0;
-            const uint32_t row = col + t0 * rs4;
-            if (reads) br.checkpoint();
+            if (reads && (DEC_RING_BLOCKS < 16 || !(t0 & 8u))) br.checkpoint();
             const bool inert = mode <= M_CONST || idx0 >= bs;
             if (mode == M_PRED && !inert && rs.fastleft == 0 && rs.rawleft == 0 && idx0 >= order) rice_param(br, rs);
             const bool fast_ok = inert || (mode == M_PRED && rs.fastleft >= 8);
