@@ -174,6 +174,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cpus(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers of the e2e leg
+    (first touched by this process) and the copies that read/write them stay on the GPU's NUMA node.  With one process
+    per GPU (torchrun) every rank otherwise shares whatever node the launcher happened to start on."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -189,6 +203,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -197,6 +213,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     s = make_stream(args.seconds)
+    numa = bind_to_gpu_cpus(local)            # after the (multi-threaded) stream generator, before any pinned allocation
     flac_len = len(s.flac)
     strong = args.scaling == "strong" and world > 1
     shard = dict(shard_index=rank, shard_count=world) if strong else {}
@@ -298,6 +315,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "seconds_per_stream": args.seconds, "streams": 1 if strong else world,
                        "frames_per_stream": len(s.frame_bs), "compressed_bytes": flac_len, "pcm_bytes": pcm_bytes_stream,
                        "parallelism": f"{'frame-range' if strong else 'file'} shards x{world}, no collective",
+                       "host_cpus_bound_to_gpu": numa,
                        "l2": "inputs (1.1 GB) and outputs (2.1 GB) exceed the 126 MB L2; no flush needed"},
             "pcm_gbps": value * 3 / 1e9,
             "pipeline_hbm_frac": (units_bytes * (1 if strong else 1)) / (ms_per_step / 1e3) / 1e9 / peak,
@@ -312,6 +330,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
+            try:
+                os.sched_setaffinity(0, range(cores))      # undo bind_to_gpu_cpus: the CPU baseline gets every host thread
+            except OSError:
+                pass
             uniq = make_stream(min(args.seconds, UNIQUE_SECONDS)) if args.seconds > UNIQUE_SECONDS else s
             n_all = uniq.total_samples * uniq.channels
             _, _, dt1 = cpu_decode_rate(uniq.flac, n_all, cores, 1)
