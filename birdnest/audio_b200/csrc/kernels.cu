@@ -1420,7 +1420,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
             const bool inert = mode <= M_CONST || idx0 >= bs;
             if (mode == M_PRED && !inert && rs.fastleft == 0 && rs.rawleft == 0 && idx0 >= order) rice_param(br, rs);
             const bool fast_ok = inert || (mode == M_PRED && rs.fastleft >= 8);
-            if (__all_sync(FULL, fast_ok)) {
+            // branch-free group of 8 Rice codewords; `commit`: this lane is really in a Rice partition with >= 8 left
+            auto rice_group = [&](const bool commit) {
                 uint32_t pos = br.pos;
                 const uint32_t k = rs.k, kp32 = rs.kp32, negP = rs.negP, c30 = rs.c30;
                 bool ovf = false;
@@ -1439,7 +1440,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                     const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
                     r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
                 }
-                if (!inert) {
+                if (commit) {
                     rs.fastleft -= 8;
                     if (!ovf) {
                         br.pos = pos;
@@ -1450,20 +1451,36 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                         for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.rice_careful(k));
                     }
                 }
-            } else {
+            };
+            if (__all_sync(FULL, fast_ok)) rice_group(!inert);
+            else {
+                // lanes that read fixed-width samples for the whole step (VERBATIM subframes, escape partitions): when they are
+                // the only reason the step is not uniform, the Rice lanes keep their branch-free group and these lanes read
+                // their 8 samples in a short loop of their own -- instead of a careful walk of every lane
+                const bool rawlane = !inert && ((mode == M_VERBATIM && idx0 + 8 <= bs) || (mode == M_PRED && rs.rawleft >= 8));
+                if (__all_sync(FULL, fast_ok || rawlane)) {
+                    rice_group(!inert && !rawlane);
+                    if (rawlane) {
+                        const uint32_t nb = mode == M_VERBATIM ? bps : rs.rawbits;
+                        if (mode == M_PRED) rs.rawleft -= 8;
 #pragma unroll 1
-                for (uint32_t j = 0; j < 8; j++) {
-                    const uint32_t idx = idx0 + j;
-                    if (mode <= M_CONST || idx >= bs) continue;
-                    int32_t v;
-                    if (mode == M_VERBATIM) v = br.gets(bps);
-                    else {
-                        if (idx < order) continue;               // parked warm-up sample
-                        if (rs.fastleft == 0 && rs.rawleft == 0) rice_param(br, rs);
-                        if (rs.rawleft) { rs.rawleft--; v = br.gets(rs.rawbits); }
-                        else { rs.fastleft--; v = br.rice_careful(rs.k); }
+                        for (uint32_t j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.gets(nb));
                     }
-                    sts32(row + j * rs4, (uint32_t)v);
+                } else {
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 8; j++) {
+                        const uint32_t idx = idx0 + j;
+                        if (mode <= M_CONST || idx >= bs) continue;
+                        int32_t v;
+                        if (mode == M_VERBATIM) v = br.gets(bps);
+                        else {
+                            if (idx < order) continue;               // parked warm-up sample
+                            if (rs.fastleft == 0 && rs.rawleft == 0) rice_param(br, rs);
+                            if (rs.rawleft) { rs.rawleft--; v = br.gets(rs.rawbits); }
+                            else { rs.fastleft--; v = br.rice_careful(rs.k); }
+                        }
+                        sts32(row + j * rs4, (uint32_t)v);
+                    }
                 }
             }
         }
