@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(256) k_cover(PassArgs a) {
 // HBM latency whenever too few warps are resident to hide it (streams with few, large frames).  With DEPTH > 0 the
 // checkpoint only waits for older groups, provided what those covered (mark[DEPTH]) reaches past everything the coming
 // period can read; a lane that consumed unusually many bits falls back to a full wait.
-template <int NBLK_, int DEPTH>
+template <int NBLK_, int DEPTH, int STEADY_ = 0>
 struct RingBitsT {
     static constexpr int NBLK = NBLK_, BLK = 16, RB_BYTES = NBLK * BLK;
     static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
@@ -607,10 +607,28 @@ struct RingBitsT {
     }
     __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
     __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-    __device__ __forceinline__ void request() {     // request every block the ring has room for (never the slot being read)
+    // fetch(b) under a predicate, without a branch (a cp.async of size 0 would zero the slot, so the instruction itself is
+    // predicated)
+    __device__ __forceinline__ void fetch_if(uint32_t b, bool p) {
+        const uint32_t n = b < navail ? 16u : 0u;
+        const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
+        const uint32_t slot = b & (NBLK - 1);
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + slot * BLK), "l"(s), "r"(n), "r"((uint32_t)p) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + RB_BYTES), "l"(s), "r"(n), "r"((uint32_t)(p && slot == 0)) : "memory");
+    }
+    // Request every block the ring has room for (never the slot being read).  STEADY = how many blocks a refill period
+    // normally frees: that many are requested branch-free under predicates (the lanes of a warp free different numbers of
+    // blocks, so a loop here diverges on nearly every call); whatever is left after a big move goes through the loop.
+    // STEADY = 0 keeps the plain loop: with many resident warps (streams of many frames) the predicated slots that turn out
+    // empty cost more issue slots than the divergence they avoid (cfg2: parse +3 %), with few warps the branches dominate
+    // (cfg3: parse 5.30 -> 4.56 ms, decode 4.65 -> 4.50 ms).
+    static constexpr int STEADY = STEADY_;
+    __device__ __forceinline__ void request() {
         const uint32_t curblk = pos / (BLK * 8);
         if (filled < curblk) filled = curblk;       // jumped over unrequested blocks
         const uint32_t lim = curblk + NBLK;
+#pragma unroll
+        for (int i = 0; i < STEADY; i++) { const bool p = filled < lim; fetch_if(filled, p); filled += p ? 1u : 0u; }
         if (filled < lim) {
 #pragma unroll 1
             do { fetch(filled); filled++; } while (filled < lim);
@@ -726,10 +744,12 @@ struct RingBitsT {
 #define DEC_RING_DEPTH 1
 #endif
 using ParseBits = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH>;   // no sample tile in k_parse: room for a longer ring and a deeper prefetch
+template <bool LEAN> using ParseBitsT = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH, LEAN ? 3 : 0>;
 #ifndef DEC_RING_BLOCKS
 #define DEC_RING_BLOCKS 8
 #endif
 using RingBits = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH>;         // k_decode (16 blocks: one refill checkpoint per 16 samples)
+template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (ORD > 12 ? 2 : 0)>;   // orders > 12: few, long subframes
 
 // ------------------------------------------------------------------------------------------------ K2 parse
 // One lane per frame: walks the subframes, records where each starts and what it is, skips the residual.  Lanes of a warp
@@ -747,7 +767,8 @@ struct ParseSub {            // per-lane state of the residual being skipped
 };
 
 // next partition parameter(s); a zero-sample partition 0 (order == partition size) is followed immediately by partition 1
-__device__ __forceinline__ bool parse_param(ParseBits& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
+template <class BR>
+__device__ __forceinline__ bool parse_param(BR& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
 #pragma unroll 1
     for (int guard = 0; guard < 2; guard++) {
         const uint32_t cnt = p.psize - (p.first ? p.order : 0);
@@ -768,19 +789,19 @@ __device__ __forceinline__ bool parse_param(ParseBits& br, ParseSub& p, const ui
 
 // N codewords of every walking lane's partition, branch-free: window, bfind, add; a codeword that does not fit one
 // 32-bit window raises a flag and the lane redoes the group one careful codeword at a time.
-template <int N>
-__device__ __forceinline__ void parse_group(ParseBits& br, ParseSub& ps, bool& walk, bool& bad) {
+template <int N, class BR>
+__device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bool& bad) {
     uint32_t pos = br.pos;
     const uint32_t k = ps.k, kp32 = ps.kp32;
     bool ovf = false;
-    ParseBits::Win3 wn = br.win_init(pos);
+    typename BR::Win3 wn = br.win_init(pos);
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const uint32_t nxt = j < N - 1 ? br.win_next(pos) : 0u;
-        const uint32_t f = bfind(ParseBits::win_peek(wn, pos));
+        const uint32_t f = bfind(BR::win_peek(wn, pos));
         ovf |= (int32_t)(f - k) < 0;
         const uint32_t np = pos + kp32 - f;
-        if (j < N - 1) ParseBits::win_advance(wn, pos, np, nxt);
+        if (j < N - 1) BR::win_advance(wn, pos, np, nxt);
         pos = np;
     }
     if (walk) {
@@ -795,6 +816,8 @@ __device__ __forceinline__ void parse_group(ParseBits& br, ParseSub& ps, bool& w
     }
 }
 
+// LEAN: branch-free ring refill (streams of few, large frames: the kernel is then a handful of warps, see RingBitsT::request)
+template <bool LEAN>
 __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     extern __shared__ __align__(16) uint8_t s_ring[];
     const uint32_t n = ncand(a);
@@ -815,7 +838,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         seg_end = sg.end;
         end_bit = (st == ST_OK ? c.off + a.flen[i] : min(sg.end, c.off + (uint64_t)sg.max_frame_bytes)) * 8;
     }
-    ParseBits br;
+    ParseBitsT<LEAN> br;
     if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
     else br.init_idle(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in);
     // end of the frame as a ring-relative bit position (frames are far below 2^32 bits)
@@ -1116,7 +1139,8 @@ struct RiceSt {
     bool first;
 };
 
-__device__ __forceinline__ void rice_param(RingBits& br, RiceSt& rs) {
+template <class BR>
+__device__ __forceinline__ void rice_param(BR& br, RiceSt& rs) {
 #pragma unroll 1
     for (int guard = 0; guard < 2; guard++) {
         const uint32_t cnt = rs.psize - (rs.first ? rs.order : 0);
@@ -1330,7 +1354,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     const uint32_t col = tile_base + lane * 4;
 
     // ---- per-subframe state (registers)
-    RingBits br;
+    DecRing<ORD> br;
     br.init_idle(ring_base + lane * RingBits::STRIDE, a.in);
     constexpr bool F64 = WIDE && !DEC_WIDE_I64;       // FP64-pipe accumulation (coefficients scaled by 2^-shift) vs mad.wide.s32
     typename std::conditional<F64, double, int32_t>::type cf[ORD], hist[ORD];
@@ -1426,16 +1450,16 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                 const uint32_t k = rs.k, kp32 = rs.kp32, negP = rs.negP, c30 = rs.c30;
                 bool ovf = false;
                 int32_t r[8];
-                RingBits::Win3 wn = br.win_init(pos);
+                typename DecRing<ORD>::Win3 wn = br.win_init(pos);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const uint32_t nxt = j < 7 ? br.win_next(pos) : 0u;
-                    const uint32_t w = RingBits::win_peek(wn, pos);
+                    const uint32_t w = DecRing<ORD>::win_peek(wn, pos);
                     const uint32_t f = bfind(w);
                     const uint32_t d = f - k;
                     ovf |= (int32_t)d < 0;
                     const uint32_t np = pos + kp32 - f;
-                    if (j < 7) RingBits::win_advance(wn, pos, np, nxt);
+                    if (j < 7) DecRing<ORD>::win_advance(wn, pos, np, nxt);
                     pos = np;
                     const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
                     r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
@@ -1541,7 +1565,10 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
     k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
-    k_parse<<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a); g_launches++;
+    // fewer than two warps per scheduler: the walk is latency-bound and its branches are what it waits for
+    if (nb < (uint32_t)sm_count() * 4u * 2u * 32u) k_parse<true><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
+    else k_parse<false><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
+    g_launches++;
 }
 void launch_resync(const PassArgs& a, void* stream) { k_resync<<<1, 256, 0, S(stream)>>>(a); g_launches++; }
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream) {
