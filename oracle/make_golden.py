@@ -48,7 +48,72 @@ def ref_encode(pcm: bytes, ch, bps, sr, bs, lpc, minpo, maxpo, ms, ex):
         return open(fo, "rb").read()
 
 
+def _block(btype: int, payload: bytes, last: bool = False) -> bytes:
+    return bytes([(0x80 if last else 0) | btype]) + len(payload).to_bytes(3, "big") + payload
+
+
+def metadata_variants(flac: bytes):
+    """The same audio behind different container prefixes (LibFLACSharp.cs:270-280 lists the block types; the
+    decoder answers STREAMINFO only, FLACDecoder.cs:431-473, and must skip the rest).  Returns {name: bytes}."""
+    assert flac[:4] == b"fLaC" and (flac[4] & 0x7f) == 0
+    si = flac[8:8 + 34]
+    pos, last = 4, False
+    while not last:                                   # first frame = after the last metadata block of the original
+        last = bool(flac[pos] & 0x80)
+        pos += 4 + int.from_bytes(flac[pos + 1:pos + 4], "big")
+    frames = flac[pos:]
+    vendor = b"reference libFLAC 1.2.1 20070917"
+    vorbis = len(vendor).to_bytes(4, "little") + vendor + (2).to_bytes(4, "little")
+    for c in (b"TITLE=synthetic", b"ARTIST=bnflac tests"):
+        vorbis += len(c).to_bytes(4, "little") + c
+    seek = b"".join(((i * 4096).to_bytes(8, "big") + (i * 9000).to_bytes(8, "big") + (4096).to_bytes(2, "big")) for i in range(3))
+    seek += b"\xff" * 8 + bytes(10)                   # one placeholder point
+    cue = bytes(128) + (0).to_bytes(8, "big") + bytes([0]) + bytes(258) + bytes([1])          # catalog, lead-in, flags, reserved, 1 track
+    cue += (0).to_bytes(8, "big") + bytes([170]) + bytes(12) + bytes([0]) + bytes(13) + bytes([0])   # lead-out track, no indices
+    mime, desc, data = b"image/png", b"cover", bytes(range(256)) * 3 + b"\xff\xf8\xc9\x18\x00\x00"      # a fake sync code inside
+    pic = (3).to_bytes(4, "big") + len(mime).to_bytes(4, "big") + mime + len(desc).to_bytes(4, "big") + desc
+    pic += (16).to_bytes(4, "big") * 2 + (24).to_bytes(4, "big") + (0).to_bytes(4, "big") + len(data).to_bytes(4, "big") + data
+    app = b"bnfl" + b"\xff\xf8" * 40                    # sync-code look-alikes inside an APPLICATION block
+    out = {}
+    out["meta_all_block_types"] = (b"fLaC" + _block(0, si) + _block(2, app) + _block(3, seek) + _block(4, vorbis) + _block(5, cue) +
+                                   _block(6, pic) + _block(1, bytes(77)) + _block(30, b"reserved type") + _block(1, bytes(5), last=True) + frames)
+    id3 = b"ID3\x03\x00\x00" + bytes([0, 0, 2, 44]) + (b"TIT2" + bytes(296))                  # syncsafe size 300
+    out["meta_id3v2_prefix"] = id3 + flac
+    out["meta_big_padding"] = b"fLaC" + _block(0, si) + _block(1, bytes(70000), last=True) + frames   # > the 16 KiB read buffer of FLACDecoder.cs:19-24
+    si_unknown = si[:13] + bytes([si[13] & 0xF0]) + bytes(4) + bytes(16)                         # total_samples = 0, md5 = 0
+    si_unknown = si_unknown[:4] + bytes(6) + si_unknown[10:]                                       # min/max frame size unknown
+    out["meta_unknown_length_no_md5"] = b"fLaC" + _block(0, si_unknown, last=True) + frames
+    return out
+
+
+def metadata_cases(out):
+    """4. container / metadata breadth: what the reference decoder does with every block type, an ID3v2 tag, a large PADDING
+    block and a STREAMINFO that does not know the length -- fixtures committed as tests/golden/meta_*.flac."""
+    import pycorpus
+    import pyoracle
+    base = pycorpus.make(ch=2, bps=16, sr=44100, seconds=0.6, bs=1152, lpc=8, seed=404)
+    out["metadata"] = {}
+    ok = True
+    for name, blob in sorted(metadata_variants(base.flac).items()):
+        r = ref_decode(blob)
+        o_pcm, o_n, _, o_err = pyoracle.decode(blob)
+        same = r.get("pcm") == o_pcm == base.pcm and r.get("errors") == o_err == [] and r.get("frames") == o_n
+        ok &= same
+        open(os.path.join(GOLD, name + ".flac"), "wb").write(blob)
+        out["metadata"][name] = {"ref_pcm_md5": hashlib.md5(r.get("pcm", b"")).hexdigest(), "frames": r.get("frames"), "state": r.get("state"), "errors": r.get("errors"),
+                                 "sr": r.get("sr"), "ch": r.get("ch"), "bps": r.get("bps"), "total": r.get("total"), "si_md5": r.get("si_md5"),
+                                 "bytes": len(r.get("pcm", b"")), "oracle_equal": bool(same)}
+        print(("OK  " if same else "FAIL"), name, len(blob), r.get("frames"), r.get("errors"), r.get("total"), r.get("failed"))
+    return ok
+
+
 def main():
+    if "--only-metadata" in sys.argv:
+        out = json.load(open(os.path.join(GOLD, "golden.json")))
+        ok = metadata_cases(out)
+        json.dump(out, open(os.path.join(GOLD, "golden.json"), "w"), indent=1, sort_keys=True)
+        print("metadata pinned" if ok else "MISMATCHES PRESENT")
+        return 0 if ok else 1
     import pycorpus
     import pyoracle
     from conftest import CASES
@@ -111,6 +176,7 @@ def main():
                                "ref_bytes": len(r.get("pcm", b"")), "frames": r.get("frames"), "errors": r.get("errors"), "error_states": r.get("error_states"),
                                "state": r.get("state"), "oracle_equal": bool(same)}
         print(("OK  " if same else "DIFF"), "fault", name, r.get("frames"), r.get("errors"), r.get("error_states"), "oracle:", o_n, o_err, len(o_pcm), len(r.get("pcm", b"")))
+    ok &= metadata_cases(out)
     json.dump(out, open(os.path.join(GOLD, "golden.json"), "w"), indent=1, sort_keys=True)
     print("all pinned" if ok else "MISMATCHES PRESENT")
     return 0 if ok else 1

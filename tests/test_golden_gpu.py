@@ -135,3 +135,54 @@ def test_empty_and_truncated_streams(streams):
         assert h.decode_all() == b"" and h.frames() == []
     with _abi.open_memory(s.flac[:len(s.flac) - 3]) as h:    # the only frame is cut short: nothing is delivered (reference: END_OF_STREAM)
         assert h.decode_all() == b""
+
+
+@pytest.mark.parametrize("name", sorted(golden["metadata"]))
+@pytest.mark.parametrize("how", ["decode_all", "read", "callbacks"])
+def test_metadata_variants_decode_to_the_reference_pcm(name, how):
+    """APPLICATION / SEEKTABLE / VORBIS_COMMENT / CUESHEET / PICTURE / PADDING / reserved blocks (with sync-code
+    look-alikes inside them), an ID3v2 prefix, 70 kB of PADDING and a STREAMINFO that knows neither length nor md5: the
+    engine must deliver what the reference decoder delivered (tests/golden/golden.json, written by oracle/make_golden.py)."""
+    from birdnest.audio_b200 import _abi
+    g = golden["metadata"][name]
+    flac = open(os.path.join(GOLD, name + ".flac"), "rb").read()
+    if how == "callbacks":
+        # FLACDecoder.ReadCallback exactly (FLACDecoder.cs:325-363): at most 16 KiB per call whatever was asked for, and
+        # end-of-stream only when the inner stream returned less than that capped length
+        import ctypes as C
+        pos = [0]
+
+        def _cb(user, buf, nbytes):
+            want = min(nbytes[0], 16384)
+            chunk = flac[pos[0]:pos[0] + want]
+            pos[0] += len(chunk)
+            C.memmove(buf, chunk, len(chunk))
+            nbytes[0] = len(chunk)
+            return 1 if len(chunk) < want else 0
+        cb = _abi.READ_CB(_cb)
+        o = _abi._opts(-1)
+        hp = C.c_void_p()
+        assert _abi.lib().bnflac_open_callbacks(cb, None, C.byref(o), C.byref(hp)) == 0
+        h = _abi.Handle(hp.value)
+    else:
+        h = _abi.open_memory(flac)
+    with h:
+        info = h.info()
+        if how == "read":
+            pcm = bytearray()
+            buf = bytearray(81920)
+            while True:
+                n = h.read_into(buf)
+                pcm += buf[:n]
+                if n < len(buf):
+                    break
+            pcm = bytes(pcm)
+        else:
+            pcm = h.decode_all()
+        frames = h.frames()
+        errs = h.errors()
+    assert hashlib.md5(pcm).hexdigest() == g["ref_pcm_md5"]
+    assert (len(frames), len(pcm), errs) == (g["frames"], g["bytes"], g["errors"])
+    assert (info.channels, info.bits_per_sample, info.sample_rate, info.total_samples) == (g["ch"], g["bps"], g["sr"], g["total"])
+    if g["total"]:
+        assert bytes(info.md5).hex() == g["si_md5"] == g["ref_pcm_md5"]

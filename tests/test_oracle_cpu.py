@@ -101,3 +101,15 @@ def test_oracle_edge_cases():
     # truncated in the middle of the only frame: reference reaches END_OF_STREAM without delivering it
     pcm, nframes, _, _ = pyoracle.decode(s.flac[:len(s.flac) - 50])
     assert (pcm, nframes) == (b"", 0)
+
+
+@pytest.mark.parametrize("name", sorted(golden["metadata"]))
+def test_oracle_matches_reference_on_metadata_variants(name):
+    """Container breadth: every metadata block type, an ID3v2 tag, a PADDING block larger than the reference's
+    16 KiB read buffer, a STREAMINFO without length / md5.  The md5 recorded is the one the reference DECODER produced."""
+    import pyoracle
+    g = golden["metadata"][name]
+    flac = open(os.path.join(GOLD, name + ".flac"), "rb").read()
+    pcm, nframes, _, errs = pyoracle.decode(flac)
+    assert hashlib.md5(pcm).hexdigest() == g["ref_pcm_md5"]
+    assert (nframes, len(pcm), errs) == (g["frames"], g["bytes"], g["errors"])
