@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <type_traits>
 #include <cstdlib>
+#include <cstdio>
 
 namespace bnf {
 
@@ -1618,6 +1619,9 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     int max_resident = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC>, 32 * DEC_WARPS, smem);
     if (max_resident < 1) max_resident = 1;
+    static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: %d CTAs of %d warps resident per SM, grid %u (%.2f waves), %zu B smem/CTA\n", ORD, (int)WIDE, SPEC, max_resident, DEC_WARPS,
+                       grid, (double)grid / ((double)n_sm * max_resident), smem);
     // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  Cap the residency
     // (by asking for more shared memory) so that the waves are equally full instead of full ones plus a nearly empty one.
     const uint64_t per_wave = (uint64_t)n_sm * max_resident;
