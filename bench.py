@@ -174,6 +174,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class StdoutToStderr:
+    """File descriptor 1 points at stderr inside the block (native libraries that printf are covered too)."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def bind_to_gpu_cpus(index: int):
     """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers of the e2e leg
     (first touched by this process) and the copies that read/write them stay on the GPU's NUMA node.  With one process
@@ -203,8 +218,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner) go to stderr: stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        with StdoutToStderr():        # NCCL prints its version banner on stdout at communicator creation: stdout carries ONE JSON line
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
