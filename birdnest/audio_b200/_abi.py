@@ -248,6 +248,8 @@ def open_memory(data, device=-1, stream=0, shard_index=0, shard_count=0, flags=0
 
 
 def open_device(d_ptr: int, length: int, header: bytes, device=-1, stream=0, shard_index=0, shard_count=0, keep=None) -> Handle:
+    """bnflac_open_device: the stream's bytes are already in device memory.  The allocation must be readable for 64 bytes past
+    d_ptr + length (allocate length + 64; contents irrelevant) -- see include/bnflac.h."""
     o = _opts(device, stream, shard_index, shard_count, 0)
     h = C.c_void_p()
     _check(lib().bnflac_open_device(d_ptr, length, _addr(header), len(header), C.byref(o), C.byref(h)), "bnflac_open_device")

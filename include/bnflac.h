@@ -101,7 +101,9 @@ int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts,
 int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* opts, bnflac_t** out);
 /* Opens a stream whose bytes are ALREADY resident in device memory (d_data stays owned by the caller and must
  * outlive the handle).  `header` = at least the first header_len bytes of the same stream in host memory
- * (metadata is parsed on the host).  Benchmark / pipeline path. */
+ * (metadata is parsed on the host).  Benchmark / pipeline path.
+ * The kernels fetch the input in aligned 16-byte units: the allocation behind d_data must be READABLE for 64
+ * bytes past d_data + len (what those bytes hold does not matter; nothing past len is ever interpreted). */
 int bnflac_open_device(const void* d_data, size_t len, const uint8_t* header, size_t header_len, const bnflac_opts* opts, bnflac_t** out);
 int bnflac_info(bnflac_t* h, bnflac_info_t* info);
 int bnflac_state(bnflac_t* h);                       /* bnflac_state_t */
