@@ -855,6 +855,32 @@ static int decode_batch_impl(const bnflac_span* clips, size_t n, const bnflac_op
     }
     uint64_t out_off = 0;
     int rc = 0;
+    // Packed input: the clips lie in ascending order inside one host buffer, a few bytes apart (a shard / archive file read in
+    // one piece).  The whole range is then uploaded ONCE, in place, and every format group's pass addresses its clips inside
+    // it: no gather into staging memory (40 of the 104 ms of a 2.5 GB batch), no second copy of the input in host memory.
+    const uint8_t* pk_lo = nullptr; uint64_t pk_span = 0;
+    {
+        uint64_t total = 0, nvalid = 0; const uint8_t* prev_end = nullptr; bool ascending = true;
+        for (size_t i = 0; i < n && ascending; i++) {
+            if (meta[i].rc) continue;
+            if (prev_end && clips[i].data < prev_end) ascending = false;
+            if (!pk_lo) pk_lo = clips[i].data;
+            prev_end = clips[i].data + clips[i].len; total += clips[i].len; nvalid++;
+        }
+        if (ascending && nvalid >= 2 && (uint64_t)(prev_end - pk_lo) <= total + total / 4 + nvalid * 1024) pk_span = (uint64_t)(prev_end - pk_lo);
+    }
+    DevBuf packed;
+    if (pk_span) {
+        int dev = opts.device; if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        CK(cudaSetDevice(dev));
+        const double t_u0 = now_ms();
+        if ((rc = packed.reserve((size_t)pk_span + 128))) return rc;
+        if (cudaMemcpy(packed.p, pk_lo, (size_t)pk_span, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset((uint8_t*)packed.p + pk_span, 0, 128) != cudaSuccess) {
+            cudaGetLastError(); packed.release(); g_cuda_err = "batch upload (packed)"; return BNFLAC_ERR_CUDA;
+        }
+        if (trace) fprintf(stderr, "[bnflac] batch: packed input, %.1f MB uploaded in place in %.2f ms\n", pk_span / 1e6, now_ms() - t_u0);
+    }
+    struct PackedGuard { DevBuf& b; ~PackedGuard() { b.release(); } } packed_guard{packed};
     for (Group& G : groups) {
         bnflac h;
         h.opts = opts; h.info = meta[G.clips[0]].info;
@@ -865,23 +891,27 @@ static int decode_batch_impl(const bnflac_span* clips, size_t n, const bnflac_op
             const ClipMeta& m = meta[ci];
             const uint64_t first = m.info.first_frame_offset, nbytes = clips[ci].len - first;
             SegDesc d{};
+            if (pk_span) pos = (uint64_t)(clips[ci].data + first - pk_lo);          // where the clip's frames already are
             d.begin = pos; d.end = pos + nbytes; d.own_begin = d.begin; d.own_end = d.end;
             d.sample_rate = m.info.sample_rate; d.min_bs = m.info.min_blocksize; d.max_bs = m.info.max_blocksize; d.max_frame_bytes = frame_bound(m.info);
             h.batch_segs.push_back(d);
             src.emplace_back(clips[ci].data + first, (size_t)nbytes); at.push_back(pos);
             pos = (pos + nbytes + 15) & ~15ull;
         }
-        h.len = pos;
+        h.len = pk_span ? pk_span : pos;
         const double t_g0 = now_ms();
         if ((rc = setup_device(&h))) return rc;
+        double t_g1 = t_g0, t_g2 = t_g0;
+        if (pk_span) { h.d_ext = packed.as<uint8_t>(); rc = run_front(&h); if (rc) return rc; }
+        else {
         // The clips are gathered into pinned staging memory by host threads, then uploaded in one copy.  Overlapping the two
         // (alternating staging buffers, upload of one run of clips while the next is gathered) was measured and is slower:
         // 104 -> 148 ms for 2.5 GB of clips, the gather drops from 62 to 19 GB/s while the DMA engine reads host memory.
         PinBuf stage;
         if ((rc = stage.reserve((size_t)pos + 64))) return rc;
-        const double t_g1 = now_ms();
+        t_g1 = now_ms();
         parallel_gather((uint8_t*)stage.p, src, at);
-        const double t_g2 = now_ms();
+        t_g2 = now_ms();
         if ((rc = h.d_in.reserve((size_t)pos + 128))) { stage.release(); return rc; }
         if (cudaMemcpyAsync(h.d_in.p, stage.p, (size_t)pos, cudaMemcpyHostToDevice, h.stream) != cudaSuccess ||
             cudaMemsetAsync((uint8_t*)h.d_in.p + pos, 0, 128, h.stream) != cudaSuccess) { stage.release(); g_cuda_err = "batch upload"; return BNFLAC_ERR_CUDA; }
@@ -889,6 +919,7 @@ static int decode_batch_impl(const bnflac_span* clips, size_t n, const bnflac_op
         rc = run_front(&h);
         stage.release();                            // run_front synchronised the stream: the upload is done
         if (rc) return rc;
+        }
         const double t_g3 = now_ms();
         const uint32_t ns = (uint32_t)h.batch_segs.size();
         if ((rc = h.d_seg_pcm.reserve(8ull * ns)) || (rc = h.d_seg_flags.reserve(4ull * ns))) return rc;

@@ -125,7 +125,9 @@ int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes);
 typedef struct { const uint8_t* data; size_t len; } bnflac_span;
 typedef struct { uint64_t pcm_offset, pcm_bytes; uint32_t sample_rate, channels, bits_per_sample, status; uint64_t total_samples; } bnflac_clip_result;
 /* Decodes n clips in one pipeline pass into one PCM buffer (clip i at results[i].pcm_offset).
- * dst==NULL: only sizes are computed.  dst_is_device: dst is a device pointer. */
+ * dst==NULL: only sizes are computed.  dst_is_device: dst is a device pointer.
+ * Clips given in ascending address order inside ONE host buffer (gaps of up to ~1 KiB per clip, e.g. archive headers)
+ * are uploaded in place with a single copy; otherwise they are gathered into pinned staging memory first. */
 int bnflac_decode_batch(const bnflac_span* clips, size_t n, const bnflac_opts* opts, uint8_t* dst, size_t cap, int dst_is_device,
                         bnflac_clip_result* results, uint64_t* written);
 

@@ -165,3 +165,32 @@ def test_batch_to_device_buffer():
     torch.cuda.synchronize()
     assert n == len(pcm) and bytes(out[:n].cpu().numpy()) == pcm
     assert [(r.pcm_offset, r.pcm_bytes) for r in res] == [(r.pcm_offset, r.pcm_bytes) for r in res2]
+
+
+def test_packed_batch_is_uploaded_in_place_and_matches():
+    """Clips that lie in ascending order inside ONE host buffer (a shard file read in one piece, tar-like 512-byte headers
+    full of sync-code look-alikes between them) take the no-gather path: same PCM, same per-clip results as separate buffers."""
+    from birdnest.audio_b200 import _abi
+    clips = _clips()
+    blobs = [c.flac for c in clips] * 4
+    want_pcm, want_res = _abi.decode_batch(blobs)
+    packed = bytearray()
+    spans = []
+    for i, b in enumerate(blobs):
+        packed += (b"\xff\xf8\xc9\x18" * 128)[:512 - (i % 3)]          # junk between the clips, odd alignments
+        spans.append((len(packed), len(b)))
+        packed += b
+    packed += bytes(100)
+    mv = memoryview(packed)
+    views = [mv[o:o + n] for o, n in spans]
+    got_pcm, got_res = _abi.decode_batch(views)
+    assert got_pcm == want_pcm
+    assert [(r.pcm_offset, r.pcm_bytes, r.channels, r.bits_per_sample, r.status) for r in got_res] == \
+           [(r.pcm_offset, r.pcm_bytes, r.channels, r.bits_per_sample, r.status) for r in want_res]
+    for c, r in zip(clips * 4, got_res):
+        assert got_pcm[r.pcm_offset:r.pcm_offset + r.pcm_bytes] == c.pcm
+    # a damaged clip in the middle of the packed buffer is reported, the others are untouched
+    o, n = spans[5]
+    packed[o + n // 2] ^= 0x20
+    bad_pcm, bad_res = _abi.decode_batch([mv[o:o + n] for o, n in spans])
+    assert bad_res[5].status != 0 and all(r.status == 0 for k, r in enumerate(bad_res) if k != 5)
