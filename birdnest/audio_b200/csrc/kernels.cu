@@ -1567,7 +1567,10 @@ void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
     // fewer than two warps per scheduler: the walk is latency-bound and its branches are what it waits for
-    if (nb < (uint32_t)sm_count() * 4u * 2u * 32u) k_parse<true><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
+    // (BNFLAC_PARSE_LEAN=0/1 forces one variant: the tests run both on the same streams)
+    const char* force = getenv("BNFLAC_PARSE_LEAN");
+    const bool lean = force ? force[0] == '1' : nb < (uint32_t)sm_count() * 4u * 2u * 32u;
+    if (lean) k_parse<true><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
     else k_parse<false><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
     g_launches++;
 }

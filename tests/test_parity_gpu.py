@@ -100,3 +100,31 @@ def test_capacity_error(streams):
         with pytest.raises(_abi.BnflacError) as e:
             h.decode_all(small)
         assert e.value.code == _abi.ERR_CAPACITY
+
+
+@pytest.mark.parametrize("lean", ["0", "1"])
+@pytest.mark.parametrize("name", ["cfg2_24bit_stereo_lpc12", "cfg3_24bit_8ch_lpc32_rice2_po8", "cfg5_6ch_special", "mono_special_escape_verbatim",
+                                  "tiled_variable", "bps20_4ch_odd_bs_zeropart", "tiny_blocks"])
+def test_both_parse_kernel_variants(streams, monkeypatch, name, lean):
+    """k_parse exists with a looped and with a branch-free predicated ring refill; the launcher picks by frame count (the
+    predicated one below ~38,000 frames).  Both must produce the oracle's PCM and subframe table on the same streams, intact
+    and damaged."""
+    import pyoracle
+    from birdnest.audio_b200 import _abi
+    monkeypatch.setenv("BNFLAC_PARSE_LEAN", lean)
+    s = streams(name)
+    for damage in (False, True):
+        blob = bytearray(s.flac)
+        if damage:
+            n = len(blob)
+            for pos, mask in ((s.frame_off[0] + (n - s.frame_off[0]) // 3, 0x04), (n - (n - s.frame_off[0]) // 4, 0x80)):
+                blob[pos] ^= mask
+        blob = bytes(blob)
+        want, oframes, _, oerrs = pyoracle.decode(blob, want_frames=True)
+        with _abi.open_memory(blob) as h:
+            out = bytearray(len(want) + (1 << 20))
+            k = h.decode_all(out)
+            frames, errs = h.frames(), h.errors()
+        assert bytes(out[:k]) == want
+        assert errs == oerrs
+        assert [(f.offset, f.length, f.status != 0) for f in frames] == [(o.offset, o.length, o.status != 0) for o in oframes]
