@@ -117,6 +117,7 @@ void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_resync(const PassArgs& a, void* stream);
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream);
+void launch_make_chunks(const SegInfo& seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks, void* stream);   // scan tiles of a one-segment pass
 void launch_clear(const PassArgs& a, void* stream);                                   // counters + totals = 0
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream);  // <= 32 words to mapped host memory
 void launch_seg_summary(const PassArgs& a, uint32_t ncand_bound, uint64_t* seg_pcm, uint32_t* seg_flags, void* stream);

@@ -331,6 +331,30 @@ static int ensure_tables(bnflac* h) {
         descs.push_back(d);
         in_len = h->d_ext ? h->len : (h->slice_end - h->slice_begin);
     }
+    if (h->batch_segs.empty()) {
+        // one segment: the tile descriptors are generated on the device (k_make_chunks), nothing is built or uploaded here
+        const SegDesc& d = descs[0];
+        SegInfo seg{};
+        seg.begin = d.begin; seg.end = d.end; seg.own_begin = d.own_begin; seg.own_end = d.own_end;
+        seg.bps = h->info.bits_per_sample; seg.channels = h->info.channels; seg.sample_rate = d.sample_rate;
+        seg.min_bs = d.min_bs; seg.max_bs = d.max_bs; seg.max_frame_bytes = d.max_frame_bytes; seg.first_chunk = 0; seg.pad = 0;
+        const uint64_t A = seg.begin & ~15ull;
+        h->nchunks = seg.end > seg.begin ? (uint32_t)((seg.end - A + SCAN_CHUNK - 1) / SCAN_CHUNK) : 0u;
+        h->nsegs = 1;
+        int rc;
+        if ((rc = h->d_segs.reserve(sizeof(SegInfo)))) return rc;
+        if ((rc = h->d_chunks.reserve(sizeof(Chunk) * std::max<size_t>(1, h->nchunks)))) return rc;
+        if ((rc = h->d_chunk_base.reserve(4ull * (h->nchunks + 1)))) return rc;
+        if ((rc = h->d_chunk_count.reserve(4ull * (h->nchunks + 1)))) return rc;
+        if ((rc = h->d_chunk_scan.reserve(4ull * (h->nchunks + 1)))) return rc;
+        if ((rc = h->d_pref.reserve(64ull * (h->nchunks + 1)))) return rc;
+        if ((rc = h->d_counters.reserve(4 * CNT_WORDS))) return rc;
+        if ((rc = h->d_totals.reserve(sizeof(Totals)))) return rc;
+        if ((rc = h->mailbox.reserve(256))) return rc;
+        if ((rc = h->d_anom.reserve(4ull * ANOM_CAP))) return rc;
+        launch_make_chunks(seg, h->d_segs.as<SegInfo>(), h->d_chunks.as<Chunk>(), h->nchunks, h->stream);
+        CK(cudaGetLastError());
+    } else {
     std::vector<SegInfo> segs(descs.size());
     std::vector<Chunk> chunks;
     for (size_t k = 0; k < descs.size(); k++) {
@@ -362,6 +386,7 @@ static int ensure_tables(bnflac* h) {
     CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), sizeof(SegInfo) * segs.size(), cudaMemcpyHostToDevice, h->stream));
     if (!chunks.empty()) CK(cudaMemcpyAsync(h->d_chunks.p, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // segs / chunks are locals
+    }
     h->args.in = h->d_ext ? h->d_ext : h->d_in.as<uint8_t>();
     h->args.in_len = in_len + 64;
     h->args.segs = h->d_segs.as<SegInfo>(); h->args.nsegs = h->nsegs;

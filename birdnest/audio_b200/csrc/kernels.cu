@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <type_traits>
 #include <cstdlib>
+#include <algorithm>
 #include <cstdio>
 
 namespace bnf {
@@ -1087,6 +1088,18 @@ __global__ void __launch_bounds__(ORD_THREADS) k_prefix(PassArgs a, uint32_t byt
 // start-of-pass reset and end-of-stage hand-off to the host.  The host learns the candidate count and the totals through
 // a few words of MAPPED pinned memory written by k_publish, not through cudaMemcpy: a small copy would queue on the copy
 // engines behind the multi-megabyte uploads/downloads of the other sub-shards of a pipelined decode and stall the pass.
+// Scan-tile descriptors of a one-segment pass, generated where they are used: tile k of the segment covers
+// [max(begin, A + k * SCAN_CHUNK), min(end, A + (k + 1) * SCAN_CHUNK)), A = begin & ~15.  The segment record travels as a kernel
+// argument, so opening a stream costs no host-built table, no small upload queued behind bulk copies and no synchronisation.
+__global__ void __launch_bounds__(256) k_make_chunks(SegInfo seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) d_seg[0] = seg;
+    if (k >= nchunks) return;
+    const uint64_t A = seg.begin & ~15ull;
+    const uint64_t b = max(seg.begin, A + (uint64_t)k * SCAN_CHUNK), e = min(seg.end, A + (uint64_t)(k + 1) * SCAN_CHUNK);
+    chunks[k] = Chunk{b, (uint32_t)(e - b), 0u};
+}
+
 __global__ void __launch_bounds__(256) k_clear(uint32_t* counters, Totals* totals) {
     for (uint32_t i = threadIdx.x; i < CNT_WORDS; i += blockDim.x) counters[i] = 0;     // counters, k_order / k_prefix CTA totals
     if (threadIdx.x < sizeof(Totals) / 4) reinterpret_cast<uint32_t*>(totals)[threadIdx.x] = 0;
@@ -1582,6 +1595,9 @@ void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_s
     if (!per) per = ORD_THREADS;
     const uint32_t grid = ncand_bound ? (ncand_bound + per - 1) / per : 1;
     k_prefix<<<grid, ORD_THREADS, 0, S(stream)>>>(a, bytes_per_sample, per, a.counters + CNT_PFX_CNT, reinterpret_cast<unsigned long long*>(a.counters + CNT_PFX_BYTES)); g_launches++;
+}
+void launch_make_chunks(const SegInfo& seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks, void* stream) {
+    k_make_chunks<<<blocks_for(std::max<uint32_t>(nchunks, 1u), 256), 256, 0, S(stream)>>>(seg, d_seg, chunks, nchunks); g_launches++;
 }
 void launch_clear(const PassArgs& a, void* stream) { k_clear<<<1, 256, 0, S(stream)>>>(a.counters, a.totals); g_launches++; }
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream) {
