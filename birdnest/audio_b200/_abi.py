@@ -18,6 +18,7 @@ AL_FORMAT_NAMES = {0: "None", 0x1100: "Mono8", 0x1101: "Mono16", 0x1102: "Stereo
 
 ERR_ARG, ERR_NOT_FLAC, ERR_TRUNCATED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY, ERR_CAPACITY, ERR_ABORTED, ERR_UNSUPPORTED, ERR_STATE = range(-1, -11, -1)
 OPT_VERIFY_MD5 = 1
+OPT_LAZY_PULL = 4      # open_callbacks pulls the metadata only; bnflac_read pulls the rest on demand
 OPT_BORROW_INPUT = 2
 
 
@@ -76,6 +77,7 @@ _PROTOS = {
     "bnflac_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(FrameRec)), C.POINTER(C.c_size_t)]),
     "bnflac_subframes": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(SubframeRec)), C.POINTER(C.c_size_t)]),
     "bnflac_errors": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
+    "bnflac_errors_so_far": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
     "bnflac_error_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
     "bnflac_last_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "bnflac_strerror": (C.c_char_p, [C.c_int]),
@@ -233,6 +235,13 @@ class Handle:
         _check(lib().bnflac_errors(self._p, C.byref(p), C.byref(n)), "bnflac_errors")
         return [int(p[i]) for i in range(n.value)]
 
+    def errors_so_far(self):
+        """Events of what a streamed Read session has decoded so far (no decode / pull ahead); else == errors()."""
+        p = C.POINTER(C.c_uint32)()
+        n = C.c_size_t()
+        _check(lib().bnflac_errors_so_far(self._p, C.byref(p), C.byref(n)), "bnflac_errors_so_far")
+        return [int(p[i]) for i in range(n.value)]
+
     def timing(self) -> Timing:
         t = Timing()
         _check(lib().bnflac_last_timing(self._p, C.byref(t)), "bnflac_last_timing")
@@ -256,8 +265,9 @@ def open_device(d_ptr: int, length: int, header: bytes, device=-1, stream=0, sha
     return Handle(h.value, keep=(keep, header))
 
 
-def open_callbacks(read_fn, device=-1) -> Handle:
-    """read_fn(n) -> bytes (b'' at end of stream); mirrors the pull model of FLACDecoder.ReadCallback."""
+def open_callbacks(read_fn, device=-1, flags=0) -> Handle:
+    """read_fn(n) -> bytes (b'' at end of stream); mirrors the pull model of FLACDecoder.ReadCallback.
+    flags=OPT_LAZY_PULL: only the metadata is pulled here, the rest as read_into() advances."""
     def _cb(user, buf, nbytes):
         want = nbytes[0]
         try:
@@ -272,10 +282,10 @@ def open_callbacks(read_fn, device=-1) -> Handle:
         nbytes[0] = k
         return 1 if k < want else 0
     cb = READ_CB(_cb)
-    o = _opts(device)
+    o = _opts(device, flags=flags)
     h = C.c_void_p()
     _check(lib().bnflac_open_callbacks(cb, None, C.byref(o), C.byref(h)), "bnflac_open_callbacks")
-    return Handle(h.value)
+    return Handle(h.value, keep=cb)        # the callback object must outlive the handle (lazy pull calls it from bnflac_read)
 
 
 def decode_batch(clips, device=-1, dst=None, dst_is_device=False):

@@ -206,6 +206,16 @@ struct SegDesc {            // host description of one segment of a pass, in coo
     uint32_t sample_rate, min_bs, max_bs, max_frame_bytes;
 };
 
+struct DiagCursor {          // the reference's sync-search state, carried across the sub-shards of a pipelined decode
+    uint64_t expect = 0;     // where its cursor stands
+    bool in_sync = true;     // LOST_SYNC is reported once per excursion
+    bool ended = false;      // a truncated header ended the stream
+    bool have_expect = true; // false: (shard > 0) start at the first frame found, whatever lies before it
+    std::vector<uint32_t>* at = nullptr;                 // per event: how many frames had been delivered before it
+    const std::vector<bnflac_frame_t>* frames = nullptr;
+    void event(std::vector<uint32_t>& errors, uint32_t code) { errors.push_back(code); if (at) at->push_back(frames ? (uint32_t)frames->size() : 0u); }
+};
+
 struct bnflac {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = false;
@@ -245,9 +255,15 @@ struct bnflac {
     // results
     std::vector<bnflac_frame_t> frames; std::vector<bnflac_subframe_t> subs; std::vector<uint32_t> errors, errors_at;
     bool diag_valid = false;
+    DiagCursor diag_cur; uint32_t diag_kids = 0; bool diag_started = false;   // streamed Read: sub-shards already folded into the tables
 
     // Stream-style read buffering
     PinBuf pcm_host; uint64_t pcm_len = 0, read_pos = 0; bool decoded = false;
+    // lazily pulled source (BNFLAC_OPT_LAZY_PULL): the read callback is called as the reader advances, see pull_more()
+    bnflac_read_cb pull_cb = nullptr; void* pull_user = nullptr; bool pull_eof = true;
+    uint64_t pl_next = 0, pl_size = 0;   // start of the next sub-shard to issue, its size
+    bool pl_session = false;             // the current streamed Read session cuts its sub-shards as the bytes arrive
+    bool front_ran = false;              // a decode has been started on this handle (the diagnostics have something to describe)
     // streaming Read session: sub-shards decoded ahead of the reader, see stream_read()
     bool rd_active = false; uint32_t rd_issued = 0, rd_cur = 0; uint64_t rd_off = 0, rd_total = 0;
 
@@ -421,6 +437,7 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
 
 // Runs K1..K2 + prefix (everything up to knowing the output size).
 static int run_front(bnflac* h) {
+    h->front_ran = true;
     int rc;
     CK(cudaSetDevice(h->device));
     h->launches0 = kernel_launch_count();
@@ -627,8 +644,12 @@ static int decode_host_pipelined(bnflac* h, const std::vector<uint64_t>& cuts, u
     return 0;
 }
 
+static int pull_all(bnflac* h);
 static int decode_host(bnflac* h, uint8_t* dst, size_t cap, uint64_t* written) {
+    if (h->rd_active && h->pull_cb) { for (bnflac* k : h->kids) delete k; h->kids.clear(); }
     h->rd_active = false;                     // a one-shot decode ends any streaming Read session on this handle
+    h->pl_session = false;
+    { int rc = pull_all(h); if (rc) return rc; }
     if (h->host_ptr && !h->d_ext && h->batch_segs.empty()) {
         const std::vector<uint64_t> cuts = pipe_cuts(std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end);
         if (cuts.size() > 2) return decode_host_pipelined(h, cuts, dst, cap, written);
@@ -666,6 +687,60 @@ static std::vector<uint64_t> read_cuts(const bnflac* h, uint64_t b, uint64_t e) 
 
 static constexpr uint32_t READ_LOOKAHEAD = 2;      // sub-shards in flight beyond the one being read
 
+// ---- lazily pulled source: FLACDecoder(Stream) reads only the metadata in its constructor and one frame's worth of bytes per
+// Read (FLACDecoder.cs:72-88,207-224,325-363).  With BNFLAC_OPT_LAZY_PULL bnflac_open_callbacks does the same -- it pulls
+// until STREAMINFO and the end of the metadata are in hand -- and bnflac_read pulls what the next sub-shard needs (its
+// byte range plus one maximum frame of overlap) right before issuing it.  Everything pulled is kept (the diagnostics replay
+// the reference's sync search over the bytes between frames).
+static int pull_more(bnflac* h, uint64_t need_len) {         // until host.size() >= need_len or end of stream
+    const size_t req = env_kb("BNFLAC_PULL_KB", 1024);        // bytes asked of the callback per call
+    try {
+        while (!h->pull_eof && h->host.size() < need_len) {
+            const size_t old = h->host.size();
+            h->host.resize(old + req);
+            size_t got = req;
+            const int st = h->pull_cb(h->pull_user, h->host.data() + old, &got);
+            if (st == 2) { h->host.resize(old); return BNFLAC_ERR_ABORTED; }
+            if (got > req) { h->host.resize(old); return BNFLAC_ERR_ARG; }
+            h->host.resize(old + got);
+            if (st == 1 || got == 0) h->pull_eof = true;
+        }
+    } catch (...) { return BNFLAC_ERR_MEMORY; }
+    h->host_ptr = h->host.data(); h->len = h->host.size();
+    return 0;
+}
+static int pull_all(bnflac* h) {                             // entry points that need the whole stream
+    if (!h->pull_cb) return 0;
+    if (!h->pull_eof) { int rc = pull_more(h, ~0ull); if (rc) return rc; }
+    compute_shard(h);                                        // the handle's own range was cut when only the metadata was in hand
+    return 0;
+}
+
+// next sub-shard of a lazily pulled stream: pull its bytes, create its handle, issue it
+static int stream_issue(bnflac* h, uint32_t k);
+static int lazy_issue_next(bnflac* h) {
+    const uint64_t first = env_kb("BNFLAC_READ_FIRST_KB", 4096), cap = std::max<uint64_t>(first, env_mb("BNFLAC_READ_MB", 64));
+    if (!h->pl_size) { h->pl_size = first; h->pl_next = h->info.first_frame_offset; }
+    const uint64_t b = h->pl_next;
+    uint64_t e = b + h->pl_size;
+    int rc = pull_more(h, e + h->pl_size / 2 + frame_bound(h->info) + 64); if (rc) return rc;
+    if (h->pull_eof && h->len <= e + h->pl_size / 2) e = h->len;          // what is left is not worth a sub-shard of its own
+    if (e > h->len) e = h->len;
+    bnflac* c = new (std::nothrow) bnflac; if (!c) return BNFLAC_ERR_MEMORY;
+    h->kids.push_back(c);
+    c->opts = h->opts; c->opts.stream = nullptr; c->opts.device = h->device; c->opts.flags &= ~(BNFLAC_OPT_VERIFY_MD5 | BNFLAC_OPT_LAZY_PULL);
+    c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = b; c->sub_end = std::max(e, b + 1);
+    if (b >= h->len) { c->sub_begin = h->len ? h->len - 1 : 0; c->sub_end = h->len; }     // empty tail
+    compute_shard(c);
+    c->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
+    if ((rc = setup_device(c))) return rc;
+    h->pl_next = e; h->pl_size = std::min<uint64_t>(2 * h->pl_size, cap);
+    if ((rc = stream_issue(h, (uint32_t)h->kids.size() - 1))) return rc;
+    h->rd_issued = (uint32_t)h->kids.size();
+    return 0;
+}
+static bool lazy_more(const bnflac* h) { return h->pl_session && !(h->pull_eof && h->pl_size && h->pl_next >= h->len); }
+
 // upload + front kernels + decode + download of sub-shard k, all asynchronous but for the two size hand-offs in run_front
 static int stream_issue(bnflac* h, uint32_t k) {
     bnflac* c = h->kids[k];
@@ -683,16 +758,19 @@ static int stream_issue(bnflac* h, uint32_t k) {
 
 static int stream_issue_all(bnflac* h) {
     while (h->rd_issued < h->kids.size()) { int rc = stream_issue(h, h->rd_issued); if (rc) return rc; h->rd_issued++; }
+    while (lazy_more(h)) { int rc = lazy_issue_next(h); if (rc) return rc; }
     return 0;
 }
 
 static int64_t stream_read(bnflac* h, uint8_t* dst, size_t count) {
     CK(cudaSetDevice(h->device));
-    const uint32_t K = (uint32_t)h->kids.size();
     size_t done = 0;
     int rc;
-    while (done < count && h->rd_cur < K) {
-        if (h->rd_issued <= h->rd_cur) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
+    while (done < count && (h->rd_cur < h->kids.size() || lazy_more(h))) {
+        if (h->rd_issued <= h->rd_cur) {
+            if (h->rd_issued < h->kids.size()) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
+            else if ((rc = lazy_issue_next(h))) return rc;
+        }
         bnflac* c = h->kids[h->rd_cur];
         CK(cudaEventSynchronize(c->ev[7]));
         const size_t n = (size_t)std::min<uint64_t>(c->pcm_len - h->rd_off, count - done);
@@ -708,8 +786,11 @@ static int64_t stream_read(bnflac* h, uint8_t* dst, size_t count) {
         }
     }
     // keep the decode ahead of the reader: at most one more sub-shard per call, so no single Read pays for several
-    if (h->rd_issued < K && h->rd_issued <= h->rd_cur + READ_LOOKAHEAD) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
-    h->state = h->rd_cur == K ? BNFLAC_STATE_END_OF_STREAM : BNFLAC_STATE_READ_FRAME;
+    if (h->rd_issued <= h->rd_cur + READ_LOOKAHEAD) {
+        if (h->rd_issued < h->kids.size()) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
+        else if (lazy_more(h) && (rc = lazy_issue_next(h))) return rc;
+    }
+    h->state = (h->rd_cur == h->kids.size() && !lazy_more(h)) ? BNFLAC_STATE_END_OF_STREAM : BNFLAC_STATE_READ_FRAME;
     return (int64_t)done;
 }
 
@@ -741,15 +822,6 @@ int header_rc(const uint8_t* p, size_t avail) {
     return unparse ? 3 : 0;
 }
 
-struct DiagCursor {          // the reference's sync-search state, carried across the sub-shards of a pipelined decode
-    uint64_t expect = 0;     // where its cursor stands
-    bool in_sync = true;     // LOST_SYNC is reported once per excursion
-    bool ended = false;      // a truncated header ended the stream
-    bool have_expect = true; // false: (shard > 0) start at the first frame found, whatever lies before it
-    std::vector<uint32_t>* at = nullptr;                 // per event: how many frames had been delivered before it
-    const std::vector<bnflac_frame_t>* frames = nullptr;
-    void event(std::vector<uint32_t>& errors, uint32_t code) { errors.push_back(code); if (at) at->push_back(frames ? (uint32_t)frames->size() : 0u); }
-};
 } // namespace
 
 // bytes [from, to) of the stream as the reference sees them while hunting for a sync code
@@ -822,15 +894,40 @@ static int collect_diag(bnflac* h, DiagCursor& cur, uint64_t pcm_base, const uin
     return 0;
 }
 
-static int fetch_diag(bnflac* h) {
+static int fetch_diag(bnflac* h, bool all = true) {
     if (h->diag_valid) return 0;
+    int rc;
+    if (h->rd_active) {
+        // streamed Read session: the tables grow sub-shard by sub-shard (each is folded in once, after its front kernels);
+        // `all` decodes what is left first, otherwise only what has been issued so far is described
+        if (all && (rc = stream_issue_all(h))) return rc;
+        if (!h->diag_started) {
+            h->frames.clear(); h->subs.clear(); h->errors.clear(); h->errors_at.clear();
+            h->diag_cur = DiagCursor{};
+            h->diag_cur.at = &h->errors_at; h->diag_cur.frames = &h->frames;
+            h->diag_cur.expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
+            h->diag_cur.have_expect = h->own_begin <= h->info.first_frame_offset;
+            h->diag_kids = 0; h->diag_started = true;
+        }
+        for (; h->diag_kids < h->rd_issued; h->diag_kids++) {
+            bnflac* c = h->kids[h->diag_kids];
+            if ((rc = collect_diag(c, h->diag_cur, c->pcm_base, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
+        }
+        if (h->rd_issued == h->kids.size() && !lazy_more(h)) {
+            if (h->pull_cb && h->pull_eof) h->own_end = std::max<uint64_t>(h->own_end, h->len);
+            if (h->own_end >= h->len && h->diag_cur.have_expect) scan_gap(h, h->host_ptr, h->len, h->diag_cur, h->len, h->errors);   // what follows the last frame
+            h->diag_valid = true;
+        }
+        return 0;
+    }
+    h->diag_started = false;
     h->frames.clear(); h->subs.clear(); h->errors.clear(); h->errors_at.clear();
+    if (h->kids.empty() && !h->front_ran) return 0;                    // nothing decoded yet: empty tables
     DiagCursor cur;
     cur.at = &h->errors_at; cur.frames = &h->frames;
+    if ((rc = pull_all(h))) return rc;
     cur.expect = std::max<uint64_t>(h->own_begin, h->info.first_frame_offset);
     cur.have_expect = h->own_begin <= h->info.first_frame_offset;      // a later shard starts wherever its first frame starts
-    int rc;
-    if (h->rd_active && (rc = stream_issue_all(h))) return rc;       // the tables cover the whole stream, read or not
     if (!h->kids.empty()) {
         for (bnflac* c : h->kids)
             if ((rc = collect_diag(c, cur, c->pcm_base, h->host_ptr, h->len, h->frames, h->subs, h->errors))) return rc;
@@ -1045,6 +1142,24 @@ int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts,
 int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* opts, bnflac_t** out) {
     if (!read || !out) return BNFLAC_ERR_ARG;
     *out = nullptr;
+    const bnflac_opts o = default_opts(opts);
+    if (o.flags & BNFLAC_OPT_LAZY_PULL) {
+        if (o.shard_count > 1) return BNFLAC_ERR_ARG;            // a shard needs the stream's length
+        bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
+        h->opts = o; h->pull_cb = read; h->pull_user = user; h->pull_eof = false;
+        int rc = 0;
+        for (uint64_t want = 64 << 10;; want *= 2) {              // until the metadata is complete
+            if ((rc = pull_more(h, want))) break;
+            bnflac_info_t probe;
+            rc = parse_metadata(h->host.data(), h->host.size(), &probe);
+            if (rc != BNFLAC_ERR_TRUNCATED || h->pull_eof) break;
+        }
+        if (!rc) rc = common_open(h, h->host_ptr, h->len);
+        if (!rc) rc = setup_device(h);
+        if (rc) { delete h; return rc; }
+        *out = h;
+        return 0;
+    }
     std::vector<uint8_t> buf;
     const size_t req = 1u << 20;   // the reference pulls <= 16 KiB per callback (FLACDecoder.cs:21,336); we ask for 1 MiB
     try {
@@ -1080,11 +1195,14 @@ int bnflac_decode_device(bnflac_t* h, void* d_dst, size_t cap, void** d_out, uin
     if (!h) return BNFLAC_ERR_ARG;
     for (bnflac* k : h->kids) delete k;
     h->kids.clear();
+    h->rd_active = false; h->pl_session = false;
+    { int rc = pull_all(h); if (rc) return rc; }
     return decode_to_device(h, d_dst, cap, d_out, written);
 }
 
 int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes) {
     if (!h || !bytes) return BNFLAC_ERR_ARG;
+    { int rc = pull_all(h); if (rc) return rc; }
     if (h->info.total_samples && (h->opts.shard_count <= 1)) {
         // STREAMINFO states it; a damaged stream may decode to less, never to more than its frame count allows.  Large
         // host streams take the pipelined path, where the exact figure is only known at the end.
@@ -1114,13 +1232,20 @@ int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written) 
 int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count) {
     if (!h || (!dst && count)) return BNFLAC_ERR_ARG;
     if (h->rd_active) return stream_read(h, dst, count);
+    if (!h->decoded && h->pull_cb && !h->pull_eof) {       // lazily pulled source: sub-shards are cut as the bytes arrive
+        CK(cudaSetDevice(h->device));
+        for (bnflac* k : h->kids) delete k;
+        h->kids.clear();
+        h->rd_active = true; h->rd_issued = h->rd_cur = 0; h->rd_off = h->rd_total = 0; h->pl_size = 0; h->pl_session = true; h->timing = bnflac_timing{}; h->diag_valid = false; h->diag_started = false;
+        return stream_read(h, dst, count);
+    }
     if (!h->decoded && h->host_ptr && !h->d_ext && h->batch_segs.empty()) {
         // large host-resident stream: decode ahead of the reader in sub-shards instead of all at once
         const std::vector<uint64_t> cuts = read_cuts(h, std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end);
         if (cuts.size() > 2) {
             CK(cudaSetDevice(h->device));
             int rc = make_kids(h, cuts); if (rc) return rc;
-            h->rd_active = true; h->rd_issued = h->rd_cur = 0; h->rd_off = h->rd_total = 0; h->timing = bnflac_timing{}; h->diag_valid = false;
+            h->rd_active = true; h->rd_issued = h->rd_cur = 0; h->rd_off = h->rd_total = 0; h->pl_session = false; h->timing = bnflac_timing{}; h->diag_valid = false; h->diag_started = false;
             return stream_read(h, dst, count);
         }
     }
@@ -1175,6 +1300,12 @@ int bnflac_subframes(bnflac_t* h, const bnflac_subframe_t** sub, size_t* n) {
 int bnflac_errors(bnflac_t* h, const uint32_t** codes, size_t* n) {
     if (!h || !codes || !n) return BNFLAC_ERR_ARG;
     int rc = fetch_diag(h); if (rc) return rc;
+    *codes = h->errors.data(); *n = h->errors.size();
+    return 0;
+}
+int bnflac_errors_so_far(bnflac_t* h, const uint32_t** codes, size_t* n) {
+    if (!h || !codes || !n) return BNFLAC_ERR_ARG;
+    int rc = fetch_diag(h, false); if (rc) return rc;
     *codes = h->errors.data(); *n = h->errors.size();
     return 0;
 }

@@ -53,6 +53,7 @@ public:
     FLACDecoder(std::istream& stream, IFLACPacketQueue* queue, IFLACDecoderLogger* logger, size_t buffer_bytes = DEFAULT_MAX_BUFFER_SIZE, int device = -1)
         : mStream(stream), mPacketQueue(queue), mLogger(logger), mInstreamBuffer(buffer_bytes) {
         bnflac_opts o{}; o.struct_size = sizeof o; o.device = device;
+        o.flags = BNFLAC_OPT_LAZY_PULL;       // like the reference: metadata in the constructor, stream bytes pulled as Read advances
         const int rc = bnflac_open_callbacks(&FLACDecoder::ReadCallback, this, &o, &mHandle);   // SetupDecoder + SetupFLACStream (:49-64)
         if (rc == BNFLAC_ERR_NOT_FLAC || rc == BNFLAC_ERR_TRUNCATED) throw ApplicationException("FLAC: Could not Could not process until end of metadata - EndOfStream!");
         if (rc == BNFLAC_ERR_ABORTED) throw ApplicationException("FLAC: Could not Could not process until end of metadata - Aborted!");
@@ -153,10 +154,10 @@ private:
     }
     void RaiseFrameErrors() {                                                  // ErrorCallback, FLACDecoder.cs:590-594
         if (mErrorsChecked) return;
+        const uint32_t* codes = nullptr; size_t n = 0;                         // polled after every packet: no decode / pull ahead
+        if (bnflac_errors_so_far(mHandle, &codes, &n) != 0 || !n) return;
         mErrorsChecked = true;
-        const uint32_t* codes = nullptr; size_t n = 0;
-        if (bnflac_errors(mHandle, &codes, &n) == 0 && n)
-            throw ApplicationException(std::string("FLAC: Could not decode frame: ") + bnflac_frame_status_name((int)codes[0] + 1) + " - " + (codes[0] >= 2 ? "ReadFrame" : "SearchForFrameSync") + "!");
+        throw ApplicationException(std::string("FLAC: Could not decode frame: ") + bnflac_frame_status_name((int)codes[0] + 1) + " - " + (codes[0] >= 2 ? "ReadFrame" : "SearchForFrameSync") + "!");
     }
     void PopTopOffQueue() { if (!mPacketQueue->TryDequeue()) throw std::runtime_error("FLAC - queue error"); }
 

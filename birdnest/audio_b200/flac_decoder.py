@@ -98,7 +98,7 @@ class FLACDecoder:
         # SetupDecoder + SetupFLACStream (FLACDecoder.cs:49-64): the engine pulls the stream through the same
         # ReadCallback contract (<= len(mInstreamBuffer) bytes per Stream.Read, short read => end of stream)
         try:
-            self._handle = _abi.open_callbacks(self._read_callback, device=device)
+            self._handle = _abi.open_callbacks(self._read_callback, device=device, flags=_abi.OPT_LAZY_PULL)   # metadata now, stream bytes on demand
         except _abi.BnflacError as e:
             if e.code in (_abi.ERR_NOT_FLAC, _abi.ERR_TRUNCATED):
                 # process_until_end_of_metadata fails in the reference (FLACDecoder.cs:66-70)
@@ -240,9 +240,9 @@ class FLACDecoder:
         """ErrorCallback (FLACDecoder.cs:590-594) throws on the first decode error the native codec reports."""
         if self._errors_checked:
             return
-        self._errors_checked = True
-        errs = self._handle.errors()
+        errs = self._handle.errors_so_far()        # polled after every packet: nothing is decoded or pulled ahead for it
         if errs:
+            self._errors_checked = True
             names = ["LostSync", "BadHeader", "FrameCrcMismatch", "UnparsableStream"]
             raise ApplicationException("FLAC: Could not decode frame: {0} - {1}!".format(names[errs[0]], "ReadFrame" if errs[0] >= 2 else "SearchForFrameSync"))
 

@@ -30,7 +30,7 @@ namespace BirdNest.Audio
 		private const int PACKET_BYTES = 1 << 20;     // PCM bytes pulled from the engine per queued packet
 
 		private IntPtr mDecoderContext;
-		private LibBnFlac.ReadCallback mReadCallback;  // kept alive for the duration of the open call
+		private LibBnFlac.ReadCallback mReadCallback;  // kept alive as long as the handle: with LazyPull the library calls it from bnflac_read
 		private bool mHitEOFYet;
 		private bool mErrorsChecked;
 		private int mBytesPerSample;
@@ -49,7 +49,8 @@ namespace BirdNest.Audio
 			mHitEOFYet = false;
 
 			mReadCallback = new LibBnFlac.ReadCallback (this.ReadCallback);
-			var opts = new LibBnFlac.Opts { StructSize = (uint) Marshal.SizeOf (typeof (LibBnFlac.Opts)), Device = -1 };
+			// LazyPull: like the reference, the constructor reads the metadata only; stream bytes are pulled as Read advances
+			var opts = new LibBnFlac.Opts { StructSize = (uint) Marshal.SizeOf (typeof (LibBnFlac.Opts)), Device = -1, Flags = (uint) LibBnFlac.OpenFlags.LazyPull };
 			int rc = LibBnFlac.bnflac_open_callbacks (mReadCallback, IntPtr.Zero, ref opts, out mDecoderContext);
 			if (rc == (int) LibBnFlac.Error.NotFlac || rc == (int) LibBnFlac.Error.Truncated)
 				throw new ApplicationException ("FLAC: Could not Could not process until end of metadata - EndOfStream!");
@@ -151,9 +152,10 @@ namespace BirdNest.Audio
 		private void RaiseFrameErrors ()
 		{
 			if (mErrorsChecked) return;
-			mErrorsChecked = true;
 			IntPtr codes; UIntPtr n;
-			if (LibBnFlac.bnflac_errors (mDecoderContext, out codes, out n) != 0 || n == UIntPtr.Zero) return;
+			// polled after every packet: only what has been decoded so far, nothing is decoded or pulled ahead for it
+			if (LibBnFlac.bnflac_errors_so_far (mDecoderContext, out codes, out n) != 0 || n == UIntPtr.Zero) return;
+			mErrorsChecked = true;
 			var status = (LibBnFlac.DecodeError) Marshal.ReadInt32 (codes);
 			var decoderState = status >= LibBnFlac.DecodeError.FrameCrcMismatch ? LibBnFlac.StreamDecoderState.ReadFrame : LibBnFlac.StreamDecoderState.SearchForFrameSync;
 			throw new ApplicationException (string.Format ("FLAC: Could not decode frame: {0} - {1}!", status, decoderState));

@@ -33,7 +33,7 @@ namespace LibBnFlacSharp
 		public enum DecodeError : int { LostSync = 0, BadHeader = 1, FrameCrcMismatch = 2, UnparsableStream = 3 }
 
 		[Flags]
-		public enum OpenFlags : uint { None = 0, VerifyMd5 = 1, BorrowInput = 2 }
+		public enum OpenFlags : uint { None = 0, VerifyMd5 = 1, BorrowInput = 2, LazyPull = 4 }   // BNFLAC_OPT_* (include/bnflac.h)
 
 		[StructLayout(LayoutKind.Sequential)]
 		public struct Opts
@@ -85,6 +85,9 @@ namespace LibBnFlacSharp
 
 		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
 		public static extern int bnflac_errors(IntPtr handle, out IntPtr codes, out UIntPtr n);
+
+		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
+		public static extern int bnflac_errors_so_far(IntPtr handle, out IntPtr codes, out UIntPtr n);
 
 		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
 		public static extern void bnflac_close(IntPtr handle);

@@ -73,6 +73,9 @@ typedef struct {
 } bnflac_opts;
 #define BNFLAC_OPT_VERIFY_MD5 1u   /* decode_all also checks md5(PCM) against STREAMINFO (host side, not timed) */
 #define BNFLAC_OPT_BORROW_INPUT 2u /* open_memory does not copy `data`: the caller keeps it valid (and ideally pinned) until close */
+#define BNFLAC_OPT_LAZY_PULL 4u    /* open_callbacks pulls only the metadata; bnflac_read pulls the rest as the reader advances (the
+                                    * callback and its `user` must then stay valid until close).  What FLACDecoder(Stream) does:
+                                    * metadata in the constructor, stream bytes on demand (FLACDecoder.cs:72-88,207-224,325-363) */
 
 /* what MetadataCallback derives (FLACDecoder.cs:431-473) plus the raw STREAMINFO fields */
 typedef struct {
@@ -97,7 +100,8 @@ typedef int (*bnflac_read_cb)(void* user, uint8_t* buf, size_t* bytes);
 /* Opens a stream held in host memory.  The library copies what it needs to the device; `data` must stay
  * valid until bnflac_close only if BNFLAC is asked to decode lazily (it always copies: caller keeps ownership). */
 int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts, bnflac_t** out);
-/* Opens from a pull callback (a C# Stream): pulls the whole stream in large requests, then as open_memory. */
+/* Opens from a pull callback (a C# Stream): pulls the whole stream in large requests, then as open_memory;
+ * with BNFLAC_OPT_LAZY_PULL only the metadata is pulled here and the rest on demand by bnflac_read. */
 int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* opts, bnflac_t** out);
 /* Opens a stream whose bytes are ALREADY resident in device memory (d_data stays owned by the caller and must
  * outlive the handle).  `header` = at least the first header_len bytes of the same stream in host memory
@@ -140,6 +144,11 @@ typedef struct { uint32_t bit_offset; uint8_t type, order, wasted, flags; } bnfl
 int bnflac_subframes(bnflac_t* h, const bnflac_subframe_t** sub, size_t* n);
 /* number of error-callback events the reference would have raised (ErrorCallback, FLACDecoder.cs:590-594) and their codes */
 int bnflac_errors(bnflac_t* h, const uint32_t** codes, size_t* n);
+/* the same list, but during a streamed bnflac_read session only the events of the sub-shards issued so far: nothing is
+ * decoded (or, with BNFLAC_OPT_LAZY_PULL, pulled) ahead for it, so a host can poll it after every Read and raise an error
+ * no later than the Read that reaches the damaged frame, like ErrorCallback does (FLACDecoder.cs:590-594).  The list
+ * only grows within a session; outside of one it equals bnflac_errors. */
+int bnflac_errors_so_far(bnflac_t* h, const uint32_t** codes, size_t* n);
 /* for each of those events, how many frames had been delivered before it was raised (lets a frame-at-a-time host such as
  * the libFLAC-symbol shim raise its error callbacks at the right moment) */
 int bnflac_error_frames(bnflac_t* h, const uint32_t** at, size_t* n);
