@@ -1122,12 +1122,118 @@ const char* bnflac_frame_status_name(int s) {
     return (s >= 0 && s < 5) ? n[s] : "Unknown";
 }
 
+// ---- Ogg FLAC.  The reference's DLL exports FLAC__stream_decoder_init_ogg_* but its C# never binds them
+// (LibFLACSharp.cs:42-85 lists the native-FLAC entry points only), so this is container breadth, not a parity surface: the
+// pages are taken apart on the host and what is left -- "fLaC", the metadata blocks, the frames -- is a native FLAC stream
+// that goes down the same pipeline.  Mapping (Ogg FLAC 1.0): page = "OggS", version 0, flags (1 continued packet, 2 first,
+// 4 last page), granule position, serial, page number, CRC-32 (polynomial 0x04C11DB7, no reflection, initial value 0, over
+// the page with the CRC field zeroed), segment count, lacing values; a lacing value < 255 ends a packet.  First packet:
+// 0x7F "FLAC" major minor, number of header packets (BE16), then "fLaC" + the STREAMINFO block; every further header packet
+// is one metadata block, every audio packet one frame.  Pages that fail their CRC or are out of sequence are dropped with the
+// packet they interrupt (the frame chain then sees a jump in the frame numbers, like any other missing frame).
+namespace {
+struct OggCrcTable {
+    uint32_t t[4][256];
+    OggCrcTable() {
+        for (uint32_t i = 0; i < 256; i++) { uint32_t r = i << 24; for (int k = 0; k < 8; k++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u); t[0][i] = r; }
+        for (int k = 1; k < 4; k++) for (uint32_t i = 0; i < 256; i++) t[k][i] = (t[k - 1][i] << 8) ^ t[0][t[k - 1][i] >> 24];
+    }
+};
+uint32_t ogg_crc(uint32_t crc, const uint8_t* p, size_t n) {
+    static const OggCrcTable T;
+    for (; n >= 4; p += 4, n -= 4) {
+        crc ^= (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+        crc = T.t[3][crc >> 24] ^ T.t[2][(crc >> 16) & 255] ^ T.t[1][(crc >> 8) & 255] ^ T.t[0][crc & 255];
+    }
+    for (; n; p++, n--) crc = (crc << 8) ^ T.t[0][(crc >> 24) ^ *p];
+    return crc;
+}
+inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+inline bool is_ogg(const uint8_t* d, size_t n) { return n >= 4 && !memcmp(d, "OggS", 4); }
+
+// 0 and the native stream in `out`; NOT_FLAC when no FLAC logical stream starts in the data, UNSUPPORTED for another mapping version
+int ogg_depage(const uint8_t* d, size_t n, std::vector<uint8_t>& out) {
+    static const uint8_t zero4[4] = {0, 0, 0, 0};
+    out.clear();
+    size_t pos = 0;
+    bool have_serial = false, in_pkt = false, meta_done = false;
+    uint32_t serial = 0, expect_seq = 0;
+    uint64_t npackets = 0;
+    std::vector<uint8_t> pkt;
+    auto resync = [&](size_t from) {                     // next capture pattern at or after `from`
+        while (from + 4 <= n) {
+            const uint8_t* q = (const uint8_t*)memchr(d + from, 'O', n - from - 3);
+            if (!q) return n;
+            if (!memcmp(q, "OggS", 4)) return (size_t)(q - d);
+            from = (size_t)(q - d) + 1;
+        }
+        return n;
+    };
+    while (pos + 27 <= n) {
+        if (memcmp(d + pos, "OggS", 4)) { pos = resync(pos + 1); in_pkt = false; pkt.clear(); continue; }
+        const uint32_t nseg = d[pos + 26];
+        if (pos + 27 + nseg > n) break;
+        size_t body = 0; for (uint32_t i = 0; i < nseg; i++) body += d[pos + 27 + i];
+        const size_t total = 27 + nseg + body;
+        if (pos + total > n) {                             // the stream ends inside this page -- or the segment table is garbage
+            const size_t nx = resync(pos + 1);
+            if (nx >= n) break;
+            pos = nx; in_pkt = false; pkt.clear(); continue;
+        }
+        uint32_t crc = ogg_crc(0, d + pos, 22);
+        crc = ogg_crc(crc, zero4, 4);
+        crc = ogg_crc(crc, d + pos + 26, total - 26);
+        if (d[pos + 4] != 0 || crc != le32(d + pos + 22)) { pos = resync(pos + 1); in_pkt = false; pkt.clear(); continue; }
+        const uint8_t flags = d[pos + 5];
+        const uint32_t ser = le32(d + pos + 14), seq = le32(d + pos + 18);
+        const uint8_t* p = d + pos + 27 + nseg;
+        if (!have_serial) {                                // the first logical stream whose first packet is an Ogg FLAC header
+            if (!(flags & 2) || body < 13 || p[0] != 0x7F || memcmp(p + 1, "FLAC", 4)) { pos += total; continue; }
+            if (p[5] != 1) return BNFLAC_ERR_UNSUPPORTED;  // mapping major version
+            have_serial = true; serial = ser; expect_seq = seq;
+        }
+        if (ser != serial) { pos += total; continue; }     // another logical stream multiplexed in
+        if (seq != expect_seq) { in_pkt = false; pkt.clear(); }       // pages are missing: the packet they carried is lost
+        expect_seq = seq + 1;
+        bool skipping = (flags & 1) && !in_pkt;            // the rest of a packet whose beginning is lost
+        if (!(flags & 1) && in_pkt) { in_pkt = false; pkt.clear(); }
+        try {
+            for (uint32_t i = 0; i < nseg; i++) {
+                const uint32_t L = d[pos + 27 + i];
+                if (skipping) { p += L; if (L < 255) skipping = false; continue; }
+                pkt.insert(pkt.end(), p, p + L); p += L; in_pkt = true;
+                if (L == 255) continue;
+                if (npackets == 0) {                       // 0x7F "FLAC" major minor nheaders(2) "fLaC" STREAMINFO block
+                    if (pkt.size() < 13 + 4 + 34 || memcmp(pkt.data() + 9, "fLaC", 4)) return BNFLAC_ERR_NOT_FLAC;
+                    out.insert(out.end(), pkt.begin() + 9, pkt.end());
+                    meta_done = (pkt[13] & 0x80) != 0;
+                } else if (!pkt.empty()) {
+                    if (!meta_done) meta_done = (pkt[0] & 0x80) != 0;      // one metadata block per header packet
+                    out.insert(out.end(), pkt.begin(), pkt.end());        // ... one frame per audio packet
+                }
+                npackets++;
+                pkt.clear(); in_pkt = false;
+            }
+        } catch (...) { return BNFLAC_ERR_MEMORY; }
+        pos += total;
+        if (flags & 4) break;                              // last page of the logical stream
+    }
+    return have_serial && npackets ? 0 : BNFLAC_ERR_NOT_FLAC;
+}
+} // namespace
+
 int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts, bnflac_t** out) {
     if (!data || !out) return BNFLAC_ERR_ARG;
     *out = nullptr;
     bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
     h->opts = default_opts(opts); h->len = len;
-    bnflac_info_t probe; int rc = parse_metadata(data, len, &probe);      // fail before touching the device
+    int rc;
+    if (is_ogg(data, len)) {                                              // Ogg FLAC: de-paged copy, never borrowed
+        if ((rc = ogg_depage(data, len, h->host))) { delete h; return rc; }
+        data = h->host.data(); len = h->len = h->host.size();
+        h->opts.flags |= BNFLAC_OPT_BORROW_INPUT;                         // (= do not copy again below)
+    }
+    bnflac_info_t probe; rc = parse_metadata(data, len, &probe);          // fail before touching the device
     if (rc) { delete h; return rc; }
     if (h->opts.flags & BNFLAC_OPT_BORROW_INPUT) h->host_ptr = data;
     else {
@@ -1150,6 +1256,11 @@ int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* op
         int rc = 0;
         for (uint64_t want = 64 << 10;; want *= 2) {              // until the metadata is complete
             if ((rc = pull_more(h, want))) break;
+            if (is_ogg(h->host.data(), h->host.size())) {         // Ogg FLAC is de-paged as a whole: pull everything now
+                std::vector<uint8_t> native;
+                if ((rc = pull_more(h, ~0ull)) || (rc = ogg_depage(h->host.data(), h->host.size(), native))) break;
+                h->host.swap(native); h->host_ptr = h->host.data(); h->len = h->host.size();
+            }
             bnflac_info_t probe;
             rc = parse_metadata(h->host.data(), h->host.size(), &probe);
             if (rc != BNFLAC_ERR_TRUNCATED || h->pull_eof) break;

@@ -98,7 +98,11 @@ typedef int (*bnflac_read_cb)(void* user, uint8_t* buf, size_t* bytes);
 
 /* ---- open / info / close ------------------------------------------------------------------ */
 /* Opens a stream held in host memory.  The library copies what it needs to the device; `data` must stay
- * valid until bnflac_close only if BNFLAC is asked to decode lazily (it always copies: caller keeps ownership). */
+ * valid until bnflac_close only with BNFLAC_OPT_BORROW_INPUT (otherwise it is copied: the caller keeps ownership).
+ * A stream that starts with an Ogg page ("OggS") is taken as Ogg FLAC (mapping 1.x): its pages are taken apart on the host
+ * (page CRC-32 and sequence checked; damaged or missing pages cost the packets they carry) and the native stream inside is
+ * decoded; frame offsets in the diagnostics then refer to that native stream.  Also through bnflac_open_callbacks (the
+ * whole stream is pulled at open); not through bnflac_open_device / bnflac_decode_batch. */
 int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts, bnflac_t** out);
 /* Opens from a pull callback (a C# Stream): pulls the whole stream in large requests, then as open_memory;
  * with BNFLAC_OPT_LAZY_PULL only the metadata is pulled here and the rest on demand by bnflac_read. */
