@@ -154,9 +154,11 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     s = make_stream(min(args.seconds, UNIQUE_SECONDS))
     n_all = s.total_samples * s.channels
-    # calibrate so that one step is ~8 s of CPU work on every host thread (bounded sample of the 1 h workload)
+    # calibrate: one step is a bounded sample of the 1 h workload on every host thread -- at most ~8 s of CPU work, and
+    # short enough that the whole --steps K --warmup W run stays within ~2.5 minutes whatever K is
     _, _, dt1 = cpu_decode_rate(s.flac, n_all, cores, 1)
-    reps = max(2, min(200, int(8.0 / max(dt1, 1e-3))))
+    per_step = min(8.0, 150.0 / max(1, args.steps + (1 if args.warmup else 0)))
+    reps = max(1, min(200, int(per_step / max(dt1, 1e-3))))
     for _ in range(1 if args.warmup else 0):
         cpu_decode_rate(s.flac, n_all, cores, 1)
     rates, kind, secs = [], "port", 0.0
