@@ -12,9 +12,19 @@ LIB := birdnest/audio_b200/libbnflac.so
 all: lib oracle corpus host shim
 
 lib: $(LIB)
-$(LIB): $(CSRC)/kernels.cu $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/kernels.cu $(CSRC)/engine.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
+# kernels.cu (device code, ~2 minutes of ptxas) and engine.cu (host runtime, seconds) are compiled separately: the engine
+# only calls the launch_* host wrappers, so no relocatable device code is needed.  Objects live in csrc/_obj (git-ignored).
+OBJ := $(CSRC)/_obj
+$(OBJ)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/bnflac_dev.h include/bnflac.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/kernels.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "error|warning" $(CSRC)/ptxas.log | grep -v "ptxas info" || true
+$(OBJ)/engine.o: $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/engine.cu 2> $(OBJ)/engine.log || (cat $(OBJ)/engine.log; exit 1)
+	@grep -E "error|warning" $(OBJ)/engine.log | grep -v "ptxas info" || true
+$(LIB): $(OBJ)/kernels.o $(OBJ)/engine.o
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)/kernels.o $(OBJ)/engine.o
 
 host: birdnest/audio_b200/flacdecoder_demo
 birdnest/audio_b200/flacdecoder_demo: $(CSRC)/flac_decoder.hpp $(CSRC)/flac_decoder_demo.cpp $(LIB)

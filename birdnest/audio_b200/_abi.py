@@ -76,6 +76,8 @@ _PROTOS = {
     "bnflac_decode_batch": (C.c_int, [C.POINTER(Span), C.c_size_t, C.POINTER(Opts), C.c_void_p, C.c_size_t, C.c_int, C.POINTER(ClipResult), C.POINTER(C.c_uint64)]),
     "bnflac_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(FrameRec)), C.POINTER(C.c_size_t)]),
     "bnflac_subframes": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(SubframeRec)), C.POINTER(C.c_size_t)]),
+    "bnflac_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Info)]),
+    "bnflac_ogg_to_native": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "bnflac_errors": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
     "bnflac_errors_so_far": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
     "bnflac_error_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]),
@@ -263,6 +265,24 @@ def open_device(d_ptr: int, length: int, header: bytes, device=-1, stream=0, sha
     h = C.c_void_p()
     _check(lib().bnflac_open_device(d_ptr, length, _addr(header), len(header), C.byref(o), C.byref(h)), "bnflac_open_device")
     return Handle(h.value, keep=(keep, header))
+
+
+def probe(data) -> Info:
+    """bnflac_probe: host-only metadata parse (native FLAC, ID3v2-prefixed, or Ogg FLAC); no device needed."""
+    info = Info()
+    _check(lib().bnflac_probe(_addr(data), len(data), C.byref(info)), "bnflac_probe")
+    return info
+
+
+def ogg_to_native(data) -> bytes:
+    """bnflac_ogg_to_native: the native FLAC stream inside an Ogg FLAC stream (host-only)."""
+    n = C.c_size_t()
+    rc = lib().bnflac_ogg_to_native(_addr(data), len(data), None, 0, C.byref(n))
+    if rc not in (0, ERR_CAPACITY):
+        _check(rc, "bnflac_ogg_to_native")
+    out = bytearray(n.value)
+    _check(lib().bnflac_ogg_to_native(_addr(data), len(data), _addr(out), len(out), C.byref(n)), "bnflac_ogg_to_native")
+    return bytes(out[:n.value])
 
 
 def open_callbacks(read_fn, device=-1, flags=0) -> Handle:

@@ -1298,6 +1298,29 @@ int bnflac_open_device(const void* d_data, size_t len, const uint8_t* header, si
     return 0;
 }
 
+int bnflac_ogg_to_native(const uint8_t* data, size_t len, uint8_t* dst, size_t cap, size_t* written) {
+    if (!data || !written || (!dst && cap)) return BNFLAC_ERR_ARG;
+    *written = 0;
+    if (!is_ogg(data, len)) return BNFLAC_ERR_NOT_FLAC;
+    std::vector<uint8_t> native;
+    int rc = ogg_depage(data, len, native); if (rc) return rc;
+    *written = native.size();
+    if (native.size() > cap) return BNFLAC_ERR_CAPACITY;
+    if (!native.empty()) memcpy(dst, native.data(), native.size());
+    return 0;
+}
+
+int bnflac_probe(const uint8_t* data, size_t len, bnflac_info_t* info) {
+    if (!data || !info) return BNFLAC_ERR_ARG;
+    if (is_ogg(data, len)) {
+        std::vector<uint8_t> native;
+        int rc = ogg_depage(data, len, native); if (rc) return rc;
+        rc = parse_metadata(native.data(), native.size(), info);
+        return rc;
+    }
+    return parse_metadata(data, len, info);
+}
+
 int bnflac_info(bnflac_t* h, bnflac_info_t* info) { if (!h || !info) return BNFLAC_ERR_ARG; *info = h->info; return 0; }
 int bnflac_state(bnflac_t* h) { return h ? h->state : BNFLAC_STATE_UNINITIALIZED; }
 void bnflac_close(bnflac_t* h) { delete h; }

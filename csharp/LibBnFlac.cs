@@ -87,6 +87,9 @@ namespace LibBnFlacSharp
 		public static extern int bnflac_errors(IntPtr handle, out IntPtr codes, out UIntPtr n);
 
 		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
+		public static extern int bnflac_probe(IntPtr data, UIntPtr len, out Info info);
+
+		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
 		public static extern int bnflac_errors_so_far(IntPtr handle, out IntPtr codes, out UIntPtr n);
 
 		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]

@@ -114,6 +114,13 @@ int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* op
  * bytes past d_data + len (what those bytes hold does not matter; nothing past len is ever interpreted). */
 int bnflac_open_device(const void* d_data, size_t len, const uint8_t* header, size_t header_len, const bnflac_opts* opts, bnflac_t** out);
 int bnflac_info(bnflac_t* h, bnflac_info_t* info);
+/* Host-only (no device needed): the metadata of a stream held in host memory -- what bnflac_open_* + bnflac_info would
+ * report, i.e. what SetupStreamInfo + MetadataCallback derive (FLACDecoder.cs:66-70,431-473).  `data` needs to hold the
+ * metadata blocks only (BNFLAC_ERR_TRUNCATED if they are cut short); ID3v2 prefixes and Ogg FLAC are accepted. */
+int bnflac_probe(const uint8_t* data, size_t len, bnflac_info_t* info);
+/* Host-only: the native FLAC stream inside an Ogg FLAC stream (what the decoder is fed after de-paging).  *written = its
+ * size; BNFLAC_ERR_CAPACITY (nothing copied) if cap is smaller, BNFLAC_ERR_NOT_FLAC if `data` is not Ogg FLAC. */
+int bnflac_ogg_to_native(const uint8_t* data, size_t len, uint8_t* dst, size_t cap, size_t* written);
 int bnflac_state(bnflac_t* h);                       /* bnflac_state_t */
 void bnflac_close(bnflac_t* h);                      /* finish + delete (FLACDecoder.cs:296-300) */
 
