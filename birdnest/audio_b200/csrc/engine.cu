@@ -526,8 +526,10 @@ static std::vector<uint64_t> pipe_cuts(uint64_t b, uint64_t e) {       // bounda
     std::vector<uint64_t> cuts{b};
     const uint64_t first = pipe_first_bytes(), cap = pipe_shard_bytes();
     if (e - b >= 3 * first) {
+        const char* g = getenv("BNFLAC_PIPE_GROWTH");                       // per cent per sub-shard
+        const uint64_t growth = g ? std::max<long>(100, std::min<long>(400, atol(g))) : 200;
         uint64_t pos = b, sz = first;
-        while (e - pos > sz + sz / 2 && cuts.size() < 256) { pos += sz; cuts.push_back(pos); sz = std::min<uint64_t>(2 * sz, cap); }
+        while (e - pos > sz + sz / 2 && cuts.size() < 256) { pos += sz; cuts.push_back(pos); sz = std::min<uint64_t>((sz * growth / 100) & ~4095ull, cap); }
     }
     cuts.push_back(e);
     return cuts;
