@@ -285,7 +285,7 @@ def ogg_to_native(data) -> bytes:
     return bytes(out[:n.value])
 
 
-def open_callbacks(read_fn, device=-1, flags=0) -> Handle:
+def open_callbacks(read_fn, device=-1, flags=0, read_chunk_frames=0) -> Handle:
     """read_fn(n) -> bytes (b'' at end of stream); mirrors the pull model of FLACDecoder.ReadCallback.
     flags=OPT_LAZY_PULL: only the metadata is pulled here, the rest as read_into() advances."""
     def _cb(user, buf, nbytes):
@@ -302,7 +302,7 @@ def open_callbacks(read_fn, device=-1, flags=0) -> Handle:
         nbytes[0] = k
         return 1 if k < want else 0
     cb = READ_CB(_cb)
-    o = _opts(device, flags=flags)
+    o = _opts(device, flags=flags, read_chunk_frames=read_chunk_frames)
     h = C.c_void_p()
     _check(lib().bnflac_open_callbacks(cb, None, C.byref(o), C.byref(h)), "bnflac_open_callbacks")
     return Handle(h.value, keep=cb)        # the callback object must outlive the handle (lazy pull calls it from bnflac_read)

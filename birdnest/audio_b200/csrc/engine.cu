@@ -721,7 +721,13 @@ static int pull_all(bnflac* h) {                             // entry points tha
 // next sub-shard of a lazily pulled stream: pull its bytes, create its handle, issue it
 static int stream_issue(bnflac* h, uint32_t k);
 static int lazy_issue_next(bnflac* h) {
-    const uint64_t first = env_kb("BNFLAC_READ_FIRST_KB", 4096), cap = std::max<uint64_t>(first, env_mb("BNFLAC_READ_MB", 64));
+    uint64_t first = env_kb("BNFLAC_READ_FIRST_KB", 4096), cap = env_mb("BNFLAC_READ_MB", 64);
+    if (h->opts.read_chunk_frames) {       // caller-chosen look-ahead batch (as read_cuts; the stream's length is not known here)
+        const uint64_t mn = h->info.min_framesize, mx = h->info.max_framesize;
+        const uint64_t per = (mn && mx) ? (mn + mx) / 2 : std::max<uint64_t>(64, frame_bound(h->info) / 2);
+        first = cap = std::max<uint64_t>(16384, per * h->opts.read_chunk_frames);
+    }
+    if (cap < first) cap = first;
     if (!h->pl_size) { h->pl_size = first; h->pl_next = h->info.first_frame_offset; }
     const uint64_t b = h->pl_next;
     uint64_t e = b + h->pl_size;

@@ -317,6 +317,21 @@ def test_lazy_pull_abort_and_tiny_streams(tiny_subshards):
         assert _read_all(h, (50001,)) == s.pcm
 
 
+def test_lazy_pull_with_read_chunk_frames(monkeypatch):
+    """bnflac_opts.read_chunk_frames on a lazily pulled source: sub-shards (and pulls) of about that many frames."""
+    import pycorpus
+    from birdnest.audio_b200 import _abi
+    monkeypatch.setenv("BNFLAC_PULL_KB", "16")
+    s = pycorpus.make(**SHAPES["cfg1_16bit_stereo"])
+    src = _CountingSource(s.flac)
+    with _abi.open_callbacks(src, flags=_abi.OPT_LAZY_PULL, read_chunk_frames=8) as h:
+        buf = bytearray(4096)
+        assert h.read_into(buf) == len(buf) and bytes(buf) == s.pcm[:4096]
+        assert src.pos < len(s.flac) // 2                            # a few 8-frame batches, not the 4 MiB default
+        assert bytes(buf) + _read_all(h, (81920,)) == s.pcm
+        assert len(h.frames()) == len(s.frame_bs)
+
+
 def test_flacdecoder_mirror_pulls_lazily(tiny_subshards):
     """FLACDecoder(stream, ...) reads the metadata in its constructor and the stream as Read advances (FLACDecoder.cs:49-88,207-224)."""
     import io
