@@ -1236,14 +1236,15 @@ int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts,
     bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
     h->opts = default_opts(opts); h->len = len;
     int rc;
-    if (is_ogg(data, len)) {                                              // Ogg FLAC: de-paged copy, never borrowed
+    bool in_place = (h->opts.flags & BNFLAC_OPT_BORROW_INPUT) != 0;       // `data` is used where it lies
+    if (is_ogg(data, len)) {                                              // Ogg FLAC: the de-paged copy is what is decoded
         if ((rc = ogg_depage(data, len, h->host))) { delete h; return rc; }
         data = h->host.data(); len = h->len = h->host.size();
-        h->opts.flags |= BNFLAC_OPT_BORROW_INPUT;                         // (= do not copy again below)
+        in_place = true;
     }
     bnflac_info_t probe; rc = parse_metadata(data, len, &probe);          // fail before touching the device
     if (rc) { delete h; return rc; }
-    if (h->opts.flags & BNFLAC_OPT_BORROW_INPUT) h->host_ptr = data;
+    if (in_place) h->host_ptr = data;
     else {
         try { h->host.assign(data, data + len); } catch (...) { delete h; return BNFLAC_ERR_MEMORY; }
         h->host_ptr = h->host.data();
