@@ -117,3 +117,50 @@ def test_ogg_lost_corrupt_and_out_of_order_pages(streams):
     assert _abi.lib().bnflac_ogg_to_native(blob, len(blob), _abi._addr(small), len(small), C.byref(n)) == _abi.ERR_CAPACITY
     assert n.value == len(s.flac) and bytes(small) == bytes(10)
     assert _abi.lib().bnflac_ogg_to_native(s.flac, len(s.flac), None, 0, C.byref(n)) == _abi.ERR_NOT_FLAC
+
+
+def test_depager_and_probe_survive_mutated_input(streams):
+    """The container layer reads untrusted bytes: random mutations (bit flips, overwritten runs, deletions, insertions,
+    truncation) of an Ogg FLAC stream and of a native header must yield an error code or a well-formed result, never a
+    crash; what comes out of the de-pager can only be bytes that went in."""
+    from oggmux import mux
+    from birdnest.audio_b200 import _abi
+    s = streams("cfg4_clip_stereo_var")
+    ogg = b"".join(mux(s, random.Random(3), max_segs=9, other_serial=5))
+    native = _abi.ogg_to_native(ogg)
+    assert native == s.flac
+    rng = random.Random(99)
+    outcomes = {"ok": 0, "err": 0}
+    for it in range(3000):
+        src = ogg if it % 3 else s.flac[:s.frame_off[0] + 200]
+        b = bytearray(src)
+        for _ in range(rng.randrange(1, 4)):
+            kind = rng.randrange(5)
+            p = rng.randrange(len(b))
+            if kind == 0:
+                b[p] ^= 1 << rng.randrange(8)
+            elif kind == 1:
+                n = rng.randrange(1, 40); b[p:p + n] = bytes(rng.getrandbits(8) for _ in range(n))
+            elif kind == 2:
+                del b[p:p + rng.randrange(1, 300)]
+            elif kind == 3:
+                b[p:p] = bytes(rng.getrandbits(8) for _ in range(rng.randrange(1, 300)))
+            else:
+                del b[p:]
+            if not b:
+                b = bytearray(b"O")
+        blob = bytes(b)
+        try:
+            info = _abi.probe(blob)
+            assert 1 <= info.channels <= 8 and info.first_frame_offset <= len(blob) + (1 << 24)
+            outcomes["ok"] += 1
+        except _abi.BnflacError as e:
+            assert e.code in (_abi.ERR_NOT_FLAC, _abi.ERR_TRUNCATED, _abi.ERR_UNSUPPORTED)
+            outcomes["err"] += 1
+        if blob[:4] == b"OggS":
+            try:
+                out = _abi.ogg_to_native(blob)
+                assert out[:4] == b"fLaC" and len(out) <= len(blob)
+            except _abi.BnflacError as e:
+                assert e.code in (_abi.ERR_NOT_FLAC, _abi.ERR_UNSUPPORTED)
+    assert outcomes["ok"] > 300 and outcomes["err"] > 50
