@@ -422,3 +422,36 @@ def test_flacdecoder_mirror_raises_when_the_reader_gets_there(tiny_subshards):
     assert str(e.value) == "FLAC: Could not decode frame: FrameCrcMismatch - ReadFrame!"
     assert len(out) > len(s.pcm) // 8 and bytes(out) == s.pcm[:len(out)]       # everything delivered before it is intact
     dec.Dispose()
+
+
+def test_lazy_pull_of_a_ten_minute_stream():
+    """cfg2 shape, 10 minutes (200 MB compressed, 346 MB PCM) behind a pull callback: the first Read needs only the head of
+    the source, the pulls stay a bounded look-ahead in front of the reader, and the streamed bytes hash to STREAMINFO's md5."""
+    import pycorpus
+    from birdnest.audio_b200 import _abi
+    s = pycorpus.make(ch=2, bps=24, sr=96000, seconds=20, bs=4096, lpc=12, maxpo=6, stereo=1, search=1, tile=30, seed=11)
+    src = _CountingSource(s.flac)
+    md5 = hashlib.md5()
+    with _abi.open_callbacks(src, flags=_abi.OPT_LAZY_PULL) as h:
+        assert src.pos <= (1 << 20)
+        pcm_total = h.info().pcm_bytes                       # (s.pcm is the un-tiled 20 s)
+        buf = bytearray(81920)
+        t0 = time.perf_counter()
+        assert h.read_into(buf) == len(buf)
+        t_first = time.perf_counter() - t0
+        md5.update(buf)
+        assert src.pos < len(s.flac) // 8                    # 4 + 8 MiB sub-shards and their look-ahead, not the stream
+        big = bytearray(1 << 22)
+        total = len(buf)
+        ahead = 0
+        while True:
+            r = h.read_into(big)
+            md5.update(memoryview(big)[:r])
+            total += r
+            ahead = max(ahead, src.pos - int(total / pcm_total * len(s.flac)))
+            if r < len(big):
+                break
+        assert h.errors() == [] and len(h.frames()) == len(s.frame_bs)
+    print(f"lazy pull: first Read(81920) {t_first * 1e3:.2f} ms; source at most {ahead / 2**20:.0f} MiB ahead of the reader")
+    assert md5.digest() == s.md5 and src.pos == len(s.flac)
+    assert (1 << 20) < ahead < (230 << 20)                   # <= 3 sub-shards of <= 64 MiB in flight + half of one pulled beyond
