@@ -18,6 +18,7 @@
 #include <thread>
 #include <utility>
 #include <vector>
+#include <sys/mman.h>
 
 using namespace bnf;
 
@@ -206,6 +207,37 @@ struct SegDesc {            // host description of one segment of a pass, in coo
     uint32_t sample_rate, min_bs, max_bs, max_frame_bytes;
 };
 
+// Bytes pulled from a read callback: one contiguous buffer that grows IN PLACE.  Address space is reserved up front
+// (anonymous, MAP_NORESERVE: pages exist once they are written) and extended with mremap when it runs out, so appending
+// never copies or zero-fills what is already there -- a std::vector grown 1 MiB at a time spent 25-55 ms on page faults
+// and copies for the first 19 MiB, ten times the decode of those bytes.
+struct GrowBuf {
+    uint8_t* p = nullptr; size_t len = 0, cap = 0;
+    GrowBuf() = default;
+    GrowBuf(const GrowBuf&) = delete; GrowBuf& operator=(const GrowBuf&) = delete;
+    ~GrowBuf() { release(); }
+    void release() { if (p) munmap(p, cap); p = nullptr; len = cap = 0; }
+    bool room(size_t more) {                              // make [len, len + more) writable
+        if (len + more <= cap) return true;
+        size_t want = cap ? cap : (size_t)1 << 32;        // 4 GiB of address space to start with
+        while (want < len + more) want <<= 1;
+        void* q;
+        if (!p) {
+            q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            while (q == MAP_FAILED && want / 2 >= len + more && want > ((size_t)1 << 24)) {      // address space limited (ulimit -v)
+                want >>= 1;
+                q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            }
+        } else q = mremap(p, cap, want, MREMAP_MAYMOVE);  // moves page tables, not bytes
+        if (q == MAP_FAILED) return false;
+        p = (uint8_t*)q; cap = want;
+#ifdef MADV_HUGEPAGE
+        madvise(p, cap, MADV_HUGEPAGE);                   // first-touch faults per 2 MiB instead of per 4 KiB where the kernel allows it
+#endif
+        return true;
+    }
+};
+
 struct DiagCursor {          // the reference's sync-search state, carried across the sub-shards of a pipelined decode
     uint64_t expect = 0;     // where its cursor stands
     bool in_sync = true;     // LOST_SYNC is reported once per excursion
@@ -225,6 +257,7 @@ struct bnflac {
 
     // input
     std::vector<uint8_t> host;          // copy of the stream when opened from host memory
+    GrowBuf pulled;                     // ... or what has been pulled from the read callback so far
     const uint8_t* host_ptr = nullptr;  // the bytes to upload (== host.data() unless BNFLAC_OPT_BORROW_INPUT)
     const uint8_t* d_ext = nullptr;     // caller-owned device copy (open_device)
     size_t len = 0;
@@ -263,6 +296,7 @@ struct bnflac {
     bnflac_read_cb pull_cb = nullptr; void* pull_user = nullptr; bool pull_eof = true;
     uint64_t pl_next = 0, pl_size = 0;   // start of the next sub-shard to issue, its size
     bool pl_session = false;             // the current streamed Read session cuts its sub-shards as the bytes arrive
+    bool pl_ahead = false;               // ... and has started to issue sub-shards ahead of the reader
     bool front_ran = false;              // a decode has been started on this handle (the diagnostics have something to describe)
     // streaming Read session: sub-shards decoded ahead of the reader, see stream_read()
     bool rd_active = false; uint32_t rd_issued = 0, rd_cur = 0; uint64_t rd_off = 0, rd_total = 0;
@@ -694,21 +728,19 @@ static constexpr uint32_t READ_LOOKAHEAD = 2;      // sub-shards in flight beyon
 // until STREAMINFO and the end of the metadata are in hand -- and bnflac_read pulls what the next sub-shard needs (its
 // byte range plus one maximum frame of overlap) right before issuing it.  Everything pulled is kept (the diagnostics replay
 // the reference's sync search over the bytes between frames).
-static int pull_more(bnflac* h, uint64_t need_len) {         // until host.size() >= need_len or end of stream
+static int pull_more(bnflac* h, uint64_t need_len) {         // until need_len bytes are in hand or the stream ends
     const size_t req = env_kb("BNFLAC_PULL_KB", 1024);        // bytes asked of the callback per call
-    try {
-        while (!h->pull_eof && h->host.size() < need_len) {
-            const size_t old = h->host.size();
-            h->host.resize(old + req);
-            size_t got = req;
-            const int st = h->pull_cb(h->pull_user, h->host.data() + old, &got);
-            if (st == 2) { h->host.resize(old); return BNFLAC_ERR_ABORTED; }
-            if (got > req) { h->host.resize(old); return BNFLAC_ERR_ARG; }
-            h->host.resize(old + got);
-            if (st == 1 || got == 0) h->pull_eof = true;
-        }
-    } catch (...) { return BNFLAC_ERR_MEMORY; }
-    h->host_ptr = h->host.data(); h->len = h->host.size();
+    GrowBuf& b = h->pulled;
+    while (!h->pull_eof && b.len < need_len) {
+        if (!b.room(req)) return BNFLAC_ERR_MEMORY;
+        size_t got = req;
+        const int st = h->pull_cb(h->pull_user, b.p + b.len, &got);
+        if (st == 2) return BNFLAC_ERR_ABORTED;
+        if (got > req) return BNFLAC_ERR_ARG;
+        b.len += got;
+        if (st == 1 || got == 0) h->pull_eof = true;
+    }
+    h->host_ptr = b.p; h->len = b.len;                        // (the buffer may have moved: kids take the pointer when they are issued)
     return 0;
 }
 static int pull_all(bnflac* h) {                             // entry points that need the whole stream
@@ -793,8 +825,11 @@ static int64_t stream_read(bnflac* h, uint8_t* dst, size_t count) {
             h->rd_cur++; h->rd_off = 0;
         }
     }
-    // keep the decode ahead of the reader: at most one more sub-shard per call, so no single Read pays for several
-    if (h->rd_issued <= h->rd_cur + READ_LOOKAHEAD) {
+    // keep the decode ahead of the reader: at most one more sub-shard per call, so no single Read pays for several -- and
+    // none in the first call of a lazily pulled session, which has just paid for pulling its first sub-shard
+    const bool first_lazy_call = h->pl_session && h->kids.size() == 1 && h->rd_cur == 0 && h->rd_issued == 1 && !h->pl_ahead;
+    h->pl_ahead = true;
+    if (!first_lazy_call && h->rd_issued <= h->rd_cur + READ_LOOKAHEAD) {
         if (h->rd_issued < h->kids.size()) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
         else if (lazy_more(h) && (rc = lazy_issue_next(h))) return rc;
     }
@@ -1258,42 +1293,28 @@ int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* op
     if (!read || !out) return BNFLAC_ERR_ARG;
     *out = nullptr;
     const bnflac_opts o = default_opts(opts);
-    if (o.flags & BNFLAC_OPT_LAZY_PULL) {
-        if (o.shard_count > 1) return BNFLAC_ERR_ARG;            // a shard needs the stream's length
-        bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
-        h->opts = o; h->pull_cb = read; h->pull_user = user; h->pull_eof = false;
-        int rc = 0;
-        for (uint64_t want = 64 << 10;; want *= 2) {              // until the metadata is complete
-            if ((rc = pull_more(h, want))) break;
-            if (is_ogg(h->host.data(), h->host.size())) {         // Ogg FLAC is de-paged as a whole: pull everything now
-                std::vector<uint8_t> native;
-                if ((rc = pull_more(h, ~0ull)) || (rc = ogg_depage(h->host.data(), h->host.size(), native))) break;
-                h->host.swap(native); h->host_ptr = h->host.data(); h->len = h->host.size();
-            }
-            bnflac_info_t probe;
-            rc = parse_metadata(h->host.data(), h->host.size(), &probe);
-            if (rc != BNFLAC_ERR_TRUNCATED || h->pull_eof) break;
-        }
-        if (!rc) rc = common_open(h, h->host_ptr, h->len);
-        if (!rc) rc = setup_device(h);
-        if (rc) { delete h; return rc; }
-        *out = h;
-        return 0;
+    const bool lazy = (o.flags & BNFLAC_OPT_LAZY_PULL) != 0;
+    if (lazy && o.shard_count > 1) return BNFLAC_ERR_ARG;        // a shard needs the stream's length
+    bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
+    h->opts = o; h->pull_cb = read; h->pull_user = user; h->pull_eof = false;
+    // the reference pulls <= 16 KiB per callback (FLACDecoder.cs:21,336); pull_more asks for 1 MiB at a time
+    int rc = 0;
+    if (!lazy) rc = pull_more(h, ~0ull);                         // the whole stream now
+    else for (uint64_t want = 64 << 10;; want *= 2) {            // only until the metadata is complete
+        if ((rc = pull_more(h, want))) break;
+        if (is_ogg(h->pulled.p, h->pulled.len)) { rc = pull_more(h, ~0ull); break; }      // Ogg FLAC is de-paged as a whole
+        bnflac_info_t probe;
+        rc = parse_metadata(h->pulled.p, h->pulled.len, &probe);
+        if (rc != BNFLAC_ERR_TRUNCATED || h->pull_eof) { rc = 0; break; }                  // (common_open reports what is wrong)
     }
-    std::vector<uint8_t> buf;
-    const size_t req = 1u << 20;   // the reference pulls <= 16 KiB per callback (FLACDecoder.cs:21,336); we ask for 1 MiB
-    try {
-        for (;;) {
-            size_t old = buf.size(); buf.resize(old + req);
-            size_t got = req;
-            int st = read(user, buf.data() + old, &got);
-            if (st == 2) return BNFLAC_ERR_ABORTED;
-            if (got > req) return BNFLAC_ERR_ARG;
-            buf.resize(old + got);
-            if (st == 1 || got == 0) break;
-        }
-    } catch (...) { return BNFLAC_ERR_MEMORY; }
-    return bnflac_open_memory(buf.data(), buf.size(), opts, out);
+    if (!rc && is_ogg(h->pulled.p, h->pulled.len)) {
+        if (!(rc = ogg_depage(h->pulled.p, h->pulled.len, h->host))) { h->pulled.release(); h->host_ptr = h->host.data(); h->len = h->host.size(); }
+    }
+    if (!rc) rc = common_open(h, h->host_ptr, h->len);
+    if (!rc) rc = setup_device(h);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
 }
 
 int bnflac_open_device(const void* d_data, size_t len, const uint8_t* header, size_t header_len, const bnflac_opts* opts, bnflac_t** out) {
@@ -1379,7 +1400,7 @@ int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count) {
         CK(cudaSetDevice(h->device));
         for (bnflac* k : h->kids) delete k;
         h->kids.clear();
-        h->rd_active = true; h->rd_issued = h->rd_cur = 0; h->rd_off = h->rd_total = 0; h->pl_size = 0; h->pl_session = true; h->timing = bnflac_timing{}; h->diag_valid = false; h->diag_started = false;
+        h->rd_active = true; h->rd_issued = h->rd_cur = 0; h->rd_off = h->rd_total = 0; h->pl_size = 0; h->pl_session = true; h->pl_ahead = false; h->timing = bnflac_timing{}; h->diag_valid = false; h->diag_started = false;
         return stream_read(h, dst, count);
     }
     if (!h->decoded && h->host_ptr && !h->d_ext && h->batch_segs.empty()) {

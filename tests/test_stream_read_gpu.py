@@ -430,6 +430,8 @@ def test_lazy_pull_of_a_ten_minute_stream():
     import pycorpus
     from birdnest.audio_b200 import _abi
     s = pycorpus.make(ch=2, bps=24, sr=96000, seconds=20, bs=4096, lpc=12, maxpo=6, stereo=1, search=1, tile=30, seed=11)
+    with _abi.open_callbacks(_CountingSource(s.flac), flags=_abi.OPT_LAZY_PULL) as h:      # warm the block pools (as the test above)
+        _read_all(h, (1 << 22,))
     src = _CountingSource(s.flac)
     md5 = hashlib.md5()
     with _abi.open_callbacks(src, flags=_abi.OPT_LAZY_PULL) as h:
