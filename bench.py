@@ -52,44 +52,78 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  Sampled in-process through
+    NVML every 4 ms (the recipe's `nvidia-smi -lms` needs ~100 ms to produce its first row: a short timed region would end
+    up with no sample at all); nvidia-smi is the fallback when pynvml is missing."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
-        self.rows = []
+        self.rows = []            # (time, sm_mhz, sm_max_mhz, set(reasons))
         self.proc = None
+        self.nvml = None
         self.index = index
+        self.stopping = False
+        self.source = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self._sample_nvml()                      # fails here rather than in the thread if the queries are unsupported
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _sample_nvml(self):
+        nv, h = self.nvml
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(h))
+        self.rows.append((time.time(), sm, mx, {n for n, b in self.BITS.items() if mask & b}))
+
+    def _poll(self):
+        while not self.stopping:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                row = (time.time(), float(f[0]), float(f[1]),
+                       {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]) if v.lower().startswith("active")})
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            self.rows.append(row)
+
+    def stop(self, t0, t1):
+        if not self.nvml and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        self.stopping = True
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or list(self.rows)
+        sm = [r[1] for r in rows]; mx = [r[2] for r in rows]
+        reasons = set().union(*[r[3] for r in rows]) if rows else set()
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baselines
