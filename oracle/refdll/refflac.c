@@ -13,6 +13,7 @@
  * binary copy made by the Makefile so the oracle can travel to the GPU box).
  *
  *   refflac dec  <dll> in.flac out.pcm        decode, write interleaved LE PCM, print frames/errors/state
+ *   refflac decogg <dll> in.oga out.pcm       the same through FLAC__stream_decoder_init_ogg_stream (Ogg FLAC pages)
  *   refflac bench <dll> in.flac iters         time `iters` full decodes (process_single loop + interleave), print ms each
  *   refflac enc  <dll> ch bps sr bs maxlpc minpo maxpo midside exhaustive in.pcm out.flac   encode packed LE PCM
  */
@@ -172,6 +173,7 @@ static u32 read_cap = 16384;   /* FLACDecoder.DEFAULT_MAX_BUFFER_SIZE (FLACDecod
 typedef int (*fn_get_state)(void*);
 static fn_get_state p_get_state; static u32 err_states[64];
 
+static int use_ogg;      /* "decogg": the same client behind FLAC__stream_decoder_init_ogg_stream (the DLL carries libogg) */
 /* ReadCallback, FLACDecoder.cs:325-363 */
 ALIGNED static int dec_read(void* d, u8* buf, size_t* bytes, void* cd) {
     (void)d; (void)cd;
@@ -181,6 +183,10 @@ ALIGNED static int dec_read(void* d, u8* buf, size_t* bytes, void* cd) {
     u32 left = in_len - in_pos, count = left < length ? left : length;
     memcpy(buf, in_buf + in_pos, count); in_pos += count;
     *bytes = count;
+    /* The C# reports END_OF_STREAM together with the last, short read (FLACDecoder.cs:345-350).  libFLAC 1.2.1's Ogg layer
+     * stops at that status without paging out what it has just been handed, so behind init_ogg_stream that convention loses
+     * the frames of the last read; "decogg" follows libFLAC's own file callback instead: END_OF_STREAM only with 0 bytes. */
+    if (use_ogg) return count == 0 ? 1 : 0;
     return count < length ? 1 : 0;
 }
 /* WriteCallback: FLACDecoder.cs:520-580 for 16-bit mono/stereo; FLACFileReader.cs:214-243 layout in general */
@@ -215,7 +221,7 @@ typedef int (*fn_init)(void*, void*, void*, void*, void*, void*, void*, void*, v
 static int final_state;
 static void decode_once(void) {
     fn_new dnew = (fn_new)pe_export("FLAC__stream_decoder_new");
-    fn_init dinit = (fn_init)pe_export("FLAC__stream_decoder_init_stream");
+    fn_init dinit = (fn_init)pe_export(use_ogg ? "FLAC__stream_decoder_init_ogg_stream" : "FLAC__stream_decoder_init_stream");
     fn_i_p meta = (fn_i_p)pe_export("FLAC__stream_decoder_process_until_end_of_metadata");
     fn_i_p single = (fn_i_p)pe_export("FLAC__stream_decoder_process_single");
     fn_i_p finish = (fn_i_p)pe_export("FLAC__stream_decoder_finish");
@@ -247,12 +253,13 @@ typedef int (*fn_einit)(void*, void*, void*, void*, void*, void*); typedef int (
 static void set_u(void* enc, const char* name, u32 v) { if (!((fn_set_u)pe_export(name))(enc, v)) { put(name); die(" rejected"); } }
 
 static int cmain(int argc, char** argv) {
-    if (argc < 4) { put("usage: refflac dec|bench|enc <LibFlac.dll> ...\n"); return 2; }
+    if (argc < 4) { put("usage: refflac dec|decogg|bench|enc <LibFlac.dll> ...\n"); return 2; }
     heap_cap = 768u << 20; heap = xmmap(0, heap_cap, 3, 0x22);
     if ((i32)heap < 0 && (i32)heap > -4096) die("cannot map heap");
     pe_load(argv[2]);
-    if (!xstrcmp(argv[1], "dec") || !xstrcmp(argv[1], "bench")) {
+    if (!xstrcmp(argv[1], "dec") || !xstrcmp(argv[1], "bench") || !xstrcmp(argv[1], "decogg")) {
         int bench = argv[1][0] == 'b';
+        use_ogg = !xstrcmp(argv[1], "decogg");
         in_buf = slurp(argv[3], &in_len);
         /* output capacity from STREAMINFO when present, else 64x input */
         out_cap = in_len * 8 + (64u << 20); if (out_cap > (1600u << 20) || out_cap < in_len) out_cap = 1600u << 20;

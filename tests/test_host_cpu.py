@@ -164,3 +164,25 @@ def test_depager_and_probe_survive_mutated_input(streams):
             except _abi.BnflacError as e:
                 assert e.code in (_abi.ERR_NOT_FLAC, _abi.ERR_UNSUPPORTED)
     assert outcomes["ok"] > 300 and outcomes["err"] > 50
+
+
+ogg_golden = json.load(open(os.path.join(GOLD, "golden_ogg.json")))
+
+
+@pytest.mark.parametrize("name", sorted(k for k in ogg_golden if k != "note"))
+def test_depager_plus_oracle_equal_the_reference_dll_on_ogg(name):
+    """The reference's LibFlac.dll decoded these pages through FLAC__stream_decoder_init_ogg_stream (oracle/make_golden_ogg.py);
+    the library's de-pager followed by the CPU oracle must produce the same PCM, frame count and (absence of) error events --
+    including the stream with a missing page, a corrupt page and junk between pages."""
+    import hashlib
+    import pyoracle
+    from birdnest.audio_b200 import _abi
+    g = ogg_golden[name]
+    blob = open(os.path.join(GOLD, name + ".oga"), "rb").read()
+    native = _abi.ogg_to_native(blob)
+    pcm, nframes, _, errs = pyoracle.decode(native)
+    assert hashlib.md5(pcm).hexdigest() == g["pcm_md5"] and len(pcm) == g["bytes"]
+    assert nframes == g["frames"] and errs == g["errors"]
+    info = _abi.probe(blob)
+    assert (info.channels, info.bits_per_sample, info.sample_rate, info.total_samples) == (g["channels"], g["bps"], g["sample_rate"], g["total_samples"])
+    assert bytes(info.md5).hex() == g["si_md5"]

@@ -1,8 +1,9 @@
 """Ogg FLAC (container breadth): the pages are taken apart on the host (`ogg_depage`, csrc/engine.cu) and the
 native stream inside goes down the same GPU pipeline.  The reference's C# binds only the native-FLAC entry points
-(LibFLACSharp.cs:42-85), so there is no reference surface to pin this against: **parity unpinned for the container layer**;
-the payload decode is the pinned native path, and these tests check that an Ogg-wrapped stream decodes to exactly what the
-oracle produces for the native stream it was made from -- through every page / packet layout the mapping allows."""
+(LibFLACSharp.cs:42-85), but its LibFlac.dll exports FLAC__stream_decoder_init_ogg_stream: the records at the end of this
+file were produced by that binary (oracle/make_golden_ogg.py) and pin the container layer; the other tests check that an
+Ogg-wrapped stream decodes to exactly what the oracle produces for the native stream it was made from -- through every
+page / packet layout the mapping allows."""
 import hashlib
 import random
 
@@ -102,3 +103,27 @@ def test_not_ogg_flac():
     with pytest.raises(_abi.BnflacError) as e:
         _abi.open_memory(page(1, 0, 2, 0, [len(v2)], bytes(v2)))
     assert e.value.code == _abi.ERR_UNSUPPORTED
+
+
+import json
+import os
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_ogg_golden = json.load(open(os.path.join(_GOLD, "golden_ogg.json")))
+
+
+@pytest.mark.parametrize("name", sorted(k for k in _ogg_golden if k != "note"))
+def test_ogg_golden_records_of_the_reference_dll(name):
+    """Pages decoded by the reference's own LibFlac.dll through init_ogg_stream (oracle/make_golden_ogg.py): same PCM, frame
+    count, end state and error events from the GPU path -- this pins the container layer to the reference binary."""
+    from birdnest.audio_b200 import _abi
+    g = _ogg_golden[name]
+    blob = open(os.path.join(_GOLD, name + ".oga"), "rb").read()
+    with _abi.open_memory(blob) as h:
+        out = bytearray(g["bytes"] + 4096)
+        n = h.decode_all(out)
+        frames, errs, state = h.frames(), h.errors(), h.state()
+        info = h.info()
+    assert n == g["bytes"] and hashlib.md5(bytes(out[:n])).hexdigest() == g["pcm_md5"]
+    assert len(frames) == g["frames"] and errs == g["errors"] and state == g["state"]
+    assert bytes(info.md5).hex() == g["si_md5"]
