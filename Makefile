@@ -36,7 +36,10 @@ shim: $(SHIM)
 $(SHIM): $(CSRC)/libflac_shim.cpp include/bnflac_legacy.h include/bnflac.h $(LIB)
 	g++ -O2 -std=c++17 -Wall -fPIC -shared -Iinclude -o $@ $(CSRC)/libflac_shim.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
 
-oracle: oracle/_build/liboracle.so oracle/_build/flac_oracle
+oracle: oracle/_build/liboracle.so oracle/_build/liboracle_next.so oracle/_build/flac_oracle
+oracle/_build/liboracle_next.so: oracle/flac_oracle.c oracle/flac_oracle.h
+	@mkdir -p oracle/_build
+	gcc -O3 -fPIC -shared -Wall -DFO_NEXT_RULES -o $@ oracle/flac_oracle.c
 oracle/_build/liboracle.so: oracle/flac_oracle.c oracle/flac_oracle.h
 	@mkdir -p oracle/_build
 	gcc -O3 -fPIC -shared -Wall -o $@ oracle/flac_oracle.c

@@ -7,9 +7,9 @@ LibFlac.dll under the PE loader) and by oracle/flac_oracle.c, and PCM md5, frame
 compared.  usage (repo root, after `make oracle ref`):  python oracle/fuzz_vs_ref.py [trials per shape and kind, default 12]
 
 Round-1 finding ("Damaged streams"): with the oracle as committed 183 of 336 streams differ from the DLL in
-the EVENT LIST or in whether ONE damaged frame is delivered zero-filled or dropped; oracle/damage_rules_next.patch (five
-rules of libFLAC 1.2.1 the restatement missed) brings that to 0 of 1120.  The engine follows the committed oracle, so the
-patch has to land together with the same rules in k_parse / k_resync / collect_diag."""
+the EVENT LIST or in whether ONE damaged frame is delivered zero-filled or dropped; the FO_NEXT_RULES build of the oracle (five
+rules of libFLAC 1.2.1 the restatement missed, `--next`) brings that to 0 of 1120.  The engine follows the committed oracle, so the
+switch has to become the default together with the same rules in k_parse / k_resync / collect_diag."""
 import sys, os, random, zlib, subprocess, hashlib, tempfile, importlib.util
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
@@ -28,8 +28,15 @@ def run_dll(blob, d):
     kv=dict(x.split('=') for x in lines[0].split())
     errs=[int(l.split('=')[1].split()[0]) for l in lines[1:] if l.startswith('error[')]
     return (hashlib.md5(pcm).hexdigest(), int(kv['frames']), errs, int(kv['errors'])), None
-TR=int(sys.argv[1]) if len(sys.argv)>1 else 12
+# usage: fuzz_vs_ref.py [trials] [--next] [--write-golden]
+#   --next          compare the FO_NEXT_RULES build of the oracle (liboracle_next.so) instead of the default one
+#   --write-golden  store what the DLL produced for every stream in tests/golden/golden_damage.json (the streams themselves
+#                   are regenerated from the seeds by tests/test_oracle_cpu.py)
+args=[a for a in sys.argv[1:] if not a.startswith('--')]
+NEXT='--next' in sys.argv; WRITE='--write-golden' in sys.argv
+TR=int(args[0]) if args else 12
 tot=bad=0
+records={}
 with tempfile.TemporaryDirectory() as d:
     for shape in sorted(fz.SHAPES):
         s=pycorpus.make(**fz.SHAPES[shape]); first=s.frame_off[0]
@@ -37,11 +44,17 @@ with tempfile.TemporaryDirectory() as d:
             rng=random.Random(zlib.crc32(f"{shape}/{kind}".encode()))
             for t in range(TR):
                 blob=fz._damage(s.flac, first, rng, kind)
-                want, nfr, _, oerrs = pyoracle.decode(blob)
+                want, nfr, _, oerrs = pyoracle.decode(blob, next_rules=NEXT)
                 ref, why = run_dll(blob, d)
                 tot+=1
                 if ref is None: bad+=1; print("DLL failed", shape, kind, t, why); continue
                 md5, rfr, rerrs, nerr = ref
+                records[f"{shape}/{kind}/{t}"]={"blob_md5": hashlib.md5(blob).hexdigest(), "pcm_md5": md5, "frames": rfr, "errors": rerrs, "n_errors": nerr}
                 ok = md5==hashlib.md5(want).hexdigest() and rfr==nfr and (rerrs==oerrs[:64]) and nerr==len(oerrs)
                 if not ok: bad+=1; print("MISMATCH", shape, kind, t, "dll", rfr, rerrs[:6], nerr, "oracle", nfr, oerrs[:6], len(oerrs))
-print("total", tot, "mismatch", bad)
+print("total", tot, "mismatch", bad, "(next rules)" if NEXT else "(round-1 rules)")
+if WRITE:
+    import json
+    out={"note": "produced by oracle/fuzz_vs_ref.py --write-golden: the reference LibFlac.dll (libFLAC 1.2.1) decoding seeded damaged streams in the build container; streams are regenerated from the seeds (tests/test_damage_fuzz_gpu.py: SHAPES, _damage, rng = Random(crc32('shape/kind')))", "trials": TR, "records": records}
+    json.dump(out, open(os.path.join('tests','golden','golden_damage.json'),'w'), indent=0, sort_keys=True)
+    print("wrote tests/golden/golden_damage.json:", len(records), "records")

@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _L = None
+_LN = None
 
 
 class StreamInfo(C.Structure):
@@ -31,27 +32,38 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _ROOT, "oracle"])
 
 
-def lib():
-    global _L
+def lib(next_rules=False):
+    """next_rules=True: the build with the five damaged-frame rules of DESIGN.md section 7 (liboracle_next.so)."""
+    global _L, _LN
+    if next_rules:
+        if _LN is None:
+            so = _SO.replace("liboracle.so", "liboracle_next.so")
+            if not os.path.exists(so):
+                build()
+            _LN = _bind(C.CDLL(so))
+        return _LN
     if _L is None:
         if not os.path.exists(_SO):
             build()
-        L = C.CDLL(_SO)
-        L.fo_read_streaminfo.restype = C.c_int
-        L.fo_read_streaminfo.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StreamInfo)]
-        L.fo_decode.restype = C.c_int64
-        L.fo_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Frame), C.c_size_t, C.POINTER(C.c_size_t),
-                                C.POINTER(Subframe), C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]
-        L.fo_decode_range.restype = C.c_int64
-        L.fo_decode_range.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StreamInfo), C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
-        L.fo_crc8.restype = C.c_uint8
-        L.fo_crc8.argtypes = [C.c_char_p, C.c_size_t]
-        L.fo_crc16.restype = C.c_uint16
-        L.fo_crc16.argtypes = [C.c_char_p, C.c_size_t]
-        L.fo_md5.restype = None
-        L.fo_md5.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
-        _L = L
+        _L = _bind(C.CDLL(_SO))
     return _L
+
+
+def _bind(L):
+    L.fo_read_streaminfo.restype = C.c_int
+    L.fo_read_streaminfo.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StreamInfo)]
+    L.fo_decode.restype = C.c_int64
+    L.fo_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Frame), C.c_size_t, C.POINTER(C.c_size_t),
+                            C.POINTER(Subframe), C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]
+    L.fo_decode_range.restype = C.c_int64
+    L.fo_decode_range.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StreamInfo), C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.fo_crc8.restype = C.c_uint8
+    L.fo_crc8.argtypes = [C.c_char_p, C.c_size_t]
+    L.fo_crc16.restype = C.c_uint16
+    L.fo_crc16.argtypes = [C.c_char_p, C.c_size_t]
+    L.fo_md5.restype = None
+    L.fo_md5.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
+    return L
 
 
 def streaminfo(data: bytes) -> StreamInfo:
@@ -62,9 +74,9 @@ def streaminfo(data: bytes) -> StreamInfo:
     return si
 
 
-def decode(data: bytes, want_frames=False):
+def decode(data: bytes, want_frames=False, next_rules=False):
     """-> (pcm bytes, frames, subframes, errors)"""
-    L = lib()
+    L = lib(next_rules)
     need = L.fo_decode(data, len(data), None, 0, None, 0, None, None, None, 0, None)
     if need < 0:
         raise ValueError(f"oracle decode failed ({need})")

@@ -113,3 +113,39 @@ def test_oracle_matches_reference_on_metadata_variants(name):
     pcm, nframes, _, errs = pyoracle.decode(flac)
     assert hashlib.md5(pcm).hexdigest() == g["ref_pcm_md5"]
     assert (nframes, len(pcm), errs) == (g["frames"], g["bytes"], g["errors"])
+
+
+def test_next_rules_oracle_matches_the_reference_dll_on_random_damage():
+    """224 seeded damaged streams (bit flips, overwritten / 0xFF / 0x00 runs, deleted and inserted bytes, truncation) decoded
+    by the reference's LibFlac.dll in the build container (oracle/fuzz_vs_ref.py --next --write-golden ->
+    tests/golden/golden_damage.json).  The FO_NEXT_RULES build of the oracle (the five damaged-frame rules of DESIGN.md
+    section 7) reproduces PCM, frame count and the complete event list of every one; the default build -- the rules the
+    engine follows in round 1 -- does not yet, and the number that agree is reported so the gap stays visible."""
+    import hashlib
+    import importlib.util
+    import random
+    import zlib
+    import pycorpus
+    import pyoracle
+    spec = importlib.util.spec_from_file_location("damage_fuzz", os.path.join(ROOT, "tests", "test_damage_fuzz_gpu.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_damage.json")))
+    trials, rec = g["trials"], g["records"]
+    seen = agree_r1 = 0
+    for shape in sorted(fz.SHAPES):
+        s = pycorpus.make(**fz.SHAPES[shape])
+        first = s.frame_off[0]
+        for kind in ["flip", "run", "ones", "zeros", "delete", "insert", "truncate"]:
+            rng = random.Random(zlib.crc32(f"{shape}/{kind}".encode()))
+            for t in range(trials):
+                blob = fz._damage(s.flac, first, rng, kind)
+                r = rec[f"{shape}/{kind}/{t}"]
+                assert hashlib.md5(blob).hexdigest() == r["blob_md5"], "the damaged stream is not the one the DLL decoded"
+                pcm, nfr, _, errs = pyoracle.decode(blob, next_rules=True)
+                assert (hashlib.md5(pcm).hexdigest(), nfr, errs[:64], len(errs)) == (r["pcm_md5"], r["frames"], r["errors"], r["n_errors"]), (shape, kind, t)
+                pcm1, nfr1, _, errs1 = pyoracle.decode(blob)
+                agree_r1 += (hashlib.md5(pcm1).hexdigest(), nfr1, errs1[:64], len(errs1)) == (r["pcm_md5"], r["frames"], r["errors"], r["n_errors"])
+                seen += 1
+    assert seen == len(rec) == 224
+    print(f"round-1 rules agree with the reference DLL on {agree_r1} of {seen} damaged streams; next rules on all")
