@@ -36,10 +36,7 @@ shim: $(SHIM)
 $(SHIM): $(CSRC)/libflac_shim.cpp include/bnflac_legacy.h include/bnflac.h $(LIB)
 	g++ -O2 -std=c++17 -Wall -fPIC -shared -Iinclude -o $@ $(CSRC)/libflac_shim.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
 
-oracle: oracle/_build/liboracle.so oracle/_build/liboracle_next.so oracle/_build/flac_oracle
-oracle/_build/liboracle_next.so: oracle/flac_oracle.c oracle/flac_oracle.h
-	@mkdir -p oracle/_build
-	gcc -O3 -fPIC -shared -Wall -DFO_NEXT_RULES -o $@ oracle/flac_oracle.c
+oracle: oracle/_build/liboracle.so oracle/_build/flac_oracle
 oracle/_build/liboracle.so: oracle/flac_oracle.c oracle/flac_oracle.h
 	@mkdir -p oracle/_build
 	gcc -O3 -fPIC -shared -Wall -o $@ oracle/flac_oracle.c
@@ -50,10 +47,10 @@ oracle/_build/flac_oracle: oracle/flac_oracle.c oracle/flac_oracle.h
 corpus: corpus/_build/libbncorpus.so corpus/_build/bncorpus
 corpus/_build/libbncorpus.so: corpus/bncorpus.c corpus/bncorpus.h
 	@mkdir -p corpus/_build
-	gcc -O3 -fPIC -shared -w -o $@ corpus/bncorpus.c -lm -lpthread
+	gcc -O3 -ffp-contract=off -fPIC -shared -w -o $@ corpus/bncorpus.c -lm -lpthread
 corpus/_build/bncorpus: corpus/bncorpus.c corpus/bncorpus.h
 	@mkdir -p corpus/_build
-	gcc -O3 -w -DBNC_MAIN -o $@ corpus/bncorpus.c -lm -lpthread
+	gcc -O3 -ffp-contract=off -w -DBNC_MAIN -o $@ corpus/bncorpus.c -lm -lpthread
 
 ref:
 	$(MAKE) -C oracle/refdll

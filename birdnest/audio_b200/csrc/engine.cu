@@ -914,10 +914,10 @@ static int collect_diag(bnflac* h, DiagCursor& cur, uint64_t pcm_base, const uin
         scan_gap(h, host_ptr, stream_len, cur, off, errors);
         if (cur.ended) break;
         if (st[i] == ST_EOS) { cur.ended = true; break; }         // the stream ended inside this frame
-        if (!is_frame) {                                          // the parse failed: reported, cursor resumes two bytes further
-            cur.event(errors, st[i] == ST_LOSTSYNC ? 0u : 3u);
-            cur.in_sync = false;
-            cur.expect = off + 2;
+        if (!is_frame) {                                          // the parse failed: reported, the search resumes where the bit reader stood
+            cur.event(errors, st[i] == ST_LOSTSYNC ? 0u : 3u);   // (libFLAC 1.2.1; it reports LOST_SYNC again when it then skips bytes)
+            cur.in_sync = true;
+            cur.expect = off + fl[i];
             continue;
         }
         bnflac_frame_t f{};

@@ -726,13 +726,13 @@ struct RingBitsT {
         return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
     }
     // skip one Rice codeword; returns false when the unary run is implausibly long (damaged data)
-    __device__ __forceinline__ bool rice_skip_careful(uint32_t k) {
+    __device__ __forceinline__ bool rice_skip_careful(uint32_t k, uint32_t limit = 1u << 16) {
         const uint32_t w = window();
         const uint32_t f = bfind(w);
         if ((int32_t)(f - k) >= 0) { pos += k + 32u - f; return true; }
-        const uint32_t q = unary(1u << 16);
+        const uint32_t q = unary(limit);
         jump(k);
-        return q <= (1u << 16);
+        return q <= limit;
     }
 };
 
@@ -762,37 +762,45 @@ template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (O
 // it was 40 % of the instructions with 8-codeword steps (ncu, cfg3: 6.4 -> 5.3 ms; cfg2: 0.42 -> 0.39 ms).  The residual of the LAST subframe of a
 // CRC-validated frame is not walked: nothing starts after it.
 constexpr int PARSE_THREADS = 64;
+// longest run of zero bits worth following from ring position `pos` in a frame that ends at `end_pos` (damaged frames: the
+// reference follows a unary run as far as it goes; capped at 8 MiB of zeros, beyond which the frame counts as running off the stream)
+__device__ __forceinline__ uint32_t unary_limit(uint32_t pos, uint32_t end_pos) { return pos < end_pos ? min(end_pos - pos, 1u << 26) : 0u; }
 
 struct ParseSub {            // per-lane state of the residual being skipped
-    uint32_t order, psize, plen, left, k, kp32;
+    uint32_t order, psize, plen, left, k, kp32, parts;
     bool first, raw;
 };
 
-// next partition parameter(s); a zero-sample partition 0 (order == partition size) is followed immediately by partition 1
+// Next partition parameter(s): 0 = a partition with samples is open, 1 = no partition is left (the residual ends here:
+// libFLAC 1.2.1 reads 2^order partitions of blocksize >> order samples even when that is not the whole block), 2 = an escape
+// partition runs past the end of the stream.  A zero-sample partition 0 (order == partition size) is followed immediately
+// by partition 1.
 template <class BR>
-__device__ __forceinline__ bool parse_param(BR& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
+__device__ __forceinline__ int parse_param(BR& br, ParseSub& p, const uint8_t* in, uint64_t end_bit) {
 #pragma unroll 1
-    for (int guard = 0; guard < 2; guard++) {
+    for (;;) {
+        if (p.parts == 0) return 1;
+        p.parts--;
         const uint32_t cnt = p.psize - (p.first ? p.order : 0);
         p.first = false;
         const uint32_t k = br.get(p.plen);
         p.raw = false;
         if (k == (p.plen == 5 ? 31u : 15u)) {
             const uint32_t nb = br.get(5);
-            if (br.abs_pos(in) + (uint64_t)cnt * nb > end_bit) return false;
+            if (br.abs_pos(in) + (uint64_t)cnt * nb > end_bit) return 2;
             br.jump(cnt * nb);
             p.raw = true;
         }
         p.k = k; p.kp32 = k + 32u; p.left = cnt;
-        if (cnt) break;
+        if (cnt) return 0;
+        br.ensure_now();
     }
-    return p.left != 0;
 }
 
 // N codewords of every walking lane's partition, branch-free: window, bfind, add; a codeword that does not fit one
 // 32-bit window raises a flag and the lane redoes the group one careful codeword at a time.
 template <int N, class BR>
-__device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bool& bad) {
+__device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bool& bad, uint32_t end_pos) {
     uint32_t pos = br.pos;
     const uint32_t k = ps.k, kp32 = ps.kp32;
     bool ovf = false;
@@ -812,11 +820,16 @@ __device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bo
             if (!ovf) br.pos = pos;
             else {
 #pragma unroll 1
-                for (int j = 0; j < N; j++) if (!br.rice_skip_careful(k)) { bad = true; walk = false; break; }
+                for (int j = 0; j < N; j++) if (!br.rice_skip_careful(k, unary_limit(br.pos, end_pos))) { bad = true; walk = false; break; }
             }
         }
     }
 }
+
+// How the parse of a frame ended, in the reference's terms (oracle/flac_oracle.c decode_span; libFLAC 1.2.1 rules pinned by
+// tests/golden/golden_damage.json): the bit reader stands where the failure was noticed, and that is where the sync search
+// resumes.
+enum : uint32_t { PF_NONE = 0, PF_UNPARSE = 1, PF_LOST = 2, PF_EOS = 3 };
 
 // LEAN: branch-free ring refill (streams of few, large frames: the kernel is then a handful of warps, see RingBitsT::request)
 template <bool LEAN>
@@ -832,36 +845,39 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     // the numbering; ST_CHECK: nothing does) are parsed to the end the way the reference would, because what the
     // reference does next depends on where that parse stops (flag 2: frame of the neighbouring shard, end marker only)
     bool live = (st == ST_OK || st == ST_CHECK || st == ST_CRC) && !(c.flags & 2);
+    const bool clean = st == ST_OK;
     const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
     const uint64_t frame_bit0 = c.off * 8;
     uint64_t end_bit = 0, seg_end = 0;
     if (live) {
         const SegInfo& sg = a.segs[c.seg];
         seg_end = sg.end;
-        end_bit = (st == ST_OK ? c.off + a.flen[i] : min(sg.end, c.off + (uint64_t)sg.max_frame_bytes)) * 8;
+        // a damaged frame is parsed as far as its (damaged) fields say, like the reference does: only the stream ends it
+        end_bit = (clean ? c.off + a.flen[i] : sg.end) * 8;
     }
     ParseBitsT<LEAN> br;
     if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
     else br.init_idle(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in);
-    // end of the frame as a ring-relative bit position (frames are far below 2^32 bits)
+    // end of the frame as a ring-relative bit position (saturated: a frame is far below 2^32 bits)
     const uint32_t end_pos = live ? (uint32_t)min((uint64_t)0xFFFFFFFFu, end_bit - (uint64_t)(br.g0 - a.in) * 8) : 0xFFFFFFFFu;
-    bool bad = false, unparse = false, padbit = false;
+    uint32_t fail = PF_NONE;
     uint32_t max_order = 0, any_wide = 0;
     const uint32_t wmax_ch = __reduce_max_sync(FULL, live ? channels : 0u);
     const uint32_t wmax_bs = __reduce_max_sync(FULL, live ? c.bs : 0u);
     for (uint32_t ch = 0; ch < wmax_ch; ch++) {
         bool walk = false;            // this lane walks a Rice-coded residual in this phase
+        bool bad = false;             // ... and ran off the stream doing so
         ParseSub ps;
-        ps.order = 0; ps.psize = 0; ps.plen = 4; ps.left = 0; ps.k = 0; ps.kp32 = 32; ps.first = true; ps.raw = false;
-        if (live && !bad && !unparse && ch < channels) {
+        ps.order = 0; ps.psize = 0; ps.plen = 4; ps.left = 0; ps.k = 0; ps.kp32 = 32; ps.parts = 0; ps.first = true; ps.raw = false;
+        if (live && fail == PF_NONE && ch < channels) {
             uint32_t bps = c.bps + (((c.assign == 8 && ch == 1) || (c.assign == 9 && ch == 0) || (c.assign == 10 && ch == 1)) ? 1u : 0u);
             SubInfo si;
             si.bit_offset = (uint32_t)(br.abs_pos(a.in) - frame_bit0);
             si.type = 0; si.order = 0; si.flags = 0; si.wasted = 0;
             uint32_t x = br.get(8);
             uint32_t type = (x >> 1) & 0x3f, w = 0;
-            if (x & 0x80) { bad = true; padbit = true; }          // pad bit set: the reference reports LOST_SYNC
-            else if ((x & 1) && (w = br.unary(64) + 1) >= bps) unparse = true;
+            if (x & 0x80) fail = PF_LOST;                          // pad bit set: the reference reports LOST_SYNC
+            else if ((x & 1) && (w = br.unary(clean ? 64u : unary_limit(br.pos, end_pos)) + 1) >= bps) fail = PF_UNPARSE;
             else {
                 br.ensure_now();
                 bps -= w;
@@ -871,73 +887,83 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                 if (type == 0) br.jump(bps);
                 else if (type == 1) {
                     si.type = 1;
-                    if (br.abs_pos(a.in) + (uint64_t)c.bs * bps > end_bit) bad = true; else br.jump(c.bs * bps);
+                    if (br.abs_pos(a.in) + (uint64_t)c.bs * bps > end_bit) fail = PF_EOS; else br.jump(c.bs * bps);
                 } else if (type >= 8 && type <= 12) { si.type = 2; order = type - 8; has_resid = true; }
                 else if (type >= 32) { si.type = 3; order = type - 31; has_resid = true; }
-                else unparse = true;
+                else fail = PF_UNPARSE;
                 if (has_resid) {
                     si.order = (uint8_t)order;
-                    if (order > c.bs) unparse = true;
-                    else if (br.abs_pos(a.in) + (uint64_t)order * bps > end_bit) bad = true;
+                    if (order > c.bs) fail = PF_UNPARSE;
+                    else if (br.abs_pos(a.in) + (uint64_t)order * bps > end_bit) fail = PF_EOS;
                     else {
                         if (order > max_order) max_order = order;
                         br.jump(order * bps);
                         if (si.type == 3) {
-                            uint32_t prec = br.get(4) + 1;
-                            int32_t shift = br.gets(5);
-                            if (prec == 16 || shift < 0) unparse = true;
+                            const uint32_t prec = br.get(4) + 1;
+                            if (prec == 16) fail = PF_LOST;        // libFLAC 1.2.1: LOST_SYNC (not UNPARSEABLE), noticed before the shift is read
                             else {
+                                br.skip(5);                        // quantisation shift; a negative one is not an error in libFLAC 1.2.1
                                 br.jump(order * prec);
                                 if (bps + prec + (uint32_t)ilog2u(order) <= 32) si.flags |= 1; else any_wide = 1;
                             }
                         } else si.flags |= 1;
-                        if (!unparse) {
-                            uint32_t method = br.get(2);
-                            if (method > 1) unparse = true;
+                        if (fail == PF_NONE) {
+                            const uint32_t method = br.get(2);
+                            if (method > 1) fail = PF_UNPARSE;
                             else {
                                 if (method) { si.flags |= 2; ps.plen = 5; }
-                                uint32_t po = br.get(4);
+                                const uint32_t po = br.get(4);
                                 ps.psize = po ? c.bs >> po : c.bs;
                                 ps.order = order;
-                                if (ps.psize == 0 || ps.psize < order) unparse = true;
-                                else walk = !(st == ST_OK && ch + 1 == channels);
+                                ps.parts = 1u << po;
+                                if (ps.psize < order) fail = PF_LOST;      // libFLAC 1.2.1: partition smaller than the predictor order is LOST_SYNC
+                                else if (ps.psize == 0) {
+                                    // blocksize < 2^po (never written by an encoder): 2^po partitions without samples, only their parameters
+#pragma unroll 1
+                                    for (uint32_t q = 0; q < ps.parts && fail == PF_NONE; q++) {
+                                        if (br.get(ps.plen) == (ps.plen == 5 ? 31u : 15u)) br.skip(5);
+                                        br.ensure_now();
+                                        if (br.pos > end_pos) fail = PF_EOS;
+                                    }
+                                } else walk = !(clean && ch + 1 == channels);
                                 br.ensure_now();
                             }
                         }
                     }
                 }
             }
-            if (!bad && !unparse) a.sub[(uint64_t)i * MAX_CH + ch] = si;
+            if (fail == PF_NONE) a.sub[(uint64_t)i * MAX_CH + ch] = si;
             else walk = false;
         }
         if (!__any_sync(FULL, walk)) continue;
+        auto next_param = [&]() {
+            const int pr = parse_param(br, ps, a.in, end_bit);
+            if (pr == 2) bad = true;
+            if (pr) walk = false;
+        };
 #pragma unroll 1
         for (uint32_t s0 = 0; s0 < wmax_bs; s0 += 16) {
             if (walk) br.checkpoint();                            // one refill checkpoint per 16 samples (ParseBits::PERIOD_REACH)
-            if (walk && ps.left == 0 && s0 >= ps.order && s0 < c.bs) {
-                if (!parse_param(br, ps, a.in, end_bit)) { bad = true; walk = false; }
-            }
+            if (walk && ps.left == 0 && s0 >= ps.order && s0 < c.bs) next_param();
             if (__all_sync(FULL, !walk || ps.left >= 16)) {
-                parse_group<16>(br, ps, walk, bad);               // the whole period in one branch-free group
+                parse_group<16>(br, ps, walk, bad, end_pos);      // the whole period in one branch-free group
                 if (walk && br.pos > end_pos) { bad = true; walk = false; }     // ran past any possible end of the frame
                 if (walk && s0 + 16 >= c.bs) walk = false;
                 continue;
             }
 #pragma unroll 1
             for (uint32_t s1 = s0; s1 < s0 + 16; s1 += 8) {
-                if (s1 != s0 && walk && ps.left == 0 && s1 >= ps.order && s1 < c.bs) {
-                    if (!parse_param(br, ps, a.in, end_bit)) { bad = true; walk = false; }
-                }
-                if (__all_sync(FULL, !walk || ps.left >= 8)) parse_group<8>(br, ps, walk, bad);
+                if (s1 != s0 && walk && ps.left == 0 && s1 >= ps.order && s1 < c.bs) next_param();
+                if (__all_sync(FULL, !walk || ps.left >= 8)) parse_group<8>(br, ps, walk, bad, end_pos);
                 else {
 #pragma unroll 1
                     for (uint32_t j = 0; j < 8; j++) {
                         const uint32_t s = s1 + j;
                         if (walk && s >= ps.order && s < c.bs) {
-                            if (ps.left == 0 && !parse_param(br, ps, a.in, end_bit)) { bad = true; walk = false; }
-                            else {
+                            if (ps.left == 0) next_param();
+                            if (walk) {
                                 ps.left--;
-                                if (!ps.raw && !br.rice_skip_careful(ps.k)) { bad = true; walk = false; }
+                                if (!ps.raw && !br.rice_skip_careful(ps.k, unary_limit(br.pos, end_pos))) { bad = true; walk = false; }
                             }
                         }
                     }
@@ -946,20 +972,35 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                 if (walk && s1 + 8 >= c.bs) walk = false;
             }
         }
+        if (bad) fail = PF_EOS;
     }
     if (!live) return;
-    // Outcome, in the reference's terms (oracle/flac_oracle.c decode_span): the parse failed -> nothing is delivered and
-    // the sync search resumes two bytes after this sync code; the parse completed -> the frame is delivered (zero-filled
-    // when the CRC-16 read where the parse stopped does not match) and the search resumes after that CRC.
+    // Outcome, in the reference's terms (oracle/flac_oracle.c decode_span).  The parse failed: nothing is delivered and the
+    // sync search resumes at the byte where the bit reader stands (flen = that distance).  The parse completed: the zero
+    // padding to the byte boundary must be zero (else LOST_SYNC, nothing delivered, search resumes after the padding); the
+    // frame is then delivered -- zero-filled when the CRC-16 read where the parse stopped does not match -- and the search
+    // resumes after that CRC.  Whatever reads past the end of the stream ends the stream (END_OF_STREAM, nothing delivered).
     const uint8_t st_in = st;
-    if (unparse) st = ST_UNPARSEABLE;
-    else if (bad) st = (!padbit && end_bit == seg_end * 8) ? ST_EOS : ST_LOSTSYNC;   // pad bit; ran off the stream / past any possible frame end
-    else if (st_in != ST_OK) {
-        const uint64_t p = ((br.abs_pos(a.in) + 7) >> 3) + 2;           // first byte after the CRC-16 the reference would read
-        if (p > seg_end) st = ST_EOS;                                  // ran off the stream: END_OF_STREAM, frame not delivered
-        else {
-            a.flen[i] = (uint32_t)(p - c.off);
-            st = span_residue(a, a.segs[c.seg], c.off, p) == 0 ? ST_OK : ST_CRC;
+    if (fail != PF_NONE || !clean) {
+        const uint64_t stop_bit = br.abs_pos(a.in);
+        if (fail == PF_EOS || stop_bit > seg_end * 8) st = ST_EOS;
+        else if (fail != PF_NONE) {
+            st = fail == PF_UNPARSE ? ST_UNPARSEABLE : ST_LOSTSYNC;
+            a.flen[i] = (uint32_t)(((stop_bit + 7) >> 3) - c.off);
+        } else {
+            uint64_t p = stop_bit >> 3;
+            bool pad_ok = true, eos = false;
+            if (stop_bit & 7) {
+                if (p >= seg_end) eos = true;
+                else { pad_ok = (a.in[p] & (0xFFu >> (stop_bit & 7))) == 0; p++; }
+            }
+            if (eos) st = ST_EOS;
+            else if (!pad_ok) { st = ST_LOSTSYNC; a.flen[i] = (uint32_t)(p - c.off); }
+            else if (p + 2 > seg_end) st = ST_EOS;
+            else {
+                a.flen[i] = (uint32_t)(p + 2 - c.off);
+                st = span_residue(a, a.segs[c.seg], c.off, p + 2) == 0 ? ST_OK : ST_CRC;
+            }
         }
     }
     a.status[i] = st;
@@ -991,7 +1032,7 @@ __global__ void __launch_bounds__(256) k_resync(PassArgs a) {
         if (st == ST_SKIP || st == ST_DROP) return;
         const Cand ca = a.cand[ai];
         if (ca.flags & 2) return;
-        const uint64_t landing = st == ST_EOS ? ~0ull : ca.off + ((st == ST_OK || st == ST_CRC) ? (uint64_t)a.flen[ai] : 2ull);
+        const uint64_t landing = st == ST_EOS ? ~0ull : ca.off + (uint64_t)a.flen[ai];      // where the reference's cursor stands after this candidate
         for (uint32_t j = ai + 1; j < n; j++) {
             const Cand& cj = a.cand[j];
             if (cj.seg != ca.seg) break;
@@ -1409,7 +1450,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                 bool narrow = true;
                 if (si.type == 3) {
                     const uint32_t prec = br.get(4) + 1;
-                    shift = (uint32_t)br.gets(5);
+                    { const int32_t sh = br.gets(5); shift = sh < 0 ? 0u : (uint32_t)sh; }   // negative: not an error in libFLAC 1.2.1 (never emitted)
                     narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
                     // libFLAC 1.2.1 width rule: narrow subframes accumulate in 32 bits (wrap), the others in 64
                     const double scale = (F64 && !narrow) ? __hiloint2double((int)((1023u - shift) << 20), 0) : 1.0;

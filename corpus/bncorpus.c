@@ -85,7 +85,18 @@ void bnc_synth(int32_t* pcm, uint64_t n, uint32_t ch, uint32_t bps, uint32_t sr,
                uint32_t special_period, uint32_t seed) {
     enum { TB = 4096 };
     static int32_t* tab = NULL;
-    if (!tab) { tab = (int32_t*)malloc(sizeof(int32_t) * TB); for (int i = 0; i < TB; i++) tab[i] = (int32_t)lrint(sin(2.0 * M_PI * i / TB) * 32767.0); }
+    if (!tab) {
+        /* round(32767 sin(2 pi i / 4096)) by an integer rotation in Q62 (no libm: the corpus must not depend on the host's
+         * sin()); the constants are cos / sin of 2 pi / 4096 scaled by 2^62, the error after 4096 steps is below 2^-48 */
+        const __int128 cd = 4611680592556051597LL, sd = 7074234977634094LL, half = (__int128)1 << 61;
+        __int128 c = (__int128)1 << 62, sn = 0;
+        tab = (int32_t*)malloc(sizeof(int32_t) * TB);
+        for (int i = 0; i < TB; i++) {
+            tab[i] = (int32_t)((sn * 32767 + half) >> 62);
+            const __int128 c2 = (c * cd - sn * sd + half) >> 62, s2 = (sn * cd + c * sd + half) >> 62;
+            c = c2; sn = s2;
+        }
+    }
     uint32_t s = seed * 2654435761u + 12345u;
     /* 4 partials per channel, phase increments in 1/2^32 cycles per sample */
     uint32_t inc[8][4], ph[8][4]; int32_t amp_shift[8][4];
@@ -232,6 +243,15 @@ static void write_residual(bw_t* b, const int32_t* r, uint32_t bs, uint32_t orde
 
 /* ------------------------------------------------------------------ prediction */
 static int ilog2u(uint32_t v) { int l = 0; while (v >>= 1) l++; return l; }
+/* log2 from IEEE +,-,*,/ in a fixed order (frexp is exact): the same double on every host, unlike libm's log() */
+static double det_log2(double x) {
+    int e; double m = frexp(x, &e);
+    if (m < 0.70710678118654752) { m *= 2.0; e--; }
+    const double t = (m - 1.0) / (m + 1.0), t2 = t * t;
+    double s = 0.0;
+    for (int k = 25; k >= 1; k -= 2) s = s * t2 + 1.0 / (double)k;      /* ln m = 2 atanh t */
+    return (double)e + 2.0 * t * s * 1.4426950408889634;
+}
 
 /* returns 0 if usable */
 static int lpc_analyse(const int32_t* x, uint32_t bs, uint32_t maxorder, double lpc[33][32], double err[33]) {
@@ -340,7 +360,7 @@ static uint64_t encode_subframe(bw_t* b, const int32_t* xin, uint32_t bs, uint32
                 double bestest = 1e300;
                 for (uint32_t o = 1; o <= maxo; o++) {
                     double e = err[o] * (0.5 * M_LN2 * M_LN2 / (double)bs);
-                    double bpr = e > 0 ? 0.5 * log(e) / M_LN2 : 0; if (bpr < 0) bpr = 0;
+                    double bpr = e > 0 ? 0.5 * det_log2(e) : 0; if (bpr < 0) bpr = 0;
                     double est = bpr * (bs - o) + (double)o * (ebps + prec);
                     if (est < bestest) { bestest = est; lo = o; }
                 }

@@ -12,15 +12,15 @@
 #include <stdlib.h>
 #include <string.h>
 
-/* FO_NEXT_RULES: five rules of libFLAC 1.2.1 on DAMAGED frames that the round-1 restatement missed, found by fuzzing this
- * file against the reference DLL (oracle/fuzz_vs_ref.py).  Built as oracle/_build/liboracle_next.so and
- * pinned by tests/golden/golden_damage.json; the default build keeps the round-1 rules, which the engine reproduces, until
- * k_parse / k_resync / collect_diag follow. */
-#ifdef FO_NEXT_RULES
-#define NEXT_LOST 0x100
-#else
-#define NEXT_LOST 0
-#endif
+/* Damaged frames: five rules of libFLAC 1.2.1 that were found by fuzzing this file against the reference DLL
+ * (oracle/fuzz_vs_ref.py) and are pinned by tests/golden/golden_damage.json (224 reference-DLL records):
+ *   1. the zero padding before the CRC-16 must be zero, else LOST_SYNC and the frame is not delivered;
+ *   2. after a failure inside a frame the sync search goes on where the bit reader stands (not two bytes after the sync
+ *      code) and reports LOST_SYNC again when it then skips bytes;
+ *   3. qlp precision 1111 is LOST_SYNC, not UNPARSEABLE;   4. a negative qlp shift is not an error;
+ *   5. a residual partition smaller than the predictor order is LOST_SYNC.
+ * LOST marks a subframe failure that libFLAC reports as LOST_SYNC (the others are UNPARSEABLE_STREAM). */
+#define LOST 0x100
 
 /* ---------------------------------------------------------------- CRC (App. A.2 / A.5) */
 static uint8_t crc8_tab[256];
@@ -238,7 +238,7 @@ static int read_residual(br_t* b, int32_t* r, uint32_t bs, uint32_t order, fo_su
     uint32_t po = br_u(b, 4);
     if (sf) { sf->rice_method = (uint8_t)method; sf->partition_order = (uint8_t)po; }
     uint32_t nparts = 1u << po;
-    if (po > 0 ? ((bs >> po) < order) : (bs < order)) return 3 + NEXT_LOST; /* libFLAC: partition smaller than predictor order (LOST_SYNC there) */
+    if (po > 0 ? ((bs >> po) < order) : (bs < order)) return 3 + LOST; /* libFLAC: partition smaller than predictor order is LOST_SYNC (rule 5) */
     if (po > 0 && (bs & (nparts - 1))) { /* libFLAC 1.2.1 does not reject this; samples = bs>>po each */ }
     uint32_t idx = 0;
     for (uint32_t p = 0; p < nparts; p++) {
@@ -264,7 +264,7 @@ static int read_residual(br_t* b, int32_t* r, uint32_t bs, uint32_t order, fo_su
 static int read_subframe(br_t* b, int32_t* out, int32_t* resid, uint32_t bs, uint32_t bps, fo_subframe* sf) {
     if (sf) { memset(sf, 0, sizeof *sf); sf->bit_offset = b->bit; }
     uint32_t x = br_u(b, 8);
-    if (x & 0x80) return 3 + 0x100; /* lost sync in libFLAC terms: pad bit set */
+    if (x & 0x80) return 3 + LOST; /* lost sync in libFLAC terms: pad bit set */
     uint32_t type = (x >> 1) & 0x3f, w = 0;
     if (x & 1) { w = br_unary(b) + 1; if (w >= bps) return 3; bps -= w; }
     if (sf) sf->wasted = (uint8_t)w;
@@ -297,18 +297,14 @@ static int read_subframe(br_t* b, int32_t* out, int32_t* resid, uint32_t bs, uin
         if (o > bs) return 3;
         for (uint32_t i = 0; i < o; i++) out[i] = br_s(b, bps);
         uint32_t prec = br_u(b, 4) + 1;
-        if (prec == 16) return 3 + NEXT_LOST;      /* LOST_SYNC in libFLAC 1.2.1 */
+        if (prec == 16) return 3 + LOST;      /* LOST_SYNC in libFLAC 1.2.1 (rule 3) */
         int32_t shift = br_s(b, 5);
         if (sf) { sf->precision = (uint8_t)prec; sf->shift = (uint8_t)shift; }
         int32_t c[32];
         for (uint32_t i = 0; i < o; i++) c[i] = br_s(b, prec);
         int rc = read_residual(b, resid, bs, o, sf);
         if (rc) return rc;
-#ifdef FO_NEXT_RULES
-        if (shift < 0) shift = 0; /* not an error in libFLAC 1.2.1 (it shifts by a negative amount); the frame then fails its CRC */
-#else
-        if (shift < 0) return 3; /* libFLAC 1.2.1 would shift by a negative amount (undefined); never emitted */
-#endif
+        if (shift < 0) shift = 0; /* rule 4: not an error in libFLAC 1.2.1 (it shifts by a negative amount); the frame then fails its CRC */
         /* width rule of libFLAC 1.2.1 (App. A.9): 32-bit accumulate iff bps+precision+ilog2(order) <= 32 */
         if (bps + prec + (uint32_t)ilog2u(o) <= 32) {
             for (uint32_t i = o; i < bs; i++) {
@@ -377,11 +373,10 @@ static int64_t decode_span(const uint8_t* d, size_t len, const fo_streaminfo* si
             if (r) bad = r;
         }
         if (bad == -1 || b.overrun) break; /* ran off the end of the stream: END_OF_STREAM, frame not delivered */
-#ifdef FO_NEXT_RULES
-        /* the sync search goes on where the bit reader stands, and reports LOST_SYNC again when it then skips bytes */
+        /* rule 2: the sync search goes on where the bit reader stands, and reports LOST_SYNC again when it then skips bytes */
         if (bad) { ERR(bad > 0x100 ? FO_ERR_LOST_SYNC : FO_ERR_UNPARSEABLE); in_sync = 1; pos = (size_t)((b.bit + 7) >> 3); continue; }
-        /* zero padding to the byte boundary (read_zero_padding_): bits that are not zero mean LOST_SYNC, the frame is not
-         * delivered and the search goes on from the byte boundary */
+        /* rule 1: zero padding to the byte boundary (read_zero_padding_): bits that are not zero mean LOST_SYNC, the frame is
+         * not delivered and the search goes on from the byte boundary */
         if (b.bit & 7) {
             const uint32_t nb = 8 - (uint32_t)(b.bit & 7);
             const size_t byte = (size_t)(b.bit >> 3);
@@ -390,10 +385,6 @@ static int64_t decode_span(const uint8_t* d, size_t len, const fo_streaminfo* si
             b.bit += nb;
             if (padv) { ERR(FO_ERR_LOST_SYNC); in_sync = 1; pos = (size_t)(b.bit >> 3); continue; }
         }
-#else
-        if (bad) { ERR(bad > 0x100 ? FO_ERR_LOST_SYNC : FO_ERR_UNPARSEABLE); in_sync = 0; pos += 2; continue; }
-        b.bit = (b.bit + 7) & ~7ull;
-#endif
         size_t fend = (size_t)(b.bit >> 3);
         if (fend + 2 > len) break;
         uint16_t want = (uint16_t)(d[fend] << 8 | d[fend+1]);

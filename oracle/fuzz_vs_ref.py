@@ -1,21 +1,20 @@
 #!/usr/bin/env python
 """Damaged-stream fuzz of the CPU oracle against the REFERENCE's own decoder binary (test infrastructure; CPU only).
 
-Seeded random damage (tests/test_damage_fuzz_gpu.py's generator: bit flips, overwritten runs, 0xFF / 0x00 runs, deleted and
+Seeded random damage (tests/damage_cases.py: bit flips, overwritten runs, 0xFF / 0x00 runs, deleted and
 inserted bytes, truncation) on four stream shapes; every damaged stream is decoded by oracle/_ref/refflac (the reference's
 LibFlac.dll under the PE loader) and by oracle/flac_oracle.c, and PCM md5, frame count and the complete error-event list are
 compared.  usage (repo root, after `make oracle ref`):  python oracle/fuzz_vs_ref.py [trials per shape and kind, default 12]
 
-Round-1 finding ("Damaged streams"): with the oracle as committed 183 of 336 streams differ from the DLL in
-the EVENT LIST or in whether ONE damaged frame is delivered zero-filled or dropped; the FO_NEXT_RULES build of the oracle (five
-rules of libFLAC 1.2.1 the restatement missed, `--next`) brings that to 0 of 1120.  The engine follows the committed oracle, so the
-switch has to become the default together with the same rules in k_parse / k_resync / collect_diag."""
-import sys, os, random, zlib, subprocess, hashlib, tempfile, importlib.util
+History ("Damaged streams"): the round-1 restatement differed from the DLL on 183 of 336 streams, in the EVENT
+LIST or in whether ONE damaged frame is delivered zero-filled or dropped; the five rules of libFLAC 1.2.1 listed at the top of
+flac_oracle.c brought that to 0 of 1120.  They are the only build now, and k_parse / k_resync / collect_diag follow them."""
+import sys, os, random, zlib, subprocess, hashlib, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 sys.path[:0]=['tests','oracle','corpus','.']
 import pycorpus, pyoracle
-spec=importlib.util.spec_from_file_location('fz','tests/test_damage_fuzz_gpu.py'); fz=importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+import damage_cases as fz
 REF, DLL = 'oracle/_ref/refflac','oracle/_ref/LibFlac.dll'
 def run_dll(blob, d):
     fi, fo = os.path.join(d,'in.flac'), os.path.join(d,'out.pcm')
@@ -28,12 +27,11 @@ def run_dll(blob, d):
     kv=dict(x.split('=') for x in lines[0].split())
     errs=[int(l.split('=')[1].split()[0]) for l in lines[1:] if l.startswith('error[')]
     return (hashlib.md5(pcm).hexdigest(), int(kv['frames']), errs, int(kv['errors'])), None
-# usage: fuzz_vs_ref.py [trials] [--next] [--write-golden]
-#   --next          compare the FO_NEXT_RULES build of the oracle (liboracle_next.so) instead of the default one
+# usage: fuzz_vs_ref.py [trials] [--write-golden]
 #   --write-golden  store what the DLL produced for every stream in tests/golden/golden_damage.json (the streams themselves
 #                   are regenerated from the seeds by tests/test_oracle_cpu.py)
 args=[a for a in sys.argv[1:] if not a.startswith('--')]
-NEXT='--next' in sys.argv; WRITE='--write-golden' in sys.argv
+WRITE='--write-golden' in sys.argv
 TR=int(args[0]) if args else 12
 tot=bad=0
 records={}
@@ -43,8 +41,8 @@ with tempfile.TemporaryDirectory() as d:
         for kind in ["flip","run","ones","zeros","delete","insert","truncate"]:
             rng=random.Random(zlib.crc32(f"{shape}/{kind}".encode()))
             for t in range(TR):
-                blob=fz._damage(s.flac, first, rng, kind)
-                want, nfr, _, oerrs = pyoracle.decode(blob, next_rules=NEXT)
+                blob=fz.damage(s.flac, first, rng, kind)
+                want, nfr, _, oerrs = pyoracle.decode(blob)
                 ref, why = run_dll(blob, d)
                 tot+=1
                 if ref is None: bad+=1; print("DLL failed", shape, kind, t, why); continue
@@ -52,9 +50,10 @@ with tempfile.TemporaryDirectory() as d:
                 records[f"{shape}/{kind}/{t}"]={"blob_md5": hashlib.md5(blob).hexdigest(), "pcm_md5": md5, "frames": rfr, "errors": rerrs, "n_errors": nerr}
                 ok = md5==hashlib.md5(want).hexdigest() and rfr==nfr and (rerrs==oerrs[:64]) and nerr==len(oerrs)
                 if not ok: bad+=1; print("MISMATCH", shape, kind, t, "dll", rfr, rerrs[:6], nerr, "oracle", nfr, oerrs[:6], len(oerrs))
-print("total", tot, "mismatch", bad, "(next rules)" if NEXT else "(round-1 rules)")
+print("total", tot, "mismatch", bad)
 if WRITE:
     import json
-    out={"note": "produced by oracle/fuzz_vs_ref.py --write-golden: the reference LibFlac.dll (libFLAC 1.2.1) decoding seeded damaged streams in the build container; streams are regenerated from the seeds (tests/test_damage_fuzz_gpu.py: SHAPES, _damage, rng = Random(crc32('shape/kind')))", "trials": TR, "records": records}
+    out={"note": "produced by oracle/fuzz_vs_ref.py --write-golden: the reference LibFlac.dll (libFLAC 1.2.1) decoding seeded damaged streams in the build container; streams are regenerated from the seeds (tests/damage_cases.py: SHAPES, damage, rng = Random(crc32('shape/kind')))", "trials": TR, "records": records}
     json.dump(out, open(os.path.join('tests','golden','golden_damage.json'),'w'), indent=0, sort_keys=True)
     print("wrote tests/golden/golden_damage.json:", len(records), "records")
+sys.exit(1 if bad else 0)

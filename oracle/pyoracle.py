@@ -8,7 +8,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _L = None
-_LN = None
 
 
 class StreamInfo(C.Structure):
@@ -32,16 +31,8 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _ROOT, "oracle"])
 
 
-def lib(next_rules=False):
-    """next_rules=True: the build with the five damaged-frame rules of DESIGN.md section 7 (liboracle_next.so)."""
-    global _L, _LN
-    if next_rules:
-        if _LN is None:
-            so = _SO.replace("liboracle.so", "liboracle_next.so")
-            if not os.path.exists(so):
-                build()
-            _LN = _bind(C.CDLL(so))
-        return _LN
+def lib():
+    global _L
     if _L is None:
         if not os.path.exists(_SO):
             build()
@@ -74,9 +65,9 @@ def streaminfo(data: bytes) -> StreamInfo:
     return si
 
 
-def decode(data: bytes, want_frames=False, next_rules=False):
+def decode(data: bytes, want_frames=False):
     """-> (pcm bytes, frames, subframes, errors)"""
-    L = lib(next_rules)
+    L = lib()
     need = L.fo_decode(data, len(data), None, 0, None, 0, None, None, None, 0, None)
     if need < 0:
         raise ValueError(f"oracle decode failed ({need})")
