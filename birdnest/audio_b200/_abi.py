@@ -20,6 +20,7 @@ ERR_ARG, ERR_NOT_FLAC, ERR_TRUNCATED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY, ERR_C
 OPT_VERIFY_MD5 = 1
 OPT_LAZY_PULL = 4      # open_callbacks pulls the metadata only; bnflac_read pulls the rest on demand
 OPT_BORROW_INPUT = 2
+OPT_PACKED_INPUT = 8   # decode_batch: the clips are views into ONE caller-owned buffer, uploaded in place
 
 
 class Opts(C.Structure):
@@ -66,6 +67,7 @@ _PROTOS = {
     "bnflac_open_memory": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
     "bnflac_open_callbacks": (C.c_int, [READ_CB, C.c_void_p, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
     "bnflac_open_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
+    "bnflac_shard_range": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "bnflac_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "bnflac_state": (C.c_int, [C.c_void_p]),
     "bnflac_close": (None, [C.c_void_p]),
@@ -196,11 +198,14 @@ class Handle:
     def decode_all(self, buf=None) -> bytes | int:
         """Decode to host memory.  With buf=None allocates a bytearray of the needed size and returns it."""
         if buf is None:
-            size = self.decoded_size()
-            out = bytearray(size)
-            w = C.c_uint64()
-            if size:
-                _check(lib().bnflac_decode_all(self._p, _addr(out), size, C.byref(w)), "bnflac_decode_all")
+            for attempt in range(2):
+                size = self.decoded_size()
+                out = bytearray(size)
+                w = C.c_uint64()
+                rc = lib().bnflac_decode_all(self._p, _addr(out), size, C.byref(w)) if size else 0
+                if rc != ERR_CAPACITY or attempt:      # STREAMINFO understated the stream: decoded_size now scans (include/bnflac.h)
+                    break
+            _check(rc, "bnflac_decode_all")
             return bytes(out[:w.value])
         w = C.c_uint64()
         n = buf.numel() * buf.element_size() if hasattr(buf, "numel") else len(buf)
@@ -267,6 +272,13 @@ def open_device(d_ptr: int, length: int, header: bytes, device=-1, stream=0, sha
     return Handle(h.value, keep=(keep, header))
 
 
+def shard_range(stream_len: int, first_frame_offset: int, index: int, count: int):
+    """bnflac_shard_range: [own_begin, own_end) of shard `index` of `count` (host-only; the engine's own arithmetic)."""
+    b, e = C.c_uint64(), C.c_uint64()
+    _check(lib().bnflac_shard_range(stream_len, first_frame_offset, index, count, C.byref(b), C.byref(e)), "bnflac_shard_range")
+    return int(b.value), int(e.value)
+
+
 def probe(data) -> Info:
     """bnflac_probe: host-only metadata parse (native FLAC, ID3v2-prefixed, or Ogg FLAC); no device needed."""
     info = Info()
@@ -288,19 +300,24 @@ def ogg_to_native(data) -> bytes:
 def open_callbacks(read_fn, device=-1, flags=0, read_chunk_frames=0) -> Handle:
     """read_fn(n) -> bytes (b'' at end of stream); mirrors the pull model of FLACDecoder.ReadCallback.
     flags=OPT_LAZY_PULL: only the metadata is pulled here, the rest as read_into() advances."""
+    spill = [b""]          # what a read_fn returned beyond the room the engine offered, served first by the next call
+
     def _cb(user, buf, nbytes):
         want = nbytes[0]
-        try:
-            chunk = read_fn(want)
-        except Exception:
-            return 2
-        if chunk is None:
-            return 2
-        k = len(chunk)
+        chunk = spill[0]
+        if not chunk:
+            try:
+                chunk = read_fn(want)
+            except Exception:
+                return 2
+            if chunk is None:
+                return 2
+        k = min(len(chunk), want)          # never write past the room the engine reserved
+        spill[0] = bytes(chunk[k:])
         if k:
-            C.memmove(buf, chunk, k)
+            C.memmove(buf, bytes(chunk[:k]) if k < len(chunk) else chunk, k)
         nbytes[0] = k
-        return 1 if k < want else 0
+        return 1 if (k == 0 and want) else 0       # end of stream only on an empty read: sockets and pipes return short reads
     cb = READ_CB(_cb)
     o = _opts(device, flags=flags, read_chunk_frames=read_chunk_frames)
     h = C.c_void_p()
@@ -308,10 +325,11 @@ def open_callbacks(read_fn, device=-1, flags=0, read_chunk_frames=0) -> Handle:
     return Handle(h.value, keep=cb)        # the callback object must outlive the handle (lazy pull calls it from bnflac_read)
 
 
-def decode_batch(clips, device=-1, dst=None, dst_is_device=False):
+def decode_batch(clips, device=-1, dst=None, dst_is_device=False, packed=False):
     """bnflac_decode_batch: many independent clips in one pipeline pass per (channels, bits) group (BASELINE cfg4).
     clips: sequence of bytes-like.  Returns (pcm, results) with pcm = bytes (dst=None), or the byte count written
-    into `dst` (a writable host buffer / torch tensor; a device pointer or CUDA tensor with dst_is_device=True)."""
+    into `dst` (a writable host buffer / torch tensor; a device pointer or CUDA tensor with dst_is_device=True).
+    packed=True: the clips are ascending views into ONE buffer the caller owns (BNFLAC_OPT_PACKED_INPUT: uploaded in place)."""
     n = len(clips)
     spans = (Span * max(1, n))()
     keep = []
@@ -320,7 +338,7 @@ def decode_batch(clips, device=-1, dst=None, dst_is_device=False):
         spans[i].data = _addr(c)
         spans[i].len = c.numel() * c.element_size() if hasattr(c, "numel") else len(c)
     res = (ClipResult * max(1, n))()
-    o = _opts(device)
+    o = _opts(device, flags=OPT_PACKED_INPUT if packed else 0)
     w = C.c_uint64()
     if dst is None:
         _check(lib().bnflac_decode_batch(spans, n, C.byref(o), None, 0, 0, res, C.byref(w)), "bnflac_decode_batch(size)")

@@ -28,6 +28,18 @@ static thread_local std::string g_cuda_err;
 // ------------------------------------------------------------------------------------------------ small helpers
 namespace {
 
+// Every entry point of the C ABI works on the handle's device and puts the caller's current device back when it returns
+// (a host that drives several GPUs from one thread must not find its device switched under it).
+struct DeviceScope {
+    int prev = -1; bool changed = false;
+    explicit DeviceScope(int dev) {
+        if (dev < 0 || cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+        if (prev != dev && cudaSetDevice(dev) == cudaSuccess) changed = true;
+    }
+    ~DeviceScope() { if (changed) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete; DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 // Process-wide cache of device and pinned-host blocks (the only global mutable state, mutex-guarded).  cudaMalloc /
 // cudaFree / cudaHostAlloc cost milliseconds per gigabyte and cudaFree synchronises the device, which would serialise
 // the pipelined host decode; handles therefore take their buffers from here and give them back on close.
@@ -275,6 +287,7 @@ struct bnflac {
     PassArgs args{};
     Totals totals{};
     uint32_t ncand = 0;
+    struct Predict { bool valid = false; uint32_t ncand = 0, n_accepted = 0, max_order = 0, any_wide = 0; uint64_t pcm_bytes = 0; } pred;   // what the last pass found
     cudaEvent_t ev[10] = {};             // 0..5 stage boundaries, 6/7 pipelined start/end, 8 upload done
     cudaStream_t up_stream = nullptr;    // (pipelined parent) all sub-shard uploads, in order
     bnflac_timing timing{};
@@ -298,12 +311,13 @@ struct bnflac {
     bool pl_session = false;             // the current streamed Read session cuts its sub-shards as the bytes arrive
     bool pl_ahead = false;               // ... and has started to issue sub-shards ahead of the reader
     bool front_ran = false;              // a decode has been started on this handle (the diagnostics have something to describe)
+    bool size_understated = false;       // a decode ran out of room although the buffer held what STREAMINFO promises: size by scanning
     // streaming Read session: sub-shards decoded ahead of the reader, see stream_read()
     bool rd_active = false; uint32_t rd_issued = 0, rd_cur = 0; uint64_t rd_off = 0, rd_total = 0;
 
     ~bnflac() {
         for (bnflac* k : kids) delete k;
-        cudaSetDevice(device);
+        DeviceScope on(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
         DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref, &d_anom,
                          &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags};
@@ -315,7 +329,7 @@ struct bnflac {
     }
 };
 
-static int setup_device(bnflac* h) {
+static int setup_device(bnflac* h) {       // leaves the handle's device current: callers hold a DeviceScope
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); g_cuda_err = "no CUDA device"; return BNFLAC_ERR_NO_DEVICE; }
     if (h->opts.device >= 0) h->device = h->opts.device; else if (cudaGetDevice(&h->device) != cudaSuccess) h->device = 0;
@@ -327,11 +341,19 @@ static int setup_device(bnflac* h) {
     return 0;
 }
 
+// byte range of frame data owned by shard i of n; exported as bnflac_shard_range
+static void shard_range(uint64_t len, uint64_t first, uint32_t i, uint32_t n, uint64_t* b, uint64_t* e) {
+    if (!n) n = 1;
+    if (i >= n) i = n - 1;
+    if (first > len) first = len;
+    const uint64_t D = len - first;
+    // D * i can pass 2^64 only for streams beyond 2^32 shards x bytes: split the product
+    *b = first + (D / n) * i + (D % n) * i / n;
+    *e = (i + 1 == n) ? len : first + (D / n) * (i + 1) + (D % n) * (i + 1) / n;
+}
 static void compute_shard(bnflac* h) {
-    const uint64_t first = h->info.first_frame_offset, D = h->len - first;
-    uint32_t n = h->opts.shard_count ? h->opts.shard_count : 1, i = std::min(h->opts.shard_index, n - 1);
-    uint64_t b = first + D * i / n;
-    uint64_t e = (i + 1 == n) ? h->len : first + D * (i + 1) / n;
+    uint64_t b, e;
+    shard_range(h->len, h->info.first_frame_offset, h->opts.shard_index, h->opts.shard_count, &b, &e);
     if (h->sub_end > h->sub_begin) { b = h->sub_begin; e = h->sub_end; }      // sub-shard of the own range
     h->own_begin = b; h->own_end = e;
     h->slice_begin = b & ~15ull;
@@ -469,7 +491,29 @@ static int reserve_cand(bnflac* h, uint32_t cap) {
     return 0;
 }
 
-// Runs K1..K2 + prefix (everything up to knowing the output size).
+// K1b..K2 + prefix for at most `nb` candidates: every kernel takes the real count from the device and leaves early
+static int launch_front_tail(bnflac* h, uint32_t nb) {
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    launch_order(h->args, h->stream);
+    launch_crc(h->args, nb, h->stream);
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    launch_link(h->args, nb, h->stream);
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    launch_parse(h->args, nb, h->stream);
+    launch_resync(h->args, h->stream);
+    launch_prefix(h->args, nb, h->info.bytes_per_sample, h->stream);
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    return 0;
+}
+static_assert(sizeof(Totals) % 4 == 0 && sizeof(Totals) / 4 <= 32 - 16, "totals fit the mailbox");
+
+static void remember_pass(bnflac* h) {          // what the next pass over the same bytes can be launched on without asking
+    h->pred.valid = true; h->pred.ncand = h->ncand; h->pred.n_accepted = h->totals.n_accepted;
+    h->pred.max_order = h->totals.max_order; h->pred.any_wide = h->totals.any_wide; h->pred.pcm_bytes = h->totals.pcm_bytes;
+}
+
+// Runs K1..K2 + prefix (everything up to knowing the output size).  Two host hand-offs: the candidate count after the
+// scan (table capacity, grid sizes) and the totals after the prefix (output size, decode variant).
 static int run_front(bnflac* h) {
     h->front_ran = true;
     int rc;
@@ -497,17 +541,7 @@ static int run_front(bnflac* h) {
         h->ncand = counters[0];
         break;
     }
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    launch_order(h->args, h->stream);
-    launch_crc(h->args, h->ncand, h->stream);
-    CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_link(h->args, h->ncand, h->stream);
-    CK(cudaEventRecord(h->ev[3], h->stream));
-    launch_parse(h->args, h->ncand, h->stream);
-    launch_resync(h->args, h->stream);
-    launch_prefix(h->args, h->ncand, h->info.bytes_per_sample, h->stream);
-    CK(cudaEventRecord(h->ev[4], h->stream));
-    static_assert(sizeof(Totals) % 4 == 0 && sizeof(Totals) / 4 <= 32 - 16, "totals fit the mailbox");
+    if ((rc = launch_front_tail(h, h->ncand))) return rc;
     launch_publish(h->d_totals.p, (uint8_t*)h->mailbox.p + 64, sizeof(Totals) / 4, h->stream);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
@@ -523,6 +557,44 @@ static int run_back(bnflac* h, uint8_t* d_out, uint64_t cap) {
         launch_decode(h->args, h->totals.n_accepted, h->info.channels, h->info.bytes_per_sample, h->totals.max_order, h->totals.any_wide != 0, h->stream);
     CK(cudaEventRecord(h->ev[5], h->stream));
     CK(cudaGetLastError());
+    remember_pass(h);
+    return 0;
+}
+
+// A pass over bytes that have been decoded before on this handle (a device-resident stream decoded again: the benchmark
+// loop, a frame-range shard re-run) is launched in one go on what the previous pass found -- candidate count, frames
+// delivered, decode variant, output size -- WITHOUT the two host hand-offs of run_front; the kernels take the real counts
+// from the device, and the host checks afterwards that the pass stayed inside what it was launched for.  Returns 1 when it
+// did not (the caller then runs the synchronous path), 0 when the result stands.
+static uint32_t order_class(uint32_t o) { return o <= 4 ? 4u : o <= 8 ? 8u : o <= 12 ? 12u : o <= 16 ? 16u : 32u; }
+static int run_pass_predicted(bnflac* h, uint8_t* d_out, uint64_t cap) {
+    const bnflac::Predict p = h->pred;
+    if (!p.valid || !h->cand_cap || !h->tables_ready || !h->uploaded || p.pcm_bytes > cap || getenv("BNFLAC_NO_PREDICT")) return 1;
+    h->front_ran = true;
+    CK(cudaSetDevice(h->device));
+    h->launches0 = kernel_launch_count();
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    const uint32_t nb = (uint32_t)std::min<uint64_t>(h->cand_cap, (uint64_t)p.ncand + p.ncand / 16 + 64);
+    const uint32_t nacc = (uint32_t)std::min<uint64_t>(nb, (uint64_t)p.n_accepted + p.n_accepted / 16 + 64);
+    launch_clear(h->args, h->stream);
+    launch_scan(h->args, h->stream);
+    int rc;
+    if ((rc = launch_front_tail(h, nb))) return rc;
+    h->args.out = d_out; h->args.out_cap = cap;
+    if (p.n_accepted) launch_decode(h->args, nacc, h->info.channels, h->info.bytes_per_sample, p.max_order, p.any_wide != 0, h->stream);
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    launch_publish(h->d_counters.p, h->mailbox.p, 2, h->stream);
+    launch_publish(h->d_totals.p, (uint8_t*)h->mailbox.p + 64, sizeof(Totals) / 4, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    const uint32_t found = ((volatile uint32_t*)h->mailbox.p)[0];
+    Totals t; memcpy(&t, (const uint8_t*)h->mailbox.p + 64, sizeof t);
+    const bool stands = found <= nb && t.n_accepted <= nacc && t.pcm_bytes <= cap && (t.n_accepted == 0) == (p.n_accepted == 0) &&
+                        order_class(t.max_order) == order_class(p.max_order) && (t.any_wide != 0) == (p.any_wide != 0);
+    if (!stands) { h->pred.valid = false; return 1; }
+    h->ncand = found; h->totals = t;
+    h->diag_valid = false;
+    remember_pass(h);
     return 0;
 }
 
@@ -536,8 +608,25 @@ static int finish_timing(bnflac* h) {
 }
 
 static int decode_to_device(bnflac* h, void* d_dst, size_t cap, void** d_out, uint64_t* written) {
-    int rc = run_front(h); if (rc) return rc;
+    int rc;
     uint8_t* out = (uint8_t*)d_dst;
+    if (h->pred.valid) {                                      // second and later passes over the same bytes: no host hand-off
+        if (!out) {
+            if ((rc = h->d_out.reserve((size_t)h->pred.pcm_bytes + 64))) return rc;
+            out = h->d_out.as<uint8_t>(); cap = h->d_out.cap;
+        }
+        rc = run_pass_predicted(h, out, cap);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            if ((rc = finish_timing(h))) return rc;
+            if (d_out) *d_out = out;
+            if (written) *written = h->totals.pcm_bytes;
+            h->state = BNFLAC_STATE_END_OF_STREAM;
+            return 0;
+        }
+        out = (uint8_t*)d_dst;
+    }
+    if ((rc = run_front(h))) return rc;
     if (!out) {
         if ((rc = h->d_out.reserve((size_t)h->totals.pcm_bytes + 64))) return rc;
         out = h->d_out.as<uint8_t>(); cap = h->d_out.cap;
@@ -1020,11 +1109,13 @@ static int decode_batch_impl(const bnflac_span* clips, size_t n, const bnflac_op
     }
     uint64_t out_off = 0;
     int rc = 0;
-    // Packed input: the clips lie in ascending order inside one host buffer, a few bytes apart (a shard / archive file read in
-    // one piece).  The whole range is then uploaded ONCE, in place, and every format group's pass addresses its clips inside
-    // it: no gather into staging memory (40 of the 104 ms of a 2.5 GB batch), no second copy of the input in host memory.
+    // Packed input (BNFLAC_OPT_PACKED_INPUT): the clips lie in ascending order inside ONE host buffer the caller owns from the
+    // first clip's first byte to the last clip's last byte (a shard / archive file read in one piece).  The whole range is then
+    // uploaded ONCE, in place, and every format group's pass addresses its clips inside it: no gather into staging memory (40
+    // of the 104 ms of a 2.5 GB batch), no second copy of the input in host memory.  Without the flag the bytes between clips
+    // are never touched: every clip is gathered.
     const uint8_t* pk_lo = nullptr; uint64_t pk_span = 0;
-    {
+    if (opts.flags & BNFLAC_OPT_PACKED_INPUT) {        // the caller vouches for the whole range: never inferred from the addresses
         uint64_t total = 0, nvalid = 0; const uint8_t* prev_end = nullptr; bool ascending = true;
         for (size_t i = 0; i < n && ascending; i++) {
             if (meta[i].rc) continue;
@@ -1267,6 +1358,8 @@ int ogg_depage(const uint8_t* d, size_t n, std::vector<uint8_t>& out) {
 
 int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts, bnflac_t** out) {
     if (!data || !out) return BNFLAC_ERR_ARG;
+    int caller_dev = -1; if (cudaGetDevice(&caller_dev) != cudaSuccess) { cudaGetLastError(); caller_dev = -1; }
+    struct Restore { int d; ~Restore() { if (d >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != d) cudaSetDevice(d); } } } restore{caller_dev};
     *out = nullptr;
     bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
     h->opts = default_opts(opts); h->len = len;
@@ -1291,6 +1384,8 @@ int bnflac_open_memory(const uint8_t* data, size_t len, const bnflac_opts* opts,
 
 int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* opts, bnflac_t** out) {
     if (!read || !out) return BNFLAC_ERR_ARG;
+    int caller_dev = -1; if (cudaGetDevice(&caller_dev) != cudaSuccess) { cudaGetLastError(); caller_dev = -1; }
+    struct Restore { int d; ~Restore() { if (d >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != d) cudaSetDevice(d); } } } restore{caller_dev};
     *out = nullptr;
     const bnflac_opts o = default_opts(opts);
     const bool lazy = (o.flags & BNFLAC_OPT_LAZY_PULL) != 0;
@@ -1319,6 +1414,8 @@ int bnflac_open_callbacks(bnflac_read_cb read, void* user, const bnflac_opts* op
 
 int bnflac_open_device(const void* d_data, size_t len, const uint8_t* header, size_t header_len, const bnflac_opts* opts, bnflac_t** out) {
     if (!d_data || !header || !out) return BNFLAC_ERR_ARG;
+    int caller_dev = -1; if (cudaGetDevice(&caller_dev) != cudaSuccess) { cudaGetLastError(); caller_dev = -1; }
+    struct Restore { int d; ~Restore() { if (d >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != d) cudaSetDevice(d); } } } restore{caller_dev};
     *out = nullptr;
     bnflac* h = new (std::nothrow) bnflac; if (!h) return BNFLAC_ERR_MEMORY;
     h->opts = default_opts(opts); h->len = len; h->d_ext = (const uint8_t*)d_data;
@@ -1351,12 +1448,19 @@ int bnflac_probe(const uint8_t* data, size_t len, bnflac_info_t* info) {
     return parse_metadata(data, len, info);
 }
 
+int bnflac_shard_range(uint64_t len, uint64_t first_frame_offset, uint32_t index, uint32_t count, uint64_t* own_begin, uint64_t* own_end) {
+    if (!own_begin || !own_end || first_frame_offset > len || (count && index >= count)) return BNFLAC_ERR_ARG;
+    shard_range(len, first_frame_offset, index, count, own_begin, own_end);
+    return 0;
+}
+
 int bnflac_info(bnflac_t* h, bnflac_info_t* info) { if (!h || !info) return BNFLAC_ERR_ARG; *info = h->info; return 0; }
 int bnflac_state(bnflac_t* h) { return h ? h->state : BNFLAC_STATE_UNINITIALIZED; }
-void bnflac_close(bnflac_t* h) { delete h; }
+void bnflac_close(bnflac_t* h) { if (!h) return; DeviceScope on(h->device); delete h; }
 
 int bnflac_decode_device(bnflac_t* h, void* d_dst, size_t cap, void** d_out, uint64_t* written) {
     if (!h) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     for (bnflac* k : h->kids) delete k;
     h->kids.clear();
     h->rd_active = false; h->pl_session = false;
@@ -1366,11 +1470,12 @@ int bnflac_decode_device(bnflac_t* h, void* d_dst, size_t cap, void** d_out, uin
 
 int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes) {
     if (!h || !bytes) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     { int rc = pull_all(h); if (rc) return rc; }
     if (h->info.total_samples && (h->opts.shard_count <= 1)) {
         // STREAMINFO states it; a damaged stream may decode to less, never to more than its frame count allows.  Large
         // host streams take the pipelined path, where the exact figure is only known at the end.
-        if (h->host_ptr && !h->d_ext && pipe_cuts(std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end).size() > 2) { *bytes = h->info.pcm_bytes; return 0; }
+        if (!h->size_understated && h->host_ptr && !h->d_ext && pipe_cuts(std::max<uint64_t>(h->own_begin, h->info.first_frame_offset), h->own_end).size() > 2) { *bytes = h->info.pcm_bytes; return 0; }
     }
     int rc = run_front(h); if (rc) return rc;
     *bytes = h->totals.pcm_bytes;
@@ -1379,8 +1484,13 @@ int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes) {
 
 int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written) {
     if (!h || !dst) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     uint64_t w = 0;
-    int rc = decode_host(h, dst, cap, &w); if (rc) return rc;
+    int rc = decode_host(h, dst, cap, &w);
+    // libFLAC decodes every frame whatever STREAMINFO.total_samples says: when a buffer of the promised size is too small, the
+    // next bnflac_decoded_size scans (exact figure) instead of quoting STREAMINFO, so the caller can size and retry
+    if (rc == BNFLAC_ERR_CAPACITY && cap >= h->info.pcm_bytes) h->size_understated = true;
+    if (rc) return rc;
     if (written) *written = w;
     h->state = BNFLAC_STATE_END_OF_STREAM;
     if (h->opts.flags & BNFLAC_OPT_VERIFY_MD5) {
@@ -1395,6 +1505,7 @@ int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written) 
 
 int64_t bnflac_read(bnflac_t* h, uint8_t* dst, size_t count) {
     if (!h || (!dst && count)) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     if (h->rd_active) return stream_read(h, dst, count);
     if (!h->decoded && h->pull_cb && !h->pull_eof) {       // lazily pulled source: sub-shards are cut as the bytes arrive
         CK(cudaSetDevice(h->device));
@@ -1446,35 +1557,43 @@ int bnflac_decode_batch(const bnflac_span* clips, size_t n, const bnflac_opts* o
     if ((!clips && n) || (!dst && cap)) return BNFLAC_ERR_ARG;
     if (written) *written = 0;
     if (!n) return 0;
-    return decode_batch_impl(clips, n, opts, dst, cap, dst_is_device, results, written);
+    int caller_dev = -1; if (cudaGetDevice(&caller_dev) != cudaSuccess) { cudaGetLastError(); caller_dev = -1; }
+    const int rc = decode_batch_impl(clips, n, opts, dst, cap, dst_is_device, results, written);
+    if (caller_dev >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != caller_dev) cudaSetDevice(caller_dev); }
+    return rc;
 }
 
 int bnflac_frames(bnflac_t* h, const bnflac_frame_t** frames, size_t* n) {
     if (!h || !frames || !n) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     int rc = fetch_diag(h); if (rc) return rc;
     *frames = h->frames.data(); *n = h->frames.size();
     return 0;
 }
 int bnflac_subframes(bnflac_t* h, const bnflac_subframe_t** sub, size_t* n) {
     if (!h || !sub || !n) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     int rc = fetch_diag(h); if (rc) return rc;
     *sub = h->subs.data(); *n = h->subs.size();
     return 0;
 }
 int bnflac_errors(bnflac_t* h, const uint32_t** codes, size_t* n) {
     if (!h || !codes || !n) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     int rc = fetch_diag(h); if (rc) return rc;
     *codes = h->errors.data(); *n = h->errors.size();
     return 0;
 }
 int bnflac_errors_so_far(bnflac_t* h, const uint32_t** codes, size_t* n) {
     if (!h || !codes || !n) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     int rc = fetch_diag(h, false); if (rc) return rc;
     *codes = h->errors.data(); *n = h->errors.size();
     return 0;
 }
 int bnflac_error_frames(bnflac_t* h, const uint32_t** at, size_t* n) {
     if (!h || !at || !n) return BNFLAC_ERR_ARG;
+    DeviceScope on(h->device);
     int rc = fetch_diag(h); if (rc) return rc;
     *at = h->errors_at.data(); *n = h->errors_at.size();
     return 0;

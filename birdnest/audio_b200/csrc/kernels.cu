@@ -19,11 +19,12 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstdio>
+#include <atomic>
 
 namespace bnf {
 
-static int g_launches = 0;
-int kernel_launch_count() { return g_launches; }
+static std::atomic<int> g_launches{0};
+int kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 #define FULL 0xffffffffu
 
@@ -1586,22 +1587,38 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
 static inline uint32_t blocks_for(uint64_t n, uint32_t per) { uint64_t b = (n + per - 1) / per; return (uint32_t)(b ? b : 1); }
 
-void launch_scan(const PassArgs& a, void* stream) {
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
-        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm < 1) n_sm = 148;
+// Function attributes (opt-in shared memory) and the SM count belong to a DEVICE, and one process may hold handles on
+// several (bnflac_opts.device): both are looked up / set per current device, once per (kernel, device).
+constexpr int MAX_DEVICES = 64;
+static int current_device() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0; return dev; }
+static int sm_count() {
+    static std::atomic<int> n_sm[MAX_DEVICES];
+    const int dev = current_device();
+    int n = n_sm[dev].load(std::memory_order_relaxed);
+    if (!n) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n < 1) n = 148;
+        if (n > 256) n = 256;          // CNT_ORDER / CNT_PFX_* hold one slot per CTA of the look-back kernels
+        n_sm[dev].store(n, std::memory_order_relaxed);
     }
+    return n;
+}
+// true exactly once per device for the caller's `done` bitmask (idempotent work: a race only repeats it)
+static bool first_use_on_device(std::atomic<uint64_t>& done) {
+    const uint64_t bit = 1ull << current_device();
+    if (done.load(std::memory_order_acquire) & bit) return false;
+    done.fetch_or(bit, std::memory_order_acq_rel);
+    return true;
+}
+
+void launch_scan(const PassArgs& a, void* stream) {
+    static std::atomic<uint64_t> attr_done{0};
+    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    const int n_sm = sm_count();
     uint32_t grid = (a.nchunks + SC_WARPS - 1) / SC_WARPS;
     if (grid > (uint32_t)n_sm) grid = (uint32_t)n_sm;
     if (!grid) grid = 1;
     k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); g_launches++;
-}
-static int sm_count() {
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; if (n_sm > 256) n_sm = 256; }
-    return n_sm;
 }
 void launch_order(const PassArgs& a, void* stream) {
     const int n_sm = sm_count();
@@ -1670,29 +1687,28 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     const uint32_t S = dec_tile_stride(C);
     const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
     size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S);
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm < 1) n_sm = 148;
-    }
-    int max_resident = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC>, 32 * DEC_WARPS, smem);
-    if (max_resident < 1) max_resident = 1;
+    static std::atomic<uint64_t> attr_done{0};
+    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int n_sm = sm_count();
     static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
-    if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: %d CTAs of %d warps resident per SM, grid %u (%.2f waves), %zu B smem/CTA\n", ORD, (int)WIDE, SPEC, max_resident, DEC_WARPS,
-                       grid, (double)grid / ((double)n_sm * max_resident), smem);
-    // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  Cap the residency
-    // (by asking for more shared memory) so that the waves are equally full instead of full ones plus a nearly empty one.
-    const uint64_t per_wave = (uint64_t)n_sm * max_resident;
-    const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
-    uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
-    if (resident < 1) resident = 1;
     static const bool balance = getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '1';
-    if (balance && resident < (uint32_t)max_resident) {
-        size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
-        if (want > 200 * 1024) want = 200 * 1024;
-        if (want > smem) smem = want;
+    if (trace || balance) {
+        int max_resident = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC>, 32 * DEC_WARPS, smem);
+        if (max_resident < 1) max_resident = 1;
+        if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: %d CTAs of %d warps resident per SM, grid %u (%.2f waves), %zu B smem/CTA\n", ORD, (int)WIDE, SPEC, max_resident, DEC_WARPS,
+                           grid, (double)grid / ((double)n_sm * max_resident), smem);
+        // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  BNFLAC_DEC_BALANCE=1 caps
+        // the residency (by asking for more shared memory) so that the waves are equally full (measured: no gain, off by default).
+        const uint64_t per_wave = (uint64_t)n_sm * max_resident;
+        const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
+        uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
+        if (resident < 1) resident = 1;
+        if (balance && resident < (uint32_t)max_resident) {
+            size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
+            if (want > 200 * 1024) want = 200 * 1024;
+            if (want > smem) smem = want;
+        }
     }
     k_decode<ORD, WIDE, SPEC><<<grid, 32 * DEC_WARPS, smem, st>>>(a, C, B, S);
     g_launches++;

@@ -5,6 +5,7 @@
 #include <bnflac.h>
 #include <bnflac_legacy.h>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -35,16 +36,21 @@ struct FLAC__StreamDecoder {
 static bool pull_stream(FLAC__StreamDecoder* d) {
     if (d->have_bytes) return true;
     if (!d->read) return false;
-    const size_t req = 1u << 20;          // the C# callback caps each read at its own byte[] (16 KiB, FLACDecoder.cs:336)
-    for (;;) {
-        const size_t old = d->bytes.size();
-        d->bytes.resize(old + req);
-        size_t got = req;
-        const int st = d->read(d, d->bytes.data() + old, &got, d->client);
-        if (st == 2 || got > req) { d->bytes.resize(old); d->state = BNFLAC_STATE_ABORTED; return false; }
-        d->bytes.resize(old + got);
-        if (st == 1 || got == 0) break;
-    }
+    // The C# callback caps each read at its own byte[] (16 KiB, FLACDecoder.cs:336).  The vector is kept at its high-water
+    // size and grown geometrically: `fill` counts what has been read, so a 16 KiB read never value-initialises a megabyte.
+    const size_t req = 1u << 20;
+    size_t fill = 0;
+    try {
+        for (;;) {
+            if (d->bytes.size() < fill + req) d->bytes.resize(std::max(fill + req, d->bytes.size() + d->bytes.size() / 2));
+            size_t got = req;
+            const int st = d->read(d, d->bytes.data() + fill, &got, d->client);
+            if (st == 2 || got > req) { d->bytes.clear(); d->state = BNFLAC_STATE_ABORTED; return false; }
+            fill += got;
+            if (st == 1 || got == 0) break;
+        }
+        d->bytes.resize(fill);
+    } catch (const std::bad_alloc&) { d->bytes.clear(); d->state = BNFLAC_STATE_MEMORY_ALLOCATION_ERROR; return false; }
     d->have_bytes = true;
     return true;
 }
@@ -72,11 +78,16 @@ static bool do_metadata(FLAC__StreamDecoder* d) {
 
 static bool do_decode(FLAC__StreamDecoder* d) {
     if (d->decoded) return true;
-    uint64_t need = 0;
-    if (bnflac_decoded_size(d->h, &need)) { d->state = BNFLAC_STATE_ABORTED; return false; }
-    d->pcm.resize((size_t)need + 64);
     uint64_t w = 0;
-    const int rc = bnflac_decode_all(d->h, d->pcm.data(), d->pcm.size(), &w);
+    int rc = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        uint64_t need = 0;
+        if (bnflac_decoded_size(d->h, &need)) { d->state = BNFLAC_STATE_ABORTED; return false; }
+        // a STREAMINFO that overstates the stream grossly must not take the process down through an extern "C" frame
+        try { d->pcm.resize((size_t)need + 64); } catch (const std::bad_alloc&) { d->state = BNFLAC_STATE_MEMORY_ALLOCATION_ERROR; return false; }
+        rc = bnflac_decode_all(d->h, d->pcm.data(), d->pcm.size(), &w);
+        if (rc != BNFLAC_ERR_CAPACITY) break;          // STREAMINFO understated the stream: decoded_size scans the second time
+    }
     if (rc) { d->state = (rc == BNFLAC_ERR_MEMORY) ? BNFLAC_STATE_MEMORY_ALLOCATION_ERROR : BNFLAC_STATE_ABORTED; return false; }
     d->pcm.resize((size_t)w);
     size_t ne2 = 0;

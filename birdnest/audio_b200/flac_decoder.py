@@ -115,6 +115,8 @@ class FLACDecoder:
         if nbytes <= 0:
             self.mHitEOFYet = True
             return None
+        if self.mHitEOFYet:
+            return b""                                         # the short read already reported the end (FLACDecoder.cs:345-350)
         out = bytearray()
         while len(out) < nbytes:                               # the engine asks for 1 MiB; the Stream is read <= buffer-size at a time
             length = min(nbytes - len(out), len(self.mInstreamBuffer))

@@ -2,20 +2,17 @@
 `count` byte ranges of its frame data; a shard owns the frames whose sync code lies inside its range, decodes them with
 no data-path collective, and the host concatenates the PCM slices in shard order.
 
-The same arithmetic lives in csrc/engine.cu (compute_shard): keep the two in step.
+The arithmetic is the engine's own: shard_ranges() asks libbnflac (bnflac_shard_range, host-only, no device needed), the
+same function bnflac_opts.shard_index / shard_count go through.
 """
 from typing import List, Sequence, Tuple
+
+from . import _abi
 
 
 def shard_ranges(stream_len: int, first_frame_offset: int, count: int) -> List[Tuple[int, int]]:
     """[own_begin, own_end) of every shard, in stream order."""
-    d = stream_len - first_frame_offset
-    out = []
-    for i in range(count):
-        lo = first_frame_offset + d * i // count
-        hi = stream_len if i + 1 == count else first_frame_offset + d * (i + 1) // count
-        out.append((lo, hi))
-    return out
+    return [_abi.shard_range(stream_len, first_frame_offset, i, count) for i in range(count)]
 
 
 def owned_frames(frame_offsets: Sequence[int], lo: int, hi: int) -> List[int]:

@@ -73,6 +73,8 @@ typedef struct {
 } bnflac_opts;
 #define BNFLAC_OPT_VERIFY_MD5 1u   /* decode_all also checks md5(PCM) against STREAMINFO (host side, not timed) */
 #define BNFLAC_OPT_BORROW_INPUT 2u /* open_memory does not copy `data`: the caller keeps it valid (and ideally pinned) until close */
+#define BNFLAC_OPT_PACKED_INPUT 8u /* decode_batch: the clips lie in ascending address order inside ONE host buffer that the caller owns from the
+                                    * first clip's first byte to the last clip's last byte (gaps included): the range is uploaded in place */
 #define BNFLAC_OPT_LAZY_PULL 4u    /* open_callbacks pulls only the metadata; bnflac_read pulls the rest as the reader advances (the
                                     * callback and its `user` must then stay valid until close).  What FLACDecoder(Stream) does:
                                     * metadata in the constructor, stream bytes on demand (FLACDecoder.cs:72-88,207-224,325-363) */
@@ -121,6 +123,10 @@ int bnflac_probe(const uint8_t* data, size_t len, bnflac_info_t* info);
 /* Host-only: the native FLAC stream inside an Ogg FLAC stream (what the decoder is fed after de-paging).  *written = its
  * size; BNFLAC_ERR_CAPACITY (nothing copied) if cap is smaller, BNFLAC_ERR_NOT_FLAC if `data` is not Ogg FLAC. */
 int bnflac_ogg_to_native(const uint8_t* data, size_t len, uint8_t* dst, size_t cap, size_t* written);
+/* Host-only: the byte range [*own_begin, *own_end) of frame data that shard `index` of `count` owns in a stream of `len` bytes
+ * whose first frame starts at `first_frame_offset` (a shard owns the frames whose sync code lies in its range).
+ * The one place this arithmetic lives: bnflac_opts.shard_index / shard_count use it, so does any host-side planner. */
+int bnflac_shard_range(uint64_t len, uint64_t first_frame_offset, uint32_t index, uint32_t count, uint64_t* own_begin, uint64_t* own_end);
 int bnflac_state(bnflac_t* h);                       /* bnflac_state_t */
 void bnflac_close(bnflac_t* h);                      /* finish + delete (FLACDecoder.cs:296-300) */
 
@@ -133,7 +139,9 @@ int bnflac_decode_all(bnflac_t* h, uint8_t* dst, size_t cap, uint64_t* written);
 /* One shot, result left in device memory.  If d_dst is NULL the library allocates (owned by the handle, valid
  * until the next decode or close) and returns it in *d_out; else writes into caller memory of capacity cap. */
 int bnflac_decode_device(bnflac_t* h, void* d_dst, size_t cap, void** d_out, uint64_t* written);
-/* Size in bytes the decode of this handle (its shard) will produce, known after the frame scan. */
+/* Size in bytes the decode of this handle (its shard) will produce, known after the frame scan.  For a large host-resident
+ * stream this is what STREAMINFO promises (no scan); if bnflac_decode_all then reports BNFLAC_ERR_CAPACITY with a buffer of
+ * that size (STREAMINFO understated the stream), the next call here scans and returns the exact figure: size again, retry. */
 int bnflac_decoded_size(bnflac_t* h, uint64_t* bytes);
 
 /* ---- batch of independent clips (BASELINE cfg4: sharded by file) --------------------------- */
@@ -141,8 +149,9 @@ typedef struct { const uint8_t* data; size_t len; } bnflac_span;
 typedef struct { uint64_t pcm_offset, pcm_bytes; uint32_t sample_rate, channels, bits_per_sample, status; uint64_t total_samples; } bnflac_clip_result;
 /* Decodes n clips in one pipeline pass into one PCM buffer (clip i at results[i].pcm_offset).
  * dst==NULL: only sizes are computed.  dst_is_device: dst is a device pointer.
- * Clips given in ascending address order inside ONE host buffer (gaps of up to ~1 KiB per clip, e.g. archive headers)
- * are uploaded in place with a single copy; otherwise they are gathered into pinned staging memory first. */
+ * With BNFLAC_OPT_PACKED_INPUT in opts->flags (clips in ascending address order inside ONE host buffer owned by the caller,
+ * e.g. an archive read in one piece) the whole range is uploaded in place with a single copy; otherwise only the clips'
+ * own bytes are read: they are gathered into pinned staging memory first. */
 int bnflac_decode_batch(const bnflac_span* clips, size_t n, const bnflac_opts* opts, uint8_t* dst, size_t cap, int dst_is_device,
                         bnflac_clip_result* results, uint64_t* written);
 

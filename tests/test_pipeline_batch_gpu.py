@@ -183,7 +183,8 @@ def test_packed_batch_is_uploaded_in_place_and_matches():
     packed += bytes(100)
     mv = memoryview(packed)
     views = [mv[o:o + n] for o, n in spans]
-    got_pcm, got_res = _abi.decode_batch(views)
+    got_pcm, got_res = _abi.decode_batch(views, packed=True)
+    assert _abi.decode_batch(views)[0] == want_pcm            # without the flag the same views are gathered: same result
     assert got_pcm == want_pcm
     assert [(r.pcm_offset, r.pcm_bytes, r.channels, r.bits_per_sample, r.status) for r in got_res] == \
            [(r.pcm_offset, r.pcm_bytes, r.channels, r.bits_per_sample, r.status) for r in want_res]
@@ -192,5 +193,5 @@ def test_packed_batch_is_uploaded_in_place_and_matches():
     # a damaged clip in the middle of the packed buffer is reported, the others are untouched
     o, n = spans[5]
     packed[o + n // 2] ^= 0x20
-    bad_pcm, bad_res = _abi.decode_batch([mv[o:o + n] for o, n in spans])
+    bad_pcm, bad_res = _abi.decode_batch([mv[o:o + n] for o, n in spans], packed=True)
     assert bad_res[5].status != 0 and all(r.status == 0 for k, r in enumerate(bad_res) if k != 5)

@@ -65,7 +65,13 @@ def test_two_rank_frame_range_shards_gather_to_the_whole(name):
 
 
 def test_shard_ranges_partition_the_frame_bytes():
+    """shard_ranges() is the engine's own arithmetic (bnflac_shard_range through the C ABI): one source for planner and engine."""
     from birdnest.audio_b200.sharding import shard_ranges, owned_frames
+    from birdnest.audio_b200 import _abi
+    assert _abi.shard_range(1_000_003, 4242, 1, 3) == (4242 + (1_000_003 - 4242) // 3, 4242 + (1_000_003 - 4242) * 2 // 3)
+    assert _abi.shard_range(10, 4, 0, 0) == (4, 10)                      # count 0 = whole stream
+    with pytest.raises(_abi.BnflacError):
+        _abi.shard_range(10, 4, 3, 3)
     for n in (1, 2, 3, 4, 8):
         r = shard_ranges(1_000_003, 4242, n)
         assert r[0][0] == 4242 and r[-1][1] == 1_000_003

@@ -43,9 +43,10 @@ for i, b in enumerate(blobs):
     pkn[off:off + len(b)] = np.frombuffer(b, dtype=np.uint8)
     pspans[i].data = pk.data_ptr() + off; pspans[i].len = len(b)
     off += len(b)
+po = _abi._opts(0, flags=_abi.OPT_PACKED_INPUT)
 for it in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    rc = L.bnflac_decode_batch(pspans, N, C.byref(o), out.data_ptr(), out.numel(), 1, res, C.byref(w))
+    rc = L.bnflac_decode_batch(pspans, N, C.byref(po), out.data_ptr(), out.numel(), 1, res, C.byref(w))
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) * 1e3
     print(f"C call, packed pinned input: rc {rc} {dt:.1f} ms = {n_all/dt/1e6:.1f} G samples/s", flush=True)
 os.environ.pop("BNFLAC_TRACE", None)

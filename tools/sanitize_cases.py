@@ -55,7 +55,7 @@ spans = []
 for c in clips:
     packed += b"\xff\xf8" * 100; spans.append((len(packed), len(c))); packed += c
 mv = memoryview(packed)
-pcm2, res2 = _abi.decode_batch([mv[o:o + n] for o, n in spans])
+pcm2, res2 = _abi.decode_batch([mv[o:o + n] for o, n in spans], packed=True)
 ok = pcm == pcm2 and [r.status for r in res] == [r.status for r in res2] == [0, 0, 0, 4, 0]
 bad += not ok; print("batch gathered/packed", "ok" if ok else "MISMATCH")
 print("FAILED" if bad else "all ok")
