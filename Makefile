@@ -12,19 +12,26 @@ LIB := birdnest/audio_b200/libbnflac.so
 all: lib oracle corpus host shim
 
 lib: $(LIB)
-# kernels.cu (device code, ~2 minutes of ptxas) and engine.cu (host runtime, seconds) are compiled separately: the engine
-# only calls the launch_* host wrappers, so no relocatable device code is needed.  Objects live in csrc/_obj (git-ignored).
+# The device code is three translation units (front kernels; decode variants with 64-bit / 32-bit accumulation) that share
+# kernels_common.cuh and compile in parallel under `make -j`; engine.cu (host runtime, seconds) only calls the launch_* host
+# wrappers, so no relocatable device code is needed.  Objects and the ptxas -v logs live in csrc/_obj (git-ignored).
 OBJ := $(CSRC)/_obj
-$(OBJ)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/bnflac_dev.h include/bnflac.h
+DEVHDR := $(CSRC)/bnflac_dev.h $(CSRC)/kernels_common.cuh include/bnflac.h
+$(OBJ)/kernels.o: $(CSRC)/kernels.cu $(DEVHDR)
 	@mkdir -p $(OBJ)
-	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/kernels.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
-	@grep -E "error|warning" $(CSRC)/ptxas.log | grep -v "ptxas info" || true
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/kernels.cu 2> $(OBJ)/kernels.log || (cat $(OBJ)/kernels.log; exit 1)
+	@grep -E "error|warning" $(OBJ)/kernels.log | grep -v "ptxas info" || true
+$(OBJ)/kernels_decode_%.o: $(CSRC)/kernels_decode_%.cu $(CSRC)/kernels_decode.cuh $(DEVHDR)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(OBJ)/kernels_decode_$*.log || (cat $(OBJ)/kernels_decode_$*.log; exit 1)
+	@grep -E "error|warning" $(OBJ)/kernels_decode_$*.log | grep -v "ptxas info" || true
 $(OBJ)/engine.o: $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/engine.cu 2> $(OBJ)/engine.log || (cat $(OBJ)/engine.log; exit 1)
 	@grep -E "error|warning" $(OBJ)/engine.log | grep -v "ptxas info" || true
-$(LIB): $(OBJ)/kernels.o $(OBJ)/engine.o
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)/kernels.o $(OBJ)/engine.o
+LIBOBJ := $(OBJ)/kernels.o $(OBJ)/kernels_decode_wide.o $(OBJ)/kernels_decode_narrow.o $(OBJ)/engine.o
+$(LIB): $(LIBOBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(LIBOBJ)
 
 host: birdnest/audio_b200/flacdecoder_demo
 birdnest/audio_b200/flacdecoder_demo: $(CSRC)/flac_decoder.hpp $(CSRC)/flac_decoder_demo.cpp $(LIB)

@@ -20,6 +20,8 @@ constexpr int MAX_CH = 8;
 // look-back kernels (at most 256 CTAs each)
 constexpr int CNT_ANOM = 2;            // candidates off the clean frame chain (k_parse -> k_resync)
 constexpr uint32_t ANOM_CAP = 8192;
+constexpr int CNT_SPEC = 3;            // speculative subframe walks queued (k_spec_find -> k_parse<.., true>)
+constexpr int CNT_SPEC_DONE = 4;       // frames whose guessed subframe starts all chained up (k_spec_resolve)
 constexpr int CNT_ORDER = 16, CNT_PFX_CNT = CNT_ORDER + 256, CNT_PFX_BYTES = CNT_PFX_CNT + 256, CNT_WORDS = CNT_PFX_BYTES + 512;
 
 // per-candidate status
@@ -67,6 +69,17 @@ struct SubInfo {            // K2 output, 8 bytes per (frame, channel)
     uint8_t flags;          // bit0: narrow (32-bit) accumulate per libFLAC's width rule; bit1: Rice2
 };
 
+// Speculative parse (streams of few, large frames): one job = one subframe walked from a GUESSED start.  The jobs of a frame
+// are contiguous; job 0 of a frame is channel 0 at its true start.
+struct SpecJob {            // 24 bytes
+    uint32_t frame;         // candidate index
+    uint32_t start_bit;     // bit offset of the (guessed) subframe header from the frame's first byte
+    uint32_t end_bit;       // where the walk of this subframe ended (k_parse<.., true>); 0 = the walk failed
+    SubInfo si;             // what the walk found there
+    uint32_t ch;            // channel the guess is for
+};
+constexpr uint32_t SPEC_MAX_PER_FRAME = 48;     // guesses kept per frame (all channels)
+
 struct Totals {             // written by the prefix-sum kernel
     uint64_t pcm_bytes;     // bytes the pass produces
     uint32_t n_accepted;    // frames delivered (OK or zero-filled)
@@ -100,6 +113,11 @@ struct PassArgs {
     uint32_t* anom;         // ANOM_CAP candidate indices that are off the clean chain (unordered)
     // K2
     SubInfo* sub;
+    SpecJob* spec_jobs;     // speculative parse: job list (spec_cap entries), per-candidate base / count / done flag
+    uint32_t spec_cap;
+    uint32_t* spec_base;
+    uint8_t* spec_count;
+    uint8_t* spec_done;     // 1: every subframe start of this (CRC-validated) frame was confirmed, k_parse has nothing to do
     // prefix
     uint64_t* pcm_off;
     uint32_t* acc_idx;
@@ -115,6 +133,7 @@ void launch_order(const PassArgs& a, void* stream);
 void launch_crc(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_link(const PassArgs& a, uint32_t ncand_bound, void* stream);
 void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
+bool parse_wants_speculation(uint32_t ncand_bound, uint32_t channels);   // few, large frames: the engine then provides PassArgs::spec_*
 void launch_resync(const PassArgs& a, void* stream);
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream);
 void launch_make_chunks(const SegInfo& seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks, void* stream);   // scan tiles of a one-segment pass

@@ -281,7 +281,7 @@ struct bnflac {
 
     // device state
     DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_pref, d_anom,
-        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags;
+        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags, d_spec_jobs, d_spec_base, d_spec_count, d_spec_done;
     uint32_t nchunks = 0, cand_cap = 0, nsegs = 0;
     bool tables_ready = false;
     PassArgs args{};
@@ -320,7 +320,7 @@ struct bnflac {
         DeviceScope on(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
         DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref, &d_anom,
-                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags};
+                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags, &d_spec_jobs, &d_spec_base, &d_spec_count, &d_spec_done};
         for (DevBuf* b : all) b->release();
         pcm_host.release(); mailbox.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -499,6 +499,15 @@ static int launch_front_tail(bnflac* h, uint32_t nb) {
     CK(cudaEventRecord(h->ev[2], h->stream));
     launch_link(h->args, nb, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
+    // few, large frames: subframe starts are guessed and walked in parallel (kernels.cu, "speculative parse")
+    if (parse_wants_speculation(nb, h->info.channels)) {
+        const uint64_t cap = (uint64_t)std::max<uint32_t>(nb, 1u) * h->info.channels * 2u + 64u;
+        int rc;
+        if ((rc = h->d_spec_jobs.reserve(sizeof(SpecJob) * cap)) || (rc = h->d_spec_base.reserve(4ull * h->cand_cap)) ||
+            (rc = h->d_spec_count.reserve(h->cand_cap)) || (rc = h->d_spec_done.reserve(h->cand_cap))) return rc;
+        h->args.spec_jobs = h->d_spec_jobs.as<SpecJob>(); h->args.spec_cap = (uint32_t)std::min<uint64_t>(cap, h->d_spec_jobs.cap / sizeof(SpecJob));
+        h->args.spec_base = h->d_spec_base.as<uint32_t>(); h->args.spec_count = h->d_spec_count.as<uint8_t>(); h->args.spec_done = h->d_spec_done.as<uint8_t>();
+    } else { h->args.spec_jobs = nullptr; h->args.spec_cap = 0; h->args.spec_base = nullptr; h->args.spec_count = nullptr; h->args.spec_done = nullptr; }
     launch_parse(h->args, nb, h->stream);
     launch_resync(h->args, h->stream);
     launch_prefix(h->args, nb, h->info.bytes_per_sample, h->stream);
@@ -604,6 +613,13 @@ static int finish_timing(bnflac* h) {
     h->timing.scan = ms(0, 1); h->timing.crc = ms(1, 2); h->timing.link = ms(2, 3); h->timing.parse = ms(3, 4);
     h->timing.decode = ms(4, 5); h->timing.total = ms(0, 5);
     h->timing.launches = (uint32_t)(kernel_launch_count() - h->launches0);
+    static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
+    if (trace && h->args.spec_jobs) {
+        uint32_t cnt[8] = {0};
+        cudaMemcpy(cnt, h->d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[bnflac] speculative parse: %u candidates, %u subframe walks queued (cap %u), %u frames confirmed, %u left to the serial walk of %u off-chain\n",
+                cnt[0], cnt[CNT_SPEC], h->args.spec_cap, cnt[CNT_SPEC_DONE], h->totals.n_accepted > cnt[CNT_SPEC_DONE] ? h->totals.n_accepted - cnt[CNT_SPEC_DONE] : 0u, cnt[CNT_ANOM]);
+    }
     return 0;
 }
 

@@ -13,46 +13,13 @@
 //
 // Replaces what the reference reaches through FLAC__stream_decoder_process_single (LibFLACSharp.cs:54-55,
 // FLACDecoder.cs:215) and the interleave loops FLACDecoder.cs:552-576 / FLACFileReader.cs:214-243.
-#include "bnflac_dev.h"
-#include <cuda_runtime.h>
-#include <type_traits>
-#include <cstdlib>
-#include <algorithm>
-#include <cstdio>
-#include <atomic>
+#include "kernels_common.cuh"
 
 namespace bnf {
 
 static std::atomic<int> g_launches{0};
 int kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
-
-#define FULL 0xffffffffu
-
-// ------------------------------------------------------------------------------------------------ CRC helpers
-__device__ __forceinline__ uint32_t crc8_update(uint32_t c, uint32_t byte) {
-    c ^= byte;
-#pragma unroll
-    for (int k = 0; k < 8; k++) c = (c & 0x80) ? ((c << 1) ^ 0x07) & 0xFF : (c << 1) & 0xFF;
-    return c;
-}
-__device__ __forceinline__ uint32_t crc16_update_bitwise(uint32_t c, uint32_t byte) {
-    c ^= byte << 8;
-#pragma unroll
-    for (int k = 0; k < 8; k++) c = (c & 0x8000) ? ((c << 1) ^ 0x8005) & 0xFFFF : (c << 1) & 0xFFFF;
-    return c;
-}
-// ------------------------------------------------------------------------------------------------ shared-memory / bit helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
-__device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
-__device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
-__device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }   // index of the leading one; 0xffffffff for 0
-__device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
-
+void count_launch() { g_launches++; }
 
 // ------------------------------------------------------------------------------------------------ frame header
 struct Hdr {
@@ -572,188 +539,6 @@ __global__ void __launch_bounds__(256) k_cover(PassArgs a) {
     for (uint32_t j = i + 1; j < nx && j < n; j++) a.status[j] = ST_DROP;
 }
 
-// ------------------------------------------------------------------------------------------------ ring bit reader
-// Every lane walks its own serial bitstream.  The bytes are staged through shared memory by per-lane cp.async
-// (LDGSTS, 16 B each) into a private 128-byte ring that runs several blocks ahead of the read position, so the serial
-// walk never waits on HBM.  Reads are position based: two LDS + byte swaps + one funnel shift give a 32-bit window; block
-// 0 of the ring is duplicated behind block 7, so the second word of a window never needs a wrap-around address.
-// Refill is CHECKPOINTED: all lanes of a warp top up their rings at the same loop iterations (every 8 samples): first
-// wait for what was requested one period ago, then request more.  Budget: blocks up to (block of pos at the previous
-// checkpoint) + 7 have landed, i.e. >= 113 bytes past that position; a period may therefore advance by A bytes with
-// 2A + 8 <= 113 (this period's reads reach pos_prev + 2A + 8).  The walkers keep A <= 42: eight samples of at most 32
-// bits each plus partition parameters; anything longer takes a synchronous path (ensure_now).
-// DEPTH = how many of the most recent refill groups may still be in flight after a checkpoint (prefetch distance in
-// checkpoint periods).  With DEPTH = 0 a checkpoint waits for what was requested one period earlier, which exposes the
-// HBM latency whenever too few warps are resident to hide it (streams with few, large frames).  With DEPTH > 0 the
-// checkpoint only waits for older groups, provided what those covered (mark[DEPTH]) reaches past everything the coming
-// period can read; a lane that consumed unusually many bits falls back to a full wait.
-template <int NBLK_, int DEPTH, int STEADY_ = 0>
-struct RingBitsT {
-    static constexpr int NBLK = NBLK_, BLK = 16, RB_BYTES = NBLK * BLK;
-    static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
-    // bytes a refill period can advance + window look-ahead: 8 samples of <= 32 bits plus parameters per 8-sample group
-    // (longer codewords take synchronous refills); rings of 16 blocks are checkpointed every 16 samples
-    static constexpr uint32_t PERIOD_REACH = (NBLK >= 16 ? 84 : 42) + 16;
-    uint32_t sring;        // shared-space address of this lane's ring
-    uint32_t pos;          // bit position relative to g0
-    uint32_t filled;       // blocks [.., filled) have been requested
-    uint32_t navail;       // whole 16-byte blocks readable from g0 (blocks past the padded input read as zero)
-    uint32_t mark[DEPTH + 1];   // `filled` after each of the last DEPTH + 1 checkpoints (mark[0] most recent)
-    const uint8_t* g0;     // global address of ring byte 0 (16 B aligned)
-
-    __device__ __forceinline__ void fetch(uint32_t b) {
-        const uint32_t n = b < navail ? 16u : 0u;
-        const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
-        const uint32_t slot = b & (NBLK - 1);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + slot * BLK), "l"(s), "r"(n) : "memory");
-        if (slot == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + RB_BYTES), "l"(s), "r"(n) : "memory");
-    }
-    __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-    __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-    // fetch(b) under a predicate, without a branch (a cp.async of size 0 would zero the slot, so the instruction itself is
-    // predicated)
-    __device__ __forceinline__ void fetch_if(uint32_t b, bool p) {
-        const uint32_t n = b < navail ? 16u : 0u;
-        const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
-        const uint32_t slot = b & (NBLK - 1);
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + slot * BLK), "l"(s), "r"(n), "r"((uint32_t)p) : "memory");
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + RB_BYTES), "l"(s), "r"(n), "r"((uint32_t)(p && slot == 0)) : "memory");
-    }
-    // Request every block the ring has room for (never the slot being read).  STEADY = how many blocks a refill period
-    // normally frees: that many are requested branch-free under predicates (the lanes of a warp free different numbers of
-    // blocks, so a loop here diverges on nearly every call); whatever is left after a big move goes through the loop.
-    // STEADY = 0 keeps the plain loop: with many resident warps (streams of many frames) the predicated slots that turn out
-    // empty cost more issue slots than the divergence they avoid (cfg2: parse +3 %), with few warps the branches dominate
-    // (cfg3: parse 5.30 -> 4.56 ms, decode 4.65 -> 4.50 ms).
-    static constexpr int STEADY = STEADY_;
-    __device__ __forceinline__ void request() {
-        const uint32_t curblk = pos / (BLK * 8);
-        if (filled < curblk) filled = curblk;       // jumped over unrequested blocks
-        const uint32_t lim = curblk + NBLK;
-#pragma unroll
-        for (int i = 0; i < STEADY; i++) { const bool p = filled < lim; fetch_if(filled, p); filled += p ? 1u : 0u; }
-        if (filled < lim) {
-#pragma unroll 1
-            do { fetch(filled); filled++; } while (filled < lim);
-        }
-        commit();                                   // one group per call, possibly empty: wait_group counts calls
-    }
-    __device__ __forceinline__ void checkpoint() {
-        if constexpr (DEPTH == 0) wait_all();
-        else {
-            if ((pos >> 3) + PERIOD_REACH <= mark[DEPTH] * (uint32_t)BLK) asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
-            else {
-                wait_all();
-#pragma unroll
-                for (int d = 0; d <= DEPTH; d++) mark[d] = filled;
-            }
-        }
-        request();
-#pragma unroll
-        for (int d = DEPTH; d > 0; d--) mark[d] = mark[d - 1];
-        mark[0] = filled;
-    }
-    __device__ __forceinline__ void ensure_now() {                               // synchronous: rare big moves, init
-        request(); wait_all();
-#pragma unroll
-        for (int d = 0; d <= DEPTH; d++) mark[d] = filled;
-    }
-    __device__ __forceinline__ void init(uint32_t sring_, const uint8_t* in, uint64_t in_len, uint64_t abs_bit) {
-        sring = sring_;
-        const uint64_t b0 = (abs_bit >> 3) & ~(uint64_t)(BLK - 1);
-        g0 = in + b0;
-        const uint64_t nb = in_len > b0 ? (in_len - b0) >> 4 : 0;
-        navail = (uint32_t)(nb > 0xffffffffull ? 0xffffffffull : nb);
-        pos = (uint32_t)(abs_bit - b0 * 8);
-        filled = 0;
-        ensure_now();
-    }
-    __device__ __forceinline__ void init_idle(uint32_t sring_, const uint8_t* in) {
-        sring = sring_; g0 = in; navail = 0; pos = 0; filled = NBLK;
-#pragma unroll
-        for (int d = 0; d <= DEPTH; d++) mark[d] = NBLK;
-    }
-    __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
-    __device__ __forceinline__ uint32_t window_at(uint32_t p) const {      // 32 bits starting at bit p, MSB first
-        const uint32_t bo = (p >> 3) & (RB_BYTES - 4);
-        const uint32_t a = lds32(sring + bo), b = lds32(sring + bo + 4);
-        return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), p);
-    }
-    __device__ __forceinline__ uint32_t window() const { return window_at(pos); }
-    // Register-cached window for the branch-free groups: w0:w1 are the two big-endian words under the read position, w2
-    // the word after them.  A codeword advances the position by at most 32 bits, so at most one word is crossed per
-    // step.  The word that a crossing shifts in (position word + 3) is loaded at the START of every step, from the
-    // position the step starts at, so the shared-memory latency is entirely off the serial
-    // position -> window -> length -> position chain (which is then SHF, FLO, IADD3, LOP3, SEL).
-    struct Win3 { uint32_t w0, w1, w2; };
-    __device__ __forceinline__ Win3 win_init(uint32_t p) const {
-        const uint32_t ad = sring + ((p >> 3) & (RB_BYTES - 4));
-        Win3 w; w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = __byte_perm(lds32(ad + 8), 0, 0x0123);
-        return w;
-    }
-    __device__ __forceinline__ uint32_t win_next(uint32_t p) const { return __byte_perm(lds32(sring + (((p >> 3) + 12) & (RB_BYTES - 4))), 0, 0x0123); }   // word of p, + 3
-    __device__ __forceinline__ static uint32_t win_peek(const Win3& w, uint32_t p) { return __funnelshift_l(w.w1, w.w0, p); }
-    __device__ __forceinline__ static void win_advance(Win3& w, uint32_t p, uint32_t np, uint32_t nxt) {
-        if ((p ^ np) & 32u) { w.w0 = w.w1; w.w1 = w.w2; w.w2 = nxt; }
-    }
-    __device__ __forceinline__ void skip(uint32_t n) { pos += n; }                        // n <= 32, covered by the checkpoint budget
-    __device__ __forceinline__ void jump(uint32_t n) { pos += n; ensure_now(); }          // any n
-    __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = shr_c(window(), 32 - n); pos += n; return v; }          // n <= 32
-    __device__ __forceinline__ int32_t gets(uint32_t n) { int32_t v = n ? sar_c((int32_t)window(), 32 - n) : 0; pos += n; return v; }
-    // unary run that did not terminate inside one window (rare): walks 32 zero bits at a time with synchronous refills
-    __device__ __forceinline__ uint32_t unary_slow(uint32_t limit) {
-        uint32_t q = 0;
-#pragma unroll 1
-        for (;;) {
-            ensure_now();
-            uint32_t w = window();
-            if (w) { uint32_t z = __clz(w); pos += z + 1; ensure_now(); return q + z; }
-            q += 32; pos += 32;
-            if (q > limit) { ensure_now(); return q; }
-        }
-    }
-    __device__ __forceinline__ uint32_t unary(uint32_t limit) {
-        uint32_t w = window();
-        if (w) { uint32_t z = __clz(w); pos += z + 1; return z; }
-        return unary_slow(limit);
-    }
-    // one Rice codeword with parameter k, any length; leaves the ring synchronised when the codeword was long
-    __device__ __forceinline__ int32_t rice_careful(uint32_t k) {
-        const uint32_t w = window();
-        const uint32_t f = bfind(w);
-        uint32_t u;
-        if ((int32_t)(f - k) >= 0) { u = (31u - f) << k | (shr_c(w, f - k) & ((1u << k) - 1u)); pos += k + 32u - f; }
-        else { const uint32_t q = unary(1u << 24); ensure_now(); u = (q << k) | get(k); ensure_now(); }
-        return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-    }
-    // skip one Rice codeword; returns false when the unary run is implausibly long (damaged data)
-    __device__ __forceinline__ bool rice_skip_careful(uint32_t k, uint32_t limit = 1u << 16) {
-        const uint32_t w = window();
-        const uint32_t f = bfind(w);
-        if ((int32_t)(f - k) >= 0) { pos += k + 32u - f; return true; }
-        const uint32_t q = unary(limit);
-        jump(k);
-        return q <= limit;
-    }
-};
-
-#ifndef PARSE_RING_BLOCKS
-#define PARSE_RING_BLOCKS 16
-#endif
-#ifndef PARSE_RING_DEPTH
-#define PARSE_RING_DEPTH 1
-#endif
-#ifndef DEC_RING_DEPTH
-#define DEC_RING_DEPTH 1
-#endif
-using ParseBits = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH>;   // no sample tile in k_parse: room for a longer ring and a deeper prefetch
-template <bool LEAN> using ParseBitsT = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH, LEAN ? 3 : 0>;
-#ifndef DEC_RING_BLOCKS
-#define DEC_RING_BLOCKS 8
-#endif
-using RingBits = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH>;         // k_decode (16 blocks: one refill checkpoint per 16 samples)
-template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (ORD > 12 ? 2 : 0)>;   // orders > 12: few, long subframes
-
 // ------------------------------------------------------------------------------------------------ K2 parse
 // One lane per frame: walks the subframes, records where each starts and what it is, skips the residual.  Lanes of a warp
 // advance channel by channel and, inside a subframe, one refill period (16 sample indices) at a time in lockstep.  A
@@ -800,7 +585,9 @@ __device__ __forceinline__ int parse_param(BR& br, ParseSub& p, const uint8_t* i
 
 // N codewords of every walking lane's partition, branch-free: window, bfind, add; a codeword that does not fit one
 // 32-bit window raises a flag and the lane redoes the group one careful codeword at a time.
-template <int N, class BR>
+// GIVE_UP (speculative jobs): a codeword longer than the window ends the job instead -- in a stream that is what it seems to be
+// this (almost) never happens, while a wrong guess walks noise and would drag its warp through the careful path
+template <int N, bool GIVE_UP, class BR>
 __device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bool& bad, uint32_t end_pos) {
     uint32_t pos = br.pos;
     const uint32_t k = ps.k, kp32 = ps.kp32;
@@ -819,6 +606,7 @@ __device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bo
         ps.left -= N;
         if (!ps.raw) {
             if (!ovf) br.pos = pos;
+            else if (GIVE_UP) { bad = true; walk = false; }
             else {
 #pragma unroll 1
                 for (int j = 0; j < N; j++) if (!br.rice_skip_careful(k, unary_limit(br.pos, end_pos))) { bad = true; walk = false; break; }
@@ -833,11 +621,21 @@ __device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bo
 enum : uint32_t { PF_NONE = 0, PF_UNPARSE = 1, PF_LOST = 2, PF_EOS = 3 };
 
 // LEAN: branch-free ring refill (streams of few, large frames: the kernel is then a handful of warps, see RingBitsT::request)
-template <bool LEAN>
+// SPEC: the speculative form (few, large frames -- see k_spec_find): a lane is one JOB, one subframe walked from a guessed
+// start, instead of one frame; it records where that subframe ends, and k_spec_resolve keeps the guesses that chain up.
+template <bool LEAN, bool SPEC>
 __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     extern __shared__ __align__(16) uint8_t s_ring[];
     const uint32_t n = ncand(a);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = lane_id;
+    uint32_t my_ch = 0, my_start = 0;
+    bool have_job = !SPEC;
+    if (SPEC) {
+        const uint32_t njobs = min(a.counters[CNT_SPEC], a.spec_cap);
+        i = n;
+        if (lane_id < njobs) { const SpecJob jb = a.spec_jobs[lane_id]; i = jb.frame; my_ch = jb.ch; my_start = jb.start_bit; have_job = true; }
+    }
     uint8_t st = ST_DROP;
     Cand c;
     c.bs = 0; c.assign = 0; c.flags = 0; c.off = 0; c.hdr_len = 0; c.bps = 0;
@@ -846,6 +644,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     // the numbering; ST_CHECK: nothing does) are parsed to the end the way the reference would, because what the
     // reference does next depends on where that parse stops (flag 2: frame of the neighbouring shard, end marker only)
     bool live = (st == ST_OK || st == ST_CHECK || st == ST_CRC) && !(c.flags & 2);
+    if (SPEC) live = have_job && st == ST_OK && !(c.flags & 2);                        // guesses are only made for clean frames
+    else if (live && st == ST_OK && a.spec_done && a.spec_done[i]) live = false;       // every subframe start already confirmed
     const bool clean = st == ST_OK;
     const uint32_t channels = c.assign < 8 ? c.assign + 1u : 2u;
     const uint64_t frame_bit0 = c.off * 8;
@@ -857,7 +657,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         end_bit = (clean ? c.off + a.flen[i] : sg.end) * 8;
     }
     ParseBitsT<LEAN> br;
-    if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + 8ull * c.hdr_len);
+    if (live) br.init(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in, a.in_len, frame_bit0 + (SPEC ? (uint64_t)my_start : 8ull * c.hdr_len));
     else br.init_idle(smem_u32(s_ring) + threadIdx.x * ParseBits::STRIDE, a.in);
     // end of the frame as a ring-relative bit position (saturated: a frame is far below 2^32 bits)
     const uint32_t end_pos = live ? (uint32_t)min((uint64_t)0xFFFFFFFFu, end_bit - (uint64_t)(br.g0 - a.in) * 8) : 0xFFFFFFFFu;
@@ -865,7 +665,9 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
     uint32_t max_order = 0, any_wide = 0;
     const uint32_t wmax_ch = __reduce_max_sync(FULL, live ? channels : 0u);
     const uint32_t wmax_bs = __reduce_max_sync(FULL, live ? c.bs : 0u);
-    for (uint32_t ch = 0; ch < wmax_ch; ch++) {
+    SubInfo spec_si; spec_si.bit_offset = 0; spec_si.type = 0; spec_si.order = 0; spec_si.wasted = 0; spec_si.flags = 0;
+    for (uint32_t it = 0; it < (SPEC ? 1u : wmax_ch); it++) {
+        const uint32_t ch = SPEC ? my_ch : it;          // a job is one subframe: every lane of the warp walks its own channel
         bool walk = false;            // this lane walks a Rice-coded residual in this phase
         bool bad = false;             // ... and ran off the stream doing so
         ParseSub ps;
@@ -933,21 +735,22 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
                     }
                 }
             }
-            if (fail == PF_NONE) a.sub[(uint64_t)i * MAX_CH + ch] = si;
-            else walk = false;
+            if (fail != PF_NONE) walk = false;
+            else if (SPEC) spec_si = si;
+            else a.sub[(uint64_t)i * MAX_CH + ch] = si;
         }
         if (!__any_sync(FULL, walk)) continue;
         auto next_param = [&]() {
             const int pr = parse_param(br, ps, a.in, end_bit);
-            if (pr == 2) bad = true;
-            if (pr) walk = false;
+            if (pr == 2 || (SPEC && ps.raw)) bad = true;          // (a speculative job also gives up on an escape partition)
+            if (pr || bad) walk = false;
         };
 #pragma unroll 1
         for (uint32_t s0 = 0; s0 < wmax_bs; s0 += 16) {
             if (walk) br.checkpoint();                            // one refill checkpoint per 16 samples (ParseBits::PERIOD_REACH)
             if (walk && ps.left == 0 && s0 >= ps.order && s0 < c.bs) next_param();
             if (__all_sync(FULL, !walk || ps.left >= 16)) {
-                parse_group<16>(br, ps, walk, bad, end_pos);      // the whole period in one branch-free group
+                parse_group<16, SPEC>(br, ps, walk, bad, end_pos);      // the whole period in one branch-free group
                 if (walk && br.pos > end_pos) { bad = true; walk = false; }     // ran past any possible end of the frame
                 if (walk && s0 + 16 >= c.bs) walk = false;
                 continue;
@@ -955,7 +758,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
 #pragma unroll 1
             for (uint32_t s1 = s0; s1 < s0 + 16; s1 += 8) {
                 if (s1 != s0 && walk && ps.left == 0 && s1 >= ps.order && s1 < c.bs) next_param();
-                if (__all_sync(FULL, !walk || ps.left >= 8)) parse_group<8>(br, ps, walk, bad, end_pos);
+                if (__all_sync(FULL, !walk || ps.left >= 8)) parse_group<8, SPEC>(br, ps, walk, bad, end_pos);
                 else {
 #pragma unroll 1
                     for (uint32_t j = 0; j < 8; j++) {
@@ -974,6 +777,16 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
             }
         }
         if (bad) fail = PF_EOS;
+    }
+    if (SPEC) {
+        // where the subframe ended (0: the guess did not parse, or ran out of the frame)
+        if (have_job) {
+            const uint64_t stop_bit = live ? br.abs_pos(a.in) - frame_bit0 : 0;
+            SpecJob& jb = a.spec_jobs[lane_id];
+            jb.end_bit = (live && fail == PF_NONE && br.abs_pos(a.in) <= end_bit) ? (uint32_t)stop_bit : 0u;
+            jb.si = spec_si;
+        }
+        return;
     }
     if (!live) return;
     // Outcome, in the reference's terms (oracle/flac_oracle.c decode_span).  The parse failed: nothing is delivered and the
@@ -1013,6 +826,188 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
         const uint32_t slot = atomicAdd(&a.counters[CNT_ANOM], 1u);
         if (slot < ANOM_CAP) a.anom[slot] = i;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ speculative parse
+// Streams of few, large frames (BASELINE cfg3: 7,000 frames of 8 x 16,384 samples).  k_parse finds where the subframes of
+// a frame start by walking them one after the other -- a serial chain of channels x blocksize codewords per frame that no
+// number of SMs shortens (4.5 ms for cfg3, with 97 % of the issue slots empty).  The walk of subframe c+1 could run beside
+// the walk of subframe c if only its start were known: so it is GUESSED, all guesses are walked in parallel (k_parse in job
+// mode), and a guess is kept only when the walk of the subframe before it ends exactly there -- channel 0's start is known,
+// so by induction every kept start is the true one, and the result is the serial parse's, bit for bit.  Frames whose
+// guesses do not chain up are simply left to the serial kernel.
+// The guess: an encoder that does not search per subframe (libFLAC without exhaustive model search, the corpus generator)
+// writes every subframe of a frame with the same header byte, quantisation precision, Rice method and partition order;
+// those 14 (FIXED) / 19 (LPC) bits, taken from subframe 0, are looked for around the place where subframe c would start
+// if all subframes were equally long.
+constexpr int SPEC_THREADS = 128;
+__device__ __forceinline__ uint32_t load_be32(const uint8_t* in, uint64_t word) { return __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(in) + word), 0, 0x0123); }
+// n <= 25 bits at absolute bit position `bit`, MSB first
+__device__ __forceinline__ uint32_t gbits(const uint8_t* in, uint64_t bit, uint32_t n) {
+    const uint64_t w = bit >> 5; const uint32_t sh = (uint32_t)bit & 31u;
+    return __funnelshift_l(load_be32(in, w + 1), load_be32(in, w), sh) >> (32u - n);
+}
+__device__ __forceinline__ uint32_t side_bit(uint32_t assign, uint32_t ch) { return ((assign == 8 && ch == 1) || (assign == 9 && ch == 0) || (assign == 10 && ch == 1)) ? 1u : 0u; }
+
+__global__ void __launch_bounds__(SPEC_THREADS) k_spec_find(PassArgs a) {
+    constexpr uint32_t SPEC_QUEUE = 2048;
+    __shared__ uint32_t s_n, s_seen, s_nq;
+    __shared__ uint32_t s_list[SPEC_MAX_PER_FRAME];
+    __shared__ uint32_t s_queue[SPEC_QUEUE];
+    const uint32_t n = ncand(a), i = blockIdx.x, tid = threadIdx.x;
+    if (i >= n) return;
+    if (tid == 0) { a.spec_count[i] = 0; a.spec_done[i] = 0; s_n = 0; s_seen = 0; s_nq = 0; }
+    const Cand c = a.cand[i];
+    const uint32_t C = c.assign < 8 ? c.assign + 1u : 2u;
+    if (a.status[i] != ST_OK || (c.flags & 2) || C < 3) return;          // (two channels: the only start to find is the last one, which needs no guess)
+    // subframe 0: the signature (every thread reads the same few words: broadcast from L2 / L1)
+    const uint64_t fb0 = c.off * 8;
+    const uint32_t start0 = 8u * c.hdr_len, end = a.flen[i] * 8u - 16u;          // frame-relative bits; `end`: where the CRC-16 starts
+    if (end <= start0 + 64u) return;
+    const uint32_t x = gbits(a.in, fb0 + start0, 8);
+    if (x & 0x81u) return;                                                      // pad bit / wasted bits: not guessed
+    const uint32_t type = (x >> 1) & 0x3fu;
+    const bool lpc = type >= 32;
+    if (!lpc && !(type >= 8 && type <= 12)) return;                             // CONSTANT / VERBATIM / reserved in front: serial
+    const uint32_t order = lpc ? type - 31u : type - 8u;
+    if (order > c.bs) return;
+    uint32_t q = start0 + 8u + order * (c.bps + side_bit(c.assign, 0));
+    uint32_t prec = 0;
+    if (lpc) { prec = gbits(a.in, fb0 + q, 4) + 1u; if (prec == 16) return; q += 9u + order * prec; }
+    if (q + 6u >= end) return;
+    const uint32_t tail0 = gbits(a.in, fb0 + q, 6);                             // Rice method (2) + partition order (4)
+    if (tail0 >= 32u) return;                                                   // reserved method
+    __syncthreads();
+    // Phase 1: every place in the windows where the header byte of subframe 0 shows up again (one in 256 positions) goes into a
+    // queue, four byte-aligned positions per test.  Phase 2: the queue is checked against the rest of the signature with all
+    // lanes busy -- done inside the scan loop, the rare hit made its whole warp wait.
+    const uint32_t avg = (end - start0) / C;
+    const uint32_t wd = 2048u + avg / 64u;
+    const uint32_t pat = x * 0x01010101u;
+    for (uint32_t ch = 1; ch + 1 < C; ch++) {          // the last subframe starts where the one before it ends and is not walked: no guess needed
+        const uint32_t f2 = 8u + order * (c.bps + side_bit(c.assign, ch)) + (lpc ? 9u + order * prec : 0u);
+        const uint32_t centre = start0 + (uint32_t)(((uint64_t)(end - start0) * ch) / C);
+        const uint32_t lo = max(start0 + 8u, centre > wd ? centre - wd : 0u), hi = min(end > f2 + 8u ? end - f2 - 8u : 0u, centre + wd);   // guesses in [lo, hi)
+        if (lo >= hi) continue;
+        const uint64_t A0 = fb0 + lo, A1 = fb0 + hi;                            // absolute bit positions
+        for (uint64_t w = (A0 >> 5) + tid; w <= ((A1 - 1) >> 5); w += SPEC_THREADS) {
+            const uint32_t w0 = load_be32(a.in, w), w1 = load_be32(a.in, w + 1);
+            uint32_t any = 0, zz[8];
+#pragma unroll
+            for (uint32_t sft = 0; sft < 8; sft++) {
+                const uint32_t v = __funnelshift_l(w1, w0, sft) ^ pat;          // bytes at bit positions 32 w + sft + 8 j
+                zz[sft] = (v - 0x01010101u) & ~v & 0x80808080u;                // a zero byte (may also flag the byte above one)
+                any |= zz[sft];
+            }
+            if (!any) continue;
+#pragma unroll
+            for (uint32_t sft = 0; sft < 8; sft++) {
+                uint32_t z = zz[sft];
+                while (z) {
+                    const uint32_t b = 31u - (uint32_t)__clz(z);               // bit 8 (3 - j) + 7
+                    z &= ~(1u << b);
+                    const uint64_t pa = (w << 5) + sft + 8u * (3u - (b >> 3));
+                    if (pa < A0 || pa >= A1) continue;
+                    const uint32_t slot = atomicAdd(&s_nq, 1u);
+                    if (slot < SPEC_QUEUE) s_queue[slot] = (ch << 28) | (uint32_t)(pa - fb0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t nq = s_nq;
+    if (nq > SPEC_QUEUE) return;                                                // a window full of look-alikes: serial
+    for (uint32_t e = tid; e < nq; e += SPEC_THREADS) {
+        const uint32_t v = s_queue[e], ch = v >> 28;
+        const uint64_t pa = fb0 + (v & 0x0FFFFFFFu);
+        const uint32_t f1 = 8u + order * (c.bps + side_bit(c.assign, ch)), f2 = f1 + (lpc ? 9u + order * prec : 0u);
+        if (gbits(a.in, pa, 8) != x) continue;                                  // (the zero-byte test over-reports)
+        if (lpc && gbits(a.in, pa + f1, 5) != ((prec - 1u) << 1)) continue;     // precision, and a shift that is not negative
+        if (gbits(a.in, pa + f2, 6) != tail0) continue;
+        const uint32_t slot = atomicAdd(&s_n, 1u);
+        if (slot < SPEC_MAX_PER_FRAME - 1u) s_list[slot] = v;
+        atomicOr(&s_seen, 1u << ch);
+    }
+    __syncthreads();
+    __shared__ uint32_t s_base;
+    const uint32_t cnt = s_n;
+    if (cnt > SPEC_MAX_PER_FRAME - 1u || s_seen != ((1u << (C - 1u)) - 2u)) return;      // too many look-alikes, or a channel without any guess
+    if (tid == 0) s_base = atomicAdd(&a.counters[CNT_SPEC], cnt + 1u);
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (base + cnt + 1u > a.spec_cap) return;
+    for (uint32_t e = tid; e <= cnt; e += SPEC_THREADS) {
+        SpecJob jb;
+        jb.frame = i; jb.end_bit = 0; jb.si.bit_offset = 0; jb.si.type = 0; jb.si.order = 0; jb.si.wasted = 0; jb.si.flags = 0;
+        if (e == 0) { jb.start_bit = start0; jb.ch = 0; }
+        else { const uint32_t v = s_list[e - 1]; jb.start_bit = v & 0x0FFFFFFFu; jb.ch = v >> 28; }
+        a.spec_jobs[base + e] = jb;
+    }
+    if (tid == 0) { a.spec_base[i] = base; a.spec_count[i] = (uint8_t)(cnt + 1u); }
+}
+
+// What k_parse records for a subframe it does not walk (the last one of a CRC-validated frame), read straight from the
+// stream; false for anything the serial walk should see for itself (wasted bits, reserved or inconsistent fields).
+__device__ bool peek_subframe(const uint8_t* in, uint64_t frame_bit0, uint32_t start, uint32_t end, uint32_t bps, uint32_t bs, SubInfo& si) {
+    si.bit_offset = start; si.type = 0; si.order = 0; si.wasted = 0; si.flags = 0;
+    if (start + 8u + bps > end) return false;
+    const uint32_t x = gbits(in, frame_bit0 + start, 8);
+    if (x & 0x81u) return false;
+    const uint32_t type = (x >> 1) & 0x3fu;
+    if (type == 0) return true;
+    if (type == 1) { si.type = 1; return (uint64_t)start + 8u + (uint64_t)bs * bps <= end; }
+    uint32_t order, q;
+    if (type >= 8 && type <= 12) { si.type = 2; order = type - 8u; si.flags = 1; q = start + 8u + order * bps; }
+    else if (type >= 32) {
+        si.type = 3; order = type - 31u;
+        q = start + 8u + order * bps;
+        if (order > bs || q + 9u >= end) return false;
+        const uint32_t prec = gbits(in, frame_bit0 + q, 4) + 1u;
+        if (prec == 16) return false;
+        if (bps + prec + (uint32_t)ilog2u(order) <= 32) si.flags = 1;
+        q += 9u + order * prec;
+    } else return false;
+    si.order = (uint8_t)order;
+    if (order > bs || q + 6u > end) return false;
+    const uint32_t tail = gbits(in, frame_bit0 + q, 6), po = tail & 15u;
+    if (tail >= 32u) return false;
+    if (tail & 16u) si.flags |= 2;
+    const uint32_t psize = po ? bs >> po : bs;
+    return psize != 0 && psize >= order;
+}
+
+// keeps the guesses that chain up: subframe c + 1 starts where the walk of subframe c ended
+__global__ void __launch_bounds__(128) k_spec_resolve(PassArgs a) {
+    const uint32_t n = ncand(a);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cnt = a.spec_count[i];
+    if (!cnt) return;
+    const uint32_t base = a.spec_base[i];
+    const Cand c = a.cand[i];
+    const uint32_t C = c.assign < 8 ? c.assign + 1u : 2u;
+    SubInfo sub[MAX_CH];
+    uint32_t e = a.spec_jobs[base].end_bit;
+    if (!e) return;
+    sub[0] = a.spec_jobs[base].si;
+    for (uint32_t ch = 1; ch + 1 < C; ch++) {
+        uint32_t hit = 0;
+        for (uint32_t k = 1; k < cnt; k++) { const SpecJob& jb = a.spec_jobs[base + k]; if (jb.ch == ch && jb.start_bit == e && jb.end_bit) { hit = k; break; } }
+        if (!hit) return;                                                          // not guessed (or the guess did not parse): the serial walk takes the frame
+        sub[ch] = a.spec_jobs[base + hit].si;
+        e = a.spec_jobs[base + hit].end_bit;
+    }
+    if (!peek_subframe(a.in, c.off * 8, e, a.flen[i] * 8u - 16u, c.bps + side_bit(c.assign, C - 1u), c.bs, sub[C - 1u])) return;
+    uint32_t max_order = 0, any_wide = 0;
+    for (uint32_t ch = 0; ch < C; ch++) {
+        a.sub[(uint64_t)i * MAX_CH + ch] = sub[ch];
+        if (sub[ch].type >= 2) max_order = max(max_order, (uint32_t)sub[ch].order);
+        if (sub[ch].type == 3 && !(sub[ch].flags & 1)) any_wide = 1;
+    }
+    if (max_order) atomicMax(&a.totals->max_order, max_order);
+    if (any_wide) atomicOr(&a.totals->any_wide, 1u);
+    a.spec_done[i] = 1;
+    atomicAdd(&a.counters[CNT_SPEC_DONE], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ resync
@@ -1163,435 +1158,13 @@ __global__ void __launch_bounds__(256) k_seg_summary(PassArgs a, uint64_t* seg_p
     else if (st == ST_UNPARSEABLE) atomicOr(&seg_flags[sg], 8u);
 }
 
-// ------------------------------------------------------------------------------------------------ K3-5 decode
-// One lane per (frame, channel); a warp (= one CTA) owns 32/C frames and works tile by tile (T samples per channel):
-//   Rice phase     each lane decodes its next T residuals into its own column of the shared-memory tile.  Groups of 8
-//                  codewords take a branch-free path (window, bfind, shift, one IMAD, zig-zag; an overflow flag instead
-//                  of a branch) whenever every lane has 8 codewords left in its partition; warm-up samples, partition
-//                  tails, escape partitions and VERBATIM subframes take the careful per-sample path.
-//   restore phase  each lane runs the FIXED/LPC recurrence over its column in place.  Coefficients and the last ORD
-//                  samples stay in registers; the loop is unrolled ORD times so every tap has a fixed register.
-//                  16-bit streams accumulate in 32-bit IMADs.  Streams that need libFLAC's 64-bit accumulator use the FP64
-//                  pipe instead: every product and partial sum is an integer below 2^53, so DFMA is exact, the
-//                  quantisation shift is folded into the coefficients (a power of two), floor() is one round-down add of
-//                  1.5*2^52, and the FP64 pipe runs beside the integer pipes the Rice phase of the other warps keeps busy.
-//   pack phase     the warp re-reads the tile row-wise (interleaved order), applies left/side, side/right, mid/side
-//                  decorrelation to stereo pairs and writes packed little-endian 8/16/24-bit PCM, 4 samples per lane.
-// Tile layout: sample t of lane l at word t*S + l, S = 32 + pad chosen so that both the column accesses of the first two
-// phases and the vector row reads of the pack phase are bank-conflict free.
-enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
-
-#ifndef DEC_MAXNREG
-#define DEC_MAXNREG 120
-#endif
-#ifndef DEC_TILE
-#define DEC_TILE 48
-#endif
-
-template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : DEC_TILE; };
-
-struct RiceSt {
-    uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
-    bool first;
-};
-
-template <class BR>
-__device__ __forceinline__ void rice_param(BR& br, RiceSt& rs) {
-#pragma unroll 1
-    for (int guard = 0; guard < 2; guard++) {
-        const uint32_t cnt = rs.psize - (rs.first ? rs.order : 0);
-        rs.first = false;
-        const uint32_t k = br.get(rs.plen);
-        if (k == (rs.plen == 5 ? 31u : 15u)) { rs.rawbits = br.get(5); rs.rawleft = cnt; rs.fastleft = 0; }
-        else { rs.fastleft = cnt; rs.rawleft = 0; rs.k = k; rs.kp32 = k + 32u; rs.negP = 0u - (1u << k); rs.c30 = 30u << k; }
-        if (cnt) break;
-    }
-}
-
-// ---- restore: one block of ORD samples of this lane's column, in place
-// `h` is a ring: before a block that starts at sample t0, h[j] holds sample t0 - ORD + j; step j reads every tap from a
-// fixed register and then overwrites h[j] (whose old value, the oldest sample, was used for the last time in that step).
-template <int ORD, bool FIRST, bool EXTRA>
-__device__ __forceinline__ void restore_block_i32(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
-                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
-#pragma unroll
-    for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
-        uint32_t sum = 0;
-#pragma unroll
-        for (int m = ORD - 1; m >= 0; m--) sum += (uint32_t)cf[m] * (uint32_t)h[(j - 1 - m + 2 * ORD) % ORD];
-        int32_t s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
-        if (FIRST) { if (j < (int)order) s = r; }
-        h[j] = s;
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
-        else sts32(addr + j * rs4, (uint32_t)s);
-    }
-}
-
-template <int ORD, bool FIRST, bool EXTRA>
-__device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, const double (&cf)[ORD], double (&h)[ORD],
-                                                  uint32_t order, uint32_t sh_n, uint32_t wasted) {
-#pragma unroll
-    for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-        for (int m = ORD - 1; m >= 0; m--) {
-            const double hv = h[(j - 1 - m + 2 * ORD) % ORD];
-            if (ORD > 16 && (m & 1)) acc1 = fma(cf[m], hv, acc1);
-            else acc0 = fma(cf[m], hv, acc0);
-        }
-        if (ORD > 16) acc0 += acc1;                                       // exact: integers (scaled by 2^-shift) below 2^53
-        const double y = __dadd_rd(acc0, 6755399441055744.0);            // + 1.5*2^52, rounded down: low word = floor(acc) mod 2^32
-        int32_t p = __double2loint(y);
-        if (EXTRA) p >>= sh_n;
-        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
-        if (FIRST) { if (j < (int)order) s = r; }
-        h[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
-        else sts32(addr + j * rs4, (uint32_t)s);
-    }
-}
-
-// 64-bit integer accumulation (mad.wide.s32): int32 coefficients and history, half the registers of the FP64 form.
-// `wasted` carries the per-lane "narrow" flag in bit 31 (EXTRA only): narrow LPC subframes wrap at 32 bits before the shift.
-template <int ORD, bool FIRST, bool EXTRA>
-__device__ __forceinline__ void restore_block_i64(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
-                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
-#pragma unroll
-    for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
-        long long acc = 0;
-#pragma unroll
-        for (int m = ORD - 1; m >= 0; m--) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(cf[m]), "r"(h[(j - 1 - m + 2 * ORD) % ORD]));
-        const uint32_t lo = (uint32_t)acc, hi = (uint32_t)((unsigned long long)acc >> 32);
-        int32_t p = (int32_t)__funnelshift_r(lo, hi, shift);               // shift < 32
-        if (EXTRA) { if (wasted & 0x80000000u) p = (int32_t)lo >> shift; }
-        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
-        if (FIRST) { if (j < (int)order) s = r; }
-        h[j] = s;
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << (wasted & 31u));
-        else sts32(addr + j * rs4, (uint32_t)s);
-    }
-}
-
-#ifndef DEC_WIDE_I64
-#define DEC_WIDE_I64 0
-#endif
-template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
-__device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const TT (&cf)[ORD], TT (&h)[ORD], uint32_t order, uint32_t shift, uint32_t wasted) {
-    if constexpr (WIDE && DEC_WIDE_I64) restore_block_i64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
-    else if constexpr (WIDE) restore_block_f64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
-    else restore_block_i32<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
-}
-
-// ---- pack: 16 consecutive samples (interleaved order) of one frame per lane -> B 16-byte stores
-__device__ __forceinline__ void pack4(uint32_t* dw, uint32_t B, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
-    if (B == 3) { dw[0] = __byte_perm(v0, v1, 0x4210); dw[1] = __byte_perm(v1, v2, 0x5421); dw[2] = __byte_perm(v2, v3, 0x6542); }
-    else if (B == 2) { dw[0] = __byte_perm(v0, v1, 0x5410); dw[1] = __byte_perm(v2, v3, 0x5410); }
-    else dw[0] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
-}
-// stereo decorrelation of one (ch0, ch1) pair.  mid/side: with m' = 2M + (S&1), L = (m'+S)>>1 = R + S and
-// R = (m'-S)>>1 = M - (S>>1) (identical in every bit that reaches the output, also when the int32 arithmetic wraps).
-__device__ __forceinline__ void decorr(uint32_t assign, uint32_t& x, uint32_t& y) {
-    if (assign == 10) { const uint32_t r = x - (uint32_t)((int32_t)y >> 1); x = r + y; y = r; }
-    else if (assign == 8) y = x - y;
-    else if (assign == 9) x = x + y;
-}
-
-__device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32_t C, uint32_t B, uint32_t F, uint32_t i0, uint32_t T,
-                                          uint32_t ftab, uint8_t* __restrict__ out, uint32_t lane) {
-    const uint32_t upf = (T * C) >> 4;                 // units of 16 samples per frame-tile (T is a multiple of 16)
-    const uint32_t total = F * upf;
-    const uint32_t rcp_upf = 65536u / upf + 1u;        // g / upf for g < 2^9
-    const uint32_t rcp_c = 65536u / C + 1u;
-    for (uint32_t g = lane; g < total; g += 32) {
-        const uint32_t f = (g * rcp_upf) >> 16, u = g - f * upf;
-        const uint32_t bs = lds32(ftab + 4 * f);
-        if (i0 >= bs) continue;
-        const uint32_t nt = min(T, bs - i0), nsamp = nt * C, q0 = 16 * u;
-        if (q0 >= nsamp) continue;
-        const uint32_t assign = lds32(ftab + 128 + 4 * f);
-        const uint2 pol = lds64(ftab + 256 + 8 * f);
-        uint8_t* dst = out + (((uint64_t)pol.y << 32) | pol.x) + ((uint64_t)i0 * C + q0) * B;
-        uint32_t v[16];
-        const uint32_t fbase = tile_base + 4 * f * C;
-        if (C == 2) {
-            const uint32_t ad = fbase + 4 * (q0 >> 1) * S;
-#pragma unroll
-            for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
-            if (assign >= 8) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) decorr(assign, v[2 * e], v[2 * e + 1]);
-            }
-        } else if (C == 1) {
-#pragma unroll
-            for (int e = 0; e < 16; e++) v[e] = lds32(fbase + 4 * (q0 + e) * S);
-        } else if (C == 4) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * ((q0 >> 2) + e) * S); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
-        } else if (C == 8) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * ((q0 >> 3) + (e >> 1)) * S + 16 * (e & 1)); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
-        } else {
-            uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
-            uint32_t ad = fbase + 4 * (t * S + c);
-            const uint32_t wrap = 4 * (S - C);
-#pragma unroll
-            for (int e = 0; e < 16; e++) { v[e] = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; } }
-        }
-        if (q0 + 16 <= nsamp && (((uintptr_t)dst) & 15u) == 0) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-            if (B == 3) {
-#pragma unroll
-                for (int e = 0; e < 3; e++) {       // 16 samples x 3 bytes = 12 words: word j holds bytes 4j..4j+3
-                    uint32_t w[4];
-#pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        const int j = 4 * e + x, q = (4 * j) / 3, r = (4 * j) % 3;
-                        w[x] = r == 0 ? __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x4210) : r == 1 ? __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x5421) : __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x6542);
-                    }
-                    d4[e] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            } else if (B == 2) {
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-                    d4[e] = make_uint4(__byte_perm(v[8 * e], v[8 * e + 1], 0x5410), __byte_perm(v[8 * e + 2], v[8 * e + 3], 0x5410),
-                                       __byte_perm(v[8 * e + 4], v[8 * e + 5], 0x5410), __byte_perm(v[8 * e + 6], v[8 * e + 7], 0x5410));
-            } else {
-                uint32_t w[4];
-#pragma unroll
-                for (int x = 0; x < 4; x++) w[x] = __byte_perm(__byte_perm(v[4 * x], v[4 * x + 1], 0x0040), __byte_perm(v[4 * x + 2], v[4 * x + 3], 0x0040), 0x5410);
-                d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        } else {
-            const uint32_t nv = min(16u, nsamp - q0);
-#pragma unroll
-            for (uint32_t e = 0; e < 16; e += 4) {
-                if (e + 4 <= nv && (((uintptr_t)dst) & 3u) == 0) pack4(reinterpret_cast<uint32_t*>(dst + e * B), B, v[e], v[e + 1], v[e + 2], v[e + 3]);
-                else {
-#pragma unroll
-                    for (uint32_t x = 0; x < 4; x++)
-                        if (e + x < nv) for (uint32_t b = 0; b < B; b++) dst[(e + x) * B + b] = (uint8_t)(v[e + x] >> (8 * b));
-                }
-            }
-        }
-    }
-}
-
-#ifndef DEC_WARPS_N
-#define DEC_WARPS_N 2
-#endif
-constexpr int DEC_WARPS = DEC_WARPS_N;        // independent warps per CTA (no CTA-wide barrier anywhere)
-__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
-
-// SPEC: 0 = any channel count / sample width (run-time C, B, S); else 4 C + B: the common formats get C, B and the tile
-// stride S as compile-time constants (tile addresses become immediates, lane -> (frame, channel) is a shift, the pack
-// phase loses its format dispatch): measured 2.10 -> 1.93 ms on the 1 h 24-bit stereo stream
-#ifndef DEC_SPECIALISE
-#define DEC_SPECIALISE 1
-#endif
-__host__ __device__ constexpr uint32_t dec_tile_stride(uint32_t C) { return 32u + ((C & 3u) == 0 ? 4u : (C & 1u) == 0 ? 2u : 1u); }
-template <int ORD, bool WIDE, int SPEC>
-__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : 255) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_) {
-    constexpr int T = DecCfg<ORD>::T;
-    const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2) : S_;
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t ring_base = smem_u32(s_dyn) + wib * dec_warp_smem(T, S);
-    const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
-    const uint32_t ftab = tile_base + T * S * 4;               // bs[32] | assign[32] | pcm offset[32] (u64)
-    const uint32_t F = 32 / C;
-    const uint32_t n_acc = a.totals->n_accepted;
-    const uint32_t fl = lane / C, ch = lane - fl * C;
-    const uint32_t kf = (blockIdx.x * DEC_WARPS + wib) * F + fl;
-    const bool active = fl < F && kf < n_acc;
-    const uint32_t rs4 = S * 4;
-    const uint32_t col = tile_base + lane * 4;
-
-    // ---- per-subframe state (registers)
-    DecRing<ORD> br;
-    br.init_idle(ring_base + lane * RingBits::STRIDE, a.in);
-    constexpr bool F64 = WIDE && !DEC_WIDE_I64;       // FP64-pipe accumulation (coefficients scaled by 2^-shift) vs mad.wide.s32
-    typename std::conditional<F64, double, int32_t>::type cf[ORD], hist[ORD];
-#pragma unroll
-    for (int j = 0; j < ORD; j++) { cf[j] = 0; hist[j] = 0; }
-    RiceSt rs;
-    rs.fastleft = 0; rs.rawleft = 0; rs.rawbits = 0; rs.k = 0; rs.kp32 = 32; rs.negP = ~0u; rs.c30 = 30; rs.psize = 0; rs.plen = 4; rs.order = 0; rs.first = true;
-    uint32_t bs = 0, assign = 0, wasted = 0, shift = 0, bps = 0;
-    int mode = M_IDLE;
-    if (fl < F && ch == 0) { sts32(ftab + 4 * fl, 0); sts32(ftab + 128 + 4 * fl, 0); }
-    if (active) {
-        const uint32_t i = a.acc_idx[kf];
-        const Cand c = a.cand[i];
-        bs = c.bs; assign = c.assign;
-        bool ok = a.status[i] == ST_OK;
-        const uint64_t po = a.pcm_off[i];
-        if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
-        if (ch == 0) { sts32(ftab + 4 * fl, bs); sts32(ftab + 128 + 4 * fl, assign); sts32(ftab + 256 + 8 * fl, (uint32_t)po); sts32(ftab + 260 + 8 * fl, (uint32_t)(po >> 32)); }
-        int32_t cval = 0;
-        mode = M_CONST;                              // damaged frames (CRC mismatch) are delivered zero-filled
-        if (ok) {
-            const SubInfo si = a.sub[(uint64_t)i * MAX_CH + ch];
-            br.init(ring_base + lane * RingBits::STRIDE, a.in, a.in_len, c.off * 8 + si.bit_offset);
-            uint32_t x = br.get(8);
-            if (x & 1) { br.unary(64); br.ensure_now(); }
-            const uint32_t order = si.order;
-            wasted = si.wasted;
-            bps = (uint32_t)c.bps + (((assign == 8 && ch == 1) || (assign == 9 && ch == 0) || (assign == 10 && ch == 1)) ? 1u : 0u) - wasted;
-            if (si.type == 0) cval = br.gets(bps);
-            else if (si.type == 1) mode = M_VERBATIM;
-            else {
-                mode = M_PRED;
-                rs.order = order;
-                // warm-up samples are parked in this lane's tile rows 0..order-1 (order <= 32 <= T)
-#pragma unroll 1
-                for (uint32_t j = 0; j < order; j++) { sts32(col + j * rs4, (uint32_t)br.gets(bps)); if ((j & 7) == 7) br.ensure_now(); }
-                br.ensure_now();
-                bool narrow = true;
-                if (si.type == 3) {
-                    const uint32_t prec = br.get(4) + 1;
-                    { const int32_t sh = br.gets(5); shift = sh < 0 ? 0u : (uint32_t)sh; }   // negative: not an error in libFLAC 1.2.1 (never emitted)
-                    narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
-                    // libFLAC 1.2.1 width rule: narrow subframes accumulate in 32 bits (wrap), the others in 64
-                    const double scale = (F64 && !narrow) ? __hiloint2double((int)((1023u - shift) << 20), 0) : 1.0;
-#pragma unroll
-                    for (int j = 0; j < ORD; j++) if (j < (int)order) {
-                        const int32_t q = br.gets(prec);
-                        if constexpr (F64) cf[j] = (double)q * scale; else cf[j] = q;
-                        if ((j & 7) == 7) br.ensure_now();
-                    }
-                    br.ensure_now();
-                    if (F64 && !narrow) shift = 0;           // folded into the coefficients
-                    if (WIDE && !F64 && narrow && shift) wasted |= 0x80000000u;    // 32-bit wrap before the shift (restore_block_i64)
-                } else {   // FIXED predictors as coefficient sets, 32-bit wrap-around arithmetic
-                    const int o = (int)order;
-                    if (ORD >= 1 && o >= 1) cf[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
-                    if (ORD >= 2 && o >= 2) cf[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
-                    if (ORD >= 3 && o >= 3) cf[2] = o == 3 ? 1 : 4;
-                    if (ORD >= 4 && o >= 4) cf[3] = -1;
-                }
-                const uint32_t method = br.get(2);
-                rs.plen = method ? 5 : 4;
-                const uint32_t porder = br.get(4);
-                rs.psize = porder ? bs >> porder : bs;
-                br.ensure_now();
-            }
-        }
-        if (mode == M_CONST) {                        // column holds the final value once and for all (restore leaves it unchanged)
-            const uint32_t v = (uint32_t)cval << wasted;
-            wasted = 0;
-#pragma unroll 1
-            for (uint32_t t = 0; t < (uint32_t)T; t++) sts32(col + t * rs4, v);
-        }
-    }
-    __syncwarp();
-    const uint32_t maxbs = __reduce_max_sync(FULL, bs);
-    const bool reads = mode >= M_VERBATIM;
-    const bool extra = __any_sync(FULL, wasted != 0 || (F64 && shift != 0));
-    const uint32_t order = rs.order;
-#pragma unroll 1
-    for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
-        // ---- Rice phase
-#pragma unroll 1
-        for (uint32_t t0 = 0, row = col; t0 < (uint32_t)T; t0 += 8, row += 8 * rs4) {      // row: loop-carried, or it is rematerialised from SR_TID every step
-            const uint32_t idx0 = i0 + t0;
-            if (reads && (DEC_RING_BLOCKS < 16 || !(t0 & 8u))) br.checkpoint();
-            const bool inert = mode <= M_CONST || idx0 >= bs;
-            if (mode == M_PRED && !inert && rs.fastleft == 0 && rs.rawleft == 0 && idx0 >= order) rice_param(br, rs);
-            const bool fast_ok = inert || (mode == M_PRED && rs.fastleft >= 8);
-            // branch-free group of 8 Rice codewords; `commit`: this lane is really in a Rice partition with >= 8 left
-            auto rice_group = [&](const bool commit) {
-                uint32_t pos = br.pos;
-                const uint32_t k = rs.k, kp32 = rs.kp32, negP = rs.negP, c30 = rs.c30;
-                bool ovf = false;
-                int32_t r[8];
-                typename DecRing<ORD>::Win3 wn = br.win_init(pos);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t nxt = j < 7 ? br.win_next(pos) : 0u;
-                    const uint32_t w = DecRing<ORD>::win_peek(wn, pos);
-                    const uint32_t f = bfind(w);
-                    const uint32_t d = f - k;
-                    ovf |= (int32_t)d < 0;
-                    const uint32_t np = pos + kp32 - f;
-                    if (j < 7) DecRing<ORD>::win_advance(wn, pos, np, nxt);
-                    pos = np;
-                    const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
-                    r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                }
-                if (commit) {
-                    rs.fastleft -= 8;
-                    if (!ovf) {
-                        br.pos = pos;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)r[j]);
-                    } else {             // a codeword longer than one window (rare): redo the group carefully
-#pragma unroll 1
-                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.rice_careful(k));
-                    }
-                }
-            };
-            if (__all_sync(FULL, fast_ok)) rice_group(!inert);
-            else {
-                // lanes that read fixed-width samples for the whole step (VERBATIM subframes, escape partitions): when they are
-                // the only reason the step is not uniform, the Rice lanes keep their branch-free group and these lanes read
-                // their 8 samples in a short loop of their own -- instead of a careful walk of every lane
-                const bool rawlane = !inert && ((mode == M_VERBATIM && idx0 + 8 <= bs) || (mode == M_PRED && rs.rawleft >= 8));
-                if (__all_sync(FULL, fast_ok || rawlane)) {
-                    rice_group(!inert && !rawlane);
-                    if (rawlane) {
-                        const uint32_t nb = mode == M_VERBATIM ? bps : rs.rawbits;
-                        if (mode == M_PRED) rs.rawleft -= 8;
-#pragma unroll 1
-                        for (uint32_t j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.gets(nb));
-                    }
-                } else {
-#pragma unroll 1
-                    for (uint32_t j = 0; j < 8; j++) {
-                        const uint32_t idx = idx0 + j;
-                        if (mode <= M_CONST || idx >= bs) continue;
-                        int32_t v;
-                        if (mode == M_VERBATIM) v = br.gets(bps);
-                        else {
-                            if (idx < order) continue;               // parked warm-up sample
-                            if (rs.fastleft == 0 && rs.rawleft == 0) rice_param(br, rs);
-                            if (rs.rawleft) { rs.rawleft--; v = br.gets(rs.rawbits); }
-                            else { rs.fastleft--; v = br.rice_careful(rs.k); }
-                        }
-                        sts32(row + j * rs4, (uint32_t)v);
-                    }
-                }
-            }
-        }
-        // ---- restore phase (own column only: no warp synchronisation needed before it)
-        if (i0 == 0) {
-            if (extra) restore_block<ORD, WIDE, true, true>(col, rs4, cf, hist, order, shift, wasted);
-            else restore_block<ORD, WIDE, true, false>(col, rs4, cf, hist, order, shift, wasted);
-        }
-        if (extra) {
-#pragma unroll 1
-            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, true>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
-        } else {
-#pragma unroll 1
-            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, false>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
-        }
-        __syncwarp();
-        // ---- pack phase
-        pack_tile(tile_base, S, C, B, F, i0, T, ftab, a.out, lane);
-        __syncwarp();
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ launchers
-static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
-static inline uint32_t blocks_for(uint64_t n, uint32_t per) { uint64_t b = (n + per - 1) / per; return (uint32_t)(b ? b : 1); }
 
 // Function attributes (opt-in shared memory) and the SM count belong to a DEVICE, and one process may hold handles on
 // several (bnflac_opts.device): both are looked up / set per current device, once per (kernel, device).
 constexpr int MAX_DEVICES = 64;
 static int current_device() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0; return dev; }
-static int sm_count() {
+int sm_count() {
     static std::atomic<int> n_sm[MAX_DEVICES];
     const int dev = current_device();
     int n = n_sm[dev].load(std::memory_order_relaxed);
@@ -1604,7 +1177,7 @@ static int sm_count() {
     return n;
 }
 // true exactly once per device for the caller's `done` bitmask (idempotent work: a race only repeats it)
-static bool first_use_on_device(std::atomic<uint64_t>& done) {
+bool first_use_on_device(std::atomic<uint64_t>& done) {
     const uint64_t bit = 1ull << current_device();
     if (done.load(std::memory_order_acquire) & bit) return false;
     done.fetch_or(bit, std::memory_order_acq_rel);
@@ -1618,7 +1191,7 @@ void launch_scan(const PassArgs& a, void* stream) {
     uint32_t grid = (a.nchunks + SC_WARPS - 1) / SC_WARPS;
     if (grid > (uint32_t)n_sm) grid = (uint32_t)n_sm;
     if (!grid) grid = 1;
-    k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); g_launches++;
+    k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); count_launch();
 }
 void launch_order(const PassArgs& a, void* stream) {
     const int n_sm = sm_count();
@@ -1627,107 +1200,57 @@ void launch_order(const PassArgs& a, void* stream) {
     per = (per + ORD_THREADS - 1) / ORD_THREADS * ORD_THREADS;
     if (!per) per = ORD_THREADS;
     const uint32_t grid = a.nchunks ? (a.nchunks + per - 1) / per : 1;
-    k_order<<<grid, ORD_THREADS, 0, S(stream)>>>(a, per, blk_tot); g_launches++;
+    k_order<<<grid, ORD_THREADS, 0, S(stream)>>>(a, per, blk_tot); count_launch();
 }
 void launch_crc(const PassArgs& a, uint32_t nb, void* stream) {
-    k_crc<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
+    k_crc<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); count_launch();
 }
 void launch_link(const PassArgs& a, uint32_t nb, void* stream) {
-    k_link<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
-    k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); g_launches++;
+    k_link<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); count_launch();
+    k_cover<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a); count_launch();
+}
+// fewer than two warps of frame lanes per scheduler: the walk is latency-bound
+static bool few_frames(uint32_t nb) { return nb < (uint32_t)sm_count() * 4u * 2u * 32u; }
+bool parse_wants_speculation(uint32_t nb, uint32_t channels) {
+    const char* force = getenv("BNFLAC_PARSE_SPEC");            // 0 / 1 forces it off / on (the tests run both on the same streams)
+    if (force) return force[0] == '1' && channels >= 3;
+    return channels >= 3 && few_frames(nb);
 }
 void launch_parse(const PassArgs& a, uint32_t nb, void* stream) {
-    // fewer than two warps per scheduler: the walk is latency-bound and its branches are what it waits for
-    // (BNFLAC_PARSE_LEAN=0/1 forces one variant: the tests run both on the same streams)
+    // few frames: branches and divergent loops are what a lone warp waits for (BNFLAC_PARSE_LEAN=0/1 forces one variant)
     const char* force = getenv("BNFLAC_PARSE_LEAN");
-    const bool lean = force ? force[0] == '1' : nb < (uint32_t)sm_count() * 4u * 2u * 32u;
-    if (lean) k_parse<true><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
-    else k_parse<false><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, PARSE_THREADS * ParseBits::STRIDE, S(stream)>>>(a);
-    g_launches++;
+    const bool lean = force ? force[0] == '1' : few_frames(nb);
+    const size_t smem = PARSE_THREADS * ParseBits::STRIDE;
+    if (a.spec_jobs) {
+        // guessed subframe starts, all walked at once; what chains up is final, the rest falls through to the serial walk below
+        k_spec_find<<<nb ? nb : 1, SPEC_THREADS, 0, S(stream)>>>(a); count_launch();
+        const uint32_t jb = blocks_for(a.spec_cap, PARSE_THREADS);
+        if (lean) k_parse<true, true><<<jb, PARSE_THREADS, smem, S(stream)>>>(a); else k_parse<false, true><<<jb, PARSE_THREADS, smem, S(stream)>>>(a);
+        count_launch();
+        k_spec_resolve<<<blocks_for(nb, 128), 128, 0, S(stream)>>>(a); count_launch();
+    }
+    if (lean) k_parse<true, false><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, smem, S(stream)>>>(a);
+    else k_parse<false, false><<<blocks_for(nb, PARSE_THREADS), PARSE_THREADS, smem, S(stream)>>>(a);
+    count_launch();
 }
-void launch_resync(const PassArgs& a, void* stream) { k_resync<<<1, 256, 0, S(stream)>>>(a); g_launches++; }
+void launch_resync(const PassArgs& a, void* stream) { k_resync<<<1, 256, 0, S(stream)>>>(a); count_launch(); }
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream) {
     const int n_sm = sm_count();
     uint32_t per = (ncand_bound + n_sm - 1) / n_sm;
     per = (per + ORD_THREADS - 1) / ORD_THREADS * ORD_THREADS;
     if (!per) per = ORD_THREADS;
     const uint32_t grid = ncand_bound ? (ncand_bound + per - 1) / per : 1;
-    k_prefix<<<grid, ORD_THREADS, 0, S(stream)>>>(a, bytes_per_sample, per, a.counters + CNT_PFX_CNT, reinterpret_cast<unsigned long long*>(a.counters + CNT_PFX_BYTES)); g_launches++;
+    k_prefix<<<grid, ORD_THREADS, 0, S(stream)>>>(a, bytes_per_sample, per, a.counters + CNT_PFX_CNT, reinterpret_cast<unsigned long long*>(a.counters + CNT_PFX_BYTES)); count_launch();
 }
 void launch_make_chunks(const SegInfo& seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks, void* stream) {
-    k_make_chunks<<<blocks_for(std::max<uint32_t>(nchunks, 1u), 256), 256, 0, S(stream)>>>(seg, d_seg, chunks, nchunks); g_launches++;
+    k_make_chunks<<<blocks_for(std::max<uint32_t>(nchunks, 1u), 256), 256, 0, S(stream)>>>(seg, d_seg, chunks, nchunks); count_launch();
 }
-void launch_clear(const PassArgs& a, void* stream) { k_clear<<<1, 256, 0, S(stream)>>>(a.counters, a.totals); g_launches++; }
+void launch_clear(const PassArgs& a, void* stream) { k_clear<<<1, 256, 0, S(stream)>>>(a.counters, a.totals); count_launch(); }
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream) {
-    k_publish<<<1, 32, 0, S(stream)>>>((const uint32_t*)src, (uint32_t*)dst_mapped, nwords); g_launches++;
+    k_publish<<<1, 32, 0, S(stream)>>>((const uint32_t*)src, (uint32_t*)dst_mapped, nwords); count_launch();
 }
 void launch_seg_summary(const PassArgs& a, uint32_t nb, uint64_t* seg_pcm, uint32_t* seg_flags, void* stream) {
-    k_seg_summary<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a, seg_pcm, seg_flags); g_launches++;
-}
-template <int ORD, bool WIDE, int SPEC>
-static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st);
-template <int ORD, bool WIDE>
-static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
-    const uint32_t key = DEC_SPECIALISE ? 4 * C + B : 0;
-    switch (key) {
-#if DEC_SPECIALISE
-    case 4 * 1 + 2: launch_decode_s<ORD, WIDE, 4 * 1 + 2>(a, nacc, C, B, st); break;     // mono 16-bit
-    case 4 * 2 + 2: launch_decode_s<ORD, WIDE, 4 * 2 + 2>(a, nacc, C, B, st); break;     // stereo 16-bit
-    case 4 * 2 + 3: launch_decode_s<ORD, WIDE, 4 * 2 + 3>(a, nacc, C, B, st); break;     // stereo 24-bit
-    case 4 * 6 + 3: launch_decode_s<ORD, WIDE, 4 * 6 + 3>(a, nacc, C, B, st); break;     // 5.1 24-bit
-    case 4 * 8 + 3: launch_decode_s<ORD, WIDE, 4 * 8 + 3>(a, nacc, C, B, st); break;     // 7.1 24-bit
-#endif
-    default: launch_decode_s<ORD, WIDE, 0>(a, nacc, C, B, st); break;
-    }
-}
-template <int ORD, bool WIDE, int SPEC>
-static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
-    constexpr int T = DecCfg<ORD>::T;
-    const uint32_t F = 32 / C;
-    const uint32_t S = dec_tile_stride(C);
-    const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
-    size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S);
-    static std::atomic<uint64_t> attr_done{0};
-    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const int n_sm = sm_count();
-    static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
-    static const bool balance = getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '1';
-    if (trace || balance) {
-        int max_resident = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC>, 32 * DEC_WARPS, smem);
-        if (max_resident < 1) max_resident = 1;
-        if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: %d CTAs of %d warps resident per SM, grid %u (%.2f waves), %zu B smem/CTA\n", ORD, (int)WIDE, SPEC, max_resident, DEC_WARPS,
-                           grid, (double)grid / ((double)n_sm * max_resident), smem);
-        // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  BNFLAC_DEC_BALANCE=1 caps
-        // the residency (by asking for more shared memory) so that the waves are equally full (measured: no gain, off by default).
-        const uint64_t per_wave = (uint64_t)n_sm * max_resident;
-        const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
-        uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
-        if (resident < 1) resident = 1;
-        if (balance && resident < (uint32_t)max_resident) {
-            size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
-            if (want > 200 * 1024) want = 200 * 1024;
-            if (want > smem) smem = want;
-        }
-    }
-    k_decode<ORD, WIDE, SPEC><<<grid, 32 * DEC_WARPS, smem, st>>>(a, C, B, S);
-    g_launches++;
-}
-void launch_decode(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, bool wide, void* stream) {
-    cudaStream_t st = S(stream);
-    if (wide) {
-        if (max_order <= 4) launch_decode_t<4, true>(a, nacc, C, B, st);
-        else if (max_order <= 8) launch_decode_t<8, true>(a, nacc, C, B, st);
-        else if (max_order <= 12) launch_decode_t<12, true>(a, nacc, C, B, st);
-        else if (max_order <= 16) launch_decode_t<16, true>(a, nacc, C, B, st);
-        else launch_decode_t<32, true>(a, nacc, C, B, st);
-    } else {
-        if (max_order <= 4) launch_decode_t<4, false>(a, nacc, C, B, st);
-        else if (max_order <= 8) launch_decode_t<8, false>(a, nacc, C, B, st);
-        else if (max_order <= 12) launch_decode_t<12, false>(a, nacc, C, B, st);
-        else if (max_order <= 16) launch_decode_t<16, false>(a, nacc, C, B, st);
-        else launch_decode_t<32, false>(a, nacc, C, B, st);
-    }
+    k_seg_summary<<<blocks_for(nb, 256), 256, 0, S(stream)>>>(a, seg_pcm, seg_flags); count_launch();
 }
 
 } // namespace bnf

@@ -1,0 +1,491 @@
+// kernels_decode.cuh -- K3-5: the decode kernel and its launcher templates.  Instantiated by kernels_decode_wide.cu (64-bit
+// accumulation) and kernels_decode_narrow.cu (32-bit) so that the two halves of the variants compile in parallel.
+#pragma once
+#include "kernels_common.cuh"
+
+namespace bnf {
+
+// ------------------------------------------------------------------------------------------------ K3-5 decode
+// One lane per (frame, channel); a warp (= one CTA) owns 32/C frames and works tile by tile (T samples per channel):
+//   Rice phase     each lane decodes its next T residuals into its own column of the shared-memory tile.  Groups of 8
+//                  codewords take a branch-free path (window, bfind, shift, one IMAD, zig-zag; an overflow flag instead
+//                  of a branch) whenever every lane has 8 codewords left in its partition; warm-up samples, partition
+//                  tails, escape partitions and VERBATIM subframes take the careful per-sample path.
+//   restore phase  each lane runs the FIXED/LPC recurrence over its column in place.  Coefficients and the last ORD
+//                  samples stay in registers; the loop is unrolled ORD times so every tap has a fixed register.
+//                  16-bit streams accumulate in 32-bit IMADs.  Streams that need libFLAC's 64-bit accumulator use the FP64
+//                  pipe instead: every product and partial sum is an integer below 2^53, so DFMA is exact, the
+//                  quantisation shift is folded into the coefficients (a power of two), floor() is one round-down add of
+//                  1.5*2^52, and the FP64 pipe runs beside the integer pipes the Rice phase of the other warps keeps busy.
+//   pack phase     the warp re-reads the tile row-wise (interleaved order), applies left/side, side/right, mid/side
+//                  decorrelation to stereo pairs and writes packed little-endian 8/16/24-bit PCM, 4 samples per lane.
+// Tile layout: sample t of lane l at word t*S + l, S = 32 + pad chosen so that both the column accesses of the first two
+// phases and the vector row reads of the pack phase are bank-conflict free.
+enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
+
+#ifndef DEC_MAXNREG
+#define DEC_MAXNREG 120
+#endif
+// orders > 12: 168 registers = three warps per scheduler, one wave for the few-large-frames streams these variants exist for
+// (ptxas: 108 bytes of spill stores for ORD = 32, none for 16)
+#ifndef DEC_MAXNREG_BIG
+#define DEC_MAXNREG_BIG 168
+#endif
+#ifndef DEC_TILE
+#define DEC_TILE 48
+#endif
+
+template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : DEC_TILE; };
+
+struct RiceSt {
+    uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
+    bool first;
+};
+
+template <class BR>
+__device__ __forceinline__ void rice_param(BR& br, RiceSt& rs) {
+#pragma unroll 1
+    for (int guard = 0; guard < 2; guard++) {
+        const uint32_t cnt = rs.psize - (rs.first ? rs.order : 0);
+        rs.first = false;
+        const uint32_t k = br.get(rs.plen);
+        if (k == (rs.plen == 5 ? 31u : 15u)) { rs.rawbits = br.get(5); rs.rawleft = cnt; rs.fastleft = 0; }
+        else { rs.fastleft = cnt; rs.rawleft = 0; rs.k = k; rs.kp32 = k + 32u; rs.negP = 0u - (1u << k); rs.c30 = 30u << k; }
+        if (cnt) break;
+    }
+}
+
+// ---- restore: one block of ORD samples of this lane's column, in place
+// `h` is a ring: before a block that starts at sample t0, h[j] holds sample t0 - ORD + j; step j reads every tap from a
+// fixed register and then overwrites h[j] (whose old value, the oldest sample, was used for the last time in that step).
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_i32(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
+                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        uint32_t sum = 0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) sum += (uint32_t)cf[m] * (uint32_t)h[(j - 1 - m + 2 * ORD) % ORD];
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
+        if (FIRST) { if (j < (int)order) s = r; }
+        h[j] = s;
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+}
+
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, const double (&cf)[ORD], double (&h)[ORD],
+                                                  uint32_t order, uint32_t sh_n, uint32_t wasted) {
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) {
+            const double hv = h[(j - 1 - m + 2 * ORD) % ORD];
+            if (ORD > 16 && (m & 1)) acc1 = fma(cf[m], hv, acc1);
+            else acc0 = fma(cf[m], hv, acc0);
+        }
+        if (ORD > 16) acc0 += acc1;                                       // exact: integers (scaled by 2^-shift) below 2^53
+        const double y = __dadd_rd(acc0, 6755399441055744.0);            // + 1.5*2^52, rounded down: low word = floor(acc) mod 2^32
+        int32_t p = __double2loint(y);
+        if (EXTRA) p >>= sh_n;
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
+        if (FIRST) { if (j < (int)order) s = r; }
+        h[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+}
+
+// 64-bit integer accumulation (mad.wide.s32): int32 coefficients and history, half the registers of the FP64 form.
+// `wasted` carries the per-lane "narrow" flag in bit 31 (EXTRA only): narrow LPC subframes wrap at 32 bits before the shift.
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_i64(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
+                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        long long acc = 0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(cf[m]), "r"(h[(j - 1 - m + 2 * ORD) % ORD]));
+        const uint32_t lo = (uint32_t)acc, hi = (uint32_t)((unsigned long long)acc >> 32);
+        int32_t p = (int32_t)__funnelshift_r(lo, hi, shift);               // shift < 32
+        if (EXTRA) { if (wasted & 0x80000000u) p = (int32_t)lo >> shift; }
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
+        if (FIRST) { if (j < (int)order) s = r; }
+        h[j] = s;
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << (wasted & 31u));
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+}
+
+#ifndef DEC_WIDE_I64
+#define DEC_WIDE_I64 0
+#endif
+template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
+__device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const TT (&cf)[ORD], TT (&h)[ORD], uint32_t order, uint32_t shift, uint32_t wasted) {
+    if constexpr (WIDE && DEC_WIDE_I64) restore_block_i64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+    else if constexpr (WIDE) restore_block_f64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+    else restore_block_i32<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+}
+
+// ---- pack: 16 consecutive samples (interleaved order) of one frame per lane -> B 16-byte stores
+__device__ __forceinline__ void pack4(uint32_t* dw, uint32_t B, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    if (B == 3) { dw[0] = __byte_perm(v0, v1, 0x4210); dw[1] = __byte_perm(v1, v2, 0x5421); dw[2] = __byte_perm(v2, v3, 0x6542); }
+    else if (B == 2) { dw[0] = __byte_perm(v0, v1, 0x5410); dw[1] = __byte_perm(v2, v3, 0x5410); }
+    else dw[0] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+}
+// stereo decorrelation of one (ch0, ch1) pair.  mid/side: with m' = 2M + (S&1), L = (m'+S)>>1 = R + S and
+// R = (m'-S)>>1 = M - (S>>1) (identical in every bit that reaches the output, also when the int32 arithmetic wraps).
+__device__ __forceinline__ void decorr(uint32_t assign, uint32_t& x, uint32_t& y) {
+    if (assign == 10) { const uint32_t r = x - (uint32_t)((int32_t)y >> 1); x = r + y; y = r; }
+    else if (assign == 8) y = x - y;
+    else if (assign == 9) x = x + y;
+}
+
+__device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32_t C, uint32_t B, uint32_t F, uint32_t i0, uint32_t T,
+                                          uint32_t ftab, uint8_t* __restrict__ out, uint32_t lane) {
+    const uint32_t upf = (T * C) >> 4;                 // units of 16 samples per frame-tile (T is a multiple of 16)
+    const uint32_t total = F * upf;
+    const uint32_t rcp_upf = 65536u / upf + 1u;        // g / upf for g < 2^9
+    const uint32_t rcp_c = 65536u / C + 1u;
+    for (uint32_t g = lane; g < total; g += 32) {
+        const uint32_t f = (g * rcp_upf) >> 16, u = g - f * upf;
+        const uint32_t bs = lds32(ftab + 4 * f);
+        if (i0 >= bs) continue;
+        const uint32_t nt = min(T, bs - i0), nsamp = nt * C, q0 = 16 * u;
+        if (q0 >= nsamp) continue;
+        const uint32_t assign = lds32(ftab + 128 + 4 * f);
+        const uint2 pol = lds64(ftab + 256 + 8 * f);
+        uint8_t* dst = out + (((uint64_t)pol.y << 32) | pol.x) + ((uint64_t)i0 * C + q0) * B;
+        uint32_t v[16];
+        const uint32_t fbase = tile_base + 4 * f * C;
+        if (C == 2) {
+            const uint32_t ad = fbase + 4 * (q0 >> 1) * S;
+#pragma unroll
+            for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
+            if (assign >= 8) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) decorr(assign, v[2 * e], v[2 * e + 1]);
+            }
+        } else if (C == 1) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] = lds32(fbase + 4 * (q0 + e) * S);
+        } else if (C == 4) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * ((q0 >> 2) + e) * S); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
+        } else if (C == 8) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * ((q0 >> 3) + (e >> 1)) * S + 16 * (e & 1)); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
+        } else {
+            uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
+            uint32_t ad = fbase + 4 * (t * S + c);
+            const uint32_t wrap = 4 * (S - C);
+#pragma unroll
+            for (int e = 0; e < 16; e++) { v[e] = lds32(ad); ad += 4; if (++c == C) { c = 0; ad += wrap; } }
+        }
+        if (q0 + 16 <= nsamp && (((uintptr_t)dst) & 15u) == 0) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            if (B == 3) {
+#pragma unroll
+                for (int e = 0; e < 3; e++) {       // 16 samples x 3 bytes = 12 words: word j holds bytes 4j..4j+3
+                    uint32_t w[4];
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const int j = 4 * e + x, q = (4 * j) / 3, r = (4 * j) % 3;
+                        w[x] = r == 0 ? __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x4210) : r == 1 ? __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x5421) : __byte_perm(v[q], v[q + 1 > 15 ? 15 : q + 1], 0x6542);
+                    }
+                    d4[e] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else if (B == 2) {
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    d4[e] = make_uint4(__byte_perm(v[8 * e], v[8 * e + 1], 0x5410), __byte_perm(v[8 * e + 2], v[8 * e + 3], 0x5410),
+                                       __byte_perm(v[8 * e + 4], v[8 * e + 5], 0x5410), __byte_perm(v[8 * e + 6], v[8 * e + 7], 0x5410));
+            } else {
+                uint32_t w[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) w[x] = __byte_perm(__byte_perm(v[4 * x], v[4 * x + 1], 0x0040), __byte_perm(v[4 * x + 2], v[4 * x + 3], 0x0040), 0x5410);
+                d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            const uint32_t nv = min(16u, nsamp - q0);
+#pragma unroll
+            for (uint32_t e = 0; e < 16; e += 4) {
+                if (e + 4 <= nv && (((uintptr_t)dst) & 3u) == 0) pack4(reinterpret_cast<uint32_t*>(dst + e * B), B, v[e], v[e + 1], v[e + 2], v[e + 3]);
+                else {
+#pragma unroll
+                    for (uint32_t x = 0; x < 4; x++)
+                        if (e + x < nv) for (uint32_t b = 0; b < B; b++) dst[(e + x) * B + b] = (uint8_t)(v[e + x] >> (8 * b));
+                }
+            }
+        }
+    }
+}
+
+#ifndef DEC_WARPS_N
+#define DEC_WARPS_N 2
+#endif
+constexpr int DEC_WARPS = DEC_WARPS_N;        // independent warps per CTA (no CTA-wide barrier anywhere)
+__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
+
+// SPEC: 0 = any channel count / sample width (run-time C, B, S); else 4 C + B: the common formats get C, B and the tile
+// stride S as compile-time constants (tile addresses become immediates, lane -> (frame, channel) is a shift, the pack
+// phase loses its format dispatch): measured 2.10 -> 1.93 ms on the 1 h 24-bit stereo stream
+#ifndef DEC_SPECIALISE
+#define DEC_SPECIALISE 1
+#endif
+__host__ __device__ constexpr uint32_t dec_tile_stride(uint32_t C) { return 32u + ((C & 3u) == 0 ? 4u : (C & 1u) == 0 ? 2u : 1u); }
+template <int ORD, bool WIDE, int SPEC>
+__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : DEC_MAXNREG_BIG) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_) {
+    constexpr int T = DecCfg<ORD>::T;
+    const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2) : S_;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t ring_base = smem_u32(s_dyn) + wib * dec_warp_smem(T, S);
+    const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
+    const uint32_t ftab = tile_base + T * S * 4;               // bs[32] | assign[32] | pcm offset[32] (u64)
+    const uint32_t F = 32 / C;
+    const uint32_t n_acc = a.totals->n_accepted;
+    const uint32_t fl = lane / C, ch = lane - fl * C;
+    const uint32_t kf = (blockIdx.x * DEC_WARPS + wib) * F + fl;
+    const bool active = fl < F && kf < n_acc;
+    const uint32_t rs4 = S * 4;
+    const uint32_t col = tile_base + lane * 4;
+
+    // ---- per-subframe state (registers)
+    DecRing<ORD> br;
+    br.init_idle(ring_base + lane * RingBits::STRIDE, a.in);
+    constexpr bool F64 = WIDE && !DEC_WIDE_I64;       // FP64-pipe accumulation (coefficients scaled by 2^-shift) vs mad.wide.s32
+    typename std::conditional<F64, double, int32_t>::type cf[ORD], hist[ORD];
+#pragma unroll
+    for (int j = 0; j < ORD; j++) { cf[j] = 0; hist[j] = 0; }
+    RiceSt rs;
+    rs.fastleft = 0; rs.rawleft = 0; rs.rawbits = 0; rs.k = 0; rs.kp32 = 32; rs.negP = ~0u; rs.c30 = 30; rs.psize = 0; rs.plen = 4; rs.order = 0; rs.first = true;
+    uint32_t bs = 0, assign = 0, wasted = 0, shift = 0, bps = 0;
+    int mode = M_IDLE;
+    if (fl < F && ch == 0) { sts32(ftab + 4 * fl, 0); sts32(ftab + 128 + 4 * fl, 0); }
+    if (active) {
+        const uint32_t i = a.acc_idx[kf];
+        const Cand c = a.cand[i];
+        bs = c.bs; assign = c.assign;
+        bool ok = a.status[i] == ST_OK;
+        const uint64_t po = a.pcm_off[i];
+        if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
+        if (ch == 0) { sts32(ftab + 4 * fl, bs); sts32(ftab + 128 + 4 * fl, assign); sts32(ftab + 256 + 8 * fl, (uint32_t)po); sts32(ftab + 260 + 8 * fl, (uint32_t)(po >> 32)); }
+        int32_t cval = 0;
+        mode = M_CONST;                              // damaged frames (CRC mismatch) are delivered zero-filled
+        if (ok) {
+            const SubInfo si = a.sub[(uint64_t)i * MAX_CH + ch];
+            br.init(ring_base + lane * RingBits::STRIDE, a.in, a.in_len, c.off * 8 + si.bit_offset);
+            uint32_t x = br.get(8);
+            if (x & 1) { br.unary(64); br.ensure_now(); }
+            const uint32_t order = si.order;
+            wasted = si.wasted;
+            bps = (uint32_t)c.bps + (((assign == 8 && ch == 1) || (assign == 9 && ch == 0) || (assign == 10 && ch == 1)) ? 1u : 0u) - wasted;
+            if (si.type == 0) cval = br.gets(bps);
+            else if (si.type == 1) mode = M_VERBATIM;
+            else {
+                mode = M_PRED;
+                rs.order = order;
+                // warm-up samples are parked in this lane's tile rows 0..order-1 (order <= 32 <= T)
+#pragma unroll 1
+                for (uint32_t j = 0; j < order; j++) { sts32(col + j * rs4, (uint32_t)br.gets(bps)); if ((j & 7) == 7) br.ensure_now(); }
+                br.ensure_now();
+                bool narrow = true;
+                if (si.type == 3) {
+                    const uint32_t prec = br.get(4) + 1;
+                    { const int32_t sh = br.gets(5); shift = sh < 0 ? 0u : (uint32_t)sh; }   // negative: not an error in libFLAC 1.2.1 (never emitted)
+                    narrow = (bps + prec + (uint32_t)ilog2u(order)) <= 32;
+                    // libFLAC 1.2.1 width rule: narrow subframes accumulate in 32 bits (wrap), the others in 64
+                    const double scale = (F64 && !narrow) ? __hiloint2double((int)((1023u - shift) << 20), 0) : 1.0;
+#pragma unroll
+                    for (int j = 0; j < ORD; j++) if (j < (int)order) {
+                        const int32_t q = br.gets(prec);
+                        if constexpr (F64) cf[j] = (double)q * scale; else cf[j] = q;
+                        if ((j & 7) == 7) br.ensure_now();
+                    }
+                    br.ensure_now();
+                    if (F64 && !narrow) shift = 0;           // folded into the coefficients
+                    if (WIDE && !F64 && narrow && shift) wasted |= 0x80000000u;    // 32-bit wrap before the shift (restore_block_i64)
+                } else {   // FIXED predictors as coefficient sets, 32-bit wrap-around arithmetic
+                    const int o = (int)order;
+                    if (ORD >= 1 && o >= 1) cf[0] = o == 1 ? 1 : o == 2 ? 2 : o == 3 ? 3 : 4;
+                    if (ORD >= 2 && o >= 2) cf[1] = o == 2 ? -1 : o == 3 ? -3 : -6;
+                    if (ORD >= 3 && o >= 3) cf[2] = o == 3 ? 1 : 4;
+                    if (ORD >= 4 && o >= 4) cf[3] = -1;
+                }
+                const uint32_t method = br.get(2);
+                rs.plen = method ? 5 : 4;
+                const uint32_t porder = br.get(4);
+                rs.psize = porder ? bs >> porder : bs;
+                br.ensure_now();
+            }
+        }
+        if (mode == M_CONST) {                        // column holds the final value once and for all (restore leaves it unchanged)
+            const uint32_t v = (uint32_t)cval << wasted;
+            wasted = 0;
+#pragma unroll 1
+            for (uint32_t t = 0; t < (uint32_t)T; t++) sts32(col + t * rs4, v);
+        }
+    }
+    __syncwarp();
+    const uint32_t maxbs = __reduce_max_sync(FULL, bs);
+    const bool reads = mode >= M_VERBATIM;
+    const bool extra = __any_sync(FULL, wasted != 0 || (F64 && shift != 0));
+    const uint32_t order = rs.order;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
+        // ---- Rice phase
+#pragma unroll 1
+        for (uint32_t t0 = 0, row = col; t0 < (uint32_t)T; t0 += 8, row += 8 * rs4) {      // row: loop-carried, or it is rematerialised from SR_TID every step
+            const uint32_t idx0 = i0 + t0;
+            if (reads && (DEC_RING_BLOCKS < 16 || !(t0 & 8u))) br.checkpoint();
+            const bool inert = mode <= M_CONST || idx0 >= bs;
+            if (mode == M_PRED && !inert && rs.fastleft == 0 && rs.rawleft == 0 && idx0 >= order) rice_param(br, rs);
+            const bool fast_ok = inert || (mode == M_PRED && rs.fastleft >= 8);
+            // branch-free group of 8 Rice codewords; `commit`: this lane is really in a Rice partition with >= 8 left
+            auto rice_group = [&](const bool commit) {
+                uint32_t pos = br.pos;
+                const uint32_t k = rs.k, kp32 = rs.kp32, negP = rs.negP, c30 = rs.c30;
+                bool ovf = false;
+                int32_t r[8];
+                typename DecRing<ORD>::Win3 wn = br.win_init(pos);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t nxt = j < 7 ? br.win_next(pos) : 0u;
+                    const uint32_t w = DecRing<ORD>::win_peek(wn, pos);
+                    const uint32_t f = bfind(w);
+                    const uint32_t d = f - k;
+                    ovf |= (int32_t)d < 0;
+                    const uint32_t np = pos + kp32 - f;
+                    if (j < 7) DecRing<ORD>::win_advance(wn, pos, np, nxt);
+                    pos = np;
+                    const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
+                    r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                }
+                if (commit) {
+                    rs.fastleft -= 8;
+                    if (!ovf) {
+                        br.pos = pos;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)r[j]);
+                    } else {             // a codeword longer than one window (rare): redo the group carefully
+#pragma unroll 1
+                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.rice_careful(k));
+                    }
+                }
+            };
+            if (__all_sync(FULL, fast_ok)) rice_group(!inert);
+            else {
+                // lanes that read fixed-width samples for the whole step (VERBATIM subframes, escape partitions): when they are
+                // the only reason the step is not uniform, the Rice lanes keep their branch-free group and these lanes read
+                // their 8 samples in a short loop of their own -- instead of a careful walk of every lane
+                const bool rawlane = !inert && ((mode == M_VERBATIM && idx0 + 8 <= bs) || (mode == M_PRED && rs.rawleft >= 8));
+                if (__all_sync(FULL, fast_ok || rawlane)) {
+                    rice_group(!inert && !rawlane);
+                    if (rawlane) {
+                        const uint32_t nb = mode == M_VERBATIM ? bps : rs.rawbits;
+                        if (mode == M_PRED) rs.rawleft -= 8;
+#pragma unroll 1
+                        for (uint32_t j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.gets(nb));
+                    }
+                } else {
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 8; j++) {
+                        const uint32_t idx = idx0 + j;
+                        if (mode <= M_CONST || idx >= bs) continue;
+                        int32_t v;
+                        if (mode == M_VERBATIM) v = br.gets(bps);
+                        else {
+                            if (idx < order) continue;               // parked warm-up sample
+                            if (rs.fastleft == 0 && rs.rawleft == 0) rice_param(br, rs);
+                            if (rs.rawleft) { rs.rawleft--; v = br.gets(rs.rawbits); }
+                            else { rs.fastleft--; v = br.rice_careful(rs.k); }
+                        }
+                        sts32(row + j * rs4, (uint32_t)v);
+                    }
+                }
+            }
+        }
+        // ---- restore phase (own column only: no warp synchronisation needed before it)
+        if (i0 == 0) {
+            if (extra) restore_block<ORD, WIDE, true, true>(col, rs4, cf, hist, order, shift, wasted);
+            else restore_block<ORD, WIDE, true, false>(col, rs4, cf, hist, order, shift, wasted);
+        }
+        if (extra) {
+#pragma unroll 1
+            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, true>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
+        } else {
+#pragma unroll 1
+            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, false>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
+        }
+        __syncwarp();
+        // ---- pack phase
+        pack_tile(tile_base, S, C, B, F, i0, T, ftab, a.out, lane);
+        __syncwarp();
+    }
+}
+
+template <int ORD, bool WIDE, int SPEC>
+static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st);
+template <int ORD, bool WIDE>
+static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
+    const uint32_t key = DEC_SPECIALISE ? 4 * C + B : 0;
+    switch (key) {
+#if DEC_SPECIALISE
+    case 4 * 1 + 2: launch_decode_s<ORD, WIDE, 4 * 1 + 2>(a, nacc, C, B, st); break;     // mono 16-bit
+    case 4 * 2 + 2: launch_decode_s<ORD, WIDE, 4 * 2 + 2>(a, nacc, C, B, st); break;     // stereo 16-bit
+    case 4 * 2 + 3: launch_decode_s<ORD, WIDE, 4 * 2 + 3>(a, nacc, C, B, st); break;     // stereo 24-bit
+    case 4 * 6 + 3: launch_decode_s<ORD, WIDE, 4 * 6 + 3>(a, nacc, C, B, st); break;     // 5.1 24-bit
+    case 4 * 8 + 3: launch_decode_s<ORD, WIDE, 4 * 8 + 3>(a, nacc, C, B, st); break;     // 7.1 24-bit
+#endif
+    default: launch_decode_s<ORD, WIDE, 0>(a, nacc, C, B, st); break;
+    }
+}
+template <int ORD, bool WIDE, int SPEC>
+static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
+    constexpr int T = DecCfg<ORD>::T;
+    const uint32_t F = 32 / C;
+    const uint32_t S = dec_tile_stride(C);
+    const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
+    size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S);
+    static std::atomic<uint64_t> attr_done{0};
+    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int n_sm = sm_count();
+    static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
+    static const bool balance = getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '1';
+    if (trace || balance) {
+        int max_resident = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC>, 32 * DEC_WARPS, smem);
+        if (max_resident < 1) max_resident = 1;
+        if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: %d CTAs of %d warps resident per SM, grid %u (%.2f waves), %zu B smem/CTA\n", ORD, (int)WIDE, SPEC, max_resident, DEC_WARPS,
+                           grid, (double)grid / ((double)n_sm * max_resident), smem);
+        // Every warp runs for about the same time (one frame per lane), so the launch proceeds in waves.  BNFLAC_DEC_BALANCE=1 caps
+        // the residency (by asking for more shared memory) so that the waves are equally full (measured: no gain, off by default).
+        const uint64_t per_wave = (uint64_t)n_sm * max_resident;
+        const uint32_t waves = (uint32_t)((grid + per_wave - 1) / per_wave);
+        uint32_t resident = (uint32_t)((grid + (uint64_t)n_sm * waves - 1) / ((uint64_t)n_sm * waves));
+        if (resident < 1) resident = 1;
+        if (balance && resident < (uint32_t)max_resident) {
+            size_t want = ((size_t)227 * 1024 / resident - 1024) & ~(size_t)127;
+            if (want > 200 * 1024) want = 200 * 1024;
+            if (want > smem) smem = want;
+        }
+    }
+    k_decode<ORD, WIDE, SPEC><<<grid, 32 * DEC_WARPS, smem, st>>>(a, C, B, S);
+    count_launch();
+}
+template <bool WIDE>
+static void launch_decode_w(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, cudaStream_t st) {
+    if (max_order <= 4) launch_decode_t<4, WIDE>(a, nacc, C, B, st);
+    else if (max_order <= 8) launch_decode_t<8, WIDE>(a, nacc, C, B, st);
+    else if (max_order <= 12) launch_decode_t<12, WIDE>(a, nacc, C, B, st);
+    else if (max_order <= 16) launch_decode_t<16, WIDE>(a, nacc, C, B, st);
+    else launch_decode_t<32, WIDE>(a, nacc, C, B, st);
+}
+
+} // namespace bnf

@@ -128,3 +128,36 @@ def test_both_parse_kernel_variants(streams, monkeypatch, name, lean):
         assert bytes(out[:k]) == want
         assert errs == oerrs
         assert [(f.offset, f.length, f.status != 0) for f in frames] == [(o.offset, o.length, o.status != 0) for o in oframes]
+
+
+@pytest.mark.parametrize("spec", ["0", "1"])
+@pytest.mark.parametrize("name", ["cfg2_24bit_stereo_lpc12", "cfg3_24bit_8ch_lpc32_rice2_po8", "cfg5_6ch_special", "stereo_escape_lpc", "force_side_right",
+                                  "tiled_variable", "bps20_4ch_odd_bs_zeropart", "ch5_24bit", "ch7_16bit", "tiny_blocks", "bps12_sihdr_padding"])
+def test_speculative_parse_equals_the_serial_parse(streams, monkeypatch, name, spec):
+    """Streams of few frames: subframe starts are guessed, walked in parallel and kept when they chain up from channel 0's
+    known start (kernels.cu, "speculative parse"); what does not chain up goes to the serial walk.  Forced on and off, intact
+    and damaged, both must give the oracle's PCM, frame table, subframe table and events."""
+    import pyoracle
+    from birdnest.audio_b200 import _abi
+    monkeypatch.setenv("BNFLAC_PARSE_SPEC", spec)
+    s = streams(name)
+    for damage in (False, True):
+        blob = bytearray(s.flac)
+        if damage:
+            n = len(blob)
+            for pos, mask in ((s.frame_off[0] + (n - s.frame_off[0]) // 3, 0x10), (n - (n - s.frame_off[0]) // 5, 0x01)):
+                blob[pos] ^= mask
+        blob = bytes(blob)
+        want, oframes, osubs, oerrs = pyoracle.decode(blob, want_frames=True)
+        with _abi.open_memory(blob) as h:
+            out = bytearray(len(want) + (1 << 20))
+            k = h.decode_all(out)
+            frames, subs, errs = h.frames(), h.subframes(), h.errors()
+        assert bytes(out[:k]) == want
+        assert errs == oerrs
+        assert [(f.offset, f.length, f.status != 0) for f in frames] == [(o.offset, o.length, o.status != 0) for o in oframes]
+        for fi, (f, of, osl) in enumerate(zip(frames, oframes, osubs)):
+            if of.status:
+                continue
+            got = [(x.bit_offset, x.type, x.order, x.wasted) for x in subs[8 * fi:8 * fi + f.channels]]
+            assert got == [(o.bit_offset - of.offset * 8, o.type, o.order, o.wasted) for o in osl], (name, fi)

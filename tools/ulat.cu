@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(32) k(uint32_t* out, uint32_t seed, long long*
     double d = (double)a, dc = 1.0000001;
     float f = (float)a, fc = 1.0001f;
     uint64_t w = a;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
     __syncwarp();
     long long t0 = clock64();
 #pragma unroll 1
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(32) k(uint32_t* out, uint32_t seed, long long*
             if (OP == 5) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a) : "r"(c), "r"(s));
             if (OP == 6) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d) : "d"(dc));
             if (OP == 7) asm volatile("add.rm.f64 %0, %0, %1;" : "+d"(d) : "d"(dc));
-            if (OP == 8) asm volatile("ld.shared.u32 %0, [%0];" : "+r"(a));
+            if (OP == 8) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(sbase + (a & 4092u)));
             if (OP == 9) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f) : "f"(fc));
             if (OP == 10) asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(w) : "r"(c), "r"(s));
             if (OP == 11) { asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "+r"(a) : "r"(c), "r"(s)); }
