@@ -30,7 +30,14 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "corpus")):
         sys.path.insert(0, _p)
 
 UNIQUE_SECONDS = 60
-WORKLOAD = "cfg2: 1 h 24-bit stereo 96 kHz FLAC, bs 4096, LPC<=12, adaptive mid/side (60 s unique synthetic audio tiled x60)"
+WORKLOAD = "cfg2: 1 h 24-bit stereo 96 kHz FLAC, bs 4096, LPC<=12, adaptive mid/side (59.99 s of unique synthetic audio tiled x60 = 84,360 frames)"
+
+
+def base_config(args, world, strong=False):
+    """the workload description both arms print (the reference arm decodes a bounded sample of the same stream shape)"""
+    return {"workload": WORKLOAD, "seconds_per_stream": args.seconds, "streams": 1 if strong else world,
+            "parallelism": f"{'frame-range' if strong else 'file'} shards x{world}, no collective",
+            "l2": "inputs (1.1 GB) and outputs (2.1 GB) exceed the 126 MB L2; no flush needed"}
 
 
 def make_stream(seconds: int):
@@ -203,7 +210,7 @@ def run_reference(args):
     sample = f"{reps} x {UNIQUE_SECONDS} s tile of the cfg2 stream per thread, {cores} threads, per step"
     line = {"metric": "decoded samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64",
-            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD},
+            "data": "synthetic", "impl": "reference", "config": base_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "pcm_gbps": value * 3 / 1e9}
@@ -239,6 +246,190 @@ def bind_to_gpu_cpus(index: int):
         return None
 
 
+# ---------------------------------------------------------------------------------------------- corpora of the other configurations
+def cfg1_kwargs(scale):
+    return dict(ch=2, bps=16, sr=44100, seconds=60, bs=4096, lpc=8, maxpo=5, tile=max(1, int(60 * scale)), seed=2026)
+
+
+def cfg3_kwargs(scale):       # 600 s: 586 tiles of 12 frames (1.024 s each)
+    return dict(ch=8, bps=24, sr=192000, samples=16384 * 12, bs=16384, lpc=32, minpo=8, maxpo=8, noise=19, search=0, tile=max(1, int(586 * scale)), seed=5)
+
+
+def cfg5_formats(scale):
+    """BASELINE configs[4] as SURVEY.md 8(d) spells it out: 10 h in six formats, each a unique pool tiled at the frame level."""
+    t = lambda n: max(1, int(n * scale))
+    return [
+        ("s16_44k_2ch_lpc8", "3 h 16-bit stereo 44.1 kHz, bs 4096, LPC<=8", dict(ch=2, bps=16, sr=44100, seconds=60, bs=4096, lpc=8, maxpo=5, tile=t(180), seed=31)),
+        ("s16_48k_mono_fixed", "2 h 16-bit mono 48 kHz, bs 1152, FIXED", dict(ch=1, bps=16, sr=48000, seconds=60, bs=1152, lpc=0, tile=t(120), seed=32)),
+        ("s24_96k_2ch_lpc12", "2 h 24-bit stereo 96 kHz, bs 4096, LPC<=12", dict(ch=2, bps=24, sr=96000, seconds=60, bs=4096, lpc=12, maxpo=6, stereo=1, search=1, tile=t(120), seed=33)),
+        ("s24_48k_6ch_special", "1 h 24-bit 6 ch 48 kHz, bs 1152, CONSTANT / VERBATIM / wasted-bits segments", dict(ch=6, bps=24, sr=48000, seconds=30, bs=1152, lpc=8, kind=1, period=1152, tile=t(120), seed=34)),
+        ("s24_192k_8ch_lpc32", "1 h 24-bit 8 ch 192 kHz, bs 16384, LPC 32, Rice2 partition order 8", dict(ch=8, bps=24, sr=192000, samples=16384 * 12, bs=16384, lpc=32, minpo=8, maxpo=8, noise=19, search=0, tile=t(3516), seed=35)),
+        ("s16_44k_2ch_var", "1 h 16-bit stereo 44.1 kHz, variable blocksize (0xFFF9)", dict(ch=2, bps=16, sr=44100, seconds=60, lpc=8, var=(4096, 1152, 4080, 720, 16, 192, 2304), tile=t(60), seed=36)),
+    ]
+
+
+def cfg4_pool():
+    import pycorpus
+    pool = []
+    for i in range(200):
+        kw = dict(ch=1 + (i & 1), bps=16, sr=44100, seconds=0.5 + (i * 37 % 26) / 10.0, lpc=0 if i % 4 < 2 else 8, seed=1000 + i)
+        if i % 10 == 3:
+            kw["var"] = (4096, 1152, 4080, 720, 16, 192, 2304)
+        else:
+            kw["bs"] = (576, 1152, 2304, 4096, 4608)[i % 5]
+        pool.append(pycorpus.make(**kw))
+    return pool
+
+
+CFG4_TOTAL_CLIPS = 100_000
+
+
+def cfg4_clip(pool, k):
+    return pool[(7 * k) % len(pool)]
+
+
+def verify_periodic(torch, d_out, written, tile_dev, start):
+    """the decoded PCM of a tiled stream is the unique tile's PCM repeated: d_out[0:written] against the tile from offset `start`"""
+    L = tile_dev.numel()
+    pos = 0
+    while pos < written:
+        off = (start + pos) % L
+        n = min(L - off, written - pos)
+        if not torch.equal(d_out[pos:pos + n], tile_dev[off:off + n]):
+            return False
+        pos += n
+    return True
+
+
+def device_pass(ctx, flac, out_cap, steps, warmup, shard=None):
+    """Device-resident decode of `flac` (host bytes / numpy view; uploaded once, outside the timed region) `steps` times.
+    -> dict(ms per step on this rank, stage ms, written bytes, d_out)"""
+    torch, _abi, dev, local, stream = ctx
+    d_out = torch.empty(int(out_cap) + 256, dtype=torch.uint8, device=dev)
+    kw = dict(shard_index=shard[0], shard_count=shard[1]) if shard else {}
+    with _abi.open_memory(flac, device=local, stream=stream.cuda_stream, flags=_abi.OPT_BORROW_INPUT, **kw) as h:
+        written = 0
+        for _ in range(max(1, warmup)):
+            _, written = h.decode_device(d_out.data_ptr(), d_out.numel())
+        stage = {"scan": 0.0, "crc": 0.0, "link": 0.0, "parse": 0.0, "decode": 0.0, "total": 0.0}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            _, written = h.decode_device(d_out.data_ptr(), d_out.numel())
+            t = h.timing()
+            for k in stage:
+                stage[k] += getattr(t, k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        for k in stage:
+            stage[k] = round(stage[k] / steps, 4)
+    return {"ms": ms, "stage_ms": stage, "written": int(written), "d_out": d_out}
+
+
+def config_entry(ctx, name, kwargs, steps, peak):
+    """one BASELINE configuration, single GPU, device-resident: generate, decode, check against the unique tile's PCM"""
+    import pycorpus
+    torch, _abi, dev, local, stream = ctx
+    t0 = time.time()
+    s = pycorpus.make(md5=False, view=True, **kwargs)
+    gen_s = time.time() - t0
+    B = (s.bps + 7) // 8
+    n_all = s.total_samples * s.channels
+    r = device_pass(ctx, s.flac, n_all * B, steps, 2)
+    tile_dev = torch.frombuffer(bytearray(s.pcm), dtype=torch.uint8).to(dev)
+    ok = r["written"] == n_all * B and verify_periodic(torch, r["d_out"], r["written"], tile_dev, 0)
+    if not ok:
+        raise SystemExit(f"bench.py: {name}: decoded PCM differs from the generator's PCM -- refusing to report a number")
+    alg = len(s.flac) + n_all * B
+    e = {"workload": name, "samples": n_all, "frames": len(s.frame_bs), "compressed_bytes": int(len(s.flac)), "pcm_bytes": n_all * B,
+         "ms_per_step": round(r["ms"], 4), "samples_per_s": n_all / (r["ms"] / 1e3), "pcm_gbps": n_all * B / (r["ms"] / 1e3) / 1e9,
+         "algorithmic_gbps": alg / (r["ms"] / 1e3) / 1e9, "hbm_frac": alg / (r["ms"] / 1e3) / 1e9 / peak, "stage_ms": r["stage_ms"],
+         "steps": steps, "pcm_check": "equal to the generator's PCM, every tile", "corpus_gen_s": round(gen_s, 1)}
+    del r, tile_dev
+    s.free()
+    torch.cuda.empty_cache()
+    _abi.lib().bnflac_trim_pools()             # the engine caches device blocks between handles: give this stream's back before the next one
+    return e
+
+
+def batch_entry(ctx, pool, ks, steps):
+    """cfg4: the clips with indices `ks` of the 100,000-clip batch, host memory -> device PCM through bnflac_decode_batch"""
+    torch, _abi, dev, local, stream = ctx
+    clips = [cfg4_clip(pool, k) for k in ks]
+    blobs = [c.flac for c in clips]
+    n_all = sum(c.total_samples * c.channels for c in clips)
+    out = torch.empty(n_all * 2 + 256, dtype=torch.uint8, device=dev)
+    res = None
+    for _ in range(2):
+        n, res = _abi.decode_batch(blobs, device=local, dst=out, dst_is_device=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n, res = _abi.decode_batch(blobs, device=local, dst=out, dst_is_device=True)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    bad = sum(1 for r, c in zip(res, clips) if r.status != 0 or r.pcm_bytes != len(c.pcm))
+    for k in list(range(0, len(clips), max(1, len(clips) // 64))):       # spot check of the PCM itself
+        r = res[k]
+        if bytes(out[r.pcm_offset:r.pcm_offset + r.pcm_bytes].cpu().numpy()) != clips[k].pcm:
+            bad += 1
+    if bad or n != n_all * 2:
+        raise SystemExit("bench.py: cfg4 batch: decoded clips differ from the generator's PCM -- refusing to report a number")
+    return {"clips": len(clips), "samples": n_all, "compressed_bytes": sum(len(b) for b in blobs), "pcm_bytes": n_all * 2, "ms_per_step": round(ms, 3),
+            "samples_per_s": n_all / (ms / 1e3), "steps": steps,
+            "path": "bnflac_decode_batch: clips in (pageable) host memory -> gathered + uploaded -> one pass per format group -> PCM left on the device; wall clock, staging and H2D included"}
+
+
+def stream_surface_entry(flac, n_all, local):
+    """e2e through the drop-in surface itself: the C++ mirror of FLACDecoder (csrc/flac_decoder.hpp) over an istream that hands out
+    <= 16 KiB per Read, drained with Read(buf, 0, 81920) into pageable memory -- OpenALDemo/Program.cs:26-38's loop -- in its own
+    process (birdnest/audio_b200/flacdecoder_demo --bench), timed inside that process."""
+    exe = os.path.join(ROOT, "birdnest", "audio_b200", "flacdecoder_demo")
+    if not os.path.exists(exe):
+        return {"unavailable": "flacdecoder_demo not built (make host)"}
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize > len(flac) + (1 << 28) else "/tmp"
+    path = os.path.join(d, f"bnflac_bench_{os.getpid()}.flac")
+    try:
+        with open(path, "wb") as f:
+            f.write(flac)
+        runs = {}
+        for mode in ("--bench", "--bench-drain"):
+            r = subprocess.run([exe, mode, path, str(local), "3"], capture_output=True, text=True, timeout=600)
+            reps = []
+            for line in r.stdout.splitlines():
+                f = line.split()
+                if f and f[0] == "rep":
+                    reps.append({f[i]: float(f[i + 1]) for i in range(2, len(f) - 1, 2)})
+            if r.returncode != 0 or not reps:
+                return {"unavailable": (r.stderr or r.stdout)[-200:]}
+            runs[mode] = reps
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+    best = min(runs["--bench"], key=lambda x: x["total_ms"])
+    drain = min(runs["--bench-drain"], key=lambda x: x["total_ms"])
+    return {"value": n_all / (best["total_ms"] / 1e3), "unit": "samples/s", "ms_total": best["total_ms"],
+            "first_read_ms": min(x["first_read_ms"] for x in runs["--bench"][1:] or runs["--bench"]),
+            "reads": int(best["reads"]), "pcm_bytes": int(best["bytes"]), "reps_ms": [round(x["total_ms"], 1) for x in runs["--bench"]],
+            "drain_only": {"value": n_all / (drain["total_ms"] / 1e3), "ms_total": drain["total_ms"], "reps_ms": [round(x["total_ms"], 1) for x in runs["--bench-drain"]],
+                           "what": "the same Read(buf,0,81920) loop with the buffer reused instead of appended to a MemoryStream: decoder + Stream buffering alone"},
+            "path": "flacdecoder_demo --bench: new FLACDecoder(istream) [BNFLAC_OPT_LAZY_PULL, <= 16 KiB per stream read] + Read(buf,0,81920) until 0, every buffer appended to a growing pageable vector (Stream.CopyTo(MemoryStream), Program.cs:33); file in tmpfs; first repetition includes CUDA context creation",
+            "where_the_time_goes": "single host thread: ~0.3 s pulling 1.2 GB through 16 KiB stream reads, ~0.1 s staging pageable uploads, ~0.25 s copying 2.07 GB of PCM out of pinned memory in 80 KB pieces; the rest of ms_total is the caller's MemoryStream (growth copies + first-touch page faults of ~4 GB); GPU work is ~3 ms per 64 MiB sub-shard, downloads are never waited for (BNFLAC_TRACE=1 prints this split)"}
+
+
+def kernels_fingerprint():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "birdnest", "audio_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -266,13 +457,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        tt = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def gather_ints(x):
+        if world == 1:
+            return [int(x)]
+        tt = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(tt, torch.tensor([int(x)], device=dev, dtype=torch.int64))
+        return [int(t.item()) for t in tt]
+
     s = make_stream(args.seconds)
     numa = bind_to_gpu_cpus(local)            # after the (multi-threaded) stream generator, before any pinned allocation
     flac_len = len(s.flac)
-    strong = args.scaling == "strong" and world > 1
-    shard = dict(shard_index=rank, shard_count=world) if strong else {}
+    strong_main = args.scaling == "strong" and world > 1
+    shard = dict(shard_index=rank, shard_count=world) if strong_main else {}
     total_samples_all = s.total_samples * s.channels          # per stream
-    job_samples = total_samples_all if strong else total_samples_all * world
+    job_samples = total_samples_all if strong_main else total_samples_all * world
     pcm_bytes_stream = total_samples_all * 3
 
     # ---- value: device-resident in, device-resident out -------------------------------------------------
@@ -281,13 +486,14 @@ def run_ours(args):
     d_in[:flac_len].copy_(host_in, non_blocking=True)
     d_out = torch.empty(pcm_bytes_stream + 256, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    ctx = (torch, _abi, dev, local, stream)
     h = _abi.open_device(d_in.data_ptr(), flac_len, s.flac[:1 << 20], device=local, stream=stream.cuda_stream, keep=d_in, **shard)
     torch.cuda.synchronize()
     written = 0
     for _ in range(args.warmup):
         _, written = h.decode_device(d_out.data_ptr(), d_out.numel())
     # correctness gate on the benchmark's own output (not timed): md5 of the decoded PCM == STREAMINFO md5
-    if not strong and args.verify:
+    if not strong_main and args.verify:
         import hashlib
         got = hashlib.md5(d_out[:written].cpu().numpy().tobytes()).digest()
         if got != s.md5:
@@ -312,15 +518,13 @@ def run_ours(args):
     launches = _abi.lib().bnflac_kernel_launches() - launches0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     value = job_samples / (ms_per_step / 1e3)
     for k in stage:
         stage[k] /= args.steps
     h.close()
+    del d_out, d_in
 
     # ---- e2e: host FLAC bytes -> host PCM through the reference-facing call, copies inside the timed region ----
     host_out = torch.empty(pcm_bytes_stream + 256, dtype=torch.uint8).pin_memory()
@@ -341,47 +545,154 @@ def run_ours(args):
     torch.cuda.synchronize()
     w1 = time.perf_counter()
     e2e_ms = (w1 - w0) * 1e3 / max(1, e2e_steps) if e2e_steps else float("inf")
-    if world > 1:
-        tt = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+    e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = job_samples / (e2e_ms / 1e3)
-    h2d = flac_len if not strong else flac_len // world
+    h2d = flac_len if not strong_main else flac_len // world
     d2h = nbytes
+    del host_out
+    peak, peak_src = peaks()
+
+    # ---- the other BASELINE configurations (single GPU: the N = 1 run carries them) ----------------------------------
+    extra = {}
+    small = args.corpus_scale
+    pool = None
+    if not args.no_configs and world == 1:
+        cfgs = {}
+        cfgs["cfg1"] = config_entry(ctx, "cfg1 shape: 1 h 16-bit stereo 44.1 kHz, bs 4096, LPC<=8 (configs[0] is the reference's CPU case; GPU run of the same shape)", cfg1_kwargs(small), 10, peak)
+        cfgs["cfg3"] = config_entry(ctx, "cfg3: 600 s 24-bit 8 ch 192 kHz, bs 16384, LPC 32, Rice2 partition order 8", cfg3_kwargs(small), 5, peak)
+        fm = {}
+        for key, label, kw in cfg5_formats(small):
+            fm[key] = config_entry(ctx, label, kw, 5, peak)
+        tot_s = sum(f["samples"] for f in fm.values()); tot_ms = sum(f["ms_per_step"] for f in fm.values())
+        tot_alg = sum(f["compressed_bytes"] + f["pcm_bytes"] for f in fm.values())
+        cfgs["cfg5"] = {"workload": "cfg5: 10 h mixed-format corpus, one pass per format back to back on one GPU", "formats": fm, "samples": tot_s, "ms_per_step": round(tot_ms, 3),
+                        "samples_per_s": tot_s / (tot_ms / 1e3), "algorithmic_gbps": tot_alg / (tot_ms / 1e3) / 1e9, "hbm_frac": tot_alg / (tot_ms / 1e3) / 1e9 / peak}
+        pool = cfg4_pool()
+        share = max(1, int(CFG4_TOTAL_CLIPS / 8 * small))
+        cfgs["cfg4_share"] = batch_entry(ctx, pool, range(0, share * 8, 8), 3)
+        cfgs["cfg4_share"]["workload"] = f"cfg4: {share} clips = one GPU's share (1/8) of the 100,000-clip batch, 16-bit mono/stereo 0.5-3 s, mixed FIXED/LPC and blocksizes"
+        extra["configs"] = cfgs
+        extra["strong"] = {"job": cfgs["cfg5"]["workload"], "n_gpus": 1, "samples": tot_s, "ms_per_step": cfgs["cfg5"]["ms_per_step"], "samples_per_s": cfgs["cfg5"]["samples_per_s"],
+                           "hbm_frac": cfgs["cfg5"]["hbm_frac"], "note": "N = 1: the corpus of `strong` on one GPU (= configs.cfg5)"}
+        extra["by_file"] = dict(cfgs["cfg4_share"], n_gpus=1, note="N = 1: one GPU's 1/8 share of the batch (the whole 100,000 clips are split over the ranks when N > 1)")
+        if not args.no_e2e:
+            extra["e2e_stream"] = stream_surface_entry(s.flac, total_samples_all, local)
+
+    # ---- N > 1: the partitions BASELINE names -- one corpus by frame ranges, the clip batch by file ---------------------
+    if not args.no_configs and world > 1:
+        import numpy as np
+        import pycorpus
+        fm = {}
+        tot = {"samples": 0, "ms": 0.0, "n1_ms": 0.0, "alg": 0, "gather_ms": 0.0}
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        for key, label, kw in cfg5_formats(small):
+            path = os.path.join(shm, f"bnflac_bench_{key}.flac")
+            meta = torch.zeros(8, dtype=torch.int64, device=dev)
+            n1 = None
+            tile_pcm = None
+            if rank == 0:
+                g = pycorpus.make(md5=False, view=True, **kw)
+                with open(path, "wb") as f:
+                    f.write(g.flac)
+                B = (g.bps + 7) // 8
+                meta[:4] = torch.tensor([len(g.flac), g.total_samples * g.channels, B, len(g.pcm)], dtype=torch.int64)
+                tile_pcm = g.pcm
+                # the same job on ONE GPU, in the same run (the other ranks wait): what the N-GPU time is compared with
+                n1 = device_pass(ctx, g.flac, g.total_samples * g.channels * B, 3, 2)
+                ok1 = verify_periodic(torch, n1["d_out"], n1["written"], torch.frombuffer(bytearray(g.pcm), dtype=torch.uint8).to(dev), 0)
+                n1 = {"ms": n1["ms"], "ok": ok1}
+                g.free()
+                torch.cuda.empty_cache()
+                _abi.lib().bnflac_trim_pools()
+            barrier()
+            dist.broadcast(meta, 0)
+            flen, n_all, B, tile_len = (int(x) for x in meta[:4].tolist())
+            tile_t = torch.empty(tile_len, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                tile_t.copy_(torch.frombuffer(bytearray(tile_pcm), dtype=torch.uint8))
+            dist.broadcast(tile_t, 0)
+            mm = np.memmap(path, dtype=np.uint8, mode="r")
+            barrier()
+            r = device_pass(ctx, mm, n_all * B // world + (64 << 20), 5, 2, shard=(rank, world))
+            ms_n = max_over_ranks(r["ms"])
+            sizes = gather_ints(r["written"])
+            ok = sum(sizes) == n_all * B and verify_periodic(torch, r["d_out"], r["written"], tile_t, sum(sizes[:rank]))
+            # host-side gather (the only exchange there is): every rank's PCM slice to host memory, timed on the device
+            gbytes = min(r["written"], 2 << 30)
+            hb = torch.empty(gbytes, dtype=torch.uint8).pin_memory()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            g0.record(stream); hb.copy_(r["d_out"][:gbytes], non_blocking=True); g1.record(stream)
+            torch.cuda.synchronize()
+            gather_ms = max_over_ranks(g0.elapsed_time(g1) * (r["written"] / max(1, gbytes)))
+            okall = max_over_ranks(0.0 if ok else 1.0) == 0.0
+            del mm, r, hb, tile_t
+            torch.cuda.empty_cache()
+            _abi.lib().bnflac_trim_pools()
+            barrier()
+            if rank == 0:
+                os.unlink(path)
+                if not okall or not n1["ok"]:
+                    raise SystemExit(f"bench.py: strong/{key}: sharded PCM differs from the generator's PCM -- refusing to report a number")
+                fm[key] = {"workload": label, "samples": n_all, "compressed_bytes": flen, "pcm_bytes": n_all * B, "ms_per_step": round(ms_n, 4), "n1_ms_per_step": round(n1["ms"], 4),
+                           "speedup_vs_n1": n1["ms"] / ms_n, "samples_per_s": n_all / (ms_n / 1e3), "host_gather_ms": round(gather_ms, 2), "shard_pcm_bytes": sizes}
+                tot["samples"] += n_all; tot["ms"] += ms_n; tot["n1_ms"] += n1["ms"]; tot["alg"] += flen + n_all * B; tot["gather_ms"] += gather_ms
+        if rank == 0:
+            extra["strong"] = {"job": "cfg5: 10 h mixed-format corpus, every format sharded by frame ranges over the ranks (bnflac_opts.shard_index / shard_count), no collective; formats back to back",
+                               "n_gpus": world, "samples": tot["samples"], "ms_per_step": round(tot["ms"], 3), "samples_per_s": tot["samples"] / (tot["ms"] / 1e3),
+                               "n1_ms_per_step": round(tot["n1_ms"], 3), "speedup_vs_n1": tot["n1_ms"] / tot["ms"], "efficiency_vs_n1": tot["n1_ms"] / tot["ms"] / world,
+                               "hbm_frac_per_gpu": tot["alg"] / world / (tot["ms"] / 1e3) / 1e9 / peak, "host_gather_ms": round(tot["gather_ms"], 1), "formats": fm,
+                               "timing": "CUDA events per rank around 5 passes over its shards (device-resident), max over ranks per format, summed over formats; n1 = the whole format on rank 0 alone, same run",
+                               "pcm_check": "every rank's slice equal to the generator's PCM at its offset; slices add up to the whole"}
+        # by file: the 100,000 clips dealt round-robin to the ranks
+        pool = cfg4_pool()
+        nclips = max(world, int(CFG4_TOTAL_CLIPS * small))
+        barrier()
+        be = batch_entry(ctx, pool, range(rank, nclips, world), 3)
+        ms_b = max_over_ranks(be["ms_per_step"])
+        tot_samples = sum(gather_ints(be["samples"]))
+        if rank == 0:
+            extra["by_file"] = {"job": f"cfg4: {nclips} clips dealt round-robin to {world} ranks, each rank one bnflac_decode_batch call per step (host clips -> device PCM), no collective",
+                                "n_gpus": world, "clips": nclips, "samples": tot_samples, "ms_per_step": round(ms_b, 3), "samples_per_s": tot_samples / (ms_b / 1e3),
+                                "rank0": be, "timing": "wall clock per rank around 3 calls (gather to pinned staging + H2D + kernels), max over ranks"}
 
     if rank == 0:
-        peak, peak_src = peaks()
         # roofline of the dominant kernel: algorithmic bytes = compressed bytes in + packed PCM bytes out,
         # the units one launch processes = the whole stream (one k_decode launch per step)
-        units_bytes = (flac_len + pcm_bytes_stream) if not strong else (flac_len + pcm_bytes_stream) / world
+        units_bytes = (flac_len + pcm_bytes_stream) if not strong_main else (flac_len + pcm_bytes_stream) / world
         dom = max(("decode", "parse", "crc", "scan"), key=lambda k: stage[k])
         dom_ms = stage[dom]
         achieved = units_bytes / (dom_ms / 1e3) / 1e9
-        traffic = None
+        # DRAM traffic of that kernel: from one `ncu --set full` capture (never measured inside a bench run), valid only for the
+        # build it was taken from -- profiles/traffic.json names the capture and carries the fingerprint of the kernel sources
+        traffic, traffic_note = None, "no capture on record"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom)
+                tj = json.load(f)
+            if tj.get("kernels_fingerprint") == kernels_fingerprint():
+                traffic, traffic_note = tj.get(dom), f"{tj.get('source')} (same kernel sources: {tj.get('kernels_fingerprint')})"
+            else:
+                traffic_note = f"{tj.get('source')} was taken from other kernel sources ({tj.get('kernels_fingerprint')} != {kernels_fingerprint()}): not quoted"
         line = {
             "metric": "decoded samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong_main else "weak", "vs_baseline": None,
             "dtype": "int32/int64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "seconds_per_stream": args.seconds, "streams": 1 if strong else world,
-                       "frames_per_stream": len(s.frame_bs), "compressed_bytes": flac_len, "pcm_bytes": pcm_bytes_stream,
-                       "parallelism": f"{'frame-range' if strong else 'file'} shards x{world}, no collective",
-                       "host_cpus_bound_to_gpu": numa,
-                       "l2": "inputs (1.1 GB) and outputs (2.1 GB) exceed the 126 MB L2; no flush needed"},
+            "config": base_config(args, world, strong_main),
+            "workload_detail": {"frames_per_stream": len(s.frame_bs), "compressed_bytes": flac_len, "pcm_bytes": pcm_bytes_stream, "host_cpus_bound_to_gpu": numa,
+                                "stream_note": "60 tiles of 1406 frames (59.99 s each: whole frames of 4096 samples) = 84,360 frames, 3599.4 s; this encoder's ratio is 0.589 (the reference encoder's on the same shape: 0.528)"},
             "pcm_gbps": value * 3 / 1e9,
-            "pipeline_hbm_frac": (units_bytes * (1 if strong else 1)) / (ms_per_step / 1e3) / 1e9 / peak,
+            "pipeline_hbm_frac": units_bytes / (ms_per_step / 1e3) / 1e9 / peak,
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "kernel": {"decode": "k_decode", "parse": "k_parse", "crc": "k_crc", "scan": "k_scan"}[dom],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": units_bytes},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "bnflac_open_memory(pinned host FLAC, BORROW_INPUT) + bnflac_decode_all(pinned host PCM): pipelined sub-shards, PCIe both ways inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             try:
@@ -411,7 +722,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", dest="verify", action="store_false")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end legs (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="only the cfg2 line: skip the other BASELINE configurations / the strong and by-file partitions")
+    ap.add_argument("--corpus-scale", type=float, default=1.0, help="shrink the corpora of --configs (tile counts, clip count) by this factor (smoke runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

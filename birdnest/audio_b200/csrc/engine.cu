@@ -314,8 +314,12 @@ struct bnflac {
     bool size_understated = false;       // a decode ran out of room although the buffer held what STREAMINFO promises: size by scanning
     // streaming Read session: sub-shards decoded ahead of the reader, see stream_read()
     bool rd_active = false; uint32_t rd_issued = 0, rd_cur = 0; uint64_t rd_off = 0, rd_total = 0;
+    double tr_pull = 0, tr_issue = 0, tr_wait = 0, tr_copy = 0; uint64_t tr_reads = 0;     // BNFLAC_TRACE: where a streamed Read session spent its host time (ms)
 
     ~bnflac() {
+        if (tr_reads && getenv("BNFLAC_TRACE"))
+            fprintf(stderr, "[bnflac] streamed Read session: %llu reads; host time: pulling the source %.1f ms, issuing sub-shards %.1f ms (of which pulls), waiting for downloads %.1f ms, copying PCM out %.1f ms\n",
+                    (unsigned long long)tr_reads, tr_pull, tr_issue, tr_wait, tr_copy);
         for (bnflac* k : kids) delete k;
         DeviceScope on(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
@@ -833,9 +837,11 @@ static constexpr uint32_t READ_LOOKAHEAD = 2;      // sub-shards in flight beyon
 // until STREAMINFO and the end of the metadata are in hand -- and bnflac_read pulls what the next sub-shard needs (its
 // byte range plus one maximum frame of overlap) right before issuing it.  Everything pulled is kept (the diagnostics replay
 // the reference's sync search over the bytes between frames).
+static double now_ms();
 static int pull_more(bnflac* h, uint64_t need_len) {         // until need_len bytes are in hand or the stream ends
     const size_t req = env_kb("BNFLAC_PULL_KB", 1024);        // bytes asked of the callback per call
     GrowBuf& b = h->pulled;
+    struct Tick { bnflac* h; double t0; ~Tick() { h->tr_pull += now_ms() - t0; } } tick{h, now_ms()};
     while (!h->pull_eof && b.len < need_len) {
         if (!b.room(req)) return BNFLAC_ERR_MEMORY;
         size_t got = req;
@@ -913,13 +919,15 @@ static int64_t stream_read(bnflac* h, uint8_t* dst, size_t count) {
     int rc;
     while (done < count && (h->rd_cur < h->kids.size() || lazy_more(h))) {
         if (h->rd_issued <= h->rd_cur) {
+            const double t0 = now_ms();
             if (h->rd_issued < h->kids.size()) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
             else if ((rc = lazy_issue_next(h))) return rc;
+            h->tr_issue += now_ms() - t0;
         }
         bnflac* c = h->kids[h->rd_cur];
-        CK(cudaEventSynchronize(c->ev[7]));
+        if (cudaEventQuery(c->ev[7]) != cudaSuccess) { const double t0 = now_ms(); CK(cudaEventSynchronize(c->ev[7])); h->tr_wait += now_ms() - t0; }
         const size_t n = (size_t)std::min<uint64_t>(c->pcm_len - h->rd_off, count - done);
-        if (n) memcpy(dst + done, (const uint8_t*)c->pcm_host.p + h->rd_off, n);
+        if (n) { const bool big = n >= (1u << 20); const double t0 = big ? now_ms() : 0; memcpy(dst + done, (const uint8_t*)c->pcm_host.p + h->rd_off, n); if (big) h->tr_copy += now_ms() - t0; }
         done += n; h->rd_off += n;
         if (h->rd_off == c->pcm_len) {               // sub-shard consumed: its blocks go back to the pool
             finish_timing(c);
@@ -934,9 +942,12 @@ static int64_t stream_read(bnflac* h, uint8_t* dst, size_t count) {
     // none in the first call of a lazily pulled session, which has just paid for pulling its first sub-shard
     const bool first_lazy_call = h->pl_session && h->kids.size() == 1 && h->rd_cur == 0 && h->rd_issued == 1 && !h->pl_ahead;
     h->pl_ahead = true;
+    h->tr_reads++;
     if (!first_lazy_call && h->rd_issued <= h->rd_cur + READ_LOOKAHEAD) {
+        const double t0 = now_ms();
         if (h->rd_issued < h->kids.size()) { if ((rc = stream_issue(h, h->rd_issued))) return rc; h->rd_issued++; }
         else if (lazy_more(h) && (rc = lazy_issue_next(h))) return rc;
+        h->tr_issue += now_ms() - t0;
     }
     h->state = (h->rd_cur == h->kids.size() && !lazy_more(h)) ? BNFLAC_STATE_END_OF_STREAM : BNFLAC_STATE_READ_FRAME;
     return (int64_t)done;

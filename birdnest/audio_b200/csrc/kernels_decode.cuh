@@ -81,14 +81,21 @@ __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, c
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
         const int32_t r = (int32_t)lds32(addr + j * rs4);
-        double acc0 = 0.0, acc1 = 0.0;
+        // NACC independent accumulation chains (every product and partial sum is an integer, scaled by 2^-shift, below 2^53: any
+        // association is exact).  Orders > 16 run as a few warps per scheduler, where one chain of ORD dependent DFMAs (8.7 cycles
+        // each, tools/ulat.cu) is what the warp waits for: 4 chains, cfg3 decode 4.38 -> 4.30 ms.  For orders <= 12 ptxas already
+        // keeps three samples in flight; 2 or 3 chains there were measured slower (cfg2 decode 1.90 -> 1.96 / 1.98 ms).
+        constexpr int NACC = ORD > 16 ? 4 : ORD > 12 ? 2 : 1;
+        double acc[NACC];
 #pragma unroll
-        for (int m = ORD - 1; m >= 0; m--) {
-            const double hv = h[(j - 1 - m + 2 * ORD) % ORD];
-            if (ORD > 16 && (m & 1)) acc1 = fma(cf[m], hv, acc1);
-            else acc0 = fma(cf[m], hv, acc0);
-        }
-        if (ORD > 16) acc0 += acc1;                                       // exact: integers (scaled by 2^-shift) below 2^53
+        for (int q = 0; q < NACC; q++) acc[q] = 0.0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 0; m--) acc[m % NACC] = fma(cf[m], h[(j - 1 - m + 2 * ORD) % ORD], acc[m % NACC]);
+#pragma unroll
+        for (int w = NACC; w > 1; w /= 2)
+#pragma unroll
+            for (int q = 0; q < w / 2; q++) acc[q] += acc[q + w / 2];
+        const double acc0 = acc[0];
         const double y = __dadd_rd(acc0, 6755399441055744.0);            // + 1.5*2^52, rounded down: low word = floor(acc) mod 2^32
         int32_t p = __double2loint(y);
         if (EXTRA) p >>= sh_n;

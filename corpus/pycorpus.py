@@ -37,7 +37,7 @@ def lib():
         L.bnc_encode.restype = C.c_int
         L.bnc_encode.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Params), C.POINTER(Stream)]
         L.bnc_tile.restype = C.c_int
-        L.bnc_tile.argtypes = [C.POINTER(Stream), C.c_uint32, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Stream)]
+        L.bnc_tile.argtypes = [C.POINTER(Stream), C.c_uint32, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(Stream)]
         L.bnc_to_variable.restype = C.c_int
         L.bnc_to_variable.argtypes = [C.POINTER(Stream), C.POINTER(Stream)]
         L.bnc_free.restype = None
@@ -50,12 +50,27 @@ def lib():
 
 class Synth:
     """Result of make(): .flac (bytes), .pcm (packed LE bytes of ONE tile), .tiles, .frame_off, .frame_bs, .md5, .total_samples"""
-    pass
+    _stream = None
+
+    def free(self):
+        if self._stream is not None:
+            self.flac = None
+            lib().bnc_free(C.byref(self._stream))
+            self._stream = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def make(ch=2, bps=16, sr=44100, samples=None, seconds=1.0, bs=4096, lpc=8, prec=0, minpo=0, maxpo=5, stereo=1, search=1,
          noise=None, kind=0, period=None, seed=2026, esc=0, verb=0, var=(), zeropart=0, sihdr=0, pad=0, tile=1, tovar=0, threads=8,
-         want_pcm=True):
+         want_pcm=True, md5=True, view=False):
+    """md5=False: the tiled stream's STREAMINFO md5 is left zero (hashing tens of gigabytes of PCM takes longer than generating the
+    stream; the benchmark compares the decoded PCM with the unique tile instead).  view=True: .flac is a numpy uint8 VIEW of the
+    generator's own buffer (no copy; streams beyond 2 GiB), released by .free() or with the object."""
     L = lib()
     n = int(samples if samples is not None else seconds * sr)
     if tile > 1 and not var:
@@ -85,13 +100,17 @@ def make(ch=2, bps=16, sr=44100, samples=None, seconds=1.0, bs=4096, lpc=8, prec
         s = v
     if tile > 1:
         t = Stream()
-        rc = L.bnc_tile(C.byref(s), tile, packed, n * ch * B, threads, C.byref(t))
+        rc = L.bnc_tile(C.byref(s), tile, packed if md5 else None, n * ch * B, threads, C.byref(t))
         if rc:
             raise RuntimeError(f"bnc_tile failed {rc}")
         L.bnc_free(C.byref(s))
         s = t
     r = Synth()
-    r.flac = C.string_at(s.data, s.len)
+    if view:
+        import numpy as np
+        r.flac = np.ctypeslib.as_array(s.data, shape=(s.len,))
+    else:
+        r.flac = C.string_at(s.data, s.len)
     r.pcm = packed.raw[:n * ch * B] if want_pcm else None
     r.tiles = tile
     r.frame_off = [s.frame_off[i] for i in range(s.nframes + 1)]
@@ -99,5 +118,8 @@ def make(ch=2, bps=16, sr=44100, samples=None, seconds=1.0, bs=4096, lpc=8, prec
     r.md5 = bytes(s.md5)
     r.total_samples = int(s.total_samples)
     r.channels, r.bps, r.sample_rate = ch, bps, sr
-    L.bnc_free(C.byref(s))
+    if view:
+        r._stream = s                      # owns .flac's memory
+    else:
+        L.bnc_free(C.byref(s))
     return r
