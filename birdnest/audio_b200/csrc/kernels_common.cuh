@@ -211,7 +211,7 @@ struct RingBitsT {
 #define PARSE_RING_BLOCKS 16
 #endif
 #ifndef PARSE_RING_DEPTH
-#define PARSE_RING_DEPTH 1
+#define PARSE_RING_DEPTH 2
 #endif
 #ifndef DEC_RING_DEPTH
 #define DEC_RING_DEPTH 1

@@ -35,7 +35,12 @@ enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 #define DEC_TILE 48
 #endif
 
-template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? 64 : DEC_TILE; };
+// orders > 16: one ring period per tile (T = 32 against 64: cfg3 decode 4.32 -> 4.13 ms, the phases of the three warps a scheduler
+// holds interleave more finely)
+#ifndef DEC_TILE_BIG
+#define DEC_TILE_BIG 32
+#endif
+template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? DEC_TILE_BIG : DEC_TILE; static_assert(T % 16 == 0 && T % ORD == 0, "a tile is whole pack units and whole ring periods"); };
 
 struct RiceSt {
     uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
@@ -442,6 +447,11 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 template <int ORD, bool WIDE>
 static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
     const uint32_t key = DEC_SPECIALISE ? 4 * C + B : 0;
+#ifdef DEC_EXPERIMENT      // kernel experiments (tools/build_variants.sh): only the variants the cfg2 / cfg3 benchmark streams use are compiled (40 s instead of 3 min)
+    if constexpr (WIDE && ORD == 12) { if (key == 11) launch_decode_s<12, true, 11>(a, nacc, C, B, st); }
+    else if constexpr (WIDE && ORD == 32) { if (key == 35) launch_decode_s<32, true, 35>(a, nacc, C, B, st); }
+    return;
+#else
     switch (key) {
 #if DEC_SPECIALISE
     case 4 * 1 + 2: launch_decode_s<ORD, WIDE, 4 * 1 + 2>(a, nacc, C, B, st); break;     // mono 16-bit
@@ -452,6 +462,7 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 #endif
     default: launch_decode_s<ORD, WIDE, 0>(a, nacc, C, B, st); break;
     }
+#endif
 }
 template <int ORD, bool WIDE, int SPEC>
 static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
@@ -488,6 +499,10 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 }
 template <bool WIDE>
 static void launch_decode_w(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, cudaStream_t st) {
+#ifdef DEC_EXPERIMENT
+    if (max_order <= 12) launch_decode_t<12, WIDE>(a, nacc, C, B, st); else launch_decode_t<32, WIDE>(a, nacc, C, B, st);
+    return;
+#endif
     if (max_order <= 4) launch_decode_t<4, WIDE>(a, nacc, C, B, st);
     else if (max_order <= 8) launch_decode_t<8, WIDE>(a, nacc, C, B, st);
     else if (max_order <= 12) launch_decode_t<12, WIDE>(a, nacc, C, B, st);
