@@ -328,7 +328,7 @@ def device_pass(ctx, flac, out_cap, steps, warmup, shard=None):
     return {"ms": ms, "stage_ms": stage, "written": int(written), "d_out": d_out}
 
 
-def config_entry(ctx, name, kwargs, steps, peak):
+def config_entry(ctx, name, kwargs, steps, peak, keep=None):
     """one BASELINE configuration, single GPU, device-resident: generate, decode, check against the unique tile's PCM"""
     import pycorpus
     torch, _abi, dev, local, stream = ctx
@@ -348,7 +348,10 @@ def config_entry(ctx, name, kwargs, steps, peak):
          "algorithmic_gbps": alg / (r["ms"] / 1e3) / 1e9, "hbm_frac": alg / (r["ms"] / 1e3) / 1e9 / peak, "stage_ms": r["stage_ms"],
          "steps": steps, "pcm_check": "equal to the generator's PCM, every tile", "corpus_gen_s": round(gen_s, 1)}
     del r, tile_dev
-    s.free()
+    if keep is not None:
+        keep.append(s)              # the caller decodes it again (and frees it)
+    else:
+        s.free()
     torch.cuda.empty_cache()
     _abi.lib().bnflac_trim_pools()             # the engine caches device blocks between handles: give this stream's back before the next one
     return e
@@ -417,6 +420,50 @@ def stream_surface_entry(flac, n_all, local):
                            "what": "the same Read(buf,0,81920) loop with the buffer reused instead of appended to a MemoryStream: decoder + Stream buffering alone"},
             "path": "flacdecoder_demo --bench: new FLACDecoder(istream) [BNFLAC_OPT_LAZY_PULL, <= 16 KiB per stream read] + Read(buf,0,81920) until 0, every buffer appended to a growing pageable vector (Stream.CopyTo(MemoryStream), Program.cs:33); file in tmpfs; first repetition includes CUDA context creation",
             "where_the_time_goes": "single host thread: ~0.3 s pulling 1.2 GB through 16 KiB stream reads, ~0.1 s staging pageable uploads, ~0.25 s copying 2.07 GB of PCM out of pinned memory in 80 KB pieces; the rest of ms_total is the caller's MemoryStream (growth copies + first-touch page faults of ~4 GB); GPU work is ~3 ms per 64 MiB sub-shard, downloads are never waited for (BNFLAC_TRACE=1 prints this split)"}
+
+
+def corpus_job(ctx, maps, info, shard, steps):
+    """the streams of a corpus decoded CONCURRENTLY on one GPU (one CUDA stream and one host thread each: a pass below one wave of
+    CTAs leaves most of the GPU idle, and the passes of different streams fill it; different handles may be used from different
+    threads, include/bnflac.h) -> (ms per step on this rank by CUDA events, output tensors, bytes written)"""
+    from concurrent.futures import ThreadPoolExecutor
+    torch, _abi, dev, local, stream = ctx
+    nf = len(maps)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nf)]
+    hs, outs = [], []
+    for fi in range(nf):
+        flen, n_all, B, _ = info[fi]
+        cap = n_all * B // (shard[1] if shard else 1) + (64 << 20)
+        outs.append(torch.empty(cap + 256, dtype=torch.uint8, device=dev))
+        kw = dict(shard_index=shard[0], shard_count=shard[1]) if shard else {}
+        hs.append(_abi.open_memory(maps[fi], device=local, stream=streams[fi].cuda_stream, flags=_abi.OPT_BORROW_INPUT, **kw))
+    written = [0] * nf
+
+    def one(fi):
+        _, written[fi] = hs[fi].decode_device(outs[fi].data_ptr(), outs[fi].numel())
+    with ThreadPoolExecutor(nf) as pool_ex:
+        def step():
+            list(pool_ex.map(one, range(nf)))
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
+        for _ in range(steps):
+            step()
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        e1.record(main)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    for hh in hs:
+        hh.close()
+    return ms, outs, written
 
 
 def kernels_fingerprint():
@@ -560,9 +607,9 @@ def run_ours(args):
         cfgs = {}
         cfgs["cfg1"] = config_entry(ctx, "cfg1 shape: 1 h 16-bit stereo 44.1 kHz, bs 4096, LPC<=8 (configs[0] is the reference's CPU case; GPU run of the same shape)", cfg1_kwargs(small), 10, peak)
         cfgs["cfg3"] = config_entry(ctx, "cfg3: 600 s 24-bit 8 ch 192 kHz, bs 16384, LPC 32, Rice2 partition order 8", cfg3_kwargs(small), 5, peak)
-        fm = {}
+        fm, kept = {}, []
         for key, label, kw in cfg5_formats(small):
-            fm[key] = config_entry(ctx, label, kw, 5, peak)
+            fm[key] = config_entry(ctx, label, kw, 5, peak, keep=kept)
         tot_s = sum(f["samples"] for f in fm.values()); tot_ms = sum(f["ms_per_step"] for f in fm.values())
         tot_alg = sum(f["compressed_bytes"] + f["pcm_bytes"] for f in fm.values())
         cfgs["cfg5"] = {"workload": "cfg5: 10 h mixed-format corpus, one pass per format back to back on one GPU", "formats": fm, "samples": tot_s, "ms_per_step": round(tot_ms, 3),
@@ -572,8 +619,21 @@ def run_ours(args):
         cfgs["cfg4_share"] = batch_entry(ctx, pool, range(0, share * 8, 8), 3)
         cfgs["cfg4_share"]["workload"] = f"cfg4: {share} clips = one GPU's share (1/8) of the 100,000-clip batch, 16-bit mono/stereo 0.5-3 s, mixed FIXED/LPC and blocksizes"
         extra["configs"] = cfgs
-        extra["strong"] = {"job": cfgs["cfg5"]["workload"], "n_gpus": 1, "samples": tot_s, "ms_per_step": cfgs["cfg5"]["ms_per_step"], "samples_per_s": cfgs["cfg5"]["samples_per_s"],
-                           "hbm_frac": cfgs["cfg5"]["hbm_frac"], "note": "N = 1: the corpus of `strong` on one GPU (= configs.cfg5)"}
+        # the same corpus as ONE job (what `strong` shards over N GPUs): the six streams decoded concurrently on this GPU
+        info5 = [(len(g.flac), g.total_samples * g.channels, (g.bps + 7) // 8, len(g.pcm)) for g in kept]
+        job_ms, outs, wr = corpus_job(ctx, [g.flac for g in kept], info5, None, 5)
+        for g, o, w in zip(kept, outs, wr):
+            if w != g.total_samples * g.channels * ((g.bps + 7) // 8) or not verify_periodic(torch, o, w, torch.frombuffer(bytearray(g.pcm), dtype=torch.uint8).to(dev), 0):
+                raise SystemExit("bench.py: strong (N = 1): decoded PCM differs from the generator's PCM -- refusing to report a number")
+        del outs
+        for g in kept:
+            g.free()
+        kept.clear()
+        torch.cuda.empty_cache()
+        _abi.lib().bnflac_trim_pools()
+        extra["strong"] = {"job": "cfg5: 10 h mixed-format corpus (six streams) as one job on one GPU, the six streams decoded concurrently (one CUDA stream + one host thread per stream); "
+                                  "N > 1 shards every stream by frame ranges over the ranks", "n_gpus": 1, "samples": tot_s, "ms_per_step": round(job_ms, 3),
+                           "samples_per_s": tot_s / (job_ms / 1e3), "hbm_frac": tot_alg / (job_ms / 1e3) / 1e9 / peak, "one_stream_at_a_time_ms": cfgs["cfg5"]["ms_per_step"]}
         extra["by_file"] = dict(cfgs["cfg4_share"], n_gpus=1, note="N = 1: one GPU's 1/8 share of the batch (the whole 100,000 clips are split over the ranks when N > 1)")
         if not args.no_e2e:
             extra["e2e_stream"] = stream_surface_entry(s.flac, total_samples_all, local)
@@ -582,68 +642,86 @@ def run_ours(args):
     if not args.no_configs and world > 1:
         import numpy as np
         import pycorpus
-        fm = {}
-        tot = {"samples": 0, "ms": 0.0, "n1_ms": 0.0, "alg": 0, "gather_ms": 0.0}
         shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        for key, label, kw in cfg5_formats(small):
-            path = os.path.join(shm, f"bnflac_bench_{key}.flac")
-            meta = torch.zeros(8, dtype=torch.int64, device=dev)
-            n1 = None
-            tile_pcm = None
+        formats = cfg5_formats(small)
+        nf = len(formats)
+        # rank 0 generates the corpus once; every rank maps it (a rank only ever reads its own byte range of each stream)
+        meta = torch.zeros(nf, 4, dtype=torch.int64, device=dev)
+        tiles = []
+        for fi, (key, label, kw) in enumerate(formats):
             if rank == 0:
                 g = pycorpus.make(md5=False, view=True, **kw)
-                with open(path, "wb") as f:
+                with open(os.path.join(shm, f"bnflac_bench_{key}.flac"), "wb") as f:
                     f.write(g.flac)
-                B = (g.bps + 7) // 8
-                meta[:4] = torch.tensor([len(g.flac), g.total_samples * g.channels, B, len(g.pcm)], dtype=torch.int64)
-                tile_pcm = g.pcm
-                # the same job on ONE GPU, in the same run (the other ranks wait): what the N-GPU time is compared with
-                n1 = device_pass(ctx, g.flac, g.total_samples * g.channels * B, 3, 2)
-                ok1 = verify_periodic(torch, n1["d_out"], n1["written"], torch.frombuffer(bytearray(g.pcm), dtype=torch.uint8).to(dev), 0)
-                n1 = {"ms": n1["ms"], "ok": ok1}
+                meta[fi] = torch.tensor([len(g.flac), g.total_samples * g.channels, (g.bps + 7) // 8, len(g.pcm)], dtype=torch.int64)
+                tiles.append(g.pcm)
                 g.free()
-                torch.cuda.empty_cache()
-                _abi.lib().bnflac_trim_pools()
-            barrier()
-            dist.broadcast(meta, 0)
-            flen, n_all, B, tile_len = (int(x) for x in meta[:4].tolist())
-            tile_t = torch.empty(tile_len, dtype=torch.uint8, device=dev)
+        barrier()
+        dist.broadcast(meta, 0)
+        info = [tuple(int(x) for x in meta[fi].tolist()) for fi in range(nf)]         # (compressed bytes, samples, bytes per sample, tile PCM bytes)
+        tile_dev = []
+        for fi in range(nf):
+            t = torch.empty(info[fi][3], dtype=torch.uint8, device=dev)
             if rank == 0:
-                tile_t.copy_(torch.frombuffer(bytearray(tile_pcm), dtype=torch.uint8))
-            dist.broadcast(tile_t, 0)
-            mm = np.memmap(path, dtype=np.uint8, mode="r")
-            barrier()
-            r = device_pass(ctx, mm, n_all * B // world + (64 << 20), 5, 2, shard=(rank, world))
-            ms_n = max_over_ranks(r["ms"])
-            sizes = gather_ints(r["written"])
-            ok = sum(sizes) == n_all * B and verify_periodic(torch, r["d_out"], r["written"], tile_t, sum(sizes[:rank]))
-            # host-side gather (the only exchange there is): every rank's PCM slice to host memory, timed on the device
-            gbytes = min(r["written"], 2 << 30)
-            hb = torch.empty(gbytes, dtype=torch.uint8).pin_memory()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            g0.record(stream); hb.copy_(r["d_out"][:gbytes], non_blocking=True); g1.record(stream)
-            torch.cuda.synchronize()
-            gather_ms = max_over_ranks(g0.elapsed_time(g1) * (r["written"] / max(1, gbytes)))
-            okall = max_over_ranks(0.0 if ok else 1.0) == 0.0
-            del mm, r, hb, tile_t
+                t.copy_(torch.frombuffer(bytearray(tiles[fi]), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            tile_dev.append(t)
+        maps = [np.memmap(os.path.join(shm, f"bnflac_bench_{key}.flac"), dtype=np.uint8, mode="r") for key, _, _ in formats]
+        # the same job on ONE GPU, in the same run (the other ranks wait): what the N-GPU time is compared with
+        n1_ms, n1_ok = 0.0, True
+        if rank == 0:
+            n1_ms, outs, written = corpus_job(ctx, maps, info, None, 3)
+            for fi in range(nf):
+                n1_ok = n1_ok and written[fi] == info[fi][1] * info[fi][2] and verify_periodic(torch, outs[fi], written[fi], tile_dev[fi], 0)
+            del outs
             torch.cuda.empty_cache()
             _abi.lib().bnflac_trim_pools()
-            barrier()
-            if rank == 0:
-                os.unlink(path)
-                if not okall or not n1["ok"]:
-                    raise SystemExit(f"bench.py: strong/{key}: sharded PCM differs from the generator's PCM -- refusing to report a number")
-                fm[key] = {"workload": label, "samples": n_all, "compressed_bytes": flen, "pcm_bytes": n_all * B, "ms_per_step": round(ms_n, 4), "n1_ms_per_step": round(n1["ms"], 4),
-                           "speedup_vs_n1": n1["ms"] / ms_n, "samples_per_s": n_all / (ms_n / 1e3), "host_gather_ms": round(gather_ms, 2), "shard_pcm_bytes": sizes}
-                tot["samples"] += n_all; tot["ms"] += ms_n; tot["n1_ms"] += n1["ms"]; tot["alg"] += flen + n_all * B; tot["gather_ms"] += gather_ms
+        barrier()
+        ms_n, outs, written = corpus_job(ctx, maps, info, (rank, world), 5)
+        ms_n = max_over_ranks(ms_n)
+        ok = True
+        sizes_all = []
+        for fi in range(nf):
+            sizes = gather_ints(written[fi])
+            sizes_all.append(sizes)
+            ok = ok and sum(sizes) == info[fi][1] * info[fi][2] and verify_periodic(torch, outs[fi], written[fi], tile_dev[fi], sum(sizes[:rank]))
+        # host-side gather (the only exchange there is): every rank's PCM slices to pinned host memory, timed on the device
+        total_w = sum(written)
+        gbytes = min(max(written), 2 << 30)
+        hb = torch.empty(gbytes, dtype=torch.uint8).pin_memory()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record(stream)
+        copied = 0
+        for fi in range(nf):
+            n = min(written[fi], gbytes)
+            hb[:n].copy_(outs[fi][:n], non_blocking=True)
+            copied += n
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gather_ms = max_over_ranks(g0.elapsed_time(g1) * (total_w / max(1, copied)))
+        okall = max_over_ranks(0.0 if ok else 1.0) == 0.0
+        del outs, hb, maps, tile_dev
+        torch.cuda.empty_cache()
+        _abi.lib().bnflac_trim_pools()
+        barrier()
         if rank == 0:
-            extra["strong"] = {"job": "cfg5: 10 h mixed-format corpus, every format sharded by frame ranges over the ranks (bnflac_opts.shard_index / shard_count), no collective; formats back to back",
-                               "n_gpus": world, "samples": tot["samples"], "ms_per_step": round(tot["ms"], 3), "samples_per_s": tot["samples"] / (tot["ms"] / 1e3),
-                               "n1_ms_per_step": round(tot["n1_ms"], 3), "speedup_vs_n1": tot["n1_ms"] / tot["ms"], "efficiency_vs_n1": tot["n1_ms"] / tot["ms"] / world,
-                               "hbm_frac_per_gpu": tot["alg"] / world / (tot["ms"] / 1e3) / 1e9 / peak, "host_gather_ms": round(tot["gather_ms"], 1), "formats": fm,
-                               "timing": "CUDA events per rank around 5 passes over its shards (device-resident), max over ranks per format, summed over formats; n1 = the whole format on rank 0 alone, same run",
-                               "pcm_check": "every rank's slice equal to the generator's PCM at its offset; slices add up to the whole"}
+            for key, _, _ in formats:
+                os.unlink(os.path.join(shm, f"bnflac_bench_{key}.flac"))
+            if not okall or not n1_ok:
+                raise SystemExit("bench.py: strong: sharded PCM differs from the generator's PCM -- refusing to report a number")
+            tot_s = sum(i[1] for i in info)
+            tot_alg = sum(i[0] + i[1] * i[2] for i in info)
+            extra["strong"] = {"job": "cfg5: 10 h mixed-format corpus (six streams), every stream sharded by frame ranges over the ranks (bnflac_opts.shard_index / shard_count), no collective; "
+                                      "a rank decodes its six shards concurrently (one CUDA stream + one host thread per stream)",
+                               "n_gpus": world, "samples": tot_s, "ms_per_step": round(ms_n, 3), "samples_per_s": tot_s / (ms_n / 1e3),
+                               "n1_ms_per_step": round(n1_ms, 3), "speedup_vs_n1": n1_ms / ms_n, "efficiency_vs_n1": n1_ms / ms_n / world,
+                               "hbm_frac_per_gpu": tot_alg / world / (ms_n / 1e3) / 1e9 / peak, "host_gather_ms": round(gather_ms, 1),
+                               "formats": {key: {"workload": label, "samples": info[fi][1], "compressed_bytes": info[fi][0], "pcm_bytes": info[fi][1] * info[fi][2], "shard_pcm_bytes": sizes_all[fi]}
+                                           for fi, (key, label, _) in enumerate(formats)},
+                               "timing": "CUDA events on this rank's streams around 5 steps (device-resident shards, uploaded before), max over ranks; n1 = the same six streams whole, "
+                                         "decoded the same concurrent way on rank 0 alone in the same run",
+                               "pcm_check": "every rank's slice of every stream equal to the generator's PCM at its offset; slices add up to the whole"}
         # by file: the 100,000 clips dealt round-robin to the ranks
         pool = cfg4_pool()
         nclips = max(world, int(CFG4_TOTAL_CLIPS * small))

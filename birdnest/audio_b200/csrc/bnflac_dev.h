@@ -121,6 +121,8 @@ struct PassArgs {
     // prefix
     uint64_t* pcm_off;
     uint32_t* acc_idx;
+    uint32_t* acc_sorted;   // variable-blocksize passes: acc_idx regrouped by blocksize class (k_bucket_*); nullptr = stream order is kept
+    uint32_t* bucket_hist;  // ... per-CTA class counts, then start positions
     Totals* totals;
     // K3-5
     uint8_t* out;
@@ -136,6 +138,8 @@ void launch_parse(const PassArgs& a, uint32_t ncand_bound, void* stream);
 bool parse_wants_speculation(uint32_t ncand_bound, uint32_t channels);   // few, large frames: the engine then provides PassArgs::spec_*
 void launch_resync(const PassArgs& a, void* stream);
 void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_sample, void* stream);
+constexpr uint32_t BUCKET_CHUNK = 4096;  // accepted frames per CTA of the regrouping kernels
+void launch_bucket(const PassArgs& a, uint32_t nacc_bound, void* stream);   // after launch_prefix; k_decode then reads a.acc_sorted
 void launch_make_chunks(const SegInfo& seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks, void* stream);   // scan tiles of a one-segment pass
 void launch_clear(const PassArgs& a, void* stream);                                   // counters + totals = 0
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream);  // <= 32 words to mapped host memory

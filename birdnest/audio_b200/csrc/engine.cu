@@ -281,7 +281,7 @@ struct bnflac {
 
     // device state
     DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_pref, d_anom,
-        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags, d_spec_jobs, d_spec_base, d_spec_count, d_spec_done;
+        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags, d_spec_jobs, d_spec_base, d_spec_count, d_spec_done, d_acc_sorted, d_bucket_hist;
     uint32_t nchunks = 0, cand_cap = 0, nsegs = 0;
     bool tables_ready = false;
     PassArgs args{};
@@ -311,6 +311,7 @@ struct bnflac {
     bool pl_session = false;             // the current streamed Read session cuts its sub-shards as the bytes arrive
     bool pl_ahead = false;               // ... and has started to issue sub-shards ahead of the reader
     bool front_ran = false;              // a decode has been started on this handle (the diagnostics have something to describe)
+    bool mixed_blocksizes = false;       // variable-blocksize stream, or a batch of clips of unlike blocksizes (set at open)
     bool size_understated = false;       // a decode ran out of room although the buffer held what STREAMINFO promises: size by scanning
     // streaming Read session: sub-shards decoded ahead of the reader, see stream_read()
     bool rd_active = false; uint32_t rd_issued = 0, rd_cur = 0; uint64_t rd_off = 0, rd_total = 0;
@@ -324,7 +325,7 @@ struct bnflac {
         DeviceScope on(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
         DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref, &d_anom,
-                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags, &d_spec_jobs, &d_spec_base, &d_spec_count, &d_spec_done};
+                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags, &d_spec_jobs, &d_spec_base, &d_spec_count, &d_spec_done, &d_acc_sorted, &d_bucket_hist};
         for (DevBuf* b : all) b->release();
         pcm_host.release(); mailbox.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -369,6 +370,7 @@ static int common_open(bnflac* h, const uint8_t* header, size_t header_len) {
     if (rc) return rc;
     if (h->info.channels > 8 || h->info.bits_per_sample > 24 || h->info.bits_per_sample < 4) return BNFLAC_ERR_UNSUPPORTED;
     compute_shard(h);
+    h->mixed_blocksizes = h->info.min_blocksize != h->info.max_blocksize;
     h->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;   // what libFLAC reports after process_until_end_of_metadata
     return 0;
 }
@@ -515,6 +517,14 @@ static int launch_front_tail(bnflac* h, uint32_t nb) {
     launch_parse(h->args, nb, h->stream);
     launch_resync(h->args, h->stream);
     launch_prefix(h->args, nb, h->info.bytes_per_sample, h->stream);
+    // frames of unlike blocksizes: regroup by blocksize class so that the frames a decode warp holds take equally long
+    h->args.acc_sorted = nullptr; h->args.bucket_hist = nullptr;
+    if (h->mixed_blocksizes && !getenv("BNFLAC_NO_BUCKETS")) {
+        int rc;
+        if ((rc = h->d_acc_sorted.reserve(4ull * h->cand_cap)) || (rc = h->d_bucket_hist.reserve(128ull * ((uint64_t)h->cand_cap / BUCKET_CHUNK + 2)))) return rc;
+        h->args.acc_sorted = h->d_acc_sorted.as<uint32_t>(); h->args.bucket_hist = h->d_bucket_hist.as<uint32_t>();
+        launch_bucket(h->args, nb, h->stream);
+    }
     CK(cudaEventRecord(h->ev[4], h->stream));
     return 0;
 }
@@ -708,7 +718,7 @@ static int make_kids(bnflac* h, const std::vector<uint64_t>& cuts) {
         bnflac* c = new (std::nothrow) bnflac; if (!c) return BNFLAC_ERR_MEMORY;
         h->kids.push_back(c);
         c->opts = h->opts; c->opts.stream = nullptr; c->opts.device = h->device; c->opts.flags &= ~BNFLAC_OPT_VERIFY_MD5;
-        c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = cuts[i]; c->sub_end = cuts[i + 1];
+        c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = cuts[i]; c->sub_end = cuts[i + 1]; c->mixed_blocksizes = h->mixed_blocksizes;
         compute_shard(c);
         c->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
         int rc = setup_device(c); if (rc) return rc;
@@ -880,7 +890,7 @@ static int lazy_issue_next(bnflac* h) {
     bnflac* c = new (std::nothrow) bnflac; if (!c) return BNFLAC_ERR_MEMORY;
     h->kids.push_back(c);
     c->opts = h->opts; c->opts.stream = nullptr; c->opts.device = h->device; c->opts.flags &= ~(BNFLAC_OPT_VERIFY_MD5 | BNFLAC_OPT_LAZY_PULL);
-    c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = b; c->sub_end = std::max(e, b + 1);
+    c->info = h->info; c->len = h->len; c->host_ptr = h->host_ptr; c->sub_begin = b; c->sub_end = std::max(e, b + 1); c->mixed_blocksizes = h->mixed_blocksizes;
     if (b >= h->len) { c->sub_begin = h->len ? h->len - 1 : 0; c->sub_end = h->len; }     // empty tail
     compute_shard(c);
     c->state = BNFLAC_STATE_SEARCH_FOR_FRAME_SYNC;
@@ -1167,6 +1177,7 @@ static int decode_batch_impl(const bnflac_span* clips, size_t n, const bnflac_op
     for (Group& G : groups) {
         bnflac h;
         h.opts = opts; h.info = meta[G.clips[0]].info;
+        for (size_t ci : G.clips) if (meta[ci].info.min_blocksize != meta[ci].info.max_blocksize || meta[ci].info.max_blocksize != h.info.max_blocksize) { h.mixed_blocksizes = true; break; }
         // layout of the group's bytes on the device: each clip's frame data (metadata stripped) at a 16-byte aligned offset
         std::vector<std::pair<const uint8_t*, size_t>> src; std::vector<uint64_t> at;
         uint64_t pos = 0;

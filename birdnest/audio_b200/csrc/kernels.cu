@@ -1122,6 +1122,48 @@ __global__ void __launch_bounds__(ORD_THREADS) k_prefix(PassArgs a, uint32_t byt
     }
 }
 
+// ------------------------------------------------------------------------------------------------ blocksize classes
+// k_decode gives a warp 32 / channels consecutive frames and runs until the longest of them is done.  In a stream of
+// variable blocksize (0xFFF9: 4096, 1152, 4080, 720, 16, 192, 2304 samples in turn) that is the 4096-sample frame every
+// time, and the lanes of the short frames idle: 122 G samples/s against 286 for the same audio at a fixed blocksize.  The
+// accepted frames are therefore regrouped by half-octave blocksize class, largest first (where a frame's PCM goes is
+// pcm_off's business, not the order of decoding): per-CTA class counts, one warp turns them into start positions, scatter.
+__device__ __forceinline__ uint32_t bs_class(uint32_t bs) {          // 0 = largest
+    const uint32_t l = (uint32_t)ilog2u(bs | 1u);
+    return 31u - min(31u, 2u * l + (l ? (bs >> (l - 1)) & 1u : 0u));
+}
+__global__ void __launch_bounds__(256) k_bucket_hist(PassArgs a) {
+    __shared__ uint32_t s_h[32];
+    const uint32_t n_acc = a.totals->n_accepted;
+    const uint32_t k0 = blockIdx.x * BUCKET_CHUNK;
+    if (threadIdx.x < 32) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t k = k0 + threadIdx.x; k < min(k0 + BUCKET_CHUNK, n_acc); k += blockDim.x) atomicAdd(&s_h[bs_class(a.cand[a.acc_idx[k]].bs)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) a.bucket_hist[blockIdx.x * 32 + threadIdx.x] = s_h[threadIdx.x];
+}
+__global__ void __launch_bounds__(32) k_bucket_scan(PassArgs a, uint32_t nblocks) {
+    const uint32_t c = threadIdx.x;
+    uint32_t tot = 0;
+    for (uint32_t b = 0; b < nblocks; b++) tot += a.bucket_hist[b * 32 + c];
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, d); if (c >= (uint32_t)d) inc += o; }
+    uint32_t run = inc - tot;                                         // where class c starts
+    for (uint32_t b = 0; b < nblocks; b++) { const uint32_t h = a.bucket_hist[b * 32 + c]; a.bucket_hist[b * 32 + c] = run; run += h; }
+}
+__global__ void __launch_bounds__(256) k_bucket_scatter(PassArgs a) {
+    __shared__ uint32_t s_cur[32];
+    const uint32_t n_acc = a.totals->n_accepted;
+    const uint32_t k0 = blockIdx.x * BUCKET_CHUNK;
+    if (threadIdx.x < 32) s_cur[threadIdx.x] = a.bucket_hist[blockIdx.x * 32 + threadIdx.x];
+    __syncthreads();
+    for (uint32_t k = k0 + threadIdx.x; k < min(k0 + BUCKET_CHUNK, n_acc); k += blockDim.x) {
+        const uint32_t i = a.acc_idx[k];
+        a.acc_sorted[atomicAdd(&s_cur[bs_class(a.cand[i].bs)], 1u)] = i;
+    }
+}
+
 // start-of-pass reset and end-of-stage hand-off to the host.  The host learns the candidate count and the totals through
 // a few words of MAPPED pinned memory written by k_publish, not through cudaMemcpy: a small copy would queue on the copy
 // engines behind the multi-megabyte uploads/downloads of the other sub-shards of a pipelined decode and stall the pass.
@@ -1243,6 +1285,12 @@ void launch_prefix(const PassArgs& a, uint32_t ncand_bound, uint32_t bytes_per_s
     if (!per) per = ORD_THREADS;
     const uint32_t grid = ncand_bound ? (ncand_bound + per - 1) / per : 1;
     k_prefix<<<grid, ORD_THREADS, 0, S(stream)>>>(a, bytes_per_sample, per, a.counters + CNT_PFX_CNT, reinterpret_cast<unsigned long long*>(a.counters + CNT_PFX_BYTES)); count_launch();
+}
+void launch_bucket(const PassArgs& a, uint32_t nacc_bound, void* stream) {
+    const uint32_t nb = blocks_for(nacc_bound, BUCKET_CHUNK);
+    k_bucket_hist<<<nb, 256, 0, S(stream)>>>(a); count_launch();
+    k_bucket_scan<<<1, 32, 0, S(stream)>>>(a, nb); count_launch();
+    k_bucket_scatter<<<nb, 256, 0, S(stream)>>>(a); count_launch();
 }
 void launch_make_chunks(const SegInfo& seg, SegInfo* d_seg, Chunk* chunks, uint32_t nchunks, void* stream) {
     k_make_chunks<<<blocks_for(std::max<uint32_t>(nchunks, 1u), 256), 256, 0, S(stream)>>>(seg, d_seg, chunks, nchunks); count_launch();

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     int mode = M_IDLE;
     if (fl < F && ch == 0) { sts32(ftab + 4 * fl, 0); sts32(ftab + 128 + 4 * fl, 0); }
     if (active) {
-        const uint32_t i = a.acc_idx[kf];
+        const uint32_t i = (a.acc_sorted ? a.acc_sorted : a.acc_idx)[kf];
         const Cand c = a.cand[i];
         bs = c.bs; assign = c.assign;
         bool ok = a.status[i] == ST_OK;
