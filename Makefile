@@ -29,7 +29,11 @@ $(OBJ)/engine.o: $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/engine.cu 2> $(OBJ)/engine.log || (cat $(OBJ)/engine.log; exit 1)
 	@grep -E "error|warning" $(OBJ)/engine.log | grep -v "ptxas info" || true
-LIBOBJ := $(OBJ)/kernels.o $(OBJ)/kernels_decode_wide.o $(OBJ)/kernels_decode_narrow.o $(OBJ)/engine.o
+$(OBJ)/encoder.o: $(CSRC)/encoder.cu $(CSRC)/encoder_kernels.cuh include/bnflac.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/encoder.cu 2> $(OBJ)/encoder.log || (cat $(OBJ)/encoder.log; exit 1)
+	@grep -E "error|warning" $(OBJ)/encoder.log | grep -v "ptxas info" || true
+LIBOBJ := $(OBJ)/kernels.o $(OBJ)/kernels_decode_wide.o $(OBJ)/kernels_decode_narrow.o $(OBJ)/engine.o $(OBJ)/encoder.o
 $(LIB): $(LIBOBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(LIBOBJ)
 
@@ -66,3 +70,9 @@ clean:
 	rm -rf $(LIB) $(SHIM) oracle/_build corpus/_build birdnest/audio_b200/flacdecoder_demo
 
 .PHONY: all lib oracle corpus ref clean host shim
+
+# the encoder kernels compiled for the CPU (one pthread per CUDA thread): logic check without a GPU, tests/test_encode_emu_cpu.py
+emu: tools/emu/_build/libencemu.so
+tools/emu/_build/libencemu.so: tools/emu/enc_emu.cpp tools/emu/cuda_emu.h birdnest/audio_b200/csrc/encoder_kernels.cuh
+	@mkdir -p tools/emu/_build
+	g++ -O1 -std=c++17 -fPIC -shared -pthread -o $@ tools/emu/enc_emu.cpp

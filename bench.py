@@ -466,6 +466,39 @@ def corpus_job(ctx, maps, info, shard, steps):
     return ms, outs, written
 
 
+def encode_entry(ctx, s, reps=8, steps=3):
+    """the GPU encoder on the cfg2 shape.  `reps` copies of the unique 60 s PCM tile, device-resident in, device-resident
+    stream out (bnflac_encode_device, MD5 off: it is serial host work); the stream is then decoded by the GPU decoder and compared with
+    the PCM on the device."""
+    torch, _abi, dev, local, stream = ctx
+    tile = torch.frombuffer(bytearray(s.pcm), dtype=torch.uint8).to(dev)
+    d_pcm = tile.repeat(reps)
+    n = d_pcm.numel()
+    B = (s.bps + 7) // 8
+    o = _abi.enc_opts(s.sample_rate, s.channels, s.bps, blocksize=4096, max_lpc_order=12, max_partition_order=6, flags=_abi.ENC_NO_MD5, device=local)
+    cap = _abi.encode_bound(n, o)
+    d_flac = torch.zeros(cap + 256, dtype=torch.uint8, device=dev)
+    best = None
+    for _ in range(steps + 1):
+        w, st = _abi.encode_device(d_pcm.data_ptr(), n, o, d_flac.data_ptr(), cap)
+        if best is None or st.total_ms < best.total_ms:
+            best = st
+    hdr = bytes(d_flac[:4096].cpu().numpy())
+    d_out = torch.empty(n + 256, dtype=torch.uint8, device=dev)
+    h = _abi.open_device(d_flac.data_ptr(), w, hdr, device=local, stream=stream.cuda_stream, keep=d_flac)
+    _, written = h.decode_device(d_out.data_ptr(), d_out.numel())
+    h.close()
+    torch.cuda.synchronize()
+    if written != n or not torch.equal(d_out[:n], d_pcm):
+        raise SystemExit("bench.py: encode: the GPU decoder does not return the PCM the GPU encoder was given -- refusing to report a number")
+    samples = n // B
+    tile_ratio_cpu = len(s.flac) / s.tiles / len(s.pcm) if getattr(s, "tiles", 0) else None
+    return {"workload": f"cfg2 shape: {reps} x 60 s 24-bit stereo 96 kHz PCM ({n / 1e6:.0f} MB), blocksize 4096, LPC <= 12, partition order <= 6, adaptive mid/side; device PCM -> device FLAC stream",
+            "samples": samples, "frames": int(best.frames), "ms": round(best.total_ms, 3), "plan_ms": round(best.plan_ms, 3), "write_ms": round(best.write_ms, 3),
+            "samples_per_s": samples / (best.total_ms / 1e3), "compressed_bytes": int(w), "ratio": w / n, "ratio_cpu_corpus_encoder": tile_ratio_cpu,
+            "check": "stream decoded by the GPU decoder == the input PCM (device compare); tests/test_encode_gpu.py decodes such streams with the oracle and the reference DLL"}
+
+
 def kernels_fingerprint():
     import hashlib
     h = hashlib.sha256()
@@ -637,6 +670,7 @@ def run_ours(args):
         extra["by_file"] = dict(cfgs["cfg4_share"], n_gpus=1, note="N = 1: one GPU's 1/8 share of the batch (the whole 100,000 clips are split over the ranks when N > 1)")
         if not args.no_e2e:
             extra["e2e_stream"] = stream_surface_entry(s.flac, total_samples_all, local)
+        extra["encode"] = encode_entry(ctx, s)
 
     # ---- N > 1: the partitions BASELINE names -- one corpus by frame ranges, the clip batch by file ---------------------
     if not args.no_configs and world > 1:

@@ -60,6 +60,20 @@ class ClipResult(C.Structure):
                 ("bits_per_sample", C.c_uint32), ("status", C.c_uint32), ("total_samples", C.c_uint64)]
 
 
+class EncOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("blocksize", C.c_uint32), ("max_lpc_order", C.c_uint32), ("qlp_precision", C.c_uint32),
+                ("min_partition_order", C.c_uint32), ("max_partition_order", C.c_uint32), ("mid_side", C.c_uint32),
+                ("compression_level", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class EncStats(C.Structure):
+    _fields_ = [("plan_ms", C.c_float), ("write_ms", C.c_float), ("total_ms", C.c_float), ("frames", C.c_uint32), ("bytes", C.c_uint64),
+                ("min_framesize", C.c_uint32), ("max_framesize", C.c_uint32), ("frame_sizes", C.POINTER(C.c_uint32)), ("frame_sizes_cap", C.c_uint64)]
+
+
+ENC_NO_MD5, ENC_INPUT_INT32, ENC_USE_LEVEL, ENC_FIXED_ORDER = 1, 2, 4, 8
+
 READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_size_t))
 
 # every symbol include/bnflac.h declares (tests check the export list against the header)
@@ -76,6 +90,9 @@ _PROTOS = {
     "bnflac_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bnflac_decoded_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bnflac_decode_batch": (C.c_int, [C.POINTER(Span), C.c_size_t, C.POINTER(Opts), C.c_void_p, C.c_size_t, C.c_int, C.POINTER(ClipResult), C.POINTER(C.c_uint64)]),
+    "bnflac_encode_bound": (C.c_int, [C.c_size_t, C.POINTER(EncOpts), C.POINTER(C.c_uint64)]),
+    "bnflac_encode": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(EncOpts), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(EncStats)]),
+    "bnflac_encode_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(EncOpts), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(EncStats)]),
     "bnflac_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(FrameRec)), C.POINTER(C.c_size_t)]),
     "bnflac_subframes": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(SubframeRec)), C.POINTER(C.c_size_t)]),
     "bnflac_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Info)]),
@@ -349,3 +366,42 @@ def decode_batch(clips, device=-1, dst=None, dst_is_device=False, packed=False):
     cap = dst.numel() * dst.element_size() if hasattr(dst, "numel") else len(dst)
     _check(lib().bnflac_decode_batch(spans, n, C.byref(o), _addr(dst), cap, 1 if dst_is_device else 0, res, C.byref(w)), "bnflac_decode_batch")
     return int(w.value), res[:n]      # views into the result array (no per-clip copies: 100k clips per call are the target)
+
+
+def enc_opts(sample_rate, channels, bits_per_sample, blocksize=4096, max_lpc_order=8, qlp_precision=0, min_partition_order=0,
+             max_partition_order=6, mid_side=True, compression_level=None, flags=0, device=-1, stream=0) -> EncOpts:
+    """Settings of the GPU encoder -- what the reference's FLAC__stream_encoder_set_* calls carry (LibFLACSharp.cs:333-369)."""
+    o = EncOpts()
+    o.struct_size = C.sizeof(EncOpts)
+    o.device, o.stream = device, stream or None
+    o.sample_rate, o.channels, o.bits_per_sample = sample_rate, channels, bits_per_sample
+    o.blocksize, o.max_lpc_order, o.qlp_precision = blocksize, max_lpc_order, qlp_precision
+    o.min_partition_order, o.max_partition_order, o.mid_side = min_partition_order, max_partition_order, 1 if mid_side else 0
+    if compression_level is not None:
+        o.compression_level, flags = compression_level, flags | ENC_USE_LEVEL
+    o.flags = flags
+    return o
+
+
+def encode_bound(pcm_bytes: int, opts: EncOpts) -> int:
+    b = C.c_uint64()
+    _check(lib().bnflac_encode_bound(pcm_bytes, C.byref(opts), C.byref(b)), "bnflac_encode_bound")
+    return b.value
+
+
+def encode(pcm, opts: EncOpts, want_stats=False):
+    """Host PCM (interleaved LE, ceil(bps/8) bytes per sample -- what the decoder returns) -> FLAC stream bytes, encoded on the GPU."""
+    n = len(pcm)
+    cap = encode_bound(n, opts)
+    out = bytearray(cap)
+    w, st = C.c_uint64(), EncStats()
+    _check(lib().bnflac_encode(_addr(pcm) if n else None, n, C.byref(opts), _addr(out), cap, C.byref(w), C.byref(st)), "bnflac_encode")
+    del out[w.value:]
+    return (bytes(out), st) if want_stats else bytes(out)
+
+
+def encode_device(d_pcm: int, pcm_bytes: int, opts: EncOpts, d_dst: int, cap: int):
+    """Device PCM -> device FLAC stream; returns (bytes written, EncStats)."""
+    w, st = C.c_uint64(), EncStats()
+    _check(lib().bnflac_encode_device(d_pcm, pcm_bytes, C.byref(opts), d_dst, cap, C.byref(w), C.byref(st)), "bnflac_encode_device")
+    return w.value, st

@@ -23,6 +23,7 @@
 using namespace bnf;
 
 static thread_local std::string g_cuda_err;
+namespace bnf { void set_cuda_error(const char* what) { g_cuda_err = what; } }   // for encoder.cu (same thread-local text behind bnflac_last_cuda_error)
 #define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); return BNFLAC_ERR_CUDA; } } while (0)
 
 // ------------------------------------------------------------------------------------------------ small helpers

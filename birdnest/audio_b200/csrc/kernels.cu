@@ -596,7 +596,7 @@ __device__ __forceinline__ void parse_group(BR& br, ParseSub& ps, bool& walk, bo
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const uint32_t nxt = j < N - 1 ? br.win_next(pos) : 0u;
-        const uint32_t f = bfind(BR::win_peek(wn, pos));
+        const uint32_t f = bfind_fast(BR::win_peek(wn, pos));
         ovf |= (int32_t)(f - k) < 0;
         const uint32_t np = pos + kp32 - f;
         if (j < N - 1) BR::win_advance(wn, pos, np, nxt);

@@ -38,6 +38,19 @@ __device__ __forceinline__ uint32_t shr_c(uint32_t v, uint32_t n) { uint32_t r; 
 __device__ __forceinline__ uint32_t shl_c(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ int32_t sar_c(int32_t v, uint32_t n) { int32_t r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }   // index of the leading one; 0xffffffff for 0
+// index of the leading one for the branch-free codeword groups.  BFIND_I2F = 1: through the integer-to-float converter (round toward zero:
+// the exponent is floor(log2 v)); 0 gives -127, negative like bfind's -1, which is all the callers test
+#ifndef BFIND_I2F
+#define BFIND_I2F 0
+#endif
+__device__ __forceinline__ uint32_t bfind_fast(uint32_t v) {
+#if BFIND_I2F
+    float f; asm("cvt.rz.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
+    return (__float_as_uint(f) >> 23) - 127u;
+#else
+    return bfind(v);
+#endif
+}
 __device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
 
 

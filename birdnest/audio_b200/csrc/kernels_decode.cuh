@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                 for (int j = 0; j < 8; j++) {
                     const uint32_t nxt = j < 7 ? br.win_next(pos) : 0u;
                     const uint32_t w = DecRing<ORD>::win_peek(wn, pos);
-                    const uint32_t f = bfind(w);
+                    const uint32_t f = bfind_fast(w);
                     const uint32_t d = f - k;
                     ovf |= (int32_t)d < 0;
                     const uint32_t np = pos + kp32 - f;

@@ -232,3 +232,149 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
 }
 
 } // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------ encoder half
+// The FLAC__stream_encoder_* symbols of LibFLACSharp.cs:322-387 over bnflac_encode: samples are collected (packed, the engine's
+// input layout), finish() encodes them on the GPU and replays libFLAC's write-callback sequence.  No encoding happens here.
+struct FLAC__StreamEncoder {
+    int state = 1;                        // FLAC__STREAM_ENCODER_UNINITIALIZED
+    unsigned channels = 2, bps = 16, sample_rate = 44100, level = 5, blocksize = 0;
+    int mid_side = -1;                    // -1: the preset's
+    bool verify = false;
+    FLAC__StreamEncoderWriteCallback write = nullptr;
+    FLAC__StreamEncoderMetadataCallback metadata = nullptr;
+    void* client = nullptr;
+    FILE* file = nullptr;
+    std::vector<uint8_t> pcm;             // interleaved, little-endian, ceil(bps/8) bytes per sample
+};
+
+static int enc_init_common(FLAC__StreamEncoder* e) {
+    if (e->state != 1) return 13;
+    if (e->channels < 1 || e->channels > 8) return 4;
+    if (e->bps < 4 || e->bps > 24) return 5;
+    if (e->sample_rate < 1 || e->sample_rate > 655350) return 6;
+    if (e->blocksize && (e->blocksize < 16 || e->blocksize > 16384)) return 7;
+    e->pcm.clear();
+    e->state = 0;
+    return 0;
+}
+static bool enc_emit(FLAC__StreamEncoder* e, const uint8_t* p, size_t n, unsigned samples, unsigned frame) {
+    if (e->file) { if (fwrite(p, 1, n, e->file) != n) { e->state = 6; return false; } return true; }
+    if (e->write(e, p, n, samples, frame, e->client) != 0) { e->state = 5; return false; }
+    return true;
+}
+
+extern "C" {
+FLAC__StreamEncoder* FLAC__stream_encoder_new(void) { return new (std::nothrow) FLAC__StreamEncoder(); }
+void FLAC__stream_encoder_delete(FLAC__StreamEncoder* e) { if (e) { if (e->file) fclose(e->file); delete e; } }
+FLAC__bool FLAC__stream_encoder_set_channels(FLAC__StreamEncoder* e, unsigned v) { if (!e || e->state != 1) return 0; e->channels = v; return 1; }
+FLAC__bool FLAC__stream_encoder_set_bits_per_sample(FLAC__StreamEncoder* e, unsigned v) { if (!e || e->state != 1) return 0; e->bps = v; return 1; }
+FLAC__bool FLAC__stream_encoder_set_sample_rate(FLAC__StreamEncoder* e, unsigned v) { if (!e || e->state != 1) return 0; e->sample_rate = v; return 1; }
+FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder* e, unsigned v) { if (!e || e->state != 1) return 0; e->level = v > 8 ? 8 : v; return 1; }
+FLAC__bool FLAC__stream_encoder_set_blocksize(FLAC__StreamEncoder* e, unsigned v) { if (!e || e->state != 1) return 0; e->blocksize = v; return 1; }
+FLAC__bool FLAC__stream_encoder_set_verify(FLAC__StreamEncoder* e, FLAC__bool v) { if (!e || e->state != 1) return 0; e->verify = v != 0; return 1; }
+FLAC__bool FLAC__stream_encoder_set_streamable_subset(FLAC__StreamEncoder* e, FLAC__bool) { return e && e->state == 1; }
+FLAC__bool FLAC__stream_encoder_set_do_mid_side_stereo(FLAC__StreamEncoder* e, FLAC__bool v) { if (!e || e->state != 1) return 0; e->mid_side = v ? 1 : 0; return 1; }
+FLAC__bool FLAC__stream_encoder_set_loose_mid_side_stereo(FLAC__StreamEncoder* e, FLAC__bool) { return e && e->state == 1; }
+int FLAC__stream_encoder_get_state(const FLAC__StreamEncoder* e) { return e ? e->state : 1; }
+
+int FLAC__stream_encoder_init_stream(FLAC__StreamEncoder* e, FLAC__StreamEncoderWriteCallback write, FLAC__StreamEncoderSeekCallback, FLAC__StreamEncoderTellCallback,
+                                     FLAC__StreamEncoderMetadataCallback metadata, void* client) {
+    if (!e) return 1;
+    if (!write) return 3;
+    const int rc = enc_init_common(e);
+    if (rc) return rc;
+    e->write = write; e->metadata = metadata; e->client = client;
+    return 0;
+}
+int FLAC__stream_encoder_init_file(FLAC__StreamEncoder* e, const char* filename, void*, void* client) {
+    if (!e) return 1;
+    const int rc = enc_init_common(e);
+    if (rc) return rc;
+    e->file = filename ? fopen(filename, "wb") : nullptr;
+    if (!e->file) { e->state = 6; return 1; }
+    e->client = client;
+    return 0;
+}
+FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder* e, const int32_t buffer[], unsigned samples) {
+    if (!e || e->state != 0 || (!buffer && samples)) return 0;
+    const unsigned B = (e->bps + 7) / 8;
+    const size_t n = (size_t)samples * e->channels, at = e->pcm.size();
+    try { e->pcm.resize(at + n * B); } catch (const std::bad_alloc&) { e->state = 8; return 0; }
+    uint8_t* o = e->pcm.data() + at;
+    for (size_t i = 0; i < n; i++) for (unsigned b = 0; b < B; b++) *o++ = (uint8_t)((uint32_t)buffer[i] >> (8 * b));
+    return 1;
+}
+FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder* e, const int32_t* const buffer[], unsigned samples) {
+    if (!e || e->state != 0 || (!buffer && samples)) return 0;
+    const unsigned B = (e->bps + 7) / 8, C = e->channels;
+    const size_t at = e->pcm.size();
+    try { e->pcm.resize(at + (size_t)samples * C * B); } catch (const std::bad_alloc&) { e->state = 8; return 0; }
+    uint8_t* o = e->pcm.data() + at;
+    for (unsigned t = 0; t < samples; t++) for (unsigned c = 0; c < C; c++) for (unsigned b = 0; b < B; b++) *o++ = (uint8_t)((uint32_t)buffer[c][t] >> (8 * b));
+    return 1;
+}
+FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
+    if (!e) return 0;
+    if (e->state == 1) return 1;                      // libFLAC: finishing an uninitialised encoder is a no-op
+    bool ok = e->state == 0;
+    if (ok) {
+        bnflac_enc_opts o{}; o.struct_size = sizeof o; o.device = -1;
+        o.sample_rate = e->sample_rate; o.channels = e->channels; o.bits_per_sample = e->bps;
+        o.blocksize = e->blocksize; o.compression_level = e->level; o.flags = BNFLAC_ENC_USE_LEVEL;
+        uint64_t bound = 0, n = 0;
+        std::vector<uint8_t> out;
+        std::vector<uint32_t> sizes;
+        bnflac_enc_stats st{};
+        int rc = bnflac_encode_bound(e->pcm.size(), &o, &bound);
+        if (!rc && e->mid_side >= 0 && e->channels == 2) {     // an explicit set_do_mid_side_stereo overrides the preset: spell the preset out
+            static const struct { uint32_t bs, lpc, po; } lv[9] = {{1152, 0, 3}, {1152, 0, 3}, {1152, 0, 3}, {4096, 6, 4}, {4096, 8, 4}, {4096, 8, 5}, {4096, 8, 6}, {4096, 8, 6}, {4096, 12, 6}};
+            o.flags = 0; o.mid_side = (uint32_t)e->mid_side; o.max_lpc_order = lv[e->level].lpc; o.max_partition_order = lv[e->level].po;
+            if (!o.blocksize) o.blocksize = lv[e->level].bs;
+            rc = bnflac_encode_bound(e->pcm.size(), &o, &bound);
+        }
+        if (!rc) {
+            const uint32_t bs = o.blocksize ? o.blocksize : (e->level < 3 ? 1152u : 4096u);
+            const size_t nf = (e->pcm.size() / ((size_t)((e->bps + 7) / 8) * e->channels) + bs - 1) / bs;
+            try { out.resize((size_t)bound); sizes.resize(nf + 1); } catch (const std::bad_alloc&) { rc = BNFLAC_ERR_MEMORY; }
+            if (!rc) { st.frame_sizes = sizes.data(); st.frame_sizes_cap = nf; rc = bnflac_encode(e->pcm.data(), e->pcm.size(), &o, out.data(), out.size(), &n, &st); }
+            if (!rc && e->verify) {                    // set_verify: the stream must decode back to what was handed in
+                bnflac_t* h = nullptr; bnflac_opts d{}; d.struct_size = sizeof d; d.device = -1; d.flags = BNFLAC_OPT_BORROW_INPUT;
+                std::vector<uint8_t> back(e->pcm.size() + 64);
+                uint64_t w = 0;
+                if (bnflac_open_memory(out.data(), (size_t)n, &d, &h) || bnflac_decode_all(h, back.data(), back.size(), &w) || w != e->pcm.size() || memcmp(back.data(), e->pcm.data(), e->pcm.size())) { e->state = 4; ok = false; }
+                if (h) bnflac_close(h);
+            }
+            if (!rc && ok) {
+                const uint32_t bsz = bs;
+                const uint64_t total = e->pcm.size() / ((size_t)((e->bps + 7) / 8) * e->channels);
+                ok = enc_emit(e, out.data(), 4, 0, 0) && enc_emit(e, out.data() + 4, 38, 0, 0);
+                size_t at = 42;
+                for (size_t f = 0; ok && f < st.frames; f++) {
+                    const unsigned smp = (unsigned)std::min<uint64_t>(bsz, total - (uint64_t)f * bsz);
+                    ok = enc_emit(e, out.data() + at, sizes[f], smp, (unsigned)f);
+                    at += sizes[f];
+                }
+                if (ok && e->metadata) {
+                    bnflac_info_t inf{};
+                    if (!bnflac_probe(out.data(), 42, &inf)) {
+                        FLAC__StreamMetadata m; memset(&m, 0, sizeof m);
+                        m.type = 0; m.is_last = 1; m.length = 34;
+                        m.stream_info.min_blocksize = inf.min_blocksize; m.stream_info.max_blocksize = inf.max_blocksize;
+                        m.stream_info.min_framesize = inf.min_framesize; m.stream_info.max_framesize = inf.max_framesize;
+                        m.stream_info.sample_rate = inf.sample_rate; m.stream_info.channels = inf.channels; m.stream_info.bits_per_sample = inf.bits_per_sample;
+                        m.stream_info.total_samples = inf.total_samples; memcpy(m.stream_info.md5sum, inf.md5, 16);
+                        e->metadata(e, &m, e->client);
+                    }
+                }
+            }
+        }
+        if (rc) { e->state = rc == BNFLAC_ERR_MEMORY ? 8 : 5; ok = false; }
+    }
+    if (e->file) { if (fclose(e->file) != 0) ok = false; e->file = nullptr; }
+    e->pcm.clear(); e->pcm.shrink_to_fit();
+    if (ok) e->state = 1;                               // back to UNINITIALIZED, ready for another init (libFLAC)
+    return ok ? 1 : 0;
+}
+}

@@ -155,6 +155,49 @@ typedef struct { uint64_t pcm_offset, pcm_bytes; uint32_t sample_rate, channels,
 int bnflac_decode_batch(const bnflac_span* clips, size_t n, const bnflac_opts* opts, uint8_t* dst, size_t cap, int dst_is_device,
                         bnflac_clip_result* results, uint64_t* written);
 
+/* ---- encode ------------------------------------------------------------------ */
+/* The encoder half of the native codec: LibFLACSharp.cs:322-387 declares libFLAC's stream encoder (new, set_channels :333,
+ * set_bits_per_sample :336, set_sample_rate :339, set_compression_level :342, set_blocksize :345, init_stream :348,
+ * process_interleaved :354, process :357, set_do_mid_side_stereo :366, finish :327, delete :330) and its write callback :375.
+ * One call here encodes a whole PCM buffer on the GPU (frames are independent: one CTA per frame); libLibFlac.so replays the
+ * result frame by frame behind those legacy symbols.  Fixed blocksize, 1-8 channels, 4-24 bits, blocksize 16..16384, FIXED 0-4 and
+ * LPC 1-32 predictors, partitioned Rice / Rice2 (partition order 0-8), all four stereo assignments, wasted bits, CONSTANT and
+ * VERBATIM subframes.  PCM layout = what the decoder returns: interleaved, little-endian, ceil(bits/8) bytes per sample
+ * (or int32 per sample with BNFLAC_ENC_INPUT_INT32, the layout of FLAC__stream_encoder_process_interleaved). */
+typedef struct {
+    uint32_t struct_size;           /* = sizeof(bnflac_enc_opts); 0-initialise the rest for defaults */
+    int32_t  device;                /* CUDA device ordinal, -1 = current device */
+    void*    stream;                /* cudaStream_t to launch on; NULL = default stream */
+    uint32_t sample_rate, channels, bits_per_sample;
+    uint32_t blocksize;             /* 0 = 4096 (or the preset's) */
+    uint32_t max_lpc_order;         /* 0 = FIXED predictors only */
+    uint32_t qlp_precision;         /* 0 = libFLAC's choice by sample width and blocksize */
+    uint32_t min_partition_order, max_partition_order;
+    uint32_t mid_side;              /* stereo only: 1 = cheapest of L/R, L/S, S/R, M/S per frame; 0 = independent channels */
+    uint32_t compression_level;     /* used with BNFLAC_ENC_USE_LEVEL: libFLAC's presets 0-8 (set_compression_level) */
+    uint32_t flags;                 /* BNFLAC_ENC_* */
+} bnflac_enc_opts;
+#define BNFLAC_ENC_NO_MD5 1u        /* leave STREAMINFO's MD5 zero (the MD5 is serial host work: it runs beside the GPU for host input, and
+                                     * costs a device-to-host copy of the PCM for bnflac_encode_device) */
+#define BNFLAC_ENC_INPUT_INT32 2u   /* one int32 per sample instead of packed bytes */
+#define BNFLAC_ENC_USE_LEVEL 4u     /* blocksize / max_lpc_order / partition orders / mid_side come from compression_level */
+#define BNFLAC_ENC_FIXED_ORDER 8u   /* always use max_lpc_order instead of the order with the fewest estimated bits */
+typedef struct {
+    float plan_ms, write_ms, total_ms;   /* CUDA-event times of the analysis kernel (+ prefix sum), the bitstream kernel, and both + the memset */
+    uint32_t frames;
+    uint64_t bytes;                      /* stream size */
+    uint32_t min_framesize, max_framesize;
+    uint32_t* frame_sizes;               /* in: NULL, or room for frame_sizes_cap entries; out: the size in bytes of every frame, in order */
+    uint64_t frame_sizes_cap;
+} bnflac_enc_stats;
+/* Host-only: an upper bound of the stream size for `pcm_bytes` of input. */
+int bnflac_encode_bound(size_t pcm_bytes, const bnflac_enc_opts* opts, uint64_t* bound);
+/* Host PCM -> host FLAC stream ("fLaC" + STREAMINFO + frames).  *written = stream size; BNFLAC_ERR_CAPACITY if cap is smaller
+ * (dst == NULL: size only).  stats may be NULL; zero-initialise it otherwise (frame_sizes is an input). */
+int bnflac_encode(const uint8_t* pcm, size_t pcm_bytes, const bnflac_enc_opts* opts, uint8_t* dst, size_t cap, uint64_t* written, bnflac_enc_stats* stats);
+/* Device PCM -> device FLAC stream (d_dst 4-byte aligned, cap bytes; bnflac_encode_bound is always enough). */
+int bnflac_encode_device(const void* d_pcm, size_t pcm_bytes, const bnflac_enc_opts* opts, void* d_dst, size_t cap, uint64_t* written, bnflac_enc_stats* stats);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* per-frame table of the last decode (host copies, owned by the handle) */
 typedef struct { uint64_t offset; uint32_t length, blocksize; uint8_t channels, bits_per_sample, assignment, status; uint32_t pad; uint64_t number; uint64_t pcm_offset; } bnflac_frame_t;

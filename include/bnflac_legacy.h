@@ -68,6 +68,38 @@ unsigned FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder*);      
 int FLAC__stream_decoder_get_state(const FLAC__StreamDecoder*);                                  /* :82, numbering of LibFLACSharp.cs:24-36 */
 FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder*);                                     /* :85 */
 
+/* ---- the encoder half (LibFLACSharp.cs:322-387), SURVEY 8f-4 ---------------------------------------------------------------------
+ * Same symbols, same argument meaning; the work is done by bnflac_encode (one CTA per frame on the GPU).  A replay layer like the
+ * decoder half: samples handed to process / process_interleaved are collected, finish() encodes them in one go and then drives the
+ * write callback the way libFLAC does -- "fLaC", the STREAMINFO block, then one call per frame (samples = blocksize, current_frame
+ * counting from 0) -- with the final STREAMINFO (frame sizes, total samples, MD5) already in place, so no seek back is needed;
+ * the metadata callback receives it after the last frame.  State numbering: libFLAC's FLAC__StreamEncoderState (0 OK,
+ * 1 UNINITIALIZED, 5 CLIENT_ERROR, 6 IO_ERROR, 8 MEMORY_ALLOCATION_ERROR); init status: 0 OK, 1 ENCODER_ERROR, 3 INVALID_CALLBACKS,
+ * 4 INVALID_NUMBER_OF_CHANNELS, 5 INVALID_BITS_PER_SAMPLE, 6 INVALID_SAMPLE_RATE, 7 INVALID_BLOCK_SIZE, 13 ALREADY_INITIALIZED. */
+typedef struct FLAC__StreamEncoder FLAC__StreamEncoder;
+typedef int (*FLAC__StreamEncoderWriteCallback)(const FLAC__StreamEncoder*, const uint8_t buffer[], size_t bytes, unsigned samples, unsigned current_frame, void* client);  /* :377; 0 ok, 1 fatal */
+typedef int (*FLAC__StreamEncoderSeekCallback)(const FLAC__StreamEncoder*, uint64_t absolute_byte_offset, void* client);      /* :380 (accepted, never called) */
+typedef int (*FLAC__StreamEncoderTellCallback)(const FLAC__StreamEncoder*, uint64_t* absolute_byte_offset, void* client);     /* :383 (accepted, never called) */
+typedef void (*FLAC__StreamEncoderMetadataCallback)(const FLAC__StreamEncoder*, const FLAC__StreamMetadata*, void* client);    /* :386 */
+FLAC__StreamEncoder* FLAC__stream_encoder_new(void);                                              /* :325 */
+FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder*);                                     /* :328 */
+void FLAC__stream_encoder_delete(FLAC__StreamEncoder*);                                           /* :331 */
+FLAC__bool FLAC__stream_encoder_set_channels(FLAC__StreamEncoder*, unsigned);                     /* :334 */
+FLAC__bool FLAC__stream_encoder_set_bits_per_sample(FLAC__StreamEncoder*, unsigned);              /* :337 */
+FLAC__bool FLAC__stream_encoder_set_sample_rate(FLAC__StreamEncoder*, unsigned);                  /* :340 */
+FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder*, unsigned);            /* :343 */
+FLAC__bool FLAC__stream_encoder_set_blocksize(FLAC__StreamEncoder*, unsigned);                    /* :346 */
+int FLAC__stream_encoder_init_stream(FLAC__StreamEncoder*, FLAC__StreamEncoderWriteCallback, FLAC__StreamEncoderSeekCallback, FLAC__StreamEncoderTellCallback,
+                                     FLAC__StreamEncoderMetadataCallback, void* client);          /* :349 */
+int FLAC__stream_encoder_init_file(FLAC__StreamEncoder*, const char* filename, void* progress_callback, void* client);   /* :352 */
+FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder*, const int32_t buffer[], unsigned samples);      /* :355 */
+FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder*, const int32_t* const buffer[], unsigned samples);          /* :358 */
+FLAC__bool FLAC__stream_encoder_set_verify(FLAC__StreamEncoder*, FLAC__bool);                     /* :361: finish() then decodes the stream again on the GPU and compares */
+FLAC__bool FLAC__stream_encoder_set_streamable_subset(FLAC__StreamEncoder*, FLAC__bool);          /* :364 (accepted; what is written is always within the subset's limits for blocksize <= 4608 / 16384) */
+FLAC__bool FLAC__stream_encoder_set_do_mid_side_stereo(FLAC__StreamEncoder*, FLAC__bool);         /* :367 */
+FLAC__bool FLAC__stream_encoder_set_loose_mid_side_stereo(FLAC__StreamEncoder*, FLAC__bool);      /* :370 (accepted: the choice is made per frame from exact sizes) */
+int FLAC__stream_encoder_get_state(const FLAC__StreamEncoder*);                                   /* :373 */
+
 #ifdef __cplusplus
 }
 #endif

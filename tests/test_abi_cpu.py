@@ -115,3 +115,59 @@ def test_legacy_shim_exports_the_symbols_the_csharp_binds():
     dec = L.FLAC__stream_decoder_new()
     assert L.FLAC__stream_decoder_get_state(dec) == 9      # Uninitialized (LibFLACSharp.cs:36)
     L.FLAC__stream_decoder_delete(dec)
+
+
+def test_encoder_entry_points_without_a_device():
+    """argument checking and the size bound are host-only; encoding itself needs the device (no CPU encoder in the product)."""
+    from birdnest.audio_b200 import _abi
+    o = _abi.enc_opts(44100, 2, 16)
+    assert _abi.encode_bound(4 * 4096 * 10, o) >= 4 * 4096 * 10
+    for bad in (dict(channels=9), dict(bits_per_sample=32), dict(blocksize=65535), dict(max_lpc_order=33), dict(max_partition_order=9)):
+        kw = dict(sample_rate=44100, channels=2, bits_per_sample=16)
+        kw.update(bad)
+        with pytest.raises(_abi.BnflacError) as e:
+            _abi.encode_bound(1024, _abi.enc_opts(**kw))
+        assert e.value.code == _abi.ERR_UNSUPPORTED
+    with pytest.raises(_abi.BnflacError) as e:
+        _abi.encode_bound(1023, o)          # not a whole number of stereo 16-bit samples
+    assert e.value.code == _abi.ERR_ARG
+    if not has_gpu():
+        with pytest.raises(_abi.BnflacError) as e:
+            _abi.encode(b"\0" * 4096, o)
+        assert e.value.code == _abi.ERR_NO_DEVICE
+
+
+def test_legacy_shim_exports_the_encoder_symbols_the_csharp_declares():
+    """every FLAC__stream_encoder_* DllImport of LibFLACSharp.cs:322-373 is declared in include/bnflac_legacy.h and exported by
+    libLibFlac.so; setters and init argument checks work without a device (encoding itself happens in finish(), on the GPU)."""
+    shim = os.path.join(ROOT, "birdnest", "audio_b200", "libLibFlac.so")
+    if not os.path.exists(shim):
+        pytest.skip("libLibFlac.so not built (make shim)")
+    want = {"FLAC__stream_encoder_" + n for n in (
+        "new", "finish", "delete", "set_channels", "set_bits_per_sample", "set_sample_rate", "set_compression_level", "set_blocksize", "init_stream",
+        "init_file", "process_interleaved", "process", "set_verify", "set_streamable_subset", "set_do_mid_side_stereo", "set_loose_mid_side_stereo", "get_state")}
+    ref = "/root/reference/Library/LibFLACSharp/LibFLACSharp.cs"
+    if os.path.exists(ref):      # the build container: the list above IS the reference's
+        assert set(re.findall(r"\b(FLAC__stream_encoder_[a-z_]+)\s*\(", open(ref).read())) == want
+    hdr = open(os.path.join(ROOT, "include", "bnflac_legacy.h")).read()
+    assert set(re.findall(r"\b(FLAC__stream_encoder_[a-z_]+)\s*\(", hdr)) == want
+    out = subprocess.check_output(["nm", "-D", "--defined-only", shim], text=True)
+    assert want <= {l.split()[-1] for l in out.splitlines() if " T " in l}
+    L = C.CDLL(shim)
+    L.FLAC__stream_encoder_new.restype = C.c_void_p
+    for n in ("get_state", "finish", "delete"):
+        getattr(L, "FLAC__stream_encoder_" + n).argtypes = [C.c_void_p]
+    for n in ("set_channels", "set_bits_per_sample", "set_sample_rate", "set_compression_level", "set_blocksize"):
+        getattr(L, "FLAC__stream_encoder_" + n).argtypes = [C.c_void_p, C.c_uint]
+    L.FLAC__stream_encoder_init_stream.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    e = L.FLAC__stream_encoder_new()
+    assert L.FLAC__stream_encoder_get_state(e) == 1                       # FLAC__STREAM_ENCODER_UNINITIALIZED
+    assert L.FLAC__stream_encoder_set_channels(e, 9) and L.FLAC__stream_encoder_init_stream(e, None, None, None, None, None) == 3   # no write callback
+    WRITE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_void_p)
+    cb = WRITE(lambda *a: 0)
+    assert L.FLAC__stream_encoder_init_stream(e, C.cast(cb, C.c_void_p), None, None, None, None) == 4    # INVALID_NUMBER_OF_CHANNELS
+    assert L.FLAC__stream_encoder_set_channels(e, 2) and L.FLAC__stream_encoder_set_bits_per_sample(e, 16) and L.FLAC__stream_encoder_set_sample_rate(e, 44100)
+    assert L.FLAC__stream_encoder_init_stream(e, C.cast(cb, C.c_void_p), None, None, None, None) == 0
+    assert L.FLAC__stream_encoder_get_state(e) == 0 and not L.FLAC__stream_encoder_set_channels(e, 1)  # setters only before init
+    assert L.FLAC__stream_encoder_init_stream(e, C.cast(cb, C.c_void_p), None, None, None, None) == 13   # ALREADY_INITIALIZED
+    L.FLAC__stream_encoder_delete(e)

@@ -146,3 +146,78 @@ def test_init_file_total_samples_and_seek_absolute(streams, tmp_path):
     assert L.FLAC__stream_decoder_seek_absolute(dec, s.total_samples + 5) == 0 and L.FLAC__stream_decoder_get_state(dec) == 6   # SeekError
     L.FLAC__stream_decoder_finish(dec)
     L.FLAC__stream_decoder_delete(dec)
+
+
+# ---------------------------------------------------------------------------------------------- encoder half
+ENC_WRITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_uint, C.c_uint, C.c_void_p)
+ENC_META_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+def _enc_lib():
+    L = _lib()
+    L.FLAC__stream_encoder_new.restype = C.c_void_p
+    for n in ("get_state", "finish", "delete"):
+        getattr(L, "FLAC__stream_encoder_" + n).argtypes = [C.c_void_p]
+    for n in ("set_channels", "set_bits_per_sample", "set_sample_rate", "set_compression_level", "set_blocksize"):
+        getattr(L, "FLAC__stream_encoder_" + n).argtypes = [C.c_void_p, C.c_uint]
+    for n in ("set_verify", "set_streamable_subset", "set_do_mid_side_stereo", "set_loose_mid_side_stereo"):
+        getattr(L, "FLAC__stream_encoder_" + n).argtypes = [C.c_void_p, C.c_int32]
+    L.FLAC__stream_encoder_init_stream.argtypes = [C.c_void_p, ENC_WRITE_CB, C.c_void_p, C.c_void_p, ENC_META_CB, C.c_void_p]
+    L.FLAC__stream_encoder_init_file.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
+    L.FLAC__stream_encoder_process_interleaved.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_uint]
+    L.FLAC__stream_encoder_process.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.c_uint]
+    return L
+
+
+@pytest.mark.parametrize("planar", [False, True])
+def test_legacy_encoder_symbols_drive_the_gpu_encoder(planar, tmp_path):
+    """The libFLAC call sequence the declarations of LibFLACSharp.cs:322-387 are for: new, setters, init_stream, process* in pieces,
+    finish, delete.  The bytes handed to the write callback are a FLAC stream that decodes to the samples, in libFLAC's call pattern."""
+    import hashlib
+    import numpy as np
+    import pycorpus
+    import pyoracle
+    L = _enc_lib()
+    s = pycorpus.make(ch=2, bps=16, sr=44100, samples=4096 * 5 + 777, bs=4096, lpc=8)
+    x = np.frombuffer(s.pcm, dtype="<i2").astype(np.int32)            # interleaved int32, what process_interleaved takes
+    calls, meta = [], []
+
+    def write(enc, buf, n, samples, frame, client):
+        calls.append((bytes(bytearray(buf[:n])), samples, frame))
+        return 0
+
+    def metadata(enc, m, client):
+        f = (C.c_uint32 * 12).from_address(m)
+        meta.append((f[0], f[8], f[9], f[10], C.c_uint64.from_address(m + 48).value, bytes((C.c_uint8 * 16).from_address(m + 56))))
+    wcb, mcb = ENC_WRITE_CB(write), ENC_META_CB(metadata)
+    e = L.FLAC__stream_encoder_new()
+    assert L.FLAC__stream_encoder_set_channels(e, 2) and L.FLAC__stream_encoder_set_bits_per_sample(e, 16) and L.FLAC__stream_encoder_set_sample_rate(e, 44100)
+    assert L.FLAC__stream_encoder_set_compression_level(e, 5) and L.FLAC__stream_encoder_set_verify(e, 1) and L.FLAC__stream_encoder_set_do_mid_side_stereo(e, 1)
+    assert L.FLAC__stream_encoder_init_stream(e, wcb, None, None, mcb, None) == 0
+    step = 1000                                                        # inter-channel samples per call
+    for at in range(0, len(x) // 2, step):
+        n = min(step, len(x) // 2 - at)
+        if planar:
+            l = np.ascontiguousarray(x[2 * at:2 * (at + n):2]); r = np.ascontiguousarray(x[2 * at + 1:2 * (at + n):2])
+            ptrs = (C.POINTER(C.c_int32) * 2)(l.ctypes.data_as(C.POINTER(C.c_int32)), r.ctypes.data_as(C.POINTER(C.c_int32)))
+            assert L.FLAC__stream_encoder_process(e, ptrs, n)
+        else:
+            chunk = np.ascontiguousarray(x[2 * at:2 * (at + n)])
+            assert L.FLAC__stream_encoder_process_interleaved(e, chunk.ctypes.data_as(C.POINTER(C.c_int32)), n)
+    assert L.FLAC__stream_encoder_finish(e) and L.FLAC__stream_encoder_get_state(e) == 1
+    L.FLAC__stream_encoder_delete(e)
+    assert calls[0] == (b"fLaC", 0, 0) and len(calls[1][0]) == 38 and calls[1][1:] == (0, 0)
+    assert [c[1:] for c in calls[2:]] == [(4096, i) for i in range(5)] + [(777, 5)]
+    flac = b"".join(c[0] for c in calls)
+    got, nframes, _, errs = pyoracle.decode(flac)
+    assert got == s.pcm and nframes == 6 and not list(errs)
+    assert meta == [(0, 44100, 2, 16, 4096 * 5 + 777, hashlib.md5(s.pcm).digest())]
+    # init_file writes the same stream to disk
+    e = L.FLAC__stream_encoder_new()
+    L.FLAC__stream_encoder_set_channels(e, 2); L.FLAC__stream_encoder_set_bits_per_sample(e, 16); L.FLAC__stream_encoder_set_sample_rate(e, 44100)
+    p = str(tmp_path / "o.flac").encode()
+    assert L.FLAC__stream_encoder_init_file(e, p, None, None) == 0
+    assert L.FLAC__stream_encoder_process_interleaved(e, np.ascontiguousarray(x).ctypes.data_as(C.POINTER(C.c_int32)), len(x) // 2)
+    assert L.FLAC__stream_encoder_finish(e)
+    L.FLAC__stream_encoder_delete(e)
+    assert open(p, "rb").read() == flac
