@@ -161,15 +161,19 @@ __device__ uint32_t make_frame_header(uint8_t* h, const EncArgs& a, uint32_t bs,
 }
 
 // ------------------------------------------------------------------------------------------------ plan kernel
+constexpr int NPART = (2 << MAX_PO) - 1;         // partitions of all orders 0..MAX_PO; order L starts at (1 << L) - 1
 struct PlanShared {
-    double red[MAX_LPC + 1][NW];
     double ac[MAX_LPC + 1];
-    double lpcs[MAX_LPC + 1][MAX_LPC];       // row o: predictor of order o (Levinson-Durbin stage o)
-    unsigned long long psum[1 << MAX_PO];     // sum of zig-zagged residuals per partition (current level)
-    uint32_t pb[3][1 << MAX_PO];              // sum of (u >> k) per partition for the three candidate parameters
-    uint8_t k0[1 << MAX_PO];
-    uint8_t kb[1 << MAX_PO];                  // best parameter per partition at the current level
+    double err[MAX_LPC + 1];
+    double est[MAX_LPC + 1];
+    double lpcs[MAX_LPC * (MAX_LPC + 1) / 2];  // predictor of order o (Levinson-Durbin stage o) at o (o - 1) / 2 ... + o
+    unsigned long long psum[NPART];           // sum of zig-zagged residuals per partition, every partition order
+    uint32_t pb[3][NPART];                    // sum of (u >> k) per partition for the three candidate parameters
+    uint8_t k0[NPART];
+    uint8_t kb[NPART];                        // best parameter per partition
+    uint32_t lvl_bits[MAX_PO + 1], lvl_big[MAX_PO + 1];
     unsigned long long scratch[NW];
+    unsigned long long red5[5][NW];
     EncSub dec[8];
     EncSub tmp;
     int32_t qc[MAX_LPC];
@@ -179,6 +183,9 @@ struct PlanShared {
 
 // The cheapest partitioned-Rice plan for residuals r[order..bs) (indexed by sample position).  Result in d->po / method / k[];
 // returns the size of the residual section in bits (method + partition order + parameters + codewords).
+// Every partition order of the allowed range is sized in the same two passes over the residuals (block-wide barriers, not
+// arithmetic, are what a CTA of this kernel waits for): sums of u per partition of the finest order -> every coarser order by
+// addition -> three candidate parameters around log2(mean) per partition -> exact bit counts of all of them in one pass.
 __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32_t order, uint32_t min_po, uint32_t max_po, PlanShared& sh, EncSub* d) {
     const uint32_t tid = threadIdx.x;
     // valid partition orders: the block divides evenly and partition 0 keeps at least one residual
@@ -187,70 +194,71 @@ __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32
     const uint32_t lo = min_po < hi ? min_po : hi;
     const uint32_t nper = (bs + NT - 1) / NT;
     const uint32_t i_begin = min(bs, max(order, tid * nper)), i_end = min(bs, (tid + 1) * nper);
-    // finest level: sums of u
-    for (uint32_t q = tid; q < (1u << hi); q += NT) sh.psum[q] = 0;
+    const uint32_t e_lo = (1u << lo) - 1u, e_hi = (2u << hi) - 1u;        // entries [e_lo, e_hi) of the per-partition tables
+    for (uint32_t e = e_lo + tid; e < e_hi; e += NT) { sh.psum[e] = 0; sh.pb[0][e] = 0; sh.pb[1][e] = 0; sh.pb[2][e] = 0; }
+    if (tid <= (uint32_t)MAX_PO) { sh.lvl_bits[tid] = 0; sh.lvl_big[tid] = 0; }
     __syncthreads();
-    {
-        const uint32_t psz = bs >> hi;
+    {   // finest order: sums of u
+        const uint32_t psz = bs >> hi, base = (1u << hi) - 1u;
         uint32_t i = i_begin;
         while (i < i_end) {
             const uint32_t q = i / psz, stop = min(i_end, (q + 1) * psz);
             unsigned long long s = 0;
             for (; i < stop; i++) s += zigzag(r[ridx(i)]);
-            atomicAdd(&sh.psum[q], s);
+            atomicAdd(&sh.psum[base + q], s);
         }
     }
     __syncthreads();
-    uint32_t best_bits = 0xffffffffu;
-    for (int L = (int)hi; L >= (int)lo; L--) {
-        const uint32_t np = 1u << L, psz = bs >> L;
-        if (L < (int)hi) {          // merge pairs of the level below
-            unsigned long long v = 0;
-            if (tid < np) v = sh.psum[2 * tid] + sh.psum[2 * tid + 1];
-            __syncthreads();
-            if (tid < np) sh.psum[tid] = v;
+    // coarser orders straight from the finest sums (no barrier per order), then the parameter estimate of every partition
+    for (uint32_t e = e_lo + tid; e < e_hi; e += NT) {
+        const uint32_t L = 31u - (uint32_t)__clz((int)(e + 1u)), q = e + 1u - (1u << L);
+        unsigned long long sum;
+        if (L == hi) sum = sh.psum[e];
+        else {
+            const uint32_t span = 1u << (hi - L), fb = (1u << hi) - 1u + q * span;
+            sum = 0;
+            for (uint32_t j = 0; j < span; j++) sum += sh.psum[fb + j];
         }
-        __syncthreads();
-        if (tid < np) {
-            const uint32_t n = psz - (tid == 0 ? order : 0);
-            const unsigned long long mean = sh.psum[tid] / n;
-            uint32_t k = mean ? 63u - (uint32_t)__clzll((long long)mean) : 0u;
-            if (k > 29) k = 29;
-            if (k < 1) k = 1;       // candidates k-1, k, k+1
-            sh.k0[tid] = (uint8_t)k;
-            sh.pb[0][tid] = 0; sh.pb[1][tid] = 0; sh.pb[2][tid] = 0;
-        }
-        __syncthreads();
-        {
-            uint32_t i = i_begin;
-            while (i < i_end) {
-                const uint32_t q = i / psz, stop = min(i_end, (q + 1) * psz);
-                const uint32_t k = sh.k0[q];
-                uint32_t s0 = 0, s1 = 0, s2 = 0;
-                for (; i < stop; i++) { const uint32_t u = zigzag(r[ridx(i)]); s0 += u >> (k - 1); s1 += u >> k; s2 += u >> (k + 1); }
-                atomicAdd(&sh.pb[0][q], s0); atomicAdd(&sh.pb[1][q], s1); atomicAdd(&sh.pb[2][q], s2);
-            }
-        }
-        __syncthreads();
-        uint32_t mybits = 0, mybig = 0;
-        if (tid < np) {
-            const uint32_t n = psz - (tid == 0 ? order : 0), k = sh.k0[tid];
-            uint32_t b = n * k + sh.pb[0][tid], kk = k - 1;                    // n * (kk + 1) + sum(u >> kk)
-            const uint32_t b1 = n * (k + 1) + sh.pb[1][tid], b2 = n * (k + 2) + sh.pb[2][tid];
-            if (b1 < b) { b = b1; kk = k; }
-            if (b2 < b) { b = b2; kk = k + 1; }
-            sh.kb[tid] = (uint8_t)kk;
-            mybits = b; mybig = kk > 14 ? 1u : 0u;
-        }
-        const uint32_t big = block_or_u32(mybig, sh.scratch);
-        const uint32_t tot = (uint32_t)block_sum_u64(mybits, sh.scratch) + np * (big ? 5u : 4u) + 6u;
-        if (tot < best_bits) {      // uniform
-            best_bits = tot;
-            if (tid < np) d->k[tid] = sh.kb[tid];
-            if (tid == 0) { d->po = (uint8_t)L; d->method = (uint8_t)big; }
-        }
-        __syncthreads();
+        const uint32_t n = (bs >> L) - (q == 0 ? order : 0);
+        const unsigned long long mean = sum / n;
+        uint32_t k = mean ? 63u - (uint32_t)__clzll((long long)mean) : 0u;
+        if (k > 29) k = 29;
+        if (k < 1) k = 1;           // candidates k-1, k, k+1
+        sh.k0[e] = (uint8_t)k;
     }
+    __syncthreads();
+    for (uint32_t L = lo; L <= hi; L++) {
+        const uint32_t psz = bs >> L, base = (1u << L) - 1u;
+        uint32_t i = i_begin;
+        while (i < i_end) {
+            const uint32_t q = i / psz, stop = min(i_end, (q + 1) * psz);
+            const uint32_t k = sh.k0[base + q];
+            uint32_t s0 = 0, s1 = 0, s2 = 0;
+            for (; i < stop; i++) { const uint32_t u = zigzag(r[ridx(i)]); s0 += u >> (k - 1); s1 += u >> k; s2 += u >> (k + 1); }
+            atomicAdd(&sh.pb[0][base + q], s0); atomicAdd(&sh.pb[1][base + q], s1); atomicAdd(&sh.pb[2][base + q], s2);
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = e_lo + tid; e < e_hi; e += NT) {
+        const uint32_t L = 31u - (uint32_t)__clz((int)(e + 1u)), q = e + 1u - (1u << L);
+        const uint32_t n = (bs >> L) - (q == 0 ? order : 0), k = sh.k0[e];
+        uint32_t bb = n * k + sh.pb[0][e], kk = k - 1;                      // n * (kk + 1) + sum(u >> kk)
+        const uint32_t b1 = n * (k + 1) + sh.pb[1][e], b2 = n * (k + 2) + sh.pb[2][e];
+        if (b1 < bb) { bb = b1; kk = k; }
+        if (b2 < bb) { bb = b2; kk = k + 1; }
+        sh.kb[e] = (uint8_t)kk;
+        atomicAdd(&sh.lvl_bits[L], bb);
+        if (kk > 14) atomicOr(&sh.lvl_big[L], 1u);
+    }
+    __syncthreads();
+    uint32_t best_bits = 0xffffffffu, best_L = hi;
+    for (int L = (int)hi; L >= (int)lo; L--) {
+        const uint32_t tot = sh.lvl_bits[L] + (1u << L) * (sh.lvl_big[L] ? 5u : 4u) + 6u;
+        if (tot < best_bits) { best_bits = tot; best_L = (uint32_t)L; }
+    }
+    for (uint32_t q = tid; q < (1u << best_L); q += NT) d->k[q] = sh.kb[(1u << best_L) - 1u + q];
+    if (tid == 0) { d->po = (uint8_t)best_L; d->method = (uint8_t)(sh.lvl_big[best_L] ? 1 : 0); }
+    __syncthreads();
     return best_bits;
 }
 
@@ -273,8 +281,16 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         const int32_t x0 = load_variant(a, base, 0, v);
         uint32_t orv = 0, differs = 0;
         for (uint32_t i = tid; i < bs; i += NT) { const int32_t s = load_variant(a, base, i, v); x[i] = s; orv |= (uint32_t)s; differs |= (uint32_t)(s != x0); }
-        orv = block_or_u32(orv, sh.scratch);
-        differs = block_or_u32(differs, sh.scratch);
+        {   // one exchange for both
+            orv = __reduce_or_sync(FULL, orv); differs = __reduce_or_sync(FULL, differs);
+            __syncthreads();
+            if ((tid & 31) == 0) sh.scratch[tid >> 5] = (unsigned long long)differs << 32 | orv;
+            __syncthreads();
+            unsigned long long t = 0;
+#pragma unroll
+            for (int wv = 0; wv < NW; wv++) t |= sh.scratch[wv];
+            orv = (uint32_t)t; differs = (uint32_t)(t >> 32);
+        }
         uint32_t w = orv ? (uint32_t)__ffs((int)orv) - 1u : 0u;
         if (w >= vbps) w = 0;
         if (w) { for (uint32_t i = tid; i < bs; i += NT) x[i] >>= w; }
@@ -300,12 +316,24 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
 #pragma unroll
             for (int o = 0; o < 5; o++) if (i >= (uint32_t)o) { const unsigned long long m = (unsigned long long)(dd[o] < 0 ? -dd[o] : dd[o]); fs[o] += m; if (m > 0x3fffffffull) fbig |= 1u << o; }
         }
-        fbig = block_or_u32(fbig, sh.scratch);
+        // one exchange for the five sums (the overflow flags ride in bit 63 of each)
+#pragma unroll
+        for (int o = 0; o < 5; o++) {
+            unsigned long long t = fs[o] | ((fbig >> o) & 1u ? 1ull << 63 : 0ull);
+            const unsigned long long flag = __reduce_or_sync(FULL, (uint32_t)(t >> 63)) ? 1ull << 63 : 0ull;
+            t &= ~(1ull << 63);
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1) t += __shfl_xor_sync(FULL, t, sft);
+            if ((tid & 31) == 0) sh.red5[o][tid >> 5] = t | flag;
+        }
+        __syncthreads();
         uint32_t fo = 0xffffffffu; unsigned long long fbest = ~0ull;
 #pragma unroll
         for (int o = 0; o < 5; o++) {
-            const unsigned long long s = block_sum_u64(fs[o], sh.scratch);
-            if ((uint32_t)o < bs && !((fbig >> o) & 1u) && s < fbest) { fbest = s; fo = (uint32_t)o; }
+            unsigned long long t = 0, flag = 0;
+#pragma unroll
+            for (int wv = 0; wv < NW; wv++) { const unsigned long long q = sh.red5[o][wv]; t += q & ~(1ull << 63); flag |= q >> 63; }
+            if ((uint32_t)o < bs && !flag && t < fbest) { fbest = t; fo = (uint32_t)o; }
         }
         // ---- LPC analysis (before r[] is used: wf aliases it)
         uint32_t maxo = min(a.max_lpc, (uint32_t)MAX_LPC);
@@ -315,30 +343,20 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
             const float half = 0.5f * (float)(bs - 1), inv = 1.0f / (half + 1.0f);
             for (uint32_t i = tid; i < bs; i += NT) { const float t = ((float)i - half) * inv; wf[i] = (float)x[i] * (1.0f - t * t); }
             __syncthreads();
-            double acc[MAX_LPC + 1];
+            // autocorrelation: a warp per lag (lags warp, warp + NW, ...), lanes stride over the samples: no per-thread table of 33
+            // running sums (registers), one barrier instead of a block-wide reduction per lag
+            for (uint32_t l = tid >> 5; l <= maxo; l += NW) {
+                double sacc = 0.0;
+                for (uint32_t i = l + (tid & 31); i < bs; i += 32) sacc = fma((double)wf[i], (double)wf[i - l], sacc);
 #pragma unroll
-            for (int l = 0; l <= MAX_LPC; l++) acc[l] = 0.0;
-            for (uint32_t i = tid; i < bs; i += NT) {
-                const double wi = (double)wf[i];
-#pragma unroll
-                for (int l = 0; l <= MAX_LPC; l++) if ((uint32_t)l <= maxo && (uint32_t)l <= i) acc[l] = fma(wi, (double)wf[i - l], acc[l]);
+                for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
+                if ((tid & 31) == 0) sh.ac[l] = sacc;
             }
-#pragma unroll
-            for (int l = 0; l <= MAX_LPC; l++) {
-                if ((uint32_t)l <= maxo) {
-                    double s = acc[l];
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-                    if ((tid & 31) == 0) sh.red[l][tid >> 5] = s;
-                }
-            }
-            __syncthreads();
-            if (tid <= maxo) { double s = 0; for (int wv = 0; wv < NW; wv++) s += sh.red[tid][wv]; sh.ac[tid] = s; }
             __syncthreads();
             if (tid == 0 && sh.ac[0] > 0.0) {
                 // Levinson-Durbin; err[o] = prediction error energy of order o
-                double e = sh.ac[0], aa[MAX_LPC], err[MAX_LPC + 1];
-                err[0] = e;
+                double e = sh.ac[0], aa[MAX_LPC];
+                sh.err[0] = e;
                 for (uint32_t i = 0; i < maxo; i++) {
                     double rr = -sh.ac[i + 1];
                     for (uint32_t j = 0; j < i; j++) rr -= aa[j] * sh.ac[i - j];
@@ -348,26 +366,31 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
                     if (i & 1) aa[i / 2] += aa[i / 2] * rr;
                     e *= (1.0 - rr * rr);
                     if (!(e > 0.0)) e = 1e-9;
-                    for (uint32_t j = 0; j <= i; j++) sh.lpcs[i + 1][j] = -aa[j];
-                    err[i + 1] = e;
+                    for (uint32_t j = 0; j <= i; j++) sh.lpcs[(i + 1) * i / 2 + j] = -aa[j];
+                    sh.err[i + 1] = e;
                 }
-                uint32_t prec = a.prec ? a.prec : (ebps > 16 ? (bs > 1152 ? 15u : 14u) : (bs > 4608 ? 13u : 12u));
-                if (prec > 15) prec = 15;
-                if (prec < 5) prec = 5;
+                sh.lpc_ok = 2;          // analysis done, order not chosen yet
+            }
+            __syncthreads();
+            const uint32_t prec_v = min(15u, max(5u, a.prec ? a.prec : (ebps > 16 ? (bs > 1152 ? 15u : 14u) : (bs > 4608 ? 13u : 12u))));
+            if (sh.lpc_ok == 2 && a.search_order && tid >= 1 && tid <= maxo) {      // libFLAC's estimate: bits per residual sample from the error energy, one order per thread
+                const double ee = sh.err[tid] * (0.5 * 0.4804530139182014 / (double)bs);
+                double bpr = ee > 0 ? 0.5 * log2(ee) : 0.0;
+                if (bpr < 0) bpr = 0;
+                sh.est[tid] = bpr * (double)(bs - tid) + (double)tid * (double)(ebps + prec_v);
+            }
+            __syncthreads();
+            if (tid == 0 && sh.lpc_ok == 2) {
+                sh.lpc_ok = 0;
+                const uint32_t prec = prec_v;
                 uint32_t lo = maxo;
-                if (a.search_order) {       // libFLAC's estimate: bits per residual sample from the error energy
+                if (a.search_order) {
                     double bestest = 1e300;
-                    for (uint32_t o = 1; o <= maxo; o++) {
-                        const double ee = err[o] * (0.5 * 0.4804530139182014 / (double)bs);
-                        double bpr = ee > 0 ? 0.5 * log2(ee) : 0.0;
-                        if (bpr < 0) bpr = 0;
-                        const double est = bpr * (double)(bs - o) + (double)o * (double)(ebps + prec);
-                        if (est < bestest) { bestest = est; lo = o; }
-                    }
+                    for (uint32_t o = 1; o <= maxo; o++) if (sh.est[o] < bestest) { bestest = sh.est[o]; lo = o; }
                 }
                 // quantise with error feedback
                 double cmax = 0;
-                for (uint32_t i = 0; i < lo; i++) { const double m = fabs(sh.lpcs[lo][i]); if (m > cmax) cmax = m; }
+                for (uint32_t i = 0; i < lo; i++) { const double m = fabs(sh.lpcs[lo * (lo - 1) / 2 + i]); if (m > cmax) cmax = m; }
                 if (cmax > 0) {
                     int l2; (void)frexp(cmax, &l2); l2--;
                     int shift = (int)prec - l2 - 2;
@@ -376,7 +399,7 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
                         const int32_t qmax = (1 << (prec - 1)) - 1, qmin = -qmax - 1;
                         double ef = 0;
                         for (uint32_t i = 0; i < lo; i++) {
-                            ef += sh.lpcs[lo][i] * (double)(1 << shift);
+                            ef += sh.lpcs[lo * (lo - 1) / 2 + i] * (double)(1 << shift);
                             long long vq = llrint(ef);
                             if (vq > qmax) vq = qmax;
                             if (vq < qmin) vq = qmin;

@@ -100,5 +100,38 @@ namespace LibBnFlacSharp
 
 		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
 		public static extern int bnflac_device_count();
+
+		// ---- encoder (SURVEY 8f-4): replaces the FLAC__stream_encoder_* DllImports of LibFLACSharp.cs:322-387 ----
+		[StructLayout(LayoutKind.Sequential)]
+		public struct EncOpts
+		{
+			public uint StructSize;       // = Marshal.SizeOf(typeof(EncOpts))
+			public int Device;            // -1 = current CUDA device
+			public IntPtr Stream;
+			public uint SampleRate, Channels, BitsPerSample;      // set_sample_rate / set_channels / set_bits_per_sample
+			public uint BlockSize;        // set_blocksize; 0 = 4096 (or the preset's)
+			public uint MaxLpcOrder, QlpPrecision, MinPartitionOrder, MaxPartitionOrder;
+			public uint MidSide;          // set_do_mid_side_stereo
+			public uint CompressionLevel; // set_compression_level, with Flags |= UseLevel
+			public uint Flags;            // 1 NoMd5, 2 InputInt32, 4 UseLevel, 8 FixedOrder
+		}
+
+		[StructLayout(LayoutKind.Sequential)]
+		public struct EncStats
+		{
+			public float PlanMs, WriteMs, TotalMs;
+			public uint Frames;
+			public ulong Bytes;
+			public uint MinFrameSize, MaxFrameSize;
+			public IntPtr FrameSizes;     // in: IntPtr.Zero or room for FrameSizesCap uints
+			public ulong FrameSizesCap;
+		}
+
+		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
+		public static extern int bnflac_encode_bound(UIntPtr pcmBytes, ref EncOpts opts, out ulong bound);
+
+		// interleaved little-endian PCM (the layout FLACDecoder.Read returns) -> "fLaC" + STREAMINFO + frames
+		[DllImport(DLLName, CallingConvention = CallingConvention.Cdecl)]
+		public static extern int bnflac_encode(byte[] pcm, UIntPtr pcmBytes, ref EncOpts opts, byte[] dst, UIntPtr cap, out ulong written, ref EncStats stats);
 	}
 }
