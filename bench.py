@@ -466,16 +466,16 @@ def corpus_job(ctx, maps, info, shard, steps):
     return ms, outs, written
 
 
-def encode_entry(ctx, s, reps=8, steps=3):
-    """the GPU encoder on the cfg2 shape.  `reps` copies of the unique 60 s PCM tile, device-resident in, device-resident
-    stream out (bnflac_encode_device, MD5 off: it is serial host work); the stream is then decoded by the GPU decoder and compared with
-    the PCM on the device."""
+def encode_entry(ctx, s, label, reps, steps=3, **enc):
+    """the GPU encoder.  `reps` copies of the unique PCM tile of stream `s`, device-resident in, device-resident stream out
+    (bnflac_encode_device, MD5 off: it is serial host work); the stream is then decoded by the GPU decoder and compared with the PCM
+    on the device."""
     torch, _abi, dev, local, stream = ctx
     tile = torch.frombuffer(bytearray(s.pcm), dtype=torch.uint8).to(dev)
     d_pcm = tile.repeat(reps)
     n = d_pcm.numel()
     B = (s.bps + 7) // 8
-    o = _abi.enc_opts(s.sample_rate, s.channels, s.bps, blocksize=4096, max_lpc_order=12, max_partition_order=6, flags=_abi.ENC_NO_MD5, device=local)
+    o = _abi.enc_opts(s.sample_rate, s.channels, s.bps, flags=_abi.ENC_NO_MD5 | enc.pop("flags", 0), device=local, **enc)
     cap = _abi.encode_bound(n, o)
     d_flac = torch.zeros(cap + 256, dtype=torch.uint8, device=dev)
     best = None
@@ -492,10 +492,10 @@ def encode_entry(ctx, s, reps=8, steps=3):
     if written != n or not torch.equal(d_out[:n], d_pcm):
         raise SystemExit("bench.py: encode: the GPU decoder does not return the PCM the GPU encoder was given -- refusing to report a number")
     samples = n // B
-    tile_ratio_cpu = len(s.flac) / s.tiles / len(s.pcm) if getattr(s, "tiles", 0) else None
-    return {"workload": f"cfg2 shape: {reps} x 60 s 24-bit stereo 96 kHz PCM ({n / 1e6:.0f} MB), blocksize 4096, LPC <= 12, partition order <= 6, adaptive mid/side; device PCM -> device FLAC stream",
+    return {"workload": f"{label}: {n / 1e6:.0f} MB of PCM, device PCM -> device FLAC stream",
             "samples": samples, "frames": int(best.frames), "ms": round(best.total_ms, 3), "plan_ms": round(best.plan_ms, 3), "write_ms": round(best.write_ms, 3),
-            "samples_per_s": samples / (best.total_ms / 1e3), "compressed_bytes": int(w), "ratio": w / n, "ratio_cpu_corpus_encoder": tile_ratio_cpu,
+            "samples_per_s": samples / (best.total_ms / 1e3), "pcm_gbps": n / (best.total_ms / 1e3) / 1e9, "compressed_bytes": int(w), "ratio": w / n,
+            "ratio_cpu_corpus_encoder": len(s.flac) / max(1, s.tiles) / len(s.pcm),
             "check": "stream decoded by the GPU decoder == the input PCM (device compare); tests/test_encode_gpu.py decodes such streams with the oracle and the reference DLL"}
 
 
@@ -670,7 +670,14 @@ def run_ours(args):
         extra["by_file"] = dict(cfgs["cfg4_share"], n_gpus=1, note="N = 1: one GPU's 1/8 share of the batch (the whole 100,000 clips are split over the ranks when N > 1)")
         if not args.no_e2e:
             extra["e2e_stream"] = stream_surface_entry(s.flac, total_samples_all, local)
-        extra["encode"] = encode_entry(ctx, s)
+        import pycorpus
+        g3 = pycorpus.make(**dict(cfg3_kwargs(small), tile=1))
+        extra["encode"] = {
+            "cfg2_shape": encode_entry(ctx, s, "8 x 60 s 24-bit stereo 96 kHz, blocksize 4096, LPC <= 12, partition order <= 6, adaptive mid/side", 8,
+                                       blocksize=4096, max_lpc_order=12, max_partition_order=6),
+            "cfg3_shape": encode_entry(ctx, g3, "100 x 12 frames 24-bit 8 ch 192 kHz, blocksize 16384, LPC 32 (fixed order), Rice2 partition order 8", 100,
+                                       blocksize=16384, max_lpc_order=32, min_partition_order=8, max_partition_order=8, flags=_abi.ENC_FIXED_ORDER)}
+        g3.free()
 
     # ---- N > 1: the partitions BASELINE names -- one corpus by frame ranges, the clip batch by file ---------------------
     if not args.no_configs and world > 1:

@@ -172,6 +172,7 @@ struct PlanShared {
     uint8_t k0[NPART];
     uint8_t kb[NPART];                        // best parameter per partition
     uint32_t lvl_bits[MAX_PO + 1], lvl_big[MAX_PO + 1];
+    unsigned long long lvl_est[MAX_PO + 1];
     unsigned long long scratch[NW];
     unsigned long long red5[5][NW];
     EncSub dec[8];
@@ -183,9 +184,9 @@ struct PlanShared {
 
 // The cheapest partitioned-Rice plan for residuals r[order..bs) (indexed by sample position).  Result in d->po / method / k[];
 // returns the size of the residual section in bits (method + partition order + parameters + codewords).
-// Every partition order of the allowed range is sized in the same two passes over the residuals (block-wide barriers, not
-// arithmetic, are what a CTA of this kernel waits for): sums of u per partition of the finest order -> every coarser order by
-// addition -> three candidate parameters around log2(mean) per partition -> exact bit counts of all of them in one pass.
+// Two passes over the residuals: sums of u per partition of the finest order -> every coarser order by addition -> the partition
+// order with the smallest ESTIMATED size (libFLAC's estimate from the sums; sizing every order exactly cost 7 x the instructions
+// for 0.1 % of the bytes) -> three candidate parameters around log2(mean) per partition of that order, sized EXACTLY.
 __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32_t order, uint32_t min_po, uint32_t max_po, PlanShared& sh, EncSub* d) {
     const uint32_t tid = threadIdx.x;
     // valid partition orders: the block divides evenly and partition 0 keeps at least one residual
@@ -196,7 +197,7 @@ __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32
     const uint32_t i_begin = min(bs, max(order, tid * nper)), i_end = min(bs, (tid + 1) * nper);
     const uint32_t e_lo = (1u << lo) - 1u, e_hi = (2u << hi) - 1u;        // entries [e_lo, e_hi) of the per-partition tables
     for (uint32_t e = e_lo + tid; e < e_hi; e += NT) { sh.psum[e] = 0; sh.pb[0][e] = 0; sh.pb[1][e] = 0; sh.pb[2][e] = 0; }
-    if (tid <= (uint32_t)MAX_PO) { sh.lvl_bits[tid] = 0; sh.lvl_big[tid] = 0; }
+    if (tid <= (uint32_t)MAX_PO) { sh.lvl_bits[tid] = 0; sh.lvl_big[tid] = 0; sh.lvl_est[tid] = 0; }
     __syncthreads();
     {   // finest order: sums of u
         const uint32_t psz = bs >> hi, base = (1u << hi) - 1u;
@@ -209,7 +210,8 @@ __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32
         }
     }
     __syncthreads();
-    // coarser orders straight from the finest sums (no barrier per order), then the parameter estimate of every partition
+    // Every coarser order straight from the finest sums (no barrier per order); per partition the parameter near log2(mean) and
+    // libFLAC's estimate of its size from the sum alone: n (k + 1) + (sum >> k) - n / 2 (each floor loses half a bit on average).
     for (uint32_t e = e_lo + tid; e < e_hi; e += NT) {
         const uint32_t L = 31u - (uint32_t)__clz((int)(e + 1u)), q = e + 1u - (1u << L);
         unsigned long long sum;
@@ -225,10 +227,23 @@ __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32
         if (k > 29) k = 29;
         if (k < 1) k = 1;           // candidates k-1, k, k+1
         sh.k0[e] = (uint8_t)k;
+        unsigned long long est = ~0ull;
+        for (uint32_t kk = k - 1; kk <= k + 1; kk++) {
+            const unsigned long long body = sum >> kk, half = kk ? n / 2 : 0;
+            const unsigned long long t = (unsigned long long)n * (kk + 1) + (body > half ? body - half : 0);
+            if (t < est) est = t;
+        }
+        atomicAdd(&sh.lvl_est[L], est + (k >= 14 ? 5u : 4u));
     }
     __syncthreads();
-    for (uint32_t L = lo; L <= hi; L++) {
-        const uint32_t psz = bs >> L, base = (1u << L) - 1u;
+    uint32_t best_L = hi;
+    {
+        unsigned long long be = ~0ull;
+        for (int L = (int)hi; L >= (int)lo; L--) if (sh.lvl_est[L] < be) { be = sh.lvl_est[L]; best_L = (uint32_t)L; }
+    }
+    // exact sizes of the three candidate parameters of every partition of the chosen order
+    const uint32_t psz = bs >> best_L, base = (1u << best_L) - 1u, np = 1u << best_L;
+    {
         uint32_t i = i_begin;
         while (i < i_end) {
             const uint32_t q = i / psz, stop = min(i_end, (q + 1) * psz);
@@ -239,24 +254,19 @@ __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32
         }
     }
     __syncthreads();
-    for (uint32_t e = e_lo + tid; e < e_hi; e += NT) {
-        const uint32_t L = 31u - (uint32_t)__clz((int)(e + 1u)), q = e + 1u - (1u << L);
-        const uint32_t n = (bs >> L) - (q == 0 ? order : 0), k = sh.k0[e];
+    for (uint32_t q = tid; q < np; q += NT) {
+        const uint32_t e = base + q;
+        const uint32_t n = psz - (q == 0 ? order : 0), k = sh.k0[e];
         uint32_t bb = n * k + sh.pb[0][e], kk = k - 1;                      // n * (kk + 1) + sum(u >> kk)
         const uint32_t b1 = n * (k + 1) + sh.pb[1][e], b2 = n * (k + 2) + sh.pb[2][e];
         if (b1 < bb) { bb = b1; kk = k; }
         if (b2 < bb) { bb = b2; kk = k + 1; }
-        sh.kb[e] = (uint8_t)kk;
-        atomicAdd(&sh.lvl_bits[L], bb);
-        if (kk > 14) atomicOr(&sh.lvl_big[L], 1u);
+        d->k[q] = (uint8_t)kk;
+        atomicAdd(&sh.lvl_bits[best_L], bb);
+        if (kk > 14) atomicOr(&sh.lvl_big[best_L], 1u);
     }
     __syncthreads();
-    uint32_t best_bits = 0xffffffffu, best_L = hi;
-    for (int L = (int)hi; L >= (int)lo; L--) {
-        const uint32_t tot = sh.lvl_bits[L] + (1u << L) * (sh.lvl_big[L] ? 5u : 4u) + 6u;
-        if (tot < best_bits) { best_bits = tot; best_L = (uint32_t)L; }
-    }
-    for (uint32_t q = tid; q < (1u << best_L); q += NT) d->k[q] = sh.kb[(1u << best_L) - 1u + q];
+    const uint32_t best_bits = sh.lvl_bits[best_L] + np * (sh.lvl_big[best_L] ? 5u : 4u) + 6u;
     if (tid == 0) { d->po = (uint8_t)best_L; d->method = (uint8_t)(sh.lvl_big[best_L] ? 1 : 0); }
     __syncthreads();
     return best_bits;
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
     const uint32_t bs = (uint32_t)min((uint64_t)a.bs, a.total_samples - s0);
     int32_t* x = reinterpret_cast<int32_t*>(dyn);
     int32_t* r = x + a.bs;
-    float* wf = reinterpret_cast<float*>(r);          // the windowed signal lives where the residuals go later
+    int32_t* wi = r;                                  // the windowed signal lives where the residuals go later
     const uint64_t base = s0 * a.ch;
     const uint32_t nvar = a.stereo ? 4u : a.ch;
 
@@ -304,17 +314,17 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         }
         const uint32_t verb_bits = 8 + w + bs * ebps;
         // ---- FIXED: order with the smallest sum of |residual|
+        // samples have at most 25 bits (24 + the side channel's extra one): every difference up to order 4 fits 29 bits, so the
+        // arithmetic is 32-bit and no residual can leave the range the Rice coder takes
         unsigned long long fs[5] = {0, 0, 0, 0, 0};
-        uint32_t fbig = 0;
+        const uint32_t fbig = 0;
         for (uint32_t i = tid; i < bs; i += NT) {
-            long long dd[5];
-            dd[0] = x[i];
-            dd[1] = i >= 1 ? dd[0] - x[i - 1] : 0;
-            dd[2] = i >= 2 ? dd[1] - ((long long)x[i - 1] - x[i - 2]) : 0;
-            dd[3] = i >= 3 ? dd[2] - ((long long)x[i - 1] - 2ll * x[i - 2] + x[i - 3]) : 0;
-            dd[4] = i >= 4 ? dd[3] - ((long long)x[i - 1] - 3ll * x[i - 2] + 3ll * x[i - 3] - x[i - 4]) : 0;
+            const int32_t v0 = x[i], v1 = i >= 1 ? x[i - 1] : 0, v2 = i >= 2 ? x[i - 2] : 0, v3 = i >= 3 ? x[i - 3] : 0, v4 = i >= 4 ? x[i - 4] : 0;
+            const int32_t p1 = v1 - v2, p2 = p1 - (v2 - v3), p3 = p2 - ((v2 - v3) - (v3 - v4));       // differences ending at i - 1
+            int32_t dd[5];
+            dd[0] = v0; dd[1] = v0 - v1; dd[2] = dd[1] - p1; dd[3] = dd[2] - p2; dd[4] = dd[3] - p3;
 #pragma unroll
-            for (int o = 0; o < 5; o++) if (i >= (uint32_t)o) { const unsigned long long m = (unsigned long long)(dd[o] < 0 ? -dd[o] : dd[o]); fs[o] += m; if (m > 0x3fffffffull) fbig |= 1u << o; }
+            for (int o = 0; o < 5; o++) if (i >= (uint32_t)o) fs[o] += (uint32_t)(dd[o] < 0 ? -dd[o] : dd[o]);
         }
         // one exchange for the five sums (the overflow flags ride in bit 63 of each)
 #pragma unroll
@@ -335,22 +345,30 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
             for (int wv = 0; wv < NW; wv++) { const unsigned long long q = sh.red5[o][wv]; t += q & ~(1ull << 63); flag |= q >> 63; }
             if ((uint32_t)o < bs && !flag && t < fbest) { fbest = t; fo = (uint32_t)o; }
         }
-        // ---- LPC analysis (before r[] is used: wf aliases it)
+        // ---- LPC analysis (before r[] is used: wi aliases it)
         uint32_t maxo = min(a.max_lpc, (uint32_t)MAX_LPC);
         if (maxo >= bs) maxo = bs - 1;
         if (tid == 0) sh.lpc_ok = 0;
         if (maxo) {
+            // Welch window in Q15 on the integer samples, autocorrelation in exact 64-bit integer arithmetic (25-bit samples: a product
+            // has 48 bits, 16384 of them 62): a warp takes a PAIR of lags (one load of sample i serves both), its lanes stride over the
+            // samples, one shuffle reduction per lag.  (FP32 running sums, libFLAC's own choice, were measured first: 2 instructions per
+            // lag-sample like this, but tonal signals lost up to 20 % of their compression to the rounding of the sums.)
             const float half = 0.5f * (float)(bs - 1), inv = 1.0f / (half + 1.0f);
-            for (uint32_t i = tid; i < bs; i += NT) { const float t = ((float)i - half) * inv; wf[i] = (float)x[i] * (1.0f - t * t); }
+            for (uint32_t i = tid; i < bs; i += NT) {
+                const float t = ((float)i - half) * inv;
+                const int32_t wq = (int32_t)(32767.0f * (1.0f - t * t));
+                wi[i] = (int32_t)(((long long)x[i] * wq) >> 15);
+            }
             __syncthreads();
-            // autocorrelation: a warp per lag (lags warp, warp + NW, ...), lanes stride over the samples: no per-thread table of 33
-            // running sums (registers), one barrier instead of a block-wide reduction per lag
-            for (uint32_t l = tid >> 5; l <= maxo; l += NW) {
-                double sacc = 0.0;
-                for (uint32_t i = l + (tid & 31); i < bs; i += 32) sacc = fma((double)wf[i], (double)wf[i - l], sacc);
+            for (uint32_t l = 2 * (tid >> 5); l <= maxo; l += 2 * NW) {
+                const uint32_t lane = tid & 31;
+                long long sa = 0, sb = 0;
+                for (uint32_t i = l + 1 + lane; i < bs; i += 32) { const long long c = wi[i]; sa += c * wi[i - l]; sb += c * wi[i - l - 1]; }
+                if (lane == 0) sa += (long long)wi[l] * wi[0];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
-                if ((tid & 31) == 0) sh.ac[l] = sacc;
+                for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(FULL, sa, o); sb += __shfl_xor_sync(FULL, sb, o); }
+                if (lane == 0) { sh.ac[l] = (double)sa; if (l + 1 <= maxo) sh.ac[l + 1] = (double)sb; }
             }
             __syncthreads();
             if (tid == 0 && sh.ac[0] > 0.0) {
@@ -417,15 +435,15 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         if (fo != 0xffffffffu) {
             for (uint32_t i = tid; i < bs; i += NT) {
                 if (i < fo) continue;
-                long long p = 0;
+                int32_t p = 0;
                 switch (fo) {
                 case 1: p = x[i - 1]; break;
-                case 2: p = 2ll * x[i - 1] - x[i - 2]; break;
-                case 3: p = 3ll * x[i - 1] - 3ll * x[i - 2] + x[i - 3]; break;
-                case 4: p = 4ll * x[i - 1] - 6ll * x[i - 2] + 4ll * x[i - 3] - x[i - 4]; break;
+                case 2: p = 2 * x[i - 1] - x[i - 2]; break;
+                case 3: p = 3 * x[i - 1] - 3 * x[i - 2] + x[i - 3]; break;
+                case 4: p = 4 * x[i - 1] - 6 * x[i - 2] + 4 * x[i - 3] - x[i - 4]; break;
                 default: break;
                 }
-                r[ridx(i)] = (int32_t)((long long)x[i] - p);
+                r[ridx(i)] = x[i] - p;
             }
             __syncthreads();
             const uint32_t rb = plan_rice(r, bs, fo, a.min_po, a.max_po, sh, d);
@@ -622,15 +640,15 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
             if (type == 2) {
                 for (uint32_t i = tid; i < bs; i += NT) {
                     if (i < order) continue;
-                    long long p = 0;
+                    int32_t p = 0;
                     switch (order) {
                     case 1: p = x[i - 1]; break;
-                    case 2: p = 2ll * x[i - 1] - x[i - 2]; break;
-                    case 3: p = 3ll * x[i - 1] - 3ll * x[i - 2] + x[i - 3]; break;
-                    case 4: p = 4ll * x[i - 1] - 6ll * x[i - 2] + 4ll * x[i - 3] - x[i - 4]; break;
+                    case 2: p = 2 * x[i - 1] - x[i - 2]; break;
+                    case 3: p = 3 * x[i - 1] - 3 * x[i - 2] + x[i - 3]; break;
+                    case 4: p = 4 * x[i - 1] - 6 * x[i - 2] + 4 * x[i - 3] - x[i - 4]; break;
                     default: break;
                     }
-                    r[ridx(i)] = (int32_t)((long long)x[i] - p);
+                    r[ridx(i)] = x[i] - p;
                 }
             } else {
                 const uint32_t prec = D.prec, shift = D.shift;
