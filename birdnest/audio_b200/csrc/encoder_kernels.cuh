@@ -75,8 +75,10 @@ __device__ __forceinline__ int32_t load_variant(const EncArgs& a, uint64_t base,
 // residuals are written with consecutive lanes on consecutive samples and read back by threads that own RUNS of consecutive samples
 // (stride = run length between lanes): one padding word per 32 keeps both patterns (nearly) free of bank conflicts
 __device__ __forceinline__ uint32_t ridx(uint32_t i) { return i + (i >> 5); }
-// dynamic shared memory of both frame kernels: x[bs] | r[bs + bs/32 + 1]
-static inline size_t enc_smem_bytes(uint32_t bs) { return ((size_t)bs * 2 + bs / 32 + 1) * 4; }
+// dynamic shared memory of both frame kernels: pad[XPAD] | x[bs] | r[bs + bs/32 + 1].  The padding lets the unrolled predictor loops
+// read x[i - 1 - j] for taps beyond the order (zero coefficients) without a bounds test.
+constexpr uint32_t XPAD = 32;
+static inline size_t enc_smem_bytes(uint32_t bs) { return ((size_t)XPAD + (size_t)bs * 2 + bs / 32 + 1) * 4; }
 __device__ __forceinline__ uint32_t zigzag(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
 
 // block-wide reductions; every thread gets the result.  `scratch` has NW entries and is reused call after call.
@@ -158,6 +160,34 @@ __device__ uint32_t make_frame_header(uint8_t* h, const EncArgs& a, uint32_t bs,
     else if (src == 14) { h[q++] = (uint8_t)((a.sample_rate / 10) >> 8); h[q++] = (uint8_t)(a.sample_rate / 10); }
     h[q] = (uint8_t)crc8_bytes(h, q); q++;
     return q;
+}
+
+// residuals of an LPC predictor, coefficients in registers, taps unrolled (taps beyond the order have zero coefficients and read the
+// padding in front of x).  Returns 1 in *big if a residual leaves the range the Rice coder is given.
+template <int NO>
+__device__ __forceinline__ uint32_t lpc_residuals(const int32_t* __restrict__ x, int32_t* __restrict__ r, uint32_t bs, uint32_t lo, const int32_t* qc_sh, uint32_t shift, bool narrow) {
+    int32_t c[NO];
+#pragma unroll
+    for (int j = 0; j < NO; j++) c[j] = (uint32_t)j < lo ? qc_sh[j] : 0;
+    uint32_t big = 0;
+    for (uint32_t i = threadIdx.x; i < bs; i += NT) {
+        if (i < lo) continue;
+        long long s = 0;
+#pragma unroll
+        for (int j = 0; j < NO; j++) s += (long long)c[j] * (long long)x[(int)i - 1 - j];
+        const int32_t p = narrow ? ((int32_t)(uint32_t)s >> shift) : (int32_t)(s >> shift);
+        const long long rr = (long long)x[i] - (long long)p;
+        if (rr > 0x3fffffffll || rr < -0x3fffffffll) big = 1;
+        r[ridx(i)] = (int32_t)rr;
+    }
+    return big;
+}
+__device__ __forceinline__ uint32_t lpc_residuals_any(const int32_t* x, int32_t* r, uint32_t bs, uint32_t lo, const int32_t* qc_sh, uint32_t shift, bool narrow) {
+    if (lo <= 4) return lpc_residuals<4>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 8) return lpc_residuals<8>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 12) return lpc_residuals<12>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 16) return lpc_residuals<16>(x, r, bs, lo, qc_sh, shift, narrow);
+    return lpc_residuals<32>(x, r, bs, lo, qc_sh, shift, narrow);
 }
 
 // ------------------------------------------------------------------------------------------------ plan kernel
@@ -278,7 +308,8 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
     const uint64_t s0 = (uint64_t)f * a.bs;
     const uint32_t bs = (uint32_t)min((uint64_t)a.bs, a.total_samples - s0);
-    int32_t* x = reinterpret_cast<int32_t*>(dyn);
+    int32_t* x = reinterpret_cast<int32_t*>(dyn) + XPAD;
+    if (threadIdx.x < XPAD) x[(int)threadIdx.x - (int)XPAD] = 0;
     int32_t* r = x + a.bs;
     int32_t* wi = r;                                  // the windowed signal lives where the residuals go later
     const uint64_t base = s0 * a.ch;
@@ -318,13 +349,21 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         // arithmetic is 32-bit and no residual can leave the range the Rice coder takes
         unsigned long long fs[5] = {0, 0, 0, 0, 0};
         const uint32_t fbig = 0;
-        for (uint32_t i = tid; i < bs; i += NT) {
-            const int32_t v0 = x[i], v1 = i >= 1 ? x[i - 1] : 0, v2 = i >= 2 ? x[i - 2] : 0, v3 = i >= 3 ? x[i - 3] : 0, v4 = i >= 4 ? x[i - 4] : 0;
-            const int32_t p1 = v1 - v2, p2 = p1 - (v2 - v3), p3 = p2 - ((v2 - v3) - (v3 - v4));       // differences ending at i - 1
+        if (tid < bs) {         // the thread's first sample may lie among the first four: orders above its index do not count it
+            const uint32_t i = tid;
+            const int32_t v0 = x[i], v1 = x[(int)i - 1], v2 = x[(int)i - 2], v3 = x[(int)i - 3], v4 = x[(int)i - 4];   // padding reads 0
+            const int32_t p1 = v1 - v2, p2 = p1 - (v2 - v3), p3 = p2 - ((v2 - v3) - (v3 - v4));
             int32_t dd[5];
             dd[0] = v0; dd[1] = v0 - v1; dd[2] = dd[1] - p1; dd[3] = dd[2] - p2; dd[4] = dd[3] - p3;
 #pragma unroll
             for (int o = 0; o < 5; o++) if (i >= (uint32_t)o) fs[o] += (uint32_t)(dd[o] < 0 ? -dd[o] : dd[o]);
+        }
+        for (uint32_t i = tid + NT; i < bs; i += NT) {
+            const int32_t v0 = x[i], v1 = x[i - 1], v2 = x[i - 2], v3 = x[i - 3], v4 = x[i - 4];
+            const int32_t p1 = v1 - v2, p2 = p1 - (v2 - v3), p3 = p2 - ((v2 - v3) - (v3 - v4));       // differences ending at i - 1
+            const int32_t d1 = v0 - v1, d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+            fs[0] += (uint32_t)(v0 < 0 ? -v0 : v0); fs[1] += (uint32_t)(d1 < 0 ? -d1 : d1); fs[2] += (uint32_t)(d2 < 0 ? -d2 : d2);
+            fs[3] += (uint32_t)(d3 < 0 ? -d3 : d3); fs[4] += (uint32_t)(d4 < 0 ? -d4 : d4);
         }
         // one exchange for the five sums (the overflow flags ride in bit 63 of each)
 #pragma unroll
@@ -455,16 +494,7 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         if (sh.lpc_ok) {
             const uint32_t lo = sh.lpc_order, prec = sh.lpc_prec, shift = sh.lpc_shift;
             const bool narrow = ebps + prec + (31u - (uint32_t)__clz(lo)) <= 32u;     // libFLAC 1.2.1's width rule: what the decoder will do
-            uint32_t big = 0;
-            for (uint32_t i = tid; i < bs; i += NT) {
-                if (i < lo) continue;
-                long long s = 0;
-                for (uint32_t j = 0; j < lo; j++) s += (long long)sh.qc[j] * (long long)x[i - 1 - j];
-                const int32_t p = narrow ? ((int32_t)(uint32_t)s >> shift) : (int32_t)(s >> shift);
-                const long long rr = (long long)x[i] - (long long)p;
-                if (rr > 0x3fffffffll || rr < -0x3fffffffll) big = 1;
-                r[ridx(i)] = (int32_t)rr;
-            }
+            uint32_t big = lpc_residuals_any(x, r, bs, lo, sh.qc, shift, narrow);
             big = block_or_u32(big, sh.scratch);
             if (!big) {
                 EncSub* t = &sh.tmp;
@@ -574,12 +604,14 @@ __device__ __forceinline__ uint32_t gf_xpow8(uint32_t nbytes) {              // 
 __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
     ENC_DYN_SMEM(dyn);
     __shared__ EncSub D;
+    __shared__ int32_t qc32[MAX_LPC];
     __shared__ unsigned long long scratch[NW];
     __shared__ uint16_t crctab[256];
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
     const EncFrame F = a.frm[f];
     const uint32_t bs = F.bs;
-    int32_t* x = reinterpret_cast<int32_t*>(dyn);
+    int32_t* x = reinterpret_cast<int32_t*>(dyn) + XPAD;
+    if (threadIdx.x < XPAD) x[(int)threadIdx.x - (int)XPAD] = 0;
     int32_t* r = x + a.bs;
     const uint64_t base = (uint64_t)f * a.bs * a.ch;
     const unsigned long long fbit = F.byte_off * 8ull;
@@ -602,6 +634,7 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
             for (uint32_t q = tid; q < sizeof(EncSub) / 4; q += NT) dst[q] = src[q];
         }
         __syncthreads();
+        if (tid < MAX_LPC) qc32[tid] = D.qc[tid];          // visible after the barrier that follows the sample load
         const uint32_t type = D.type, order = D.order, w = D.wasted, variant = D.variant;
         const uint32_t vbps = a.bps + ((a.stereo && variant == 3) ? 1u : 0u), ebps = vbps - w;
         const uint32_t emask = ebps >= 32 ? 0xffffffffu : (1u << ebps) - 1u;
@@ -653,13 +686,7 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
             } else {
                 const uint32_t prec = D.prec, shift = D.shift;
                 const bool narrow = ebps + prec + (31u - (uint32_t)__clz(order)) <= 32u;
-                for (uint32_t i = tid; i < bs; i += NT) {
-                    if (i < order) continue;
-                    long long s = 0;
-                    for (uint32_t j = 0; j < order; j++) s += (long long)D.qc[j] * (long long)x[i - 1 - j];
-                    const int32_t p = narrow ? ((int32_t)(uint32_t)s >> shift) : (int32_t)(s >> shift);
-                    r[ridx(i)] = (int32_t)((long long)x[i] - (long long)p);
-                }
+                (void)lpc_residuals_any(x, r, bs, order, qc32, shift, narrow);
             }
             __syncthreads();
             const uint32_t po = D.po, psz = bs >> po, plen = D.method ? 5u : 4u;
