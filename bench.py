@@ -499,14 +499,18 @@ def encode_entry(ctx, s, label, reps, steps=3, **enc):
             "check": "stream decoded by the GPU decoder == the input PCM (device compare); tests/test_encode_gpu.py decodes such streams with the oracle and the reference DLL"}
 
 
+DECODE_KERNEL_SOURCES = ("bnflac_dev.h", "kernels.cu", "kernels_common.cuh", "kernels_decode.cuh", "kernels_decode_narrow.cu", "kernels_decode_wide.cu")
+
+
 def kernels_fingerprint():
+    """Hash of the sources the DECODE kernels are compiled from (what their DRAM traffic depends on; the host runtime and the encoder
+    are other translation units)."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "birdnest", "audio_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            with open(os.path.join(d, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
+    for name in DECODE_KERNEL_SOURCES:
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 
