@@ -237,6 +237,7 @@ extern "C" int bnflac_encode_device(const void* d_pcm, size_t pcm_bytes, const b
     if (!d_pcm || !d_dst || !written) return BNFLAC_ERR_ARG;
     if (int e = resolve(opts, &r)) return e;
     if (pcm_bytes % ((size_t)r.bin * r.ch)) return BNFLAC_ERR_ARG;
+    if ((r.bin == 2 && ((uintptr_t)d_pcm & 1u)) || (r.bin == 4 && ((uintptr_t)d_pcm & 3u))) return BNFLAC_ERR_ARG;   // 16-bit / int32 samples are fetched as such
     DeviceScope ds(opts->device);
     if (!ds.ok) return BNFLAC_ERR_NO_DEVICE;
     const uint64_t total = pcm_bytes / ((size_t)r.bin * r.ch);

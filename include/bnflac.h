@@ -195,7 +195,8 @@ int bnflac_encode_bound(size_t pcm_bytes, const bnflac_enc_opts* opts, uint64_t*
 /* Host PCM -> host FLAC stream ("fLaC" + STREAMINFO + frames).  *written = stream size; BNFLAC_ERR_CAPACITY if cap is smaller
  * (dst == NULL: size only).  stats may be NULL; zero-initialise it otherwise (frame_sizes is an input). */
 int bnflac_encode(const uint8_t* pcm, size_t pcm_bytes, const bnflac_enc_opts* opts, uint8_t* dst, size_t cap, uint64_t* written, bnflac_enc_stats* stats);
-/* Device PCM -> device FLAC stream (d_dst 4-byte aligned, cap bytes; bnflac_encode_bound is always enough). */
+/* Device PCM -> device FLAC stream (d_dst 4-byte aligned, cap bytes; bnflac_encode_bound is always enough; d_pcm aligned to the
+ * sample container when that is 2 or 4 bytes). */
 int bnflac_encode_device(const void* d_pcm, size_t pcm_bytes, const bnflac_enc_opts* opts, void* d_dst, size_t cap, uint64_t* written, bnflac_enc_stats* stats);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
