@@ -74,3 +74,27 @@ def test_encoder_kernels_round_trip_through_oracle_and_reference(name):
     ref = _ref_decode(flac)
     if ref is not None:
         assert ref == pcm, "the reference decoder (LibFlac.dll) disagrees"
+
+
+def test_encoder_kernels_compress_no_worse_than_the_reference_encoder():
+    """Same PCM, same settings, the reference DLL's own encoder (FLAC__stream_encoder_*, driven by oracle/refdll `refflac enc`) beside the
+    encoder kernels: the stream written here is not larger (1 % tolerance).  Runs where 32-bit binaries run."""
+    import pycorpus
+    import pyencemu
+    exe, dll = os.path.join(ROOT, "oracle", "_ref", "refflac"), os.path.join(ROOT, "oracle", "_ref", "LibFlac.dll")
+    if not (os.path.exists(exe) and os.path.exists(dll)):
+        pytest.skip("oracle/_ref not built")
+    try:
+        if subprocess.run([exe], capture_output=True, timeout=10).returncode != 2:
+            pytest.skip("32-bit binaries do not run on this host")
+    except OSError:
+        pytest.skip("32-bit binaries do not run on this host")
+    for kw, enc in ((dict(ch=2, bps=24, sr=96000, samples=4096 * 8, bs=4096, lpc=12, maxpo=6), ("2", "24", "96000", "4096", "12", "0", "6", "1")),
+                    (dict(ch=2, bps=16, sr=44100, samples=4096 * 8, bs=4096, lpc=8, maxpo=5), ("2", "16", "44100", "4096", "8", "0", "5", "1"))):
+        s = pycorpus.make(**kw)
+        with tempfile.TemporaryDirectory() as d:
+            open(os.path.join(d, "i.pcm"), "wb").write(s.pcm)
+            subprocess.check_call([exe, "enc", dll, *enc, "0", os.path.join(d, "i.pcm"), os.path.join(d, "o.flac")], stdout=subprocess.DEVNULL)
+            ref = os.path.getsize(os.path.join(d, "o.flac"))
+        ours = len(pyencemu.encode(s.pcm, kw["ch"], kw["bps"], kw["sr"], bs=kw["bs"], lpc=kw["lpc"], maxpo=kw["maxpo"]))
+        assert ours <= ref * 1.01, (ours, ref)
