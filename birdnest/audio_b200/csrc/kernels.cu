@@ -1218,17 +1218,17 @@ int sm_count() {
     }
     return n;
 }
-// true exactly once per device for the caller's `done` bitmask (idempotent work: a race only repeats it)
-bool first_use_on_device(std::atomic<uint64_t>& done) {
-    const uint64_t bit = 1ull << current_device();
-    if (done.load(std::memory_order_acquire) & bit) return false;
-    done.fetch_or(bit, std::memory_order_acq_rel);
-    return true;
-}
+// Once-per-(kernel, device) work such as opting in to large dynamic shared memory.  first_use_on_device() says whether the work is still to be
+// done on the current device, used_on_device() records it AFTER it has been done: two threads that start their first pass at the same moment
+// (handles on different host threads) both do the idempotent work -- neither can launch before its own attribute call has returned.
+// (Setting the flag first let the second thread launch k_scan with 226 KB of dynamic shared memory before the first had opted in:
+// "invalid argument" on the very first concurrent decode of a process.)
+bool first_use_on_device(std::atomic<uint64_t>& done) { return !(done.load(std::memory_order_acquire) & (1ull << current_device())); }
+void used_on_device(std::atomic<uint64_t>& done) { done.fetch_or(1ull << current_device(), std::memory_order_release); }
 
 void launch_scan(const PassArgs& a, void* stream) {
     static std::atomic<uint64_t> attr_done{0};
-    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    if (first_use_on_device(attr_done)) { cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM); used_on_device(attr_done); }
     const int n_sm = sm_count();
     uint32_t grid = (a.nchunks + SC_WARPS - 1) / SC_WARPS;
     if (grid > (uint32_t)n_sm) grid = (uint32_t)n_sm;

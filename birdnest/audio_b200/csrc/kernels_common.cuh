@@ -242,6 +242,7 @@ template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (O
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
 static inline uint32_t blocks_for(uint64_t n, uint32_t per) { uint64_t b = (n + per - 1) / per; return (uint32_t)(b ? b : 1); }
 int sm_count();                                             // of the current device (kernels.cu)
-bool first_use_on_device(std::atomic<uint64_t>& done);     // true once per device for the caller's bitmask (kernels.cu)
+bool first_use_on_device(std::atomic<uint64_t>& done);     // per-device once-only work still to be done for the caller's bitmask? (kernels.cu)
+void used_on_device(std::atomic<uint64_t>& done);          // ... it has been done
 
 } // namespace bnf

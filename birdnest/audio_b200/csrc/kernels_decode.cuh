@@ -472,7 +472,7 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
     size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S);
     static std::atomic<uint64_t> attr_done{0};
-    if (first_use_on_device(attr_done)) cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (first_use_on_device(attr_done)) { cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); used_on_device(attr_done); }
     const int n_sm = sm_count();
     static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
     static const bool balance = getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '1';

@@ -2,8 +2,11 @@
 concatenated (no collective), handles on two devices alive at the same time (function attributes and SM counts are
 per device), and the caller's current device left as it was.  Skipped on boxes with one GPU."""
 import hashlib
+import os
 
 import pytest
+
+from conftest import ROOT, has_gpu
 
 pytestmark = pytest.mark.gpu
 
@@ -53,3 +56,32 @@ def test_device_resident_decode_on_the_second_device(streams):
             _, w = h.decode_device(d_out.data_ptr(), d_out.numel())
             assert bytes(d_out[:w].cpu().numpy()) == s.pcm
         assert torch.cuda.current_device() == 0
+
+
+def test_first_decode_of_a_process_from_many_threads():
+    """Handles are single-threaded, different handles may be used from different threads (include/bnflac.h) -- also when the very first
+    decodes of a process start at the same moment: the once-per-device kernel attributes (k_scan's 226 KB of dynamic shared memory) must be
+    in place before ANY thread launches.  A fresh process, eight threads, eight handles, first pass of each at once."""
+    import subprocess
+    import sys
+    if not has_gpu():
+        pytest.skip("no CUDA device")
+    code = r'''
+import sys, threading
+sys.path[:0] = [%r, %r, %r]
+import pycorpus
+from birdnest.audio_b200 import _abi
+s = pycorpus.make(ch=2, bps=24, sr=96000, seconds=1, bs=4096, lpc=12, maxpo=6)
+hs = [_abi.open_memory(s.flac) for _ in range(8)]
+out, bar = [None] * 8, threading.Barrier(8)
+def work(i):
+    bar.wait()
+    out[i] = bytes(hs[i].decode_all())
+ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+[t.start() for t in ts]; [t.join() for t in ts]
+assert all(o == s.pcm for o in out), [None if o is None else len(o) for o in out]
+print("ok")
+''' % (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "corpus"))
+    for _ in range(3):       # a race: give it a few chances to show
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
