@@ -422,17 +422,16 @@ def stream_surface_entry(flac, n_all, local):
             "where_the_time_goes": "single host thread: ~0.3 s pulling 1.2 GB through 16 KiB stream reads, ~0.1 s staging pageable uploads, ~0.25 s copying 2.07 GB of PCM out of pinned memory in 80 KB pieces; the rest of ms_total is the caller's MemoryStream (growth copies + first-touch page faults of ~4 GB); GPU work is ~3 ms per 64 MiB sub-shard, downloads are never waited for (BNFLAC_TRACE=1 prints this split)"}
 
 
-def corpus_job(ctx, maps, info, shard, steps, prio=None):
+def corpus_job(ctx, maps, info, shard, steps, prio=False):
     """the streams of a corpus decoded CONCURRENTLY on one GPU (one CUDA stream and one host thread each: a pass below one wave of
     CTAs leaves most of the GPU idle, and the passes of different streams fill it; different handles may be used from different
     threads, include/bnflac.h) -> (ms per step on this rank by CUDA events, output tensors, bytes written)"""
     from concurrent.futures import ThreadPoolExecutor
     torch, _abi, dev, local, stream = ctx
     nf = len(maps)
-    # The job ends when its longest pass ends: the stream with the most samples (the 8-channel one: a handful of warps walking long
-    # subframes) gets a high-priority CUDA stream, so its CTAs are placed before those of the passes that merely fill the GPU around it.
-    if prio is None:
-        prio = os.environ.get("BNFLAC_BENCH_PRIO", "1") != "0"
+    # prio: the stream with the most samples (the 8-channel one: a handful of warps walking long subframes) on a high-priority CUDA
+    # stream.  Measured with tools/strong_probe.py (one rank's eighth of the corpus on one GPU): 7.58 ms without, 7.68 ms with -- CTA
+    # placement is not what the longest pass waits for; off.
     big = max(range(nf), key=lambda fi: info[fi][1]) if prio else -1
     streams = [torch.cuda.Stream(device=dev, priority=-1 if fi == big else 0) for fi in range(nf)]
     hs, outs = [], []
