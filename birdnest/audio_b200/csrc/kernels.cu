@@ -160,6 +160,9 @@ __device__ uint32_t res_bytes(const uint8_t* p, uint32_t n) {
 #define SC_WARPS_N 14
 #endif
 constexpr int SC_WARPS = SC_WARPS_N;
+#ifndef SC_CTAS_PER_SM
+#define SC_CTAS_PER_SM (14 / SC_WARPS_N)      // persistent grid: this many CTAs per SM (14 warps of 16 KB double-buffered tiles fill an SM)
+#endif
 constexpr int SC_THREADS = 32 * SC_WARPS;
 constexpr int SC_PIECE = SCAN_CHUNK / 32;                  // bytes per lane and tile
 constexpr int SC_PWORDS = SC_PIECE / 4;
@@ -1231,7 +1234,7 @@ void launch_scan(const PassArgs& a, void* stream) {
     if (first_use_on_device(attr_done)) { cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM); used_on_device(attr_done); }
     const int n_sm = sm_count();
     uint32_t grid = (a.nchunks + SC_WARPS - 1) / SC_WARPS;
-    if (grid > (uint32_t)n_sm) grid = (uint32_t)n_sm;
+    if (grid > (uint32_t)n_sm * SC_CTAS_PER_SM) grid = (uint32_t)n_sm * SC_CTAS_PER_SM;
     if (!grid) grid = 1;
     k_scan<<<grid, SC_THREADS, SC_SMEM, S(stream)>>>(a); count_launch();
 }

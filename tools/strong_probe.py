@@ -1,6 +1,5 @@
 #!/usr/bin/env python
-"""One rank's share of the strong job (bench.py corpus_job) on ONE GPU: shard (r, n) of every cfg5 stream, with and without the
-high-priority stream for the largest pass.  usage: strong_probe.py [scale] [n]"""
+"""One rank's share of the strong job (bench.py corpus_job) on ONE GPU: shard (r, n) of every cfg5 stream.  usage: strong_probe.py [scale] [n]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "corpus")):
@@ -17,8 +16,7 @@ kept = [pycorpus.make(md5=False, view=True, **kw) for _, _, kw in bench.cfg5_for
 info = [(len(g.flac), g.total_samples * g.channels, (g.bps + 7) // 8, len(g.pcm)) for g in kept]
 maps = [g.flac for g in kept]
 for shard in (None, (0, n), (n // 2, n)):
-    for prio in (False, True):
-        ms, outs, wr = bench.corpus_job(ctx, maps, info, shard, 5, prio=prio)
-        del outs
-        torch.cuda.empty_cache()
-        print(f"shard {shard} prio {prio}: {ms:.3f} ms", flush=True)
+    ms, outs, wr = bench.corpus_job(ctx, maps, info, shard, 5)
+    del outs
+    torch.cuda.empty_cache()
+    print(f"shard {shard}: {ms:.3f} ms", flush=True)
