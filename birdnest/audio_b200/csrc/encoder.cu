@@ -163,7 +163,7 @@ static int encode_on_device(const Resolved& r, const uint8_t* d_pcm, uint64_t to
     EncArgs a{};
     size_t smem_plan = 0, smem_write = 0;
     if (((uintptr_t)d_out & 3u) != 0) return BNFLAC_ERR_ARG;
-    if (!nframes) { *written = 42; *minfs = 0; *maxfs = 0; return out_cap >= 42 ? 0 : BNFLAC_ERR_CAPACITY; }
+    if (!nframes) { *written = 42; *minfs = 0; *maxfs = 0; if (st) { st->frames = 0; st->bytes = 42; } return out_cap >= 42 ? 0 : BNFLAC_ERR_CAPACITY; }
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&d_sub, (size_t)nframes * 8 * sizeof(EncSub)));
     CK(cudaMalloc(&d_frm, (size_t)nframes * sizeof(EncFrame)));

@@ -65,6 +65,13 @@ def test_gpu_encoder_on_corpus_shapes(streams, name):
     assert len(flac) <= len(s.flac) * 1.01 + 64, (len(flac), len(s.flac))
 
 
+def test_gpu_encoder_empty_input_is_a_metadata_only_stream():
+    if not has_gpu():
+        pytest.skip("no CUDA device")
+    flac, st = _roundtrip(b"", 2, 16, 44100)
+    assert len(flac) == 42 and st.frames == 0
+
+
 def test_gpu_encoder_compression_levels_and_int32_input():
     if not has_gpu():
         pytest.skip("no CUDA device")
