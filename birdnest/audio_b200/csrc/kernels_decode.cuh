@@ -137,9 +137,53 @@ __device__ __forceinline__ void restore_block_i64(uint32_t addr, uint32_t rs4, c
 #ifndef DEC_WIDE_I64
 #define DEC_WIDE_I64 0
 #endif
+
+// Orders > 16 (streams of few, long subframes: a scheduler holds two or three warps, each of which would issue its dot product to ONE
+// pipe): the 16 most recent taps accumulate on the FP64 pipe (DFMA, history as doubles), the 16 older ones on the integer multiply
+// pipe (mad.wide.s32, history as int32) -- a warp that alternates two pipes issues 0.55 instructions per clock where one pipe gives
+// it 0.29 (tools/ulat.cu).  Both sums are exact integers: the DFMA chain starts at 1.5 * 2^52, so the bits of its result are
+// 0x4338000000000000 + sum, and the integer chain starts at -0x4338000000000000: one 64-bit add gives the whole dot product, the
+// quantisation shift is a funnel shift.  `wasted` carries the per-lane "narrow" flag in bit 31 as in restore_block_i64.
+// h: the last 32 samples (int32, slot = sample index mod 32); hD: the last 16 as doubles (slot = index mod 16).
+// MEASURED AND NOT USED (bit-exact, cfg3 decode 4.12 -> 4.86 ms): mad.wide.s32 with a 64-bit accumulator costs the warp more issue
+// time than the DFMA it replaces, and the 64-bit recombination adds six instructions per sample.  Kept as a build variant (-DDEC_MIX=1).
+#ifndef DEC_MIX
+#define DEC_MIX 0
+#endif
+template <int ORD, bool WIDE> __host__ __device__ constexpr bool dec_mix() { return WIDE && ORD > 16 && DEC_MIX && !DEC_WIDE_I64; }
+template <int ORD, bool FIRST, bool EXTRA>
+__device__ __forceinline__ void restore_block_mix(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD], const double (&cfD)[16], double (&hD)[16],
+                                                  uint32_t order, uint32_t shift, uint32_t wasted) {
+    static_assert(ORD == 32, "two halves of 16 taps");
+#pragma unroll
+    for (int j = 0; j < ORD; j++) {
+        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        long long ai0 = -0x4338000000000000ll, ai1 = 0;
+#pragma unroll
+        for (int m = ORD - 1; m >= 16; m--) {
+            if (m & 1) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(ai1) : "r"(cf[m]), "r"(h[(j - 1 - m + 2 * ORD) % ORD]));
+            else asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(ai0) : "r"(cf[m]), "r"(h[(j - 1 - m + 2 * ORD) % ORD]));
+        }
+        double ad[4] = {6755399441055744.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int m = 15; m >= 0; m--) ad[m & 3] = fma(cfD[m], hD[(j - 1 - m + 32) % 16], ad[m & 3]);
+        const double y = (ad[0] + ad[1]) + (ad[2] + ad[3]);
+        const long long tot = __double_as_longlong(y) + ai0 + ai1;
+        const uint32_t lo = (uint32_t)tot, hi = (uint32_t)((unsigned long long)tot >> 32);
+        int32_t p = (int32_t)__funnelshift_r(lo, hi, shift);               // shift < 32
+        if (EXTRA) { if (wasted & 0x80000000u) p = (int32_t)lo >> shift; }
+        int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
+        if (FIRST) { if (j < (int)order) s = r; }
+        h[j] = s;
+        hD[j % 16] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
+        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << (wasted & 31u));
+        else sts32(addr + j * rs4, (uint32_t)s);
+    }
+}
 template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
-__device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const TT (&cf)[ORD], TT (&h)[ORD], uint32_t order, uint32_t shift, uint32_t wasted) {
-    if constexpr (WIDE && DEC_WIDE_I64) restore_block_i64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
+__device__ __forceinline__ void restore_block(uint32_t addr, uint32_t rs4, const TT (&cf)[ORD], TT (&h)[ORD], const double (&cfD)[16], double (&hD)[16], uint32_t order, uint32_t shift, uint32_t wasted) {
+    if constexpr (dec_mix<ORD, WIDE>()) restore_block_mix<ORD, FIRST, EXTRA>(addr, rs4, cf, h, cfD, hD, order, shift, wasted);
+    else if constexpr (WIDE && DEC_WIDE_I64) restore_block_i64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
     else if constexpr (WIDE) restore_block_f64<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
     else restore_block_i32<ORD, FIRST, EXTRA>(addr, rs4, cf, h, order, shift, wasted);
 }
@@ -271,7 +315,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     // ---- per-subframe state (registers)
     DecRing<ORD> br;
     br.init_idle(ring_base + lane * RingBits::STRIDE, a.in);
-    constexpr bool F64 = WIDE && !DEC_WIDE_I64;       // FP64-pipe accumulation (coefficients scaled by 2^-shift) vs mad.wide.s32
+    constexpr bool MIX = dec_mix<ORD, WIDE>();         // orders > 16: half the taps on the FP64 pipe, half on the integer pipe (restore_block_mix)
+    constexpr bool F64 = WIDE && !DEC_WIDE_I64 && !MIX;       // FP64-pipe accumulation (coefficients scaled by 2^-shift) vs mad.wide.s32
     typename std::conditional<F64, double, int32_t>::type cf[ORD], hist[ORD];
 #pragma unroll
     for (int j = 0; j < ORD; j++) { cf[j] = 0; hist[j] = 0; }
@@ -343,6 +388,11 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
 #pragma unroll 1
             for (uint32_t t = 0; t < (uint32_t)T; t++) sts32(col + t * rs4, v);
         }
+    }
+    double cfD[16], hD[16];                             // MIX only: the 16 most recent taps as doubles (dead code otherwise)
+    if constexpr (MIX) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) { cfD[j] = (double)cf[j]; hD[j] = 0.0; }
     }
     __syncwarp();
     const uint32_t maxbs = __reduce_max_sync(FULL, bs);
@@ -425,15 +475,15 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
         }
         // ---- restore phase (own column only: no warp synchronisation needed before it)
         if (i0 == 0) {
-            if (extra) restore_block<ORD, WIDE, true, true>(col, rs4, cf, hist, order, shift, wasted);
-            else restore_block<ORD, WIDE, true, false>(col, rs4, cf, hist, order, shift, wasted);
+            if (extra) restore_block<ORD, WIDE, true, true>(col, rs4, cf, hist, cfD, hD, order, shift, wasted);
+            else restore_block<ORD, WIDE, true, false>(col, rs4, cf, hist, cfD, hD, order, shift, wasted);
         }
         if (extra) {
 #pragma unroll 1
-            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, true>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
+            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, true>(col + t * rs4, rs4, cf, hist, cfD, hD, order, shift, wasted);
         } else {
 #pragma unroll 1
-            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, false>(col + t * rs4, rs4, cf, hist, order, shift, wasted);
+            for (uint32_t t = (i0 == 0 ? ORD : 0); t < (uint32_t)T; t += ORD) restore_block<ORD, WIDE, false, false>(col + t * rs4, rs4, cf, hist, cfD, hD, order, shift, wasted);
         }
         __syncwarp();
         // ---- pack phase
