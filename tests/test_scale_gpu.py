@@ -86,3 +86,30 @@ def test_cpp_host_mirror_demo(tmp_path):
     with open(src, "rb") as f:
         want = pyoracle.decode(f.read())[0]
     assert out.read_bytes() == want
+
+
+def test_encoder_ten_minutes_round_trip_and_reference_spot_check():
+    """SURVEY 8f-4 at size: 600 s of the cfg2 shape (20 s of unique PCM x 30) encoded on the GPU from host memory, md5 in STREAMINFO,
+    decoded back by the GPU decoder (whole) and -- where 32-bit binaries run -- by the reference DLL (the first 20 s re-encoded alone)."""
+    import pycorpus
+    from birdnest.audio_b200 import _abi
+    from test_encode_emu_cpu import _ref_decode
+    s = pycorpus.make(ch=2, bps=24, sr=96000, seconds=20, bs=4096, lpc=12, maxpo=6, seed=11)
+    pcm = s.pcm * 30
+    o = _abi.enc_opts(96000, 2, 24, max_lpc_order=12)
+    flac, st = _abi.encode(pcm, o, want_stats=True)
+    assert st.frames == (len(pcm) // 6 + 4095) // 4096 and len(flac) < 0.62 * len(pcm)
+    back, info, errs = _decode(flac)
+    assert errs == [] and back == pcm
+    assert bytes(info.md5) == hashlib.md5(pcm).digest() and info.total_samples == len(pcm) // 6
+    # frames are independent: the first tile's frames are the same bytes whether 20 s or 600 s are encoded
+    one = _abi.encode(s.pcm, o)
+    nfull = (len(s.pcm) // 6) // 4096
+    with _abi.open_memory(one) as h:
+        h.decode_all()
+        fr = h.frames()
+    end = fr[nfull - 1].offset + fr[nfull - 1].length
+    assert flac[42:end] == one[42:end]
+    ref = _ref_decode(one)
+    if ref is not None:
+        assert ref == s.pcm
