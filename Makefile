@@ -29,7 +29,7 @@ $(OBJ)/engine.o: $(CSRC)/engine.cu $(CSRC)/bnflac_dev.h include/bnflac.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/engine.cu 2> $(OBJ)/engine.log || (cat $(OBJ)/engine.log; exit 1)
 	@grep -E "error|warning" $(OBJ)/engine.log | grep -v "ptxas info" || true
-$(OBJ)/encoder.o: $(CSRC)/encoder.cu $(CSRC)/encoder_kernels.cuh include/bnflac.h
+$(OBJ)/encoder.o: $(CSRC)/encoder.cu $(CSRC)/encoder_kernels.cuh $(CSRC)/md5.hpp include/bnflac.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/encoder.cu 2> $(OBJ)/encoder.log || (cat $(OBJ)/encoder.log; exit 1)
 	@grep -E "error|warning" $(OBJ)/encoder.log | grep -v "ptxas info" || true
@@ -44,8 +44,8 @@ birdnest/audio_b200/flacdecoder_demo: $(CSRC)/flac_decoder.hpp $(CSRC)/flac_deco
 # the libFLAC 1.2.1 stream-decoder symbols the unmodified C# binds, replayed from a bnflac handle
 SHIM := birdnest/audio_b200/libLibFlac.so
 shim: $(SHIM)
-$(SHIM): $(CSRC)/libflac_shim.cpp include/bnflac_legacy.h include/bnflac.h $(LIB)
-	g++ -O2 -std=c++17 -Wall -fPIC -shared -Iinclude -o $@ $(CSRC)/libflac_shim.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
+$(SHIM): $(CSRC)/libflac_shim.cpp $(CSRC)/md5.hpp include/bnflac_legacy.h include/bnflac.h $(LIB)
+	g++ -O2 -std=c++17 -Wall -fPIC -shared -Iinclude -I$(CSRC) -o $@ $(CSRC)/libflac_shim.cpp -Lbirdnest/audio_b200 -lbnflac -Wl,-rpath,'$$ORIGIN'
 
 oracle: oracle/_build/liboracle.so oracle/_build/flac_oracle
 oracle/_build/liboracle.so: oracle/flac_oracle.c oracle/flac_oracle.h

@@ -64,7 +64,7 @@ class EncOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
                 ("bits_per_sample", C.c_uint32), ("blocksize", C.c_uint32), ("max_lpc_order", C.c_uint32), ("qlp_precision", C.c_uint32),
                 ("min_partition_order", C.c_uint32), ("max_partition_order", C.c_uint32), ("mid_side", C.c_uint32),
-                ("compression_level", C.c_uint32), ("flags", C.c_uint32)]
+                ("compression_level", C.c_uint32), ("flags", C.c_uint32), ("first_frame_number", C.c_uint64)]
 
 
 class EncStats(C.Structure):
@@ -369,7 +369,7 @@ def decode_batch(clips, device=-1, dst=None, dst_is_device=False, packed=False):
 
 
 def enc_opts(sample_rate, channels, bits_per_sample, blocksize=4096, max_lpc_order=8, qlp_precision=0, min_partition_order=0,
-             max_partition_order=6, mid_side=True, compression_level=None, flags=0, device=-1, stream=0) -> EncOpts:
+             max_partition_order=6, mid_side=True, compression_level=None, flags=0, device=-1, stream=0, first_frame_number=0) -> EncOpts:
     """Settings of the GPU encoder -- what the reference's FLAC__stream_encoder_set_* calls carry (LibFLACSharp.cs:333-369)."""
     o = EncOpts()
     o.struct_size = C.sizeof(EncOpts)
@@ -380,6 +380,7 @@ def enc_opts(sample_rate, channels, bits_per_sample, blocksize=4096, max_lpc_ord
     if compression_level is not None:
         o.compression_level, flags = compression_level, flags | ENC_USE_LEVEL
     o.flags = flags
+    o.first_frame_number = first_frame_number
     return o
 
 

@@ -49,6 +49,7 @@ struct EncArgs {
     uint32_t max_lpc, prec, min_po, max_po, stereo, search_order;
     uint32_t nframes;
     uint64_t first_frame;           // bytes of metadata before the first frame
+    uint64_t first_number;          // coded number of the first frame (a stream encoded in several calls)
     EncSub* sub;                    // [nframes][8]
     EncFrame* frm;
     EncTotals* totals;
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
             if (bM + bS < bb) { bb = bM + bS; assign = 10; s_pick[0] = 2; s_pick[1] = 3; }
         } else for (uint32_t c = 0; c < a.ch; c++) s_pick[c] = c;
         EncFrame* F = &a.frm[f];
-        const uint32_t hl = make_frame_header(sh.hdr, a, bs, assign, f);
+        const uint32_t hl = make_frame_header(sh.hdr, a, bs, assign, a.first_number + f);
         uint32_t bit = hl * 8;
         for (uint32_t c = 0; c < 8; c++) { F->sub_bit[c] = bit; if (c < a.ch) bit += sh.dec[s_pick[c]].bits; }
         F->byte_off = 0; F->nbytes = (bit + 7) / 8 + 2; F->bs = bs; F->assignment = (uint8_t)assign; F->hdr_len = (uint8_t)hl;

@@ -235,34 +235,114 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
 
 
 // ------------------------------------------------------------------------------------------------ encoder half
-// The FLAC__stream_encoder_* symbols of LibFLACSharp.cs:322-387 over bnflac_encode: samples are collected (packed, the engine's
-// input layout), finish() encodes them on the GPU and replays libFLAC's write-callback sequence.  No encoding happens here.
+// The FLAC__stream_encoder_* symbols of LibFLACSharp.cs:322-387 over bnflac_encode.  Samples are collected (packed, the engine's input
+// layout); whenever ENC_CHUNK_FRAMES whole blocks are in hand they are encoded on the GPU in one call (frames are independent: the call is
+// told the number of its first frame) and handed to the write callback frame by frame, as libFLAC does during process(); finish()
+// encodes the rest, then puts the final STREAMINFO in place -- through the seek callback (or fseek) when there is one, like libFLAC,
+// otherwise it is only reported through the metadata callback.  No encoding happens here.
+#include "md5.hpp"
+static constexpr size_t ENC_CHUNK_FRAMES = 1024;
+
 struct FLAC__StreamEncoder {
     int state = 1;                        // FLAC__STREAM_ENCODER_UNINITIALIZED
     unsigned channels = 2, bps = 16, sample_rate = 44100, level = 5, blocksize = 0;
     int mid_side = -1;                    // -1: the preset's
     bool verify = false;
     FLAC__StreamEncoderWriteCallback write = nullptr;
+    FLAC__StreamEncoderSeekCallback seek = nullptr;
     FLAC__StreamEncoderMetadataCallback metadata = nullptr;
     void* client = nullptr;
     FILE* file = nullptr;
-    std::vector<uint8_t> pcm;             // interleaved, little-endian, ceil(bps/8) bytes per sample
+    std::vector<uint8_t> pcm;             // interleaved, little-endian, ceil(bps/8) bytes per sample: not yet encoded
+    std::vector<uint8_t> out, back;
+    std::vector<uint32_t> sizes;
+    bnflac_enc_opts o{};
+    bnfe::Md5 md5;
+    uint64_t frames = 0, samples = 0;     // emitted so far
+    uint32_t min_fs = 0xffffffffu, max_fs = 0;
+    size_t frame_bytes() const { return (size_t)o.blocksize * channels * ((bps + 7) / 8); }
 };
 
+static void enc_streaminfo(const FLAC__StreamEncoder* e, uint8_t o[38], const uint8_t md5[16]) {      // block header + 34 bytes
+    const uint32_t bs = e->o.blocksize, mn = e->frames ? e->min_fs : 0, mx = e->max_fs;
+    size_t q = 0;
+    o[q++] = 0x80; o[q++] = 0; o[q++] = 0; o[q++] = 34;
+    o[q++] = (uint8_t)(bs >> 8); o[q++] = (uint8_t)bs; o[q++] = (uint8_t)(bs >> 8); o[q++] = (uint8_t)bs;
+    o[q++] = (uint8_t)(mn >> 16); o[q++] = (uint8_t)(mn >> 8); o[q++] = (uint8_t)mn;
+    o[q++] = (uint8_t)(mx >> 16); o[q++] = (uint8_t)(mx >> 8); o[q++] = (uint8_t)mx;
+    const uint64_t x = ((uint64_t)e->sample_rate << 44) | ((uint64_t)(e->channels - 1) << 41) | ((uint64_t)(e->bps - 1) << 36) | (e->samples & 0xFFFFFFFFFull);
+    for (int i = 7; i >= 0; i--) o[q++] = (uint8_t)(x >> (8 * i));
+    memcpy(o + q, md5, 16);
+}
+static bool enc_emit(FLAC__StreamEncoder* e, const uint8_t* p, size_t n, unsigned samples, unsigned frame) {
+    if (e->file) { if (fwrite(p, 1, n, e->file) != n) { e->state = 6; return false; } return true; }
+    if (e->write(e, p, n, samples, frame, e->client) != 0) { e->state = 5; return false; }
+    return true;
+}
 static int enc_init_common(FLAC__StreamEncoder* e) {
     if (e->state != 1) return 13;
     if (e->channels < 1 || e->channels > 8) return 4;
     if (e->bps < 4 || e->bps > 24) return 5;
     if (e->sample_rate < 1 || e->sample_rate > 655350) return 6;
     if (e->blocksize && (e->blocksize < 16 || e->blocksize > 16384)) return 7;
-    e->pcm.clear();
+    // the preset spelled out (an explicit set_do_mid_side_stereo overrides its stereo setting)
+    static const struct { uint32_t bs, lpc, ms, po; } lv[9] = {{1152, 0, 0, 3}, {1152, 0, 1, 3}, {1152, 0, 1, 3}, {4096, 6, 0, 4}, {4096, 8, 1, 4}, {4096, 8, 1, 5}, {4096, 8, 1, 6}, {4096, 8, 1, 6}, {4096, 12, 1, 6}};
+    bnflac_enc_opts& o = e->o;
+    o = bnflac_enc_opts{}; o.struct_size = sizeof o; o.device = -1;
+    o.sample_rate = e->sample_rate; o.channels = e->channels; o.bits_per_sample = e->bps;
+    o.blocksize = e->blocksize ? e->blocksize : lv[e->level].bs;
+    o.max_lpc_order = lv[e->level].lpc; o.max_partition_order = lv[e->level].po;
+    o.mid_side = e->channels == 2 ? (e->mid_side >= 0 ? (uint32_t)e->mid_side : lv[e->level].ms) : 0u;
+    o.flags = BNFLAC_ENC_NO_MD5;          // the running digest over all chunks is kept here
+    e->pcm.clear(); e->md5 = bnfe::Md5(); e->frames = e->samples = 0; e->min_fs = 0xffffffffu; e->max_fs = 0;
     e->state = 0;
     return 0;
 }
-static bool enc_emit(FLAC__StreamEncoder* e, const uint8_t* p, size_t n, unsigned samples, unsigned frame) {
-    if (e->file) { if (fwrite(p, 1, n, e->file) != n) { e->state = 6; return false; } return true; }
-    if (e->write(e, p, n, samples, frame, e->client) != 0) { e->state = 5; return false; }
+// encodes and emits the first `nbytes` of the collected PCM (whole blocks, or everything at finish)
+static bool enc_flush(FLAC__StreamEncoder* e, size_t nbytes) {
+    if (!nbytes) return true;
+    const size_t spb = (size_t)e->channels * ((e->bps + 7) / 8), nsamp = nbytes / spb, bs = e->o.blocksize, nf = (nsamp + bs - 1) / bs;
+    uint64_t bound = 0, n = 0;
+    e->o.first_frame_number = e->frames;
+    int rc = bnflac_encode_bound(nbytes, &e->o, &bound);
+    if (!rc) {
+        try { if (e->out.size() < bound) e->out.resize((size_t)bound); if (e->sizes.size() < nf) e->sizes.resize(nf); } catch (const std::bad_alloc&) { rc = BNFLAC_ERR_MEMORY; }
+    }
+    bnflac_enc_stats st{};
+    if (!rc) { st.frame_sizes = e->sizes.data(); st.frame_sizes_cap = nf; rc = bnflac_encode(e->pcm.data(), nbytes, &e->o, e->out.data(), e->out.size(), &n, &st); }
+    if (rc) { e->state = rc == BNFLAC_ERR_MEMORY ? 8 : 5; return false; }
+    if (e->verify) {                       // set_verify: what was written must decode back to what was handed in
+        bnflac_t* h = nullptr; bnflac_opts d{}; d.struct_size = sizeof d; d.device = -1; d.flags = BNFLAC_OPT_BORROW_INPUT;
+        uint64_t w = 0;
+        bool same = false;
+        try {
+            e->back.resize(nbytes + 64);
+            same = !bnflac_open_memory(e->out.data(), (size_t)n, &d, &h) && !bnflac_decode_all(h, e->back.data(), e->back.size(), &w) && w == nbytes && !memcmp(e->back.data(), e->pcm.data(), nbytes);
+        } catch (const std::bad_alloc&) {}
+        if (h) bnflac_close(h);
+        if (!same) { e->state = 4; return false; }      // FLAC__STREAM_ENCODER_VERIFY_MISMATCH_IN_AUDIO_DATA
+    }
+    e->md5.update(e->pcm.data(), nbytes);
+    size_t at = 42;
+    for (size_t f = 0; f < st.frames; f++) {
+        const unsigned smp = (unsigned)std::min<size_t>(bs, nsamp - f * bs);
+        if (!enc_emit(e, e->out.data() + at, e->sizes[f], smp, (unsigned)(e->frames + f))) return false;
+        at += e->sizes[f];
+    }
+    e->frames += st.frames; e->samples += nsamp;
+    if (st.frames) { e->min_fs = std::min(e->min_fs, st.min_framesize); e->max_fs = std::max(e->max_fs, st.max_framesize); }
+    e->pcm.erase(e->pcm.begin(), e->pcm.begin() + (ptrdiff_t)nbytes);
     return true;
+}
+static bool enc_maybe_flush(FLAC__StreamEncoder* e) {
+    const size_t fb = e->frame_bytes();
+    if (e->pcm.size() < ENC_CHUNK_FRAMES * fb) return true;
+    return enc_flush(e, e->pcm.size() / fb * fb);
+}
+static bool enc_begin_stream(FLAC__StreamEncoder* e) {           // libFLAC writes the marker and the (provisional) STREAMINFO at init
+    uint8_t si[38]; const uint8_t zero[16] = {0};
+    enc_streaminfo(e, si, zero);
+    return enc_emit(e, (const uint8_t*)"fLaC", 4, 0, 0) && enc_emit(e, si, 38, 0, 0);
 }
 
 extern "C" {
@@ -279,14 +359,14 @@ FLAC__bool FLAC__stream_encoder_set_do_mid_side_stereo(FLAC__StreamEncoder* e, F
 FLAC__bool FLAC__stream_encoder_set_loose_mid_side_stereo(FLAC__StreamEncoder* e, FLAC__bool) { return e && e->state == 1; }
 int FLAC__stream_encoder_get_state(const FLAC__StreamEncoder* e) { return e ? e->state : 1; }
 
-int FLAC__stream_encoder_init_stream(FLAC__StreamEncoder* e, FLAC__StreamEncoderWriteCallback write, FLAC__StreamEncoderSeekCallback, FLAC__StreamEncoderTellCallback,
+int FLAC__stream_encoder_init_stream(FLAC__StreamEncoder* e, FLAC__StreamEncoderWriteCallback write, FLAC__StreamEncoderSeekCallback seek, FLAC__StreamEncoderTellCallback,
                                      FLAC__StreamEncoderMetadataCallback metadata, void* client) {
     if (!e) return 1;
     if (!write) return 3;
     const int rc = enc_init_common(e);
     if (rc) return rc;
-    e->write = write; e->metadata = metadata; e->client = client;
-    return 0;
+    e->write = write; e->seek = seek; e->metadata = metadata; e->client = client;
+    return enc_begin_stream(e) ? 0 : 1;
 }
 int FLAC__stream_encoder_init_file(FLAC__StreamEncoder* e, const char* filename, void*, void* client) {
     if (!e) return 1;
@@ -295,7 +375,7 @@ int FLAC__stream_encoder_init_file(FLAC__StreamEncoder* e, const char* filename,
     e->file = filename ? fopen(filename, "wb") : nullptr;
     if (!e->file) { e->state = 6; return 1; }
     e->client = client;
-    return 0;
+    return enc_begin_stream(e) ? 0 : 1;
 }
 FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder* e, const int32_t buffer[], unsigned samples) {
     if (!e || e->state != 0 || (!buffer && samples)) return 0;
@@ -304,7 +384,7 @@ FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder* e, cons
     try { e->pcm.resize(at + n * B); } catch (const std::bad_alloc&) { e->state = 8; return 0; }
     uint8_t* o = e->pcm.data() + at;
     for (size_t i = 0; i < n; i++) for (unsigned b = 0; b < B; b++) *o++ = (uint8_t)((uint32_t)buffer[i] >> (8 * b));
-    return 1;
+    return enc_maybe_flush(e) ? 1 : 0;
 }
 FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder* e, const int32_t* const buffer[], unsigned samples) {
     if (!e || e->state != 0 || (!buffer && samples)) return 0;
@@ -313,67 +393,32 @@ FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder* e, const int32_t* c
     try { e->pcm.resize(at + (size_t)samples * C * B); } catch (const std::bad_alloc&) { e->state = 8; return 0; }
     uint8_t* o = e->pcm.data() + at;
     for (unsigned t = 0; t < samples; t++) for (unsigned c = 0; c < C; c++) for (unsigned b = 0; b < B; b++) *o++ = (uint8_t)((uint32_t)buffer[c][t] >> (8 * b));
-    return 1;
+    return enc_maybe_flush(e) ? 1 : 0;
 }
 FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
     if (!e) return 0;
     if (e->state == 1) return 1;                      // libFLAC: finishing an uninitialised encoder is a no-op
-    bool ok = e->state == 0;
+    bool ok = e->state == 0 && enc_flush(e, e->pcm.size());
     if (ok) {
-        bnflac_enc_opts o{}; o.struct_size = sizeof o; o.device = -1;
-        o.sample_rate = e->sample_rate; o.channels = e->channels; o.bits_per_sample = e->bps;
-        o.blocksize = e->blocksize; o.compression_level = e->level; o.flags = BNFLAC_ENC_USE_LEVEL;
-        uint64_t bound = 0, n = 0;
-        std::vector<uint8_t> out;
-        std::vector<uint32_t> sizes;
-        bnflac_enc_stats st{};
-        int rc = bnflac_encode_bound(e->pcm.size(), &o, &bound);
-        if (!rc && e->mid_side >= 0 && e->channels == 2) {     // an explicit set_do_mid_side_stereo overrides the preset: spell the preset out
-            static const struct { uint32_t bs, lpc, po; } lv[9] = {{1152, 0, 3}, {1152, 0, 3}, {1152, 0, 3}, {4096, 6, 4}, {4096, 8, 4}, {4096, 8, 5}, {4096, 8, 6}, {4096, 8, 6}, {4096, 12, 6}};
-            o.flags = 0; o.mid_side = (uint32_t)e->mid_side; o.max_lpc_order = lv[e->level].lpc; o.max_partition_order = lv[e->level].po;
-            if (!o.blocksize) o.blocksize = lv[e->level].bs;
-            rc = bnflac_encode_bound(e->pcm.size(), &o, &bound);
+        uint8_t digest[16], si[38];
+        e->md5.final(digest);
+        enc_streaminfo(e, si, digest);
+        // the final STREAMINFO goes where the provisional one is, when the sink can seek (libFLAC does the same); the metadata
+        // callback reports it either way
+        if (e->file) { ok = fseek(e->file, 4, SEEK_SET) == 0 && fwrite(si, 1, 38, e->file) == 38 && fseek(e->file, 0, SEEK_END) == 0; if (!ok) e->state = 6; }
+        else if (e->seek) { if (e->seek(e, 4, e->client) == 0) ok = enc_emit(e, si, 38, 0, 0); }
+        if (ok && e->metadata) {
+            FLAC__StreamMetadata m; memset(&m, 0, sizeof m);
+            m.type = 0; m.is_last = 1; m.length = 34;
+            m.stream_info.min_blocksize = m.stream_info.max_blocksize = e->o.blocksize;
+            m.stream_info.min_framesize = e->frames ? e->min_fs : 0; m.stream_info.max_framesize = e->max_fs;
+            m.stream_info.sample_rate = e->sample_rate; m.stream_info.channels = e->channels; m.stream_info.bits_per_sample = e->bps;
+            m.stream_info.total_samples = e->samples; memcpy(m.stream_info.md5sum, digest, 16);
+            e->metadata(e, &m, e->client);
         }
-        if (!rc) {
-            const uint32_t bs = o.blocksize ? o.blocksize : (e->level < 3 ? 1152u : 4096u);
-            const size_t nf = (e->pcm.size() / ((size_t)((e->bps + 7) / 8) * e->channels) + bs - 1) / bs;
-            try { out.resize((size_t)bound); sizes.resize(nf + 1); } catch (const std::bad_alloc&) { rc = BNFLAC_ERR_MEMORY; }
-            if (!rc) { st.frame_sizes = sizes.data(); st.frame_sizes_cap = nf; rc = bnflac_encode(e->pcm.data(), e->pcm.size(), &o, out.data(), out.size(), &n, &st); }
-            if (!rc && e->verify) {                    // set_verify: the stream must decode back to what was handed in
-                bnflac_t* h = nullptr; bnflac_opts d{}; d.struct_size = sizeof d; d.device = -1; d.flags = BNFLAC_OPT_BORROW_INPUT;
-                std::vector<uint8_t> back(e->pcm.size() + 64);
-                uint64_t w = 0;
-                if (bnflac_open_memory(out.data(), (size_t)n, &d, &h) || bnflac_decode_all(h, back.data(), back.size(), &w) || w != e->pcm.size() || memcmp(back.data(), e->pcm.data(), e->pcm.size())) { e->state = 4; ok = false; }
-                if (h) bnflac_close(h);
-            }
-            if (!rc && ok) {
-                const uint32_t bsz = bs;
-                const uint64_t total = e->pcm.size() / ((size_t)((e->bps + 7) / 8) * e->channels);
-                ok = enc_emit(e, out.data(), 4, 0, 0) && enc_emit(e, out.data() + 4, 38, 0, 0);
-                size_t at = 42;
-                for (size_t f = 0; ok && f < st.frames; f++) {
-                    const unsigned smp = (unsigned)std::min<uint64_t>(bsz, total - (uint64_t)f * bsz);
-                    ok = enc_emit(e, out.data() + at, sizes[f], smp, (unsigned)f);
-                    at += sizes[f];
-                }
-                if (ok && e->metadata) {
-                    bnflac_info_t inf{};
-                    if (!bnflac_probe(out.data(), 42, &inf)) {
-                        FLAC__StreamMetadata m; memset(&m, 0, sizeof m);
-                        m.type = 0; m.is_last = 1; m.length = 34;
-                        m.stream_info.min_blocksize = inf.min_blocksize; m.stream_info.max_blocksize = inf.max_blocksize;
-                        m.stream_info.min_framesize = inf.min_framesize; m.stream_info.max_framesize = inf.max_framesize;
-                        m.stream_info.sample_rate = inf.sample_rate; m.stream_info.channels = inf.channels; m.stream_info.bits_per_sample = inf.bits_per_sample;
-                        m.stream_info.total_samples = inf.total_samples; memcpy(m.stream_info.md5sum, inf.md5, 16);
-                        e->metadata(e, &m, e->client);
-                    }
-                }
-            }
-        }
-        if (rc) { e->state = rc == BNFLAC_ERR_MEMORY ? 8 : 5; ok = false; }
     }
     if (e->file) { if (fclose(e->file) != 0) ok = false; e->file = nullptr; }
-    e->pcm.clear(); e->pcm.shrink_to_fit();
+    e->pcm.clear(); e->pcm.shrink_to_fit(); e->out.clear(); e->out.shrink_to_fit(); e->back.clear(); e->back.shrink_to_fit();
     if (ok) e->state = 1;                               // back to UNINITIALIZED, ready for another init (libFLAC)
     return ok ? 1 : 0;
 }

@@ -114,6 +114,7 @@ namespace LibBnFlacSharp
 			public uint MidSide;          // set_do_mid_side_stereo
 			public uint CompressionLevel; // set_compression_level, with Flags |= UseLevel
 			public uint Flags;            // 1 NoMd5, 2 InputInt32, 4 UseLevel, 8 FixedOrder
+			public ulong FirstFrameNumber; // a stream encoded in several calls: the coded number of this call's first frame
 		}
 
 		[StructLayout(LayoutKind.Sequential)]

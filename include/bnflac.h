@@ -176,6 +176,8 @@ typedef struct {
     uint32_t mid_side;              /* stereo only: 1 = cheapest of L/R, L/S, S/R, M/S per frame; 0 = independent channels */
     uint32_t compression_level;     /* used with BNFLAC_ENC_USE_LEVEL: libFLAC's presets 0-8 (set_compression_level) */
     uint32_t flags;                 /* BNFLAC_ENC_* */
+    uint64_t first_frame_number;    /* coded number of the first frame: a stream encoded in several calls (frames are independent; the caller
+                                     * keeps only the frames of the later calls and writes STREAMINFO itself -- what libLibFlac.so does) */
 } bnflac_enc_opts;
 #define BNFLAC_ENC_NO_MD5 1u        /* leave STREAMINFO's MD5 zero (the MD5 is serial host work: it runs beside the GPU for host input, and
                                      * costs a device-to-host copy of the PCM for bnflac_encode_device) */

@@ -70,15 +70,16 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder*);                    
 
 /* ---- the encoder half (LibFLACSharp.cs:322-387), SURVEY 8f-4 ---------------------------------------------------------------------
  * Same symbols, same argument meaning; the work is done by bnflac_encode (one CTA per frame on the GPU).  A replay layer like the
- * decoder half: samples handed to process / process_interleaved are collected, finish() encodes them in one go and then drives the
- * write callback the way libFLAC does -- "fLaC", the STREAMINFO block, then one call per frame (samples = blocksize, current_frame
- * counting from 0) -- with the final STREAMINFO (frame sizes, total samples, MD5) already in place, so no seek back is needed;
- * the metadata callback receives it after the last frame.  State numbering: libFLAC's FLAC__StreamEncoderState (0 OK,
+ * decoder half: init writes "fLaC" and a provisional STREAMINFO block through the write callback, samples handed to process /
+ * process_interleaved are collected and, every 1024 blocks, encoded in one GPU call and handed out frame by frame (samples = blocksize,
+ * current_frame counting from 0) -- output flows during process(), as with libFLAC; finish() encodes the rest and then puts the final
+ * STREAMINFO (frame sizes, total samples, MD5 kept as a running digest) where the provisional one is when the sink can seek (the seek
+ * callback, or the file of init_file), and reports it through the metadata callback.  State numbering: libFLAC's FLAC__StreamEncoderState (0 OK,
  * 1 UNINITIALIZED, 5 CLIENT_ERROR, 6 IO_ERROR, 8 MEMORY_ALLOCATION_ERROR); init status: 0 OK, 1 ENCODER_ERROR, 3 INVALID_CALLBACKS,
  * 4 INVALID_NUMBER_OF_CHANNELS, 5 INVALID_BITS_PER_SAMPLE, 6 INVALID_SAMPLE_RATE, 7 INVALID_BLOCK_SIZE, 13 ALREADY_INITIALIZED. */
 typedef struct FLAC__StreamEncoder FLAC__StreamEncoder;
 typedef int (*FLAC__StreamEncoderWriteCallback)(const FLAC__StreamEncoder*, const uint8_t buffer[], size_t bytes, unsigned samples, unsigned current_frame, void* client);  /* :377; 0 ok, 1 fatal */
-typedef int (*FLAC__StreamEncoderSeekCallback)(const FLAC__StreamEncoder*, uint64_t absolute_byte_offset, void* client);      /* :380 (accepted, never called) */
+typedef int (*FLAC__StreamEncoderSeekCallback)(const FLAC__StreamEncoder*, uint64_t absolute_byte_offset, void* client);      /* :380: used once, by finish(), to rewrite STREAMINFO */
 typedef int (*FLAC__StreamEncoderTellCallback)(const FLAC__StreamEncoder*, uint64_t* absolute_byte_offset, void* client);     /* :383 (accepted, never called) */
 typedef void (*FLAC__StreamEncoderMetadataCallback)(const FLAC__StreamEncoder*, const FLAC__StreamMetadata*, void* client);    /* :386 */
 FLAC__StreamEncoder* FLAC__stream_encoder_new(void);                                              /* :325 */

@@ -171,3 +171,19 @@ def test_legacy_shim_exports_the_encoder_symbols_the_csharp_declares():
     assert L.FLAC__stream_encoder_get_state(e) == 0 and not L.FLAC__stream_encoder_set_channels(e, 1)  # setters only before init
     assert L.FLAC__stream_encoder_init_stream(e, C.cast(cb, C.c_void_p), None, None, None, None) == 13   # ALREADY_INITIALIZED
     L.FLAC__stream_encoder_delete(e)
+
+
+def test_encoder_struct_layouts_match_the_header():
+    from birdnest.audio_b200 import _abi
+    src = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "bnflac.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(bnflac_enc_opts), offsetof(bnflac_enc_opts, flags), offsetof(bnflac_enc_opts, first_frame_number),
+        sizeof(bnflac_enc_stats), offsetof(bnflac_enc_stats, frame_sizes)); return 0; }"""
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")], text=True).split()]
+    assert got == [C.sizeof(_abi.EncOpts), _abi.EncOpts.flags.offset, _abi.EncOpts.first_frame_number.offset, C.sizeof(_abi.EncStats), _abi.EncStats.frame_sizes.offset]

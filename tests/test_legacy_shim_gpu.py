@@ -208,11 +208,11 @@ def test_legacy_encoder_symbols_drive_the_gpu_encoder(planar, tmp_path):
     L.FLAC__stream_encoder_delete(e)
     assert calls[0] == (b"fLaC", 0, 0) and len(calls[1][0]) == 38 and calls[1][1:] == (0, 0)
     assert [c[1:] for c in calls[2:]] == [(4096, i) for i in range(5)] + [(777, 5)]
-    flac = b"".join(c[0] for c in calls)
+    flac = b"".join(c[0] for c in calls)                 # no seek callback: the STREAMINFO in the stream stays the provisional one of init
     got, nframes, _, errs = pyoracle.decode(flac)
     assert got == s.pcm and nframes == 6 and not list(errs)
     assert meta == [(0, 44100, 2, 16, 4096 * 5 + 777, hashlib.md5(s.pcm).digest())]
-    # init_file writes the same stream to disk
+    # init_file writes the same frames to disk, with the final STREAMINFO in place (it can seek)
     e = L.FLAC__stream_encoder_new()
     L.FLAC__stream_encoder_set_channels(e, 2); L.FLAC__stream_encoder_set_bits_per_sample(e, 16); L.FLAC__stream_encoder_set_sample_rate(e, 44100)
     p = str(tmp_path / "o.flac").encode()
@@ -220,4 +220,52 @@ def test_legacy_encoder_symbols_drive_the_gpu_encoder(planar, tmp_path):
     assert L.FLAC__stream_encoder_process_interleaved(e, np.ascontiguousarray(x).ctypes.data_as(C.POINTER(C.c_int32)), len(x) // 2)
     assert L.FLAC__stream_encoder_finish(e)
     L.FLAC__stream_encoder_delete(e)
-    assert open(p, "rb").read() == flac
+    disk = open(p, "rb").read()
+    assert disk[42:] == flac[42:] and disk[:4] == b"fLaC"
+    si = pyoracle.streaminfo(disk)
+    assert bytes(si.md5) == hashlib.md5(s.pcm).digest() and si.total_samples == 4096 * 5 + 777 and si.min_framesize > 0
+
+
+def test_legacy_encoder_emits_while_processing_and_rewrites_streaminfo_through_seek():
+    """Frames leave through the write callback during process() (every 1024 blocks are encoded in one GPU call, numbered on from the last), and a
+    sink that can seek gets the final STREAMINFO written over the provisional one -- libFLAC's behaviour."""
+    import hashlib
+    import numpy as np
+    import pycorpus
+    import pyoracle
+    L = _enc_lib()
+    SEEK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
+    L.FLAC__stream_encoder_init_stream.argtypes = [C.c_void_p, ENC_WRITE_CB, SEEK, C.c_void_p, ENC_META_CB, C.c_void_p]
+    s = pycorpus.make(ch=1, bps=16, sr=8000, samples=256 * 2500 + 10, bs=256, lpc=4, maxpo=3)
+    x = np.frombuffer(s.pcm, dtype="<i2").astype(np.int32)
+    sink, pos, progress = bytearray(), [0], []
+
+    def write(enc, buf, n, samples, frame, client):
+        data = bytes(bytearray(buf[:n]))
+        sink[pos[0]:pos[0] + n] = data
+        pos[0] += n
+        return 0
+
+    def seek(enc, off, client):
+        pos[0] = off
+        return 0
+    wcb, scb, mcb = ENC_WRITE_CB(write), SEEK(seek), ENC_META_CB(lambda *a: None)
+    e = L.FLAC__stream_encoder_new()
+    L.FLAC__stream_encoder_set_channels(e, 1); L.FLAC__stream_encoder_set_bits_per_sample(e, 16); L.FLAC__stream_encoder_set_sample_rate(e, 8000)
+    L.FLAC__stream_encoder_set_blocksize(e, 256); L.FLAC__stream_encoder_set_compression_level(e, 3)
+    assert L.FLAC__stream_encoder_init_stream(e, wcb, scb, None, mcb, None) == 0
+    for at in range(0, len(x), 50000):
+        chunk = np.ascontiguousarray(x[at:at + 50000])
+        assert L.FLAC__stream_encoder_process_interleaved(e, chunk.ctypes.data_as(C.POINTER(C.c_int32)), len(chunk))
+        progress.append(len(sink))
+    assert progress[-1] > progress[0] > 42          # output grew while samples were still being handed in
+    assert L.FLAC__stream_encoder_finish(e)
+    L.FLAC__stream_encoder_delete(e)
+    flac = bytes(sink)
+    got, nframes, _, errs = pyoracle.decode(flac)
+    assert got == s.pcm and nframes == 2501 and not list(errs)
+    si = pyoracle.streaminfo(flac)
+    assert bytes(si.md5) == hashlib.md5(s.pcm).digest() and si.total_samples == 256 * 2500 + 10
+    from birdnest.audio_b200 import _abi
+    with _abi.open_memory(flac) as h:
+        assert bytes(h.decode_all()) == s.pcm

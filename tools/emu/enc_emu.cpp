@@ -16,7 +16,7 @@ extern "C" int enc_emu(const uint8_t* pcm, uint64_t total_samples, uint32_t ch, 
     EncArgs a{};
     a.pcm = pcm; a.total_samples = total_samples; a.ch = ch; a.bps = bps; a.bin = bin; a.bs = bs; a.sample_rate = sr;
     a.max_lpc = max_lpc; a.prec = prec; a.min_po = min_po; a.max_po = max_po; a.stereo = stereo; a.search_order = search;
-    a.nframes = nframes; a.first_frame = 42; a.sub = sub.data(); a.frm = frm.data(); a.totals = &tot; a.out = out;
+    a.nframes = nframes; a.first_frame = 42; a.first_number = 0; a.sub = sub.data(); a.frm = frm.data(); a.totals = &tot; a.out = out;
     emu_launch(k_enc_plan, nframes, NT, enc_smem_bytes(bs), a);
     emu_launch(k_enc_scan, 1, 1024, 0, a);
     if (tot.total_bytes + 4 > cap) return -7;
