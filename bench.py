@@ -810,6 +810,7 @@ def run_ours(args):
                                 "stream_note": "60 tiles of 1406 frames (59.99 s each: whole frames of 4096 samples) = 84,360 frames, 3599.4 s; this encoder's ratio is 0.589 (the reference encoder's on the same shape: 0.528)"},
             "pcm_gbps": value * 3 / 1e9,
             "pipeline_hbm_frac": units_bytes / (ms_per_step / 1e3) / 1e9 / peak,
+            "pipeline_hbm_frac_of_nominal_8000_gbps": units_bytes / (ms_per_step / 1e3) / 1e9 / 8000.0,      # both denominators
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "kernel": {"decode": "k_decode", "parse": "k_parse", "crc": "k_crc", "scan": "k_scan"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
