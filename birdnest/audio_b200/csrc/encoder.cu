@@ -32,6 +32,7 @@
 #include <cstddef>
 #include <cstring>
 #include <cstdio>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -206,7 +207,8 @@ extern "C" int bnflac_encode_device(const void* d_pcm, size_t pcm_bytes, const b
     if (rc) return rc;
     uint8_t hdr[42], md5[16] = {0};
     if (!(r.flags & BNFLAC_ENC_NO_MD5)) {        // device-resident PCM: fetched for the (serial) MD5 only when asked for
-        std::vector<uint8_t> host(pcm_bytes);
+        std::vector<uint8_t> host;
+        try { host.resize(pcm_bytes); } catch (const std::bad_alloc&) { return BNFLAC_ERR_MEMORY; }      // never through the extern "C" frame
         if (cudaMemcpy(host.data(), d_pcm, pcm_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return cuda_fail("cudaMemcpy(md5)", cudaGetLastError());
         md5_pcm(host.data(), total * r.ch, r, md5);
     }
