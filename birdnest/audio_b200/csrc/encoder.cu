@@ -123,6 +123,7 @@ static int encode_on_device(const Resolved& r, const uint8_t* d_pcm, uint64_t to
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     EncArgs a{};
     size_t smem_plan = 0, smem_write = 0;
+    const bool big = r.bs >= NT_BIG_FROM_BS;       // large blocks: CTAs of 1024 threads (the staged samples leave room for one CTA per SM)
     if (((uintptr_t)d_out & 3u) != 0) return BNFLAC_ERR_ARG;
     if (!nframes) { *written = 42; *minfs = 0; *maxfs = 0; if (st) { st->frames = 0; st->bytes = 42; } return out_cap >= 42 ? 0 : BNFLAC_ERR_CAPACITY; }
     for (auto& e : ev) CK(cudaEventCreate(&e));
@@ -133,10 +134,16 @@ static int encode_on_device(const Resolved& r, const uint8_t* d_pcm, uint64_t to
     a.max_lpc = r.max_lpc; a.prec = r.prec; a.min_po = r.min_po; a.max_po = r.max_po; a.stereo = r.stereo; a.search_order = r.search;
     a.nframes = nframes; a.first_frame = 42; a.first_number = r.first_number; a.sub = d_sub; a.frm = d_frm; a.totals = d_tot; a.out = d_out;
     smem_plan = smem_write = enc_smem_bytes(r.bs);
-    CK(cudaFuncSetAttribute(k_enc_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan));
-    CK(cudaFuncSetAttribute(k_enc_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+    if (big) {
+        CK(cudaFuncSetAttribute(k_enc_plan<NT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan));
+        CK(cudaFuncSetAttribute(k_enc_write<NT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+    } else {
+        CK(cudaFuncSetAttribute(k_enc_plan<NT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan));
+        CK(cudaFuncSetAttribute(k_enc_write<NT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+    }
     CK(cudaEventRecord(ev[0], stream));
-    k_enc_plan<<<nframes, NT, smem_plan, stream>>>(a); bnf::count_launch();
+    if (big) k_enc_plan<NT_BIG><<<nframes, NT_BIG, smem_plan, stream>>>(a); else k_enc_plan<NT_SMALL><<<nframes, NT_SMALL, smem_plan, stream>>>(a);
+    bnf::count_launch();
     k_enc_scan<<<1, 1024, 0, stream>>>(a); bnf::count_launch();
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev[1], stream));
@@ -145,7 +152,8 @@ static int encode_on_device(const Resolved& r, const uint8_t* d_pcm, uint64_t to
     if (tot.total_bytes + 4 > out_cap) { rc = BNFLAC_ERR_CAPACITY; *written = tot.total_bytes; goto done; }
     CK(cudaMemsetAsync(d_out, 0, (size_t)((tot.total_bytes + 3) & ~3ull), stream));
     CK(cudaEventRecord(ev[2], stream));
-    k_enc_write<<<nframes, NT, smem_write, stream>>>(a); bnf::count_launch();
+    if (big) k_enc_write<NT_BIG><<<nframes, NT_BIG, smem_write, stream>>>(a); else k_enc_write<NT_SMALL><<<nframes, NT_SMALL, smem_write, stream>>>(a);
+    bnf::count_launch();
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev[3], stream));
     CK(cudaStreamSynchronize(stream));

@@ -12,8 +12,10 @@
 namespace bnfe {
 
 #define FULL 0xffffffffu
-constexpr int NT = 256;             // threads per CTA of both frame kernels (>= 2^MAX_PO partitions)
-constexpr int NW = NT / 32;
+// threads per CTA of both frame kernels: a template parameter NT (256 for blocks up to 4608 samples, 1024 above: a CTA of 256 threads with
+// 130 KB of staged samples would be alone on its SM with two warps per scheduler)
+constexpr int NT_SMALL = 256, NT_BIG = 1024, NW_MAX = NT_BIG / 32;
+constexpr uint32_t NT_BIG_FROM_BS = 4609;
 constexpr int MAX_PO = 8;
 constexpr uint32_t MAX_BS = 16384;
 constexpr int MAX_LPC = 32;
@@ -83,7 +85,9 @@ static inline size_t enc_smem_bytes(uint32_t bs) { return ((size_t)XPAD + (size_
 __device__ __forceinline__ uint32_t zigzag(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
 
 // block-wide reductions; every thread gets the result.  `scratch` has NW entries and is reused call after call.
+template <int NT>
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* scratch) {
+    constexpr int NW = NT / 32;
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     __syncthreads();
@@ -94,7 +98,9 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     for (int w = 0; w < NW; w++) t += scratch[w];
     return t;
 }
+template <int NT>
 __device__ __forceinline__ uint32_t block_or_u32(uint32_t v, unsigned long long* scratch) {
+    constexpr int NW = NT / 32;
     v = __reduce_or_sync(FULL, v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
@@ -105,7 +111,9 @@ __device__ __forceinline__ uint32_t block_or_u32(uint32_t v, unsigned long long*
     return t;
 }
 // exclusive prefix sum over the block's threads; *total = sum of all
+template <int NT>
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, unsigned long long* scratch, uint32_t* total) {
+    constexpr int NW = NT / 32;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -165,7 +173,7 @@ __device__ uint32_t make_frame_header(uint8_t* h, const EncArgs& a, uint32_t bs,
 
 // residuals of an LPC predictor, coefficients in registers, taps unrolled (taps beyond the order have zero coefficients and read the
 // padding in front of x).  Returns 1 in *big if a residual leaves the range the Rice coder is given.
-template <int NO>
+template <int NO, int NT>
 __device__ __forceinline__ uint32_t lpc_residuals(const int32_t* __restrict__ x, int32_t* __restrict__ r, uint32_t bs, uint32_t lo, const int32_t* qc_sh, uint32_t shift, bool narrow) {
     int32_t c[NO];
 #pragma unroll
@@ -183,12 +191,13 @@ __device__ __forceinline__ uint32_t lpc_residuals(const int32_t* __restrict__ x,
     }
     return big;
 }
+template <int NT>
 __device__ __forceinline__ uint32_t lpc_residuals_any(const int32_t* x, int32_t* r, uint32_t bs, uint32_t lo, const int32_t* qc_sh, uint32_t shift, bool narrow) {
-    if (lo <= 4) return lpc_residuals<4>(x, r, bs, lo, qc_sh, shift, narrow);
-    if (lo <= 8) return lpc_residuals<8>(x, r, bs, lo, qc_sh, shift, narrow);
-    if (lo <= 12) return lpc_residuals<12>(x, r, bs, lo, qc_sh, shift, narrow);
-    if (lo <= 16) return lpc_residuals<16>(x, r, bs, lo, qc_sh, shift, narrow);
-    return lpc_residuals<32>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 4) return lpc_residuals<4, NT>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 8) return lpc_residuals<8, NT>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 12) return lpc_residuals<12, NT>(x, r, bs, lo, qc_sh, shift, narrow);
+    if (lo <= 16) return lpc_residuals<16, NT>(x, r, bs, lo, qc_sh, shift, narrow);
+    return lpc_residuals<32, NT>(x, r, bs, lo, qc_sh, shift, narrow);
 }
 
 // ------------------------------------------------------------------------------------------------ plan kernel
@@ -204,8 +213,8 @@ struct PlanShared {
     uint8_t kb[NPART];                        // best parameter per partition
     uint32_t lvl_bits[MAX_PO + 1], lvl_big[MAX_PO + 1];
     unsigned long long lvl_est[MAX_PO + 1];
-    unsigned long long scratch[NW];
-    unsigned long long red5[5][NW];
+    unsigned long long scratch[NW_MAX];
+    unsigned long long red5[5][NW_MAX];
     EncSub dec[8];
     EncSub tmp;
     int32_t qc[MAX_LPC];
@@ -218,6 +227,7 @@ struct PlanShared {
 // Two passes over the residuals: sums of u per partition of the finest order -> every coarser order by addition -> the partition
 // order with the smallest ESTIMATED size (libFLAC's estimate from the sums; sizing every order exactly cost 7 x the instructions
 // for 0.1 % of the bytes) -> three candidate parameters around log2(mean) per partition of that order, sized EXACTLY.
+template <int NT>
 __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32_t order, uint32_t min_po, uint32_t max_po, PlanShared& sh, EncSub* d) {
     const uint32_t tid = threadIdx.x;
     // valid partition orders: the block divides evenly and partition 0 keeps at least one residual
@@ -303,7 +313,9 @@ __device__ uint32_t plan_rice(const int32_t* __restrict__ r, uint32_t bs, uint32
     return best_bits;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
+    constexpr int NW = NT / 32;
     ENC_DYN_SMEM(dyn);
     __shared__ PlanShared sh;
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
@@ -486,7 +498,7 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
                 r[ridx(i)] = x[i] - p;
             }
             __syncthreads();
-            const uint32_t rb = plan_rice(r, bs, fo, a.min_po, a.max_po, sh, d);
+            const uint32_t rb = plan_rice<NT>(r, bs, fo, a.min_po, a.max_po, sh, d);
             const uint32_t fb = 8 + w + fo * ebps + rb;
             if (fb < best_bits) { best_bits = fb; if (tid == 0) { d->type = 2; d->order = (uint8_t)fo; } }
         }
@@ -495,11 +507,11 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         if (sh.lpc_ok) {
             const uint32_t lo = sh.lpc_order, prec = sh.lpc_prec, shift = sh.lpc_shift;
             const bool narrow = ebps + prec + (31u - (uint32_t)__clz(lo)) <= 32u;     // libFLAC 1.2.1's width rule: what the decoder will do
-            uint32_t big = lpc_residuals_any(x, r, bs, lo, sh.qc, shift, narrow);
-            big = block_or_u32(big, sh.scratch);
+            uint32_t big = lpc_residuals_any<NT>(x, r, bs, lo, sh.qc, shift, narrow);
+            big = block_or_u32<NT>(big, sh.scratch);
             if (!big) {
                 EncSub* t = &sh.tmp;
-                const uint32_t rb = plan_rice(r, bs, lo, a.min_po, a.max_po, sh, t);
+                const uint32_t rb = plan_rice<NT>(r, bs, lo, a.min_po, a.max_po, sh, t);
                 const uint32_t lb = 8 + w + lo * ebps + 9 + lo * prec + rb;
                 if (lb < best_bits) {
                     best_bits = lb;
@@ -602,11 +614,13 @@ __device__ __forceinline__ uint32_t gf_xpow8(uint32_t nbytes) {              // 
     return res;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
+    constexpr int NW = NT / 32;
     ENC_DYN_SMEM(dyn);
     __shared__ EncSub D;
     __shared__ int32_t qc32[MAX_LPC];
-    __shared__ unsigned long long scratch[NW];
+    __shared__ unsigned long long scratch[NW_MAX];
     __shared__ uint16_t crctab[256];
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
     const EncFrame F = a.frm[f];
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
     int32_t* r = x + a.bs;
     const uint64_t base = (uint64_t)f * a.bs * a.ch;
     const unsigned long long fbit = F.byte_off * 8ull;
-    {
+    if (tid < 256) {
         uint32_t c = tid << 8;
         for (int k = 0; k < 8; k++) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) & 0xffffu : (c << 1) & 0xffffu;
         crctab[tid] = (uint16_t)c;
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
             } else {
                 const uint32_t prec = D.prec, shift = D.shift;
                 const bool narrow = ebps + prec + (31u - (uint32_t)__clz(order)) <= 32u;
-                (void)lpc_residuals_any(x, r, bs, order, qc32, shift, narrow);
+                (void)lpc_residuals_any<NT>(x, r, bs, order, qc32, shift, narrow);
             }
             __syncthreads();
             const uint32_t po = D.po, psz = bs >> po, plen = D.method ? 5u : 4u;
@@ -700,7 +714,7 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
                 mybits += (zigzag(r[ridx(i)]) >> k) + 1u + k;
             }
             uint32_t total;
-            const uint32_t start = block_excl_scan_u32(mybits, scratch, &total);
+            const uint32_t start = block_excl_scan_u32<NT>(mybits, scratch, &total);
             if (ib < ie) {
                 BitW bw; bw.init(a.out, sbit + head_bits + start);
                 for (uint32_t i = ib; i < ie; i++) {

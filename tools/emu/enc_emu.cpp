@@ -17,11 +17,12 @@ extern "C" int enc_emu(const uint8_t* pcm, uint64_t total_samples, uint32_t ch, 
     a.pcm = pcm; a.total_samples = total_samples; a.ch = ch; a.bps = bps; a.bin = bin; a.bs = bs; a.sample_rate = sr;
     a.max_lpc = max_lpc; a.prec = prec; a.min_po = min_po; a.max_po = max_po; a.stereo = stereo; a.search_order = search;
     a.nframes = nframes; a.first_frame = 42; a.first_number = 0; a.sub = sub.data(); a.frm = frm.data(); a.totals = &tot; a.out = out;
-    emu_launch(k_enc_plan, nframes, NT, enc_smem_bytes(bs), a);
+    const bool big = bs >= NT_BIG_FROM_BS;
+    if (big) emu_launch(k_enc_plan<NT_BIG>, nframes, NT_BIG, enc_smem_bytes(bs), a); else emu_launch(k_enc_plan<NT_SMALL>, nframes, NT_SMALL, enc_smem_bytes(bs), a);
     emu_launch(k_enc_scan, 1, 1024, 0, a);
     if (tot.total_bytes + 4 > cap) return -7;
     memset(out, 0, (size_t)((tot.total_bytes + 3) & ~3ull));
-    emu_launch(k_enc_write, nframes, NT, enc_smem_bytes(bs), a);
+    if (big) emu_launch(k_enc_write<NT_BIG>, nframes, NT_BIG, enc_smem_bytes(bs), a); else emu_launch(k_enc_write<NT_SMALL>, nframes, NT_SMALL, enc_smem_bytes(bs), a);
     *written = tot.total_bytes; *minfs = tot.min_fs; *maxfs = tot.max_fs;
     return 0;
 }
