@@ -334,7 +334,17 @@ __global__ void __launch_bounds__(NT) k_enc_plan(EncArgs a) {
         // ---- stage the signal, wasted bits, CONSTANT
         const int32_t x0 = load_variant(a, base, 0, v);
         uint32_t orv = 0, differs = 0;
-        for (uint32_t i = tid; i < bs; i += NT) { const int32_t s = load_variant(a, base, i, v); x[i] = s; orv |= (uint32_t)s; differs |= (uint32_t)(s != x0); }
+        {   // four samples per trip: the global loads of a trip are issued together (the staging loop is what waits for memory)
+            uint32_t i = tid;
+            for (; i + 3 * NT < bs; i += 4 * NT) {
+                int32_t sv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) sv[q] = load_variant(a, base, i + q * NT, v);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { x[i + q * NT] = sv[q]; orv |= (uint32_t)sv[q]; differs |= (uint32_t)(sv[q] != x0); }
+            }
+            for (; i < bs; i += NT) { const int32_t s = load_variant(a, base, i, v); x[i] = s; orv |= (uint32_t)s; differs |= (uint32_t)(s != x0); }
+        }
         {   // one exchange for both
             orv = __reduce_or_sync(FULL, orv); differs = __reduce_or_sync(FULL, differs);
             __syncthreads();
@@ -654,7 +664,17 @@ __global__ void __launch_bounds__(NT) k_enc_write(EncArgs a) {
         const uint32_t vbps = a.bps + ((a.stereo && variant == 3) ? 1u : 0u), ebps = vbps - w;
         const uint32_t emask = ebps >= 32 ? 0xffffffffu : (1u << ebps) - 1u;
         const unsigned long long sbit = fbit + F.sub_bit[c];
-        if (type != 0) { for (uint32_t i = tid; i < bs; i += NT) x[i] = load_variant(a, base, i, variant) >> w; }
+        if (type != 0) {
+            uint32_t i = tid;
+            for (; i + 3 * NT < bs; i += 4 * NT) {
+                int32_t sv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) sv[q] = load_variant(a, base, i + q * NT, variant);
+#pragma unroll
+                for (int q = 0; q < 4; q++) x[i + q * NT] = sv[q] >> w;
+            }
+            for (; i < bs; i += NT) x[i] = load_variant(a, base, i, variant) >> w;
+        }
         __syncthreads();
         uint32_t head_bits = 8 + w;                      // bits before the per-sample part, all written by thread 0
         if (type >= 2) head_bits += order * ebps + (type == 3 ? 9u + order * D.prec : 0u) + 6u;
