@@ -40,7 +40,12 @@ enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 #ifndef DEC_TILE_BIG
 #define DEC_TILE_BIG 32
 #endif
-template <int ORD> struct DecCfg { static constexpr int T = (ORD > 16) ? DEC_TILE_BIG : DEC_TILE; static_assert(T % 16 == 0 && T % ORD == 0, "a tile is whole pack units and whole ring periods"); };
+// FT: rows of the per-warp frame table (bs | assign | PCM offset); formats with two or more channels hold at most 16 frames per warp
+template <int ORD, int SPEC = 0> struct DecCfg {
+    static constexpr int T = (ORD > 16) ? DEC_TILE_BIG : DEC_TILE;
+    static constexpr int FT = (SPEC && (SPEC >> 2) >= 2) ? 16 : 32;
+    static_assert(T % 8 == 0 && T % ORD == 0 && (T * (SPEC ? (SPEC >> 2) : 1)) % 16 == 0, "a tile is whole Rice groups, whole restore blocks and whole pack units");
+};
 
 struct RiceSt {
     uint32_t fastleft, rawleft, rawbits, k, kp32, negP, c30, psize, plen, order;
@@ -194,16 +199,28 @@ __device__ __forceinline__ void pack4(uint32_t* dw, uint32_t B, uint32_t v0, uin
     else if (B == 2) { dw[0] = __byte_perm(v0, v1, 0x5410); dw[1] = __byte_perm(v2, v3, 0x5410); }
     else dw[0] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
 }
-// stereo decorrelation of one (ch0, ch1) pair.  mid/side: with m' = 2M + (S&1), L = (m'+S)>>1 = R + S and
-// R = (m'-S)>>1 = M - (S>>1) (identical in every bit that reaches the output, also when the int32 arithmetic wraps).
-__device__ __forceinline__ void decorr(uint32_t assign, uint32_t& x, uint32_t& y) {
-    if (assign == 10) { const uint32_t r = x - (uint32_t)((int32_t)y >> 1); x = r + y; y = r; }
-    else if (assign == 8) y = x - y;
-    else if (assign == 9) x = x + y;
+// stereo decorrelation of one (ch0, ch1) pair, branch free: the lanes of a pack step hold different frames, so a
+// branch per assignment diverges on streams with adaptive stereo (ncu: the branchy form was 10 instructions per pair and 13 % of
+// the kernel's stall samples).  With d = x - (y >> sh), sh = 1 for mid/side and 0 otherwise:
+//   left/side  (8): ch1 = x - y = d,            ch0 = x = d + y
+//   mid/side  (10): ch1 = M - (S >> 1) = d,     ch0 = ch1 + S = d + y      (m' = 2M + (S&1): L = (m'+S)>>1 = R + S, R = (m'-S)>>1;
+//                                                                            identical in every bit that reaches the output, also when int32 wraps)
+//   side/right (9): ch0 = x + y,                ch1 = y
+// i.e. ch0 = (useD ? d : x) + (y & addm), ch1 = useD ? d : y.
+struct DecorrSel { uint32_t sh, addm; bool useD; };
+__device__ __forceinline__ DecorrSel decorr_sel(uint32_t assign) {
+    DecorrSel k; k.sh = assign == 10 ? 1u : 0u; k.addm = assign >= 8 ? ~0u : 0u; k.useD = assign == 8 || assign == 10;
+    return k;
+}
+__device__ __forceinline__ void decorr(const DecorrSel& k, uint32_t& x, uint32_t& y) {
+    const uint32_t d = x - (uint32_t)((int32_t)y >> k.sh);
+    const uint32_t b = k.useD ? d : x;
+    x = b + (y & k.addm);
+    y = k.useD ? d : y;
 }
 
 __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32_t C, uint32_t B, uint32_t F, uint32_t i0, uint32_t T,
-                                          uint32_t ftab, uint8_t* __restrict__ out, uint32_t lane) {
+                                          uint32_t ftab, uint32_t FT, uint8_t* __restrict__ out, uint32_t lane) {
     const uint32_t upf = (T * C) >> 4;                 // units of 16 samples per frame-tile (T is a multiple of 16)
     const uint32_t total = F * upf;
     const uint32_t rcp_upf = 65536u / upf + 1u;        // g / upf for g < 2^9
@@ -211,22 +228,20 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
     for (uint32_t g = lane; g < total; g += 32) {
         const uint32_t f = (g * rcp_upf) >> 16, u = g - f * upf;
         const uint32_t bs = lds32(ftab + 4 * f);
-        if (i0 >= bs) continue;
-        const uint32_t nt = min(T, bs - i0), nsamp = nt * C, q0 = 16 * u;
+        const uint32_t nt = bs > i0 ? min(T, bs - i0) : 0u, nsamp = nt * C, q0 = 16 * u;
         if (q0 >= nsamp) continue;
-        const uint32_t assign = lds32(ftab + 128 + 4 * f);
-        const uint2 pol = lds64(ftab + 256 + 8 * f);
-        uint8_t* dst = out + (((uint64_t)pol.y << 32) | pol.x) + ((uint64_t)i0 * C + q0) * B;
+        const uint32_t assign = lds32(ftab + 4 * FT + 4 * f);
+        const uint2 pol = lds64(ftab + 8 * FT + 8 * f);
+        uint8_t* dst = out + ((((uint64_t)pol.y << 32) | pol.x) + (i0 * C + q0) * B);      // 32-bit offset inside the frame: blocksize * channels * bytes < 2^22
         uint32_t v[16];
         const uint32_t fbase = tile_base + 4 * f * C;
         if (C == 2) {
             const uint32_t ad = fbase + 4 * (q0 >> 1) * S;
 #pragma unroll
             for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
-            if (assign >= 8) {
+            const DecorrSel ds = decorr_sel(assign);
 #pragma unroll
-                for (int e = 0; e < 8; e++) decorr(assign, v[2 * e], v[2 * e + 1]);
-            }
+            for (int e = 0; e < 8; e++) decorr(ds, v[2 * e], v[2 * e + 1]);
         } else if (C == 1) {
 #pragma unroll
             for (int e = 0; e < 16; e++) v[e] = lds32(fbase + 4 * (q0 + e) * S);
@@ -282,11 +297,17 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
     }
 }
 
+#ifndef DEC_CKPT16
+#define DEC_CKPT16 1
+#endif
+#ifndef DEC_ZZ_BFE
+#define DEC_ZZ_BFE 1
+#endif
 #ifndef DEC_WARPS_N
 #define DEC_WARPS_N 2
 #endif
 constexpr int DEC_WARPS = DEC_WARPS_N;        // independent warps per CTA (no CTA-wide barrier anywhere)
-__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 512u; }
+__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S, int FT) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 16u * (uint32_t)FT; }
 
 // SPEC: 0 = any channel count / sample width (run-time C, B, S); else 4 C + B: the common formats get C, B and the tile
 // stride S as compile-time constants (tile addresses become immediates, lane -> (frame, channel) is a shift, the pack
@@ -297,11 +318,12 @@ __host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S) { return
 __host__ __device__ constexpr uint32_t dec_tile_stride(uint32_t C) { return 32u + ((C & 3u) == 0 ? 4u : (C & 1u) == 0 ? 2u : 1u); }
 template <int ORD, bool WIDE, int SPEC>
 __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : DEC_MAXNREG_BIG) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_) {
-    constexpr int T = DecCfg<ORD>::T;
+    constexpr int T = DecCfg<ORD, SPEC>::T, FT = DecCfg<ORD, SPEC>::FT;
     const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2) : S_;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t ring_base = smem_u32(s_dyn) + wib * dec_warp_smem(T, S);
+    // through a shuffle: ptxas otherwise rematerialises this address from SR_CgaCtaId / SR_TID in every pack step (two S2R + four more)
+    const uint32_t ring_base = __shfl_sync(FULL, smem_u32(s_dyn) + wib * dec_warp_smem(T, S, FT), 0);
     const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
     const uint32_t ftab = tile_base + T * S * 4;               // bs[32] | assign[32] | pcm offset[32] (u64)
     const uint32_t F = 32 / C;
@@ -324,7 +346,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     rs.fastleft = 0; rs.rawleft = 0; rs.rawbits = 0; rs.k = 0; rs.kp32 = 32; rs.negP = ~0u; rs.c30 = 30; rs.psize = 0; rs.plen = 4; rs.order = 0; rs.first = true;
     uint32_t bs = 0, assign = 0, wasted = 0, shift = 0, bps = 0;
     int mode = M_IDLE;
-    if (fl < F && ch == 0) { sts32(ftab + 4 * fl, 0); sts32(ftab + 128 + 4 * fl, 0); }
+    if (fl < F && ch == 0) { sts32(ftab + 4 * fl, 0); sts32(ftab + 4 * FT + 4 * fl, 0); }
     if (active) {
         const uint32_t i = (a.acc_sorted ? a.acc_sorted : a.acc_idx)[kf];
         const Cand c = a.cand[i];
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
         bool ok = a.status[i] == ST_OK;
         const uint64_t po = a.pcm_off[i];
         if (po + (uint64_t)bs * C * B > a.out_cap) { ok = false; bs = 0; }   // never write past the caller's buffer
-        if (ch == 0) { sts32(ftab + 4 * fl, bs); sts32(ftab + 128 + 4 * fl, assign); sts32(ftab + 256 + 8 * fl, (uint32_t)po); sts32(ftab + 260 + 8 * fl, (uint32_t)(po >> 32)); }
+        if (ch == 0) { sts32(ftab + 4 * fl, bs); sts32(ftab + 4 * FT + 4 * fl, assign); sts32(ftab + 8 * FT + 8 * fl, (uint32_t)po); sts32(ftab + 8 * FT + 4 + 8 * fl, (uint32_t)(po >> 32)); }
         int32_t cval = 0;
         mode = M_CONST;                              // damaged frames (CRC mismatch) are delivered zero-filled
         if (ok) {
@@ -405,7 +427,12 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
 #pragma unroll 1
         for (uint32_t t0 = 0, row = col; t0 < (uint32_t)T; t0 += 8, row += 8 * rs4) {      // row: loop-carried, or it is rematerialised from SR_TID every step
             const uint32_t idx0 = i0 + t0;
+#if DEC_CKPT16
+            if (!(idx0 & 8u)) { if (reads) br.ckpt_full(); }
+            else if (__any_sync(FULL, reads && br.ckpt_mid_needed())) br.ckpt_mid_wait();
+#else
             if (reads && (DEC_RING_BLOCKS < 16 || !(t0 & 8u))) br.checkpoint();
+#endif
             const bool inert = mode <= M_CONST || idx0 >= bs;
             if (mode == M_PRED && !inert && rs.fastleft == 0 && rs.rawleft == 0 && idx0 >= order) rice_param(br, rs);
             const bool fast_ok = inert || (mode == M_PRED && rs.fastleft >= 8);
@@ -427,7 +454,11 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                     if (j < 7) DecRing<ORD>::win_advance(wn, pos, np, nxt);
                     pos = np;
                     const uint32_t u = f * negP + shr_c(w, d) + c30;      // (31-f) << k | low bits, stop bit cancelled
+#if DEC_ZZ_BFE
+                    { int32_t m; asm("bfe.s32 %0, %1, 0, 1;" : "=r"(m) : "r"(u)); r[j] = (int32_t)(u >> 1) ^ m; }      // -(u & 1) as one sign-extending field extract
+#else
                     r[j] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+#endif
                 }
                 if (commit) {
                     rs.fastleft -= 8;
@@ -487,7 +518,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
         }
         __syncwarp();
         // ---- pack phase
-        pack_tile(tile_base, S, C, B, F, i0, T, ftab, a.out, lane);
+        pack_tile(tile_base, S, C, B, F, i0, T, ftab, FT, a.out, lane);
         __syncwarp();
     }
 }
@@ -500,6 +531,7 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 #ifdef DEC_EXPERIMENT      // kernel experiments (tools/build_variants.sh): only the variants the cfg2 / cfg3 benchmark streams use are compiled (40 s instead of 3 min)
     if constexpr (WIDE && ORD == 12) { if (key == 11) launch_decode_s<12, true, 11>(a, nacc, C, B, st); }
     else if constexpr (WIDE && ORD == 32) { if (key == 35) launch_decode_s<32, true, 35>(a, nacc, C, B, st); }
+    else if constexpr (!WIDE && ORD == 8) { if (key == 10) launch_decode_s<8, false, 10>(a, nacc, C, B, st); }
     return;
 #else
     switch (key) {
@@ -516,11 +548,11 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 }
 template <int ORD, bool WIDE, int SPEC>
 static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
-    constexpr int T = DecCfg<ORD>::T;
+    constexpr int T = DecCfg<ORD, SPEC>::T, FT = DecCfg<ORD, SPEC>::FT;
     const uint32_t F = 32 / C;
     const uint32_t S = dec_tile_stride(C);
     const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
-    size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S);
+    size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S, FT);
     static std::atomic<uint64_t> attr_done{0};
     if (first_use_on_device(attr_done)) { cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); used_on_device(attr_done); }
     const int n_sm = sm_count();
@@ -550,7 +582,8 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 template <bool WIDE>
 static void launch_decode_w(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, cudaStream_t st) {
 #ifdef DEC_EXPERIMENT
-    if (max_order <= 12) launch_decode_t<12, WIDE>(a, nacc, C, B, st); else launch_decode_t<32, WIDE>(a, nacc, C, B, st);
+    if (!WIDE && max_order <= 8) launch_decode_t<8, WIDE>(a, nacc, C, B, st);
+    else if (max_order <= 12) launch_decode_t<12, WIDE>(a, nacc, C, B, st); else launch_decode_t<32, WIDE>(a, nacc, C, B, st);
     return;
 #endif
     if (max_order <= 4) launch_decode_t<4, WIDE>(a, nacc, C, B, st);
