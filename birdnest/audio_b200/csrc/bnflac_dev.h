@@ -127,6 +127,11 @@ struct PassArgs {
     // K3-5
     uint8_t* out;
     uint64_t out_cap;
+    // balanced decode schedule (kernels_decode.cuh): per slot one flag word and the state of a job handed over to the next slot;
+    // nullptr = plain launch (one job per warp)
+    uint32_t* dec_flags;
+    uint32_t* dec_state;
+    uint32_t dec_slots;     // slots the two arrays hold
 };
 
 // launchers (kernels.cu); all asynchronous on `stream`
@@ -145,6 +150,11 @@ void launch_clear(const PassArgs& a, void* stream);                             
 void launch_publish(const void* src, void* dst_mapped, uint32_t nwords, void* stream);  // <= 32 words to mapped host memory
 void launch_seg_summary(const PassArgs& a, uint32_t ncand_bound, uint64_t* seg_pcm, uint32_t* seg_flags, void* stream);
 void launch_decode(const PassArgs& a, uint32_t nacc_bound, uint32_t channels, uint32_t bytes_per_sample, uint32_t max_order, bool wide, void* stream);
+// Slots (resident decode warps) a pass of `nacc_bound` frames could be cut over, 0 when the plain launch is used anyway (at most one
+// wave of jobs, or switched off): the engine then provides PassArgs::dec_flags (4 bytes per slot, zeroed once) and dec_state
+// (decode_sched_state_bytes per slot).
+uint32_t decode_sched_slots(uint32_t nacc_bound, uint32_t channels);
+uint64_t decode_sched_state_bytes();
 int kernel_launch_count();   // kernels launched so far by this process (bench "gpu_launches")
 
 } // namespace bnf

@@ -282,7 +282,7 @@ struct bnflac {
 
     // device state
     DevBuf d_in, d_segs, d_chunks, d_cand_tmp, d_cand, d_chunk_base, d_chunk_count, d_chunk_scan, d_counters, d_seg_crc, d_next, d_pref, d_anom,
-        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags, d_spec_jobs, d_spec_base, d_spec_count, d_spec_done, d_acc_sorted, d_bucket_hist;
+        d_flen, d_status, d_sub, d_pcm_off, d_acc_idx, d_totals, d_out, d_seg_pcm, d_seg_flags, d_spec_jobs, d_spec_base, d_spec_count, d_spec_done, d_acc_sorted, d_bucket_hist, d_dec_sched;
     uint32_t nchunks = 0, cand_cap = 0, nsegs = 0;
     bool tables_ready = false;
     PassArgs args{};
@@ -326,7 +326,7 @@ struct bnflac {
         DeviceScope on(device);
         if (stream) cudaStreamSynchronize(stream);     // buffers go back to the shared pool: nothing may still be using them
         DevBuf* all[] = {&d_in, &d_segs, &d_chunks, &d_cand_tmp, &d_cand, &d_chunk_base, &d_chunk_count, &d_chunk_scan, &d_counters, &d_seg_crc, &d_pref, &d_anom,
-                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags, &d_spec_jobs, &d_spec_base, &d_spec_count, &d_spec_done, &d_acc_sorted, &d_bucket_hist};
+                         &d_next, &d_flen, &d_status, &d_sub, &d_pcm_off, &d_acc_idx, &d_totals, &d_out, &d_seg_pcm, &d_seg_flags, &d_spec_jobs, &d_spec_base, &d_spec_count, &d_spec_done, &d_acc_sorted, &d_bucket_hist, &d_dec_sched};
         for (DevBuf* b : all) b->release();
         pcm_host.release(); mailbox.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -574,9 +574,27 @@ static int run_front(bnflac* h) {
     return 0;
 }
 
+// Passes of more than one wave of decode warps get the scratch of the balanced schedule (kernels_decode.cuh): a flag word and one
+// job state per slot.  Without it (small passes, no memory) launch_decode uses the plain launch.
+static int prepare_decode_sched(bnflac* h, uint32_t nacc) {
+    h->args.dec_flags = nullptr; h->args.dec_state = nullptr; h->args.dec_slots = 0;
+    const uint32_t slots = decode_sched_slots(nacc, h->info.channels);
+    if (!slots) return 0;
+    const uint64_t flag_bytes = ((uint64_t)slots * 4 + 255) & ~255ull;
+    const void* before = h->d_dec_sched.p;
+    if (h->d_dec_sched.reserve(flag_bytes + (uint64_t)slots * decode_sched_state_bytes())) { cudaGetLastError(); return 0; }
+    if (h->d_dec_sched.p != before) CK(cudaMemsetAsync(h->d_dec_sched.p, 0, flag_bytes, h->stream));   // whatever the block held before is not an epoch
+    h->args.dec_flags = h->d_dec_sched.as<uint32_t>();
+    h->args.dec_state = reinterpret_cast<uint32_t*>(h->d_dec_sched.as<uint8_t>() + flag_bytes);
+    h->args.dec_slots = slots;
+    return 0;
+}
+
 static int run_back(bnflac* h, uint8_t* d_out, uint64_t cap) {
     if (h->totals.pcm_bytes > cap) return BNFLAC_ERR_CAPACITY;
     h->args.out = d_out; h->args.out_cap = cap;
+    int rc_s;
+    if ((rc_s = prepare_decode_sched(h, h->totals.n_accepted))) return rc_s;
     if (h->totals.n_accepted)
         launch_decode(h->args, h->totals.n_accepted, h->info.channels, h->info.bytes_per_sample, h->totals.max_order, h->totals.any_wide != 0, h->stream);
     CK(cudaEventRecord(h->ev[5], h->stream));
@@ -605,6 +623,7 @@ static int run_pass_predicted(bnflac* h, uint8_t* d_out, uint64_t cap) {
     int rc;
     if ((rc = launch_front_tail(h, nb))) return rc;
     h->args.out = d_out; h->args.out_cap = cap;
+    if ((rc = prepare_decode_sched(h, nacc))) return rc;
     if (p.n_accepted) launch_decode(h->args, nacc, h->info.channels, h->info.bytes_per_sample, p.max_order, p.any_wide != 0, h->stream);
     CK(cudaEventRecord(h->ev[5], h->stream));
     launch_publish(h->d_counters.p, h->mailbox.p, 2, h->stream);

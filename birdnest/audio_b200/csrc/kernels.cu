@@ -20,6 +20,12 @@ namespace bnf {
 static std::atomic<int> g_launches{0};
 int kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void count_launch() { g_launches++; }
+uint32_t next_decode_epoch() {
+    static std::atomic<uint32_t> ctr{0};
+    uint32_t e;
+    do e = ctr.fetch_add(1, std::memory_order_relaxed) + 1; while (e == 0);
+    return e;
+}
 
 // ------------------------------------------------------------------------------------------------ frame header
 struct Hdr {

@@ -3,6 +3,20 @@
 #pragma once
 #include "kernels_common.cuh"
 
+// build knobs of the kernel experiments (tools/build_variants.sh); the defaults are what was measured fastest
+#ifndef DEC_PACK_UNIFORM
+#define DEC_PACK_UNIFORM 0
+#endif
+#ifndef DEC_I2D_CVT
+#define DEC_I2D_CVT 1
+#endif
+#ifndef DEC_CKPT16
+#define DEC_CKPT16 1
+#endif
+#ifndef DEC_ZZ_BFE
+#define DEC_ZZ_BFE 1
+#endif
+
 namespace bnf {
 
 // ------------------------------------------------------------------------------------------------ K3-5 decode
@@ -26,7 +40,7 @@ enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 #ifndef DEC_MAXNREG
 #define DEC_MAXNREG 120
 #endif
-// orders > 12: 168 registers = three warps per scheduler, one wave for the few-large-frames streams these variants exist for
+// orders > 16: 168 registers = three warps per scheduler, one wave for the few-large-frames streams these variants exist for
 // (ptxas: 108 bytes of spill stores for ORD = 32, none for 16)
 #ifndef DEC_MAXNREG_BIG
 #define DEC_MAXNREG_BIG 168
@@ -111,7 +125,11 @@ __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, c
         if (EXTRA) p >>= sh_n;
         int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
         if (FIRST) { if (j < (int)order) s = r; }
+#if DEC_I2D_CVT
+        h[j] = (double)s;                                                            // I2F.F64.S32: one instruction instead of three
+#else
         h[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
+#endif
         if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
         else sts32(addr + j * rs4, (uint32_t)s);
     }
@@ -240,8 +258,16 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
 #pragma unroll
             for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
             const DecorrSel ds = decorr_sel(assign);
+#if DEC_PACK_UNIFORM
+            if (__all_sync(__activemask(), ds.useD)) {       // every unit of this step is left/side or mid/side (the usual choices of an adaptive encoder): 3 instead of 6 per pair
 #pragma unroll
-            for (int e = 0; e < 8; e++) decorr(ds, v[2 * e], v[2 * e + 1]);
+                for (int e = 0; e < 8; e++) { const uint32_t d = v[2 * e] - (uint32_t)((int32_t)v[2 * e + 1] >> ds.sh); v[2 * e] = d + v[2 * e + 1]; v[2 * e + 1] = d; }
+            } else
+#endif
+            {
+#pragma unroll
+                for (int e = 0; e < 8; e++) decorr(ds, v[2 * e], v[2 * e + 1]);
+            }
         } else if (C == 1) {
 #pragma unroll
             for (int e = 0; e < 16; e++) v[e] = lds32(fbase + 4 * (q0 + e) * S);
@@ -297,12 +323,6 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
     }
 }
 
-#ifndef DEC_CKPT16
-#define DEC_CKPT16 1
-#endif
-#ifndef DEC_ZZ_BFE
-#define DEC_ZZ_BFE 1
-#endif
 #ifndef DEC_WARPS_N
 #define DEC_WARPS_N 2
 #endif
@@ -316,8 +336,24 @@ __host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S, int FT) 
 #define DEC_SPECIALISE 1
 #endif
 __host__ __device__ constexpr uint32_t dec_tile_stride(uint32_t C) { return 32u + ((C & 3u) == 0 ? 4u : (C & 1u) == 0 ? 2u : 1u); }
-template <int ORD, bool WIDE, int SPEC>
-__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : DEC_MAXNREG_BIG) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_) {
+// Balanced schedule (epoch != 0): the launch is ONE resident wave of warps ("slots") and the job list -- job j = the 32/C frames a
+// warp decodes side by side, NT nominal tiles each -- is cut into equal runs of tiles, one run per slot, wherever the cut falls.
+// A plain launch of J jobs on M slots takes ceil(J / M) subframe chains however small the last wave is (cfg2: 2.23 waves cost 3,
+// the 16-bit hour 1.02 waves cost 2); cut this way every slot is busy for J / M chains.  A job cut in two is handed over through
+// HBM: the slot that decodes its first tiles does so FIRST (slots walk their run from its last job to its first), saves per lane
+// the bit position, the Rice partition state and the last ORD samples, and raises flag[slot]; the slot that owns the rest of the job
+// reaches it LAST, re-reads the subframe header (coefficients, shift) and resumes from the saved state.  The producer is the
+// lower-numbered slot and never waits itself, so CTAs dispatched in index order cannot deadlock even when they are not all resident.
+// the cut schedule exists for the format-specialised variants of orders <= 16 (streams of many frames; few-large-frame streams are
+// a single wave or many full ones): keeps the number of kernels to compile in bounds
+template <int ORD, int SPEC> constexpr bool dec_has_balanced() { return ORD <= 16 && SPEC != 0; }
+inline uint32_t dec_force_slots() { static const uint32_t v = getenv("BNFLAC_BALANCE_SLOTS") ? (uint32_t)atoi(getenv("BNFLAC_BALANCE_SLOTS")) : 0u; return v; }
+constexpr uint32_t DEC_STATE_WORDS = 8 + 32;               // per lane: position (2), fastleft, rawleft, rawbits, k | first, 2 spare, history
+constexpr uint32_t DEC_SLOT_WORDS = DEC_STATE_WORDS * 32;  // word w of lane l at [w * 32 + l]
+// BAL = false is the plain launch (one job per warp: the job loop below runs once and the hand-over code is not compiled); the cut
+// schedule is a second instantiation because the loop-carried state costs the plain kernel 2 - 4 % (cfg2 decode 1.72 -> 1.79 ms).
+template <int ORD, bool WIDE, int SPEC, bool BAL>
+__global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : ORD <= 16 ? 128 : DEC_MAXNREG_BIG) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_, uint32_t epoch) {
     constexpr int T = DecCfg<ORD, SPEC>::T, FT = DecCfg<ORD, SPEC>::FT;
     const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2) : S_;
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -325,14 +361,29 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     // through a shuffle: ptxas otherwise rematerialises this address from SR_CgaCtaId / SR_TID in every pack step (two S2R + four more)
     const uint32_t ring_base = __shfl_sync(FULL, smem_u32(s_dyn) + wib * dec_warp_smem(T, S, FT), 0);
     const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
-    const uint32_t ftab = tile_base + T * S * 4;               // bs[32] | assign[32] | pcm offset[32] (u64)
+    const uint32_t ftab = tile_base + T * S * 4;               // bs[FT] | assign[FT] | pcm offset[FT] (u64)
     const uint32_t F = 32 / C;
     const uint32_t n_acc = a.totals->n_accepted;
     const uint32_t fl = lane / C, ch = lane - fl * C;
-    const uint32_t kf = (blockIdx.x * DEC_WARPS + wib) * F + fl;
-    const bool active = fl < F && kf < n_acc;
     const uint32_t rs4 = S * 4;
     const uint32_t col = tile_base + lane * 4;
+    const uint32_t slot = blockIdx.x * DEC_WARPS + wib;
+    // this warp's run: jobs j_lo .. j_hi, tiles [tb, ..) of j_lo and [.., te) of j_hi
+    uint32_t j_lo = slot, j_hi = slot, tb = 0, te = 0xffffu;
+    if constexpr (BAL) {
+        const uint32_t NT = max(1u, (a.totals->max_bs + T - 1) / T), J = (n_acc + F - 1) / F, M = gridDim.x * DEC_WARPS;
+        const uint32_t W = J * NT, q = (W + M - 1) / M;               // the host takes this path only when J * NT < 2^31
+        const uint32_t g0 = min(W, slot * q), g1 = min(W, g0 + q);
+        if (g0 >= g1) return;
+        j_lo = g0 / NT; tb = g0 - j_lo * NT;
+        j_hi = (g1 - 1) / NT; te = g1 - j_hi * NT;
+    }
+    uint32_t job = j_hi;
+#pragma unroll 1
+    for (;;) {
+    const uint32_t t_begin = job == j_lo ? tb : 0u, t_end = job == j_hi ? te : 0xffffu;
+    const uint32_t kf = job * F + fl;
+    const bool active = fl < F && kf < n_acc;
 
     // ---- per-subframe state (registers)
     DecRing<ORD> br;
@@ -421,8 +472,26 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     const bool reads = mode >= M_VERBATIM;
     const bool extra = __any_sync(FULL, wasted != 0 || (F64 && shift != 0));
     const uint32_t order = rs.order;
+    const uint32_t i0_begin = t_begin * T, i0_end = min(maxbs, t_end * (uint32_t)T);
+    if (BAL && i0_begin && i0_begin < maxbs) {      // the rest of a job another slot began: wait for its state
+        const uint32_t* st = a.dec_state + (uint64_t)(slot - 1) * DEC_SLOT_WORDS + lane;
+        const uint32_t* flag = a.dec_flags + (slot - 1);
+        while (ld_acquire_u32(flag) != epoch) __nanosleep(200);
+        if (reads) {
+            const uint64_t abs_bit = (uint64_t)__ldcg(st) | ((uint64_t)__ldcg(st + 32) << 32);
+            br.init(ring_base + lane * RingBits::STRIDE, a.in, a.in_len, abs_bit);
+            rs.fastleft = __ldcg(st + 64); rs.rawleft = __ldcg(st + 96); rs.rawbits = __ldcg(st + 128);
+            const uint32_t kw = __ldcg(st + 160);
+            rs.first = (kw >> 31) != 0;
+            const uint32_t k = kw & 31u;
+            rs.k = k; rs.kp32 = k + 32u; rs.negP = 0u - (1u << k); rs.c30 = 30u << k;
+#pragma unroll
+            for (int j = 0; j < ORD; j++) { const int32_t v = (int32_t)__ldcg(st + 256 + 32 * j); hist[j] = v; if constexpr (MIX) hD[j % 16] = (double)v; }
+        }
+        __syncwarp();
+    }
 #pragma unroll 1
-    for (uint32_t i0 = 0; i0 < maxbs; i0 += T) {
+    for (uint32_t i0 = i0_begin; i0 < i0_end; i0 += T) {
         // ---- Rice phase
 #pragma unroll 1
         for (uint32_t t0 = 0, row = col; t0 < (uint32_t)T; t0 += 8, row += 8 * rs4) {      // row: loop-carried, or it is rematerialised from SR_TID every step
@@ -521,6 +590,23 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
         pack_tile(tile_base, S, C, B, F, i0, T, ftab, FT, a.out, lane);
         __syncwarp();
     }
+    if (BAL && i0_end < maxbs) {                     // the job goes on in the next slot: hand over
+        uint32_t* st = a.dec_state + (uint64_t)slot * DEC_SLOT_WORDS + lane;
+        if (reads) {
+            const uint64_t abs_bit = br.abs_pos(a.in);
+            __stcg(st, (uint32_t)abs_bit); __stcg(st + 32, (uint32_t)(abs_bit >> 32));
+            __stcg(st + 64, rs.fastleft); __stcg(st + 96, rs.rawleft); __stcg(st + 128, rs.rawbits); __stcg(st + 160, rs.k | (rs.first ? 0x80000000u : 0u));
+#pragma unroll
+            for (int j = 0; j < ORD; j++) __stcg(st + 256 + 32 * j, (uint32_t)(int32_t)hist[j]);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(a.dec_flags + slot, epoch);
+    }
+    if (!BAL || job == j_lo) break;
+    --job;
+    __syncwarp();
+    }
 }
 
 template <int ORD, bool WIDE, int SPEC>
@@ -554,13 +640,13 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
     const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
     size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S, FT);
     static std::atomic<uint64_t> attr_done{0};
-    if (first_use_on_device(attr_done)) { cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); used_on_device(attr_done); }
+    if (first_use_on_device(attr_done)) { cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); used_on_device(attr_done); }
     const int n_sm = sm_count();
     static const bool trace = getenv("BNFLAC_TRACE") != nullptr;
     static const bool balance = getenv("BNFLAC_DEC_BALANCE") && getenv("BNFLAC_DEC_BALANCE")[0] == '1';
     if (trace || balance) {
         int max_resident = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC>, 32 * DEC_WARPS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_resident, k_decode<ORD, WIDE, SPEC, false>, 32 * DEC_WARPS, smem);
         if (max_resident < 1) max_resident = 1;
         if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: %d CTAs of %d warps resident per SM, grid %u (%.2f waves), %zu B smem/CTA\n", ORD, (int)WIDE, SPEC, max_resident, DEC_WARPS,
                            grid, (double)grid / ((double)n_sm * max_resident), smem);
@@ -576,7 +662,35 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
             if (want > smem) smem = want;
         }
     }
-    k_decode<ORD, WIDE, SPEC><<<grid, 32 * DEC_WARPS, smem, st>>>(a, C, B, S);
+    // balanced schedule: one resident wave of slots, the job list cut into equal runs of tiles (see k_decode); only when there is
+    // more than one wave of jobs -- a single wave cannot be shortened by cutting it
+    if constexpr (dec_has_balanced<ORD, SPEC>()) if (a.dec_state && a.dec_flags && !a.acc_sorted) {
+        static std::atomic<uint64_t> attr_done_b{0};
+        if (first_use_on_device(attr_done_b)) { cudaFuncSetAttribute(k_decode<ORD, WIDE, SPEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); used_on_device(attr_done_b); }
+        static std::atomic<int> resident_per_sm{0};         // of this variant (same on every device of one kind)
+        int mr = resident_per_sm.load(std::memory_order_relaxed);
+        if (!mr) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mr, k_decode<ORD, WIDE, SPEC, true>, 32 * DEC_WARPS, smem);
+            if (mr < 1) mr = 1;
+            resident_per_sm.store(mr, std::memory_order_relaxed);
+        }
+        uint32_t slots = (uint32_t)n_sm * (uint32_t)mr * DEC_WARPS;
+        if (const uint32_t cap = dec_force_slots()) slots = std::max<uint32_t>(DEC_WARPS, std::min(slots, cap) / DEC_WARPS * DEC_WARPS);   // tests: hand-overs on small streams
+        const uint32_t J = blocks_for(nacc, F);
+        // A plain launch of w = J / slots waves takes floor(w) chains at full residency plus one chain of the last, partial wave; that
+        // last chain is short when few warps share the SM (measured on the 16-bit hour: 0.26 ms alone against 0.73 ms at full
+        // residency), so cutting only pays when the partial wave is small: cfg1, 1.02 waves, 0.99 -> 0.75 ms; cfg2, 2.23 waves, no gain.
+        const uint32_t rem = J % slots;
+        const bool pays = dec_force_slots() || (rem != 0 && rem * 5u <= slots);
+        if (J > slots && pays && slots <= a.dec_slots && (uint64_t)J * (65536u / T + 1u) < (1ull << 31)) {
+            const uint32_t epoch = next_decode_epoch();       // process-wide and never 0: flag words left behind by any earlier launch do not match
+            if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: balanced over %u slots, %u jobs (%.2f waves)\n", ORD, (int)WIDE, SPEC, slots, J, (double)J / slots);
+            k_decode<ORD, WIDE, SPEC, true><<<slots / DEC_WARPS, 32 * DEC_WARPS, smem, st>>>(a, C, B, S, epoch);
+            count_launch();
+            return;
+        }
+    }
+    k_decode<ORD, WIDE, SPEC, false><<<grid, 32 * DEC_WARPS, smem, st>>>(a, C, B, S, 0u);
     count_launch();
 }
 template <bool WIDE>
