@@ -132,6 +132,7 @@ struct PassArgs {
     uint32_t* dec_flags;
     uint32_t* dec_state;
     uint32_t dec_slots;     // slots the two arrays hold
+    uint32_t dec_expect;    // frames the pass is expected to deliver (the previous pass's count; the launch bound is ~6 % above it): what the choice of schedule goes by
 };
 
 // launchers (kernels.cu); all asynchronous on `stream`

@@ -576,8 +576,8 @@ static int run_front(bnflac* h) {
 
 // Passes of more than one wave of decode warps get the scratch of the balanced schedule (kernels_decode.cuh): a flag word and one
 // job state per slot.  Without it (small passes, no memory) launch_decode uses the plain launch.
-static int prepare_decode_sched(bnflac* h, uint32_t nacc) {
-    h->args.dec_flags = nullptr; h->args.dec_state = nullptr; h->args.dec_slots = 0;
+static int prepare_decode_sched(bnflac* h, uint32_t nacc, uint32_t expect) {
+    h->args.dec_flags = nullptr; h->args.dec_state = nullptr; h->args.dec_slots = 0; h->args.dec_expect = expect;
     const uint32_t slots = decode_sched_slots(nacc, h->info.channels);
     if (!slots) return 0;
     const uint64_t flag_bytes = ((uint64_t)slots * 4 + 255) & ~255ull;
@@ -594,7 +594,7 @@ static int run_back(bnflac* h, uint8_t* d_out, uint64_t cap) {
     if (h->totals.pcm_bytes > cap) return BNFLAC_ERR_CAPACITY;
     h->args.out = d_out; h->args.out_cap = cap;
     int rc_s;
-    if ((rc_s = prepare_decode_sched(h, h->totals.n_accepted))) return rc_s;
+    if ((rc_s = prepare_decode_sched(h, h->totals.n_accepted, h->totals.n_accepted))) return rc_s;
     if (h->totals.n_accepted)
         launch_decode(h->args, h->totals.n_accepted, h->info.channels, h->info.bytes_per_sample, h->totals.max_order, h->totals.any_wide != 0, h->stream);
     CK(cudaEventRecord(h->ev[5], h->stream));
@@ -623,7 +623,7 @@ static int run_pass_predicted(bnflac* h, uint8_t* d_out, uint64_t cap) {
     int rc;
     if ((rc = launch_front_tail(h, nb))) return rc;
     h->args.out = d_out; h->args.out_cap = cap;
-    if ((rc = prepare_decode_sched(h, nacc))) return rc;
+    if ((rc = prepare_decode_sched(h, nacc, p.n_accepted))) return rc;
     if (p.n_accepted) launch_decode(h->args, nacc, h->info.channels, h->info.bytes_per_sample, p.max_order, p.any_wide != 0, h->stream);
     CK(cudaEventRecord(h->ev[5], h->stream));
     launch_publish(h->d_counters.p, h->mailbox.p, 2, h->stream);

@@ -10,6 +10,9 @@
 #ifndef DEC_I2D_CVT
 #define DEC_I2D_CVT 1
 #endif
+#ifndef DEC_DEPHASE_NS
+#define DEC_DEPHASE_NS 0
+#endif
 #ifndef DEC_CKPT16
 #define DEC_CKPT16 1
 #endif
@@ -368,6 +371,12 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
     const uint32_t rs4 = S * 4;
     const uint32_t col = tile_base + lane * 4;
     const uint32_t slot = blockIdx.x * DEC_WARPS + wib;
+#if DEC_DEPHASE_NS
+    // Warps launched together do identical work and stay in step: all the warps of a scheduler are in the restore phase (FP64 pipe)
+    // or in the Rice phase (integer pipe) at the same time and queue for one pipe while the others idle.  A pseudo-random start
+    // delay of up to one tile period spreads the phases for the rest of the launch.
+    __nanosleep(((slot * 2654435761u) >> 19) % (uint32_t)DEC_DEPHASE_NS);
+#endif
     // this warp's run: jobs j_lo .. j_hi, tiles [tb, ..) of j_lo and [.., te) of j_hi
     uint32_t j_lo = slot, j_hi = slot, tb = 0, te = 0xffffu;
     if constexpr (BAL) {
@@ -617,7 +626,7 @@ static void launch_decode_t(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 #ifdef DEC_EXPERIMENT      // kernel experiments (tools/build_variants.sh): only the variants the cfg2 / cfg3 benchmark streams use are compiled (40 s instead of 3 min)
     if constexpr (WIDE && ORD == 12) { if (key == 11) launch_decode_s<12, true, 11>(a, nacc, C, B, st); }
     else if constexpr (WIDE && ORD == 32) { if (key == 35) launch_decode_s<32, true, 35>(a, nacc, C, B, st); }
-    else if constexpr (!WIDE && ORD == 8) { if (key == 10) launch_decode_s<8, false, 10>(a, nacc, C, B, st); }
+    else if constexpr (WIDE && ORD == 8) { if (key == 10) launch_decode_s<8, true, 10>(a, nacc, C, B, st); }
     return;
 #else
     switch (key) {
@@ -680,9 +689,9 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
         // A plain launch of w = J / slots waves takes floor(w) chains at full residency plus one chain of the last, partial wave; that
         // last chain is short when few warps share the SM (measured on the 16-bit hour: 0.26 ms alone against 0.73 ms at full
         // residency), so cutting only pays when the partial wave is small: cfg1, 1.02 waves, 0.99 -> 0.75 ms; cfg2, 2.23 waves, no gain.
-        const uint32_t rem = J % slots;
+        const uint32_t Jd = blocks_for(a.dec_expect ? std::min(a.dec_expect, nacc) : nacc, F), rem = Jd % slots;
         const bool pays = dec_force_slots() || (rem != 0 && rem * 5u <= slots);
-        if (J > slots && pays && slots <= a.dec_slots && (uint64_t)J * (65536u / T + 1u) < (1ull << 31)) {
+        if (Jd > slots && pays && slots <= a.dec_slots && (uint64_t)J * (65536u / T + 1u) < (1ull << 31)) {
             const uint32_t epoch = next_decode_epoch();       // process-wide and never 0: flag words left behind by any earlier launch do not match
             if (trace) fprintf(stderr, "[bnflac] k_decode<%d,%d,%d>: balanced over %u slots, %u jobs (%.2f waves)\n", ORD, (int)WIDE, SPEC, slots, J, (double)J / slots);
             k_decode<ORD, WIDE, SPEC, true><<<slots / DEC_WARPS, 32 * DEC_WARPS, smem, st>>>(a, C, B, S, epoch);
@@ -696,7 +705,7 @@ static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32
 template <bool WIDE>
 static void launch_decode_w(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, uint32_t max_order, cudaStream_t st) {
 #ifdef DEC_EXPERIMENT
-    if (!WIDE && max_order <= 8) launch_decode_t<8, WIDE>(a, nacc, C, B, st);
+    if (WIDE && max_order <= 8) launch_decode_t<8, WIDE>(a, nacc, C, B, st);
     else if (max_order <= 12) launch_decode_t<12, WIDE>(a, nacc, C, B, st); else launch_decode_t<32, WIDE>(a, nacc, C, B, st);
     return;
 #endif

@@ -9,6 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/run_cfg.py cfg2 3 > $O/${T}_cfg2_plain.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:k_ --launch-skip 20 -c 12 -o /tmp/${T}_cfg2 python tools/run_cfg.py cfg2 3 > $O/${T}_cfg2_ncu.log 2>&1
 ncu -i /tmp/${T}_cfg2.ncu-rep --page raw --csv > $O/${T}_cfg2_raw.csv 2>/dev/null
+ncu -i /tmp/${T}_cfg2.ncu-rep --page source --csv -k regex:k_decode > $O/${T}_cfg2_decode_src.csv 2>/dev/null
 python tools/enc_profile.py cfg2 > $O/${T}_enc_plain.log 2>&1 || exit 1
 python tools/enc_profile.py cfg3 >> $O/${T}_enc_plain.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_enc --launch-skip 6 -c 3 -o /tmp/${T}_enc python tools/enc_profile.py cfg2 > $O/${T}_enc_ncu.log 2>&1
