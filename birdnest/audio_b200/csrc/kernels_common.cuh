@@ -73,7 +73,12 @@ __device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
 // HBM latency whenever too few warps are resident to hide it (streams with few, large frames).  With DEPTH > 0 the
 // checkpoint only waits for older groups, provided what those covered (mark[DEPTH]) reaches past everything the coming
 // period can read; a lane that consumed unusually many bits falls back to a full wait.
-template <int NBLK_, int DEPTH, int STEADY_ = 0>
+// DUP = false (k_decode): no duplicate of block 0 -- every reader wraps its own addresses (three masks more per group of 8 codewords)
+// and a refill is one cp.async per block instead of a second, almost always predicated-off one plus its branch.
+#ifndef RING_LEAN_FETCH
+#define RING_LEAN_FETCH 0
+#endif
+template <int NBLK_, int DEPTH, int STEADY_ = 0, bool DUP = true>
 struct RingBitsT {
     static constexpr int NBLK = NBLK_, BLK = 16, RB_BYTES = NBLK * BLK;
     static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
@@ -88,11 +93,14 @@ struct RingBitsT {
     const uint8_t* g0;     // global address of ring byte 0 (16 B aligned)
 
     __device__ __forceinline__ void fetch(uint32_t b) {
-        const uint32_t n = b < navail ? 16u : 0u;
-        const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
+        const bool in = b < navail;
+        const uint32_t n = in ? 16u : 0u;
+        // k_decode's ring: one select on the block index and one wide multiply-add (request loop 26 -> 13 instructions per block together
+        // with DUP = false; cfg2 decode 1.70 -> 1.67 ms).  k_parse keeps the other form: the same change made the guessed walks of cfg3 3 % slower.
+        const uint8_t* s = (!DUP || RING_LEAN_FETCH) ? g0 + (uint64_t)(in ? b : 0u) * BLK : g0 + (n ? (uint64_t)b * BLK : 0ull);
         const uint32_t slot = b & (NBLK - 1);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + slot * BLK), "l"(s), "r"(n) : "memory");
-        if (slot == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + RB_BYTES), "l"(s), "r"(n) : "memory");
+        if (DUP && slot == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + RB_BYTES), "l"(s), "r"(n) : "memory");
     }
     __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
     __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -103,7 +111,7 @@ struct RingBitsT {
         const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
         const uint32_t slot = b & (NBLK - 1);
         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + slot * BLK), "l"(s), "r"(n), "r"((uint32_t)p) : "memory");
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + RB_BYTES), "l"(s), "r"(n), "r"((uint32_t)(p && slot == 0)) : "memory");
+        if (DUP) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + RB_BYTES), "l"(s), "r"(n), "r"((uint32_t)(p && slot == 0)) : "memory");
     }
     // Request every block the ring has room for (never the slot being read).  STEADY = how many blocks a refill period
     // normally frees: that many are requested branch-free under predicates (the lanes of a warp free different numbers of
@@ -178,7 +186,7 @@ struct RingBitsT {
     __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
     __device__ __forceinline__ uint32_t window_at(uint32_t p) const {      // 32 bits starting at bit p, MSB first
         const uint32_t bo = (p >> 3) & (RB_BYTES - 4);
-        const uint32_t a = lds32(sring + bo), b = lds32(sring + bo + 4);
+        const uint32_t a = lds32(sring + bo), b = lds32(sring + (DUP ? bo + 4 : ((bo + 4) & (RB_BYTES - 4))));
         return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), p);
     }
     __device__ __forceinline__ uint32_t window() const { return window_at(pos); }
@@ -189,8 +197,16 @@ struct RingBitsT {
     // position -> window -> length -> position chain (which is then SHF, FLO, IADD3, LOP3, SEL).
     struct Win3 { uint32_t w0, w1, w2; };
     __device__ __forceinline__ Win3 win_init(uint32_t p) const {
-        const uint32_t ad = sring + ((p >> 3) & (RB_BYTES - 4));
-        Win3 w; w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = __byte_perm(lds32(ad + 8), 0, 0x0123);
+        Win3 w;
+        if (DUP) {
+            const uint32_t ad = sring + ((p >> 3) & (RB_BYTES - 4));
+            w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = __byte_perm(lds32(ad + 8), 0, 0x0123);
+        } else {
+            const uint32_t by = p >> 3;
+            w.w0 = __byte_perm(lds32(sring + (by & (RB_BYTES - 4))), 0, 0x0123);
+            w.w1 = __byte_perm(lds32(sring + ((by + 4) & (RB_BYTES - 4))), 0, 0x0123);
+            w.w2 = __byte_perm(lds32(sring + ((by + 8) & (RB_BYTES - 4))), 0, 0x0123);
+        }
         return w;
     }
     __device__ __forceinline__ uint32_t win_next(uint32_t p) const { return __byte_perm(lds32(sring + (((p >> 3) + 12) & (RB_BYTES - 4))), 0, 0x0123); }   // word of p, + 3
@@ -254,7 +270,13 @@ template <bool LEAN> using ParseBitsT = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_
 #define DEC_RING_BLOCKS 8
 #endif
 using RingBits = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH>;         // k_decode (16 blocks: one refill checkpoint per 16 samples)
-template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (ORD > 12 ? 2 : 0)>;   // orders > 12: few, long subframes
+#ifndef DEC_RING_STEADY_SMALL
+#define DEC_RING_STEADY_SMALL 0
+#endif
+#ifndef DEC_RING_NODUP
+#define DEC_RING_NODUP 1
+#endif
+template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (ORD > 12 ? 2 : DEC_RING_STEADY_SMALL), !DEC_RING_NODUP>;   // orders > 12: few, long subframes
 
 
 // ------------------------------------------------------------------------------------------------ launch helpers
