@@ -13,6 +13,12 @@
 #ifndef DEC_DEPHASE_NS
 #define DEC_DEPHASE_NS 0
 #endif
+// DEC_LANE_MAJOR: sample t of lane l at word l * (T + 4) + t (a lane's samples are contiguous) instead of t * S + l: the Rice phase
+// stores and the restore phase loads and stores four samples per instruction (conflict free: T + 4 = 4 mod 8, so the 16-byte
+// accesses of a quarter warp fall into eight different groups of four banks); the pack phase reads 16-byte runs per channel
+#ifndef DEC_LANE_MAJOR
+#define DEC_LANE_MAJOR 1
+#endif
 #ifndef DEC_CKPT16
 #define DEC_CKPT16 1
 #endif
@@ -88,26 +94,33 @@ __device__ __forceinline__ void rice_param(BR& br, RiceSt& rs) {
 template <int ORD, bool FIRST, bool EXTRA>
 __device__ __forceinline__ void restore_block_i32(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
                                                   uint32_t order, uint32_t shift, uint32_t wasted) {
+    uint4 v4 = make_uint4(0, 0, 0, 0);      // lane-major tile: four residuals in, four samples out per access
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        if (DEC_LANE_MAJOR && j % 4 == 0) v4 = lds128(addr + 4 * j);
+        const int32_t r = DEC_LANE_MAJOR ? (int32_t)get4(v4, j % 4) : (int32_t)lds32(addr + j * rs4);
         uint32_t sum = 0;
 #pragma unroll
         for (int m = ORD - 1; m >= 0; m--) sum += (uint32_t)cf[m] * (uint32_t)h[(j - 1 - m + 2 * ORD) % ORD];
         int32_t s = (int32_t)((uint32_t)r + (uint32_t)((int32_t)sum >> shift));
         if (FIRST) { if (j < (int)order) s = r; }
         h[j] = s;
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
-        else sts32(addr + j * rs4, (uint32_t)s);
+        {
+            const uint32_t o = EXTRA ? (uint32_t)s << wasted : (uint32_t)s;
+            if (DEC_LANE_MAJOR) { set4(v4, j % 4, o); if (j % 4 == 3) sts128(addr + 4 * (j - 3), v4); }
+            else sts32(addr + j * rs4, o);
+        }
     }
 }
 
 template <int ORD, bool FIRST, bool EXTRA>
 __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, const double (&cf)[ORD], double (&h)[ORD],
                                                   uint32_t order, uint32_t sh_n, uint32_t wasted) {
+    uint4 v4 = make_uint4(0, 0, 0, 0);      // lane-major tile: four residuals in, four samples out per access
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        if (DEC_LANE_MAJOR && j % 4 == 0) v4 = lds128(addr + 4 * j);
+        const int32_t r = DEC_LANE_MAJOR ? (int32_t)get4(v4, j % 4) : (int32_t)lds32(addr + j * rs4);
         // NACC independent accumulation chains (every product and partial sum is an integer, scaled by 2^-shift, below 2^53: any
         // association is exact).  Orders > 16 run as a few warps per scheduler, where one chain of ORD dependent DFMAs (8.7 cycles
         // each, tools/ulat.cu) is what the warp waits for: 4 chains, cfg3 decode 4.38 -> 4.30 ms.  For orders <= 12 ptxas already
@@ -133,8 +146,11 @@ __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, c
 #else
         h[j] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
 #endif
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << wasted);
-        else sts32(addr + j * rs4, (uint32_t)s);
+        {
+            const uint32_t o = EXTRA ? (uint32_t)s << wasted : (uint32_t)s;
+            if (DEC_LANE_MAJOR) { set4(v4, j % 4, o); if (j % 4 == 3) sts128(addr + 4 * (j - 3), v4); }
+            else sts32(addr + j * rs4, o);
+        }
     }
 }
 
@@ -143,9 +159,11 @@ __device__ __forceinline__ void restore_block_f64(uint32_t addr, uint32_t rs4, c
 template <int ORD, bool FIRST, bool EXTRA>
 __device__ __forceinline__ void restore_block_i64(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD],
                                                   uint32_t order, uint32_t shift, uint32_t wasted) {
+    uint4 v4 = make_uint4(0, 0, 0, 0);      // lane-major tile: four residuals in, four samples out per access
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        if (DEC_LANE_MAJOR && j % 4 == 0) v4 = lds128(addr + 4 * j);
+        const int32_t r = DEC_LANE_MAJOR ? (int32_t)get4(v4, j % 4) : (int32_t)lds32(addr + j * rs4);
         long long acc = 0;
 #pragma unroll
         for (int m = ORD - 1; m >= 0; m--) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(cf[m]), "r"(h[(j - 1 - m + 2 * ORD) % ORD]));
@@ -155,8 +173,11 @@ __device__ __forceinline__ void restore_block_i64(uint32_t addr, uint32_t rs4, c
         int32_t s = (int32_t)((uint32_t)r + (uint32_t)p);
         if (FIRST) { if (j < (int)order) s = r; }
         h[j] = s;
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << (wasted & 31u));
-        else sts32(addr + j * rs4, (uint32_t)s);
+        {
+            const uint32_t o = EXTRA ? (uint32_t)s << (wasted & 31u) : (uint32_t)s;
+            if (DEC_LANE_MAJOR) { set4(v4, j % 4, o); if (j % 4 == 3) sts128(addr + 4 * (j - 3), v4); }
+            else sts32(addr + j * rs4, o);
+        }
     }
 }
 
@@ -181,9 +202,11 @@ template <int ORD, bool FIRST, bool EXTRA>
 __device__ __forceinline__ void restore_block_mix(uint32_t addr, uint32_t rs4, const int32_t (&cf)[ORD], int32_t (&h)[ORD], const double (&cfD)[16], double (&hD)[16],
                                                   uint32_t order, uint32_t shift, uint32_t wasted) {
     static_assert(ORD == 32, "two halves of 16 taps");
+    uint4 v4 = make_uint4(0, 0, 0, 0);      // lane-major tile: four residuals in, four samples out per access
 #pragma unroll
     for (int j = 0; j < ORD; j++) {
-        const int32_t r = (int32_t)lds32(addr + j * rs4);
+        if (DEC_LANE_MAJOR && j % 4 == 0) v4 = lds128(addr + 4 * j);
+        const int32_t r = DEC_LANE_MAJOR ? (int32_t)get4(v4, j % 4) : (int32_t)lds32(addr + j * rs4);
         long long ai0 = -0x4338000000000000ll, ai1 = 0;
 #pragma unroll
         for (int m = ORD - 1; m >= 16; m--) {
@@ -202,8 +225,11 @@ __device__ __forceinline__ void restore_block_mix(uint32_t addr, uint32_t rs4, c
         if (FIRST) { if (j < (int)order) s = r; }
         h[j] = s;
         hD[j % 16] = __hiloint2double(0x43300000, s ^ 0x80000000) - 4503601774854144.0;   // (double)s, exact: 2^52 + 2^31 bias
-        if (EXTRA) sts32(addr + j * rs4, (uint32_t)s << (wasted & 31u));
-        else sts32(addr + j * rs4, (uint32_t)s);
+        {
+            const uint32_t o = EXTRA ? (uint32_t)s << (wasted & 31u) : (uint32_t)s;
+            if (DEC_LANE_MAJOR) { set4(v4, j % 4, o); if (j % 4 == 3) sts128(addr + 4 * (j - 3), v4); }
+            else sts32(addr + j * rs4, o);
+        }
     }
 }
 template <int ORD, bool WIDE, bool FIRST, bool EXTRA, class TT>
@@ -255,11 +281,19 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
         const uint2 pol = lds64(ftab + 8 * FT + 8 * f);
         uint8_t* dst = out + ((((uint64_t)pol.y << 32) | pol.x) + (i0 * C + q0) * B);      // 32-bit offset inside the frame: blocksize * channels * bytes < 2^22
         uint32_t v[16];
-        const uint32_t fbase = tile_base + 4 * f * C;
+        const uint32_t LS4 = 4 * S;                                     // lane-major tile: bytes between the channels (lanes) of a frame
+        const uint32_t fbase = DEC_LANE_MAJOR ? tile_base + f * C * LS4 : tile_base + 4 * f * C;
         if (C == 2) {
-            const uint32_t ad = fbase + 4 * (q0 >> 1) * S;
+            if (DEC_LANE_MAJOR) {                                      // 8 time steps: two 16-byte runs per channel
+                const uint32_t ad = fbase + 4 * (q0 >> 1);
+                const uint4 a0 = lds128(ad), a1 = lds128(ad + 16), b0 = lds128(ad + LS4), b1 = lds128(ad + LS4 + 16);
+                v[0] = a0.x; v[2] = a0.y; v[4] = a0.z; v[6] = a0.w; v[8] = a1.x; v[10] = a1.y; v[12] = a1.z; v[14] = a1.w;
+                v[1] = b0.x; v[3] = b0.y; v[5] = b0.z; v[7] = b0.w; v[9] = b1.x; v[11] = b1.y; v[13] = b1.z; v[15] = b1.w;
+            } else {
+                const uint32_t ad = fbase + 4 * (q0 >> 1) * S;
 #pragma unroll
-            for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
+                for (int e = 0; e < 8; e++) { const uint2 p = lds64(ad + 4 * e * S); v[2 * e] = p.x; v[2 * e + 1] = p.y; }
+            }
             const DecorrSel ds = decorr_sel(assign);
 #if DEC_PACK_UNIFORM
             if (__all_sync(__activemask(), ds.useD)) {       // every unit of this step is left/side or mid/side (the usual choices of an adaptive encoder): 3 instead of 6 per pair
@@ -270,6 +304,23 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
             {
 #pragma unroll
                 for (int e = 0; e < 8; e++) decorr(ds, v[2 * e], v[2 * e + 1]);
+            }
+        } else if (DEC_LANE_MAJOR) {
+            if (C == 1) {                                              // 16 time steps of one lane
+#pragma unroll
+                for (int e = 0; e < 4; e++) { const uint4 p = lds128(fbase + 4 * q0 + 16 * e); v[4 * e] = p.x; v[4 * e + 1] = p.y; v[4 * e + 2] = p.z; v[4 * e + 3] = p.w; }
+            } else if (C == 4) {                                       // 4 time steps x 4 channels
+#pragma unroll
+                for (int c = 0; c < 4; c++) { const uint4 p = lds128(fbase + c * LS4 + 4 * (q0 >> 2)); v[c] = p.x; v[4 + c] = p.y; v[8 + c] = p.z; v[12 + c] = p.w; }
+            } else if (C == 8) {                                       // 2 time steps x 8 channels
+#pragma unroll
+                for (int c = 0; c < 8; c++) { const uint2 p = lds64(fbase + c * LS4 + 4 * (q0 >> 3)); v[c] = p.x; v[8 + c] = p.y; }
+            } else {
+                uint32_t t = (q0 * rcp_c) >> 16, c = q0 - t * C;
+                uint32_t ad = fbase + c * LS4 + 4 * t;
+                const uint32_t wrap = (C - 1) * LS4 - 4;                // from the last channel of step t back to channel 0 of step t + 1
+#pragma unroll
+                for (int e = 0; e < 16; e++) { v[e] = lds32(ad); ad += LS4; if (++c == C) { c = 0; ad -= wrap + LS4; } }
             }
         } else if (C == 1) {
 #pragma unroll
@@ -330,7 +381,9 @@ __device__ __forceinline__ void pack_tile(uint32_t tile_base, uint32_t S, uint32
 #define DEC_WARPS_N 2
 #endif
 constexpr int DEC_WARPS = DEC_WARPS_N;        // independent warps per CTA (no CTA-wide barrier anywhere)
-__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S, int FT) { return 32u * RingBits::STRIDE + (uint32_t)T * S * 4u + 16u * (uint32_t)FT; }
+// S: column-major tile: words between consecutive samples of a lane (32 + pad); lane-major tile: words between lanes (T + 4)
+__host__ __device__ constexpr uint32_t dec_tile_words(int T, uint32_t S) { return DEC_LANE_MAJOR ? 32u * S : (uint32_t)T * S; }
+__host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S, int FT) { return 32u * RingBits::STRIDE + dec_tile_words(T, S) * 4u + 16u * (uint32_t)FT; }
 
 // SPEC: 0 = any channel count / sample width (run-time C, B, S); else 4 C + B: the common formats get C, B and the tile
 // stride S as compile-time constants (tile addresses become immediates, lane -> (frame, channel) is a shift, the pack
@@ -338,7 +391,7 @@ __host__ __device__ constexpr uint32_t dec_warp_smem(int T, uint32_t S, int FT) 
 #ifndef DEC_SPECIALISE
 #define DEC_SPECIALISE 1
 #endif
-__host__ __device__ constexpr uint32_t dec_tile_stride(uint32_t C) { return 32u + ((C & 3u) == 0 ? 4u : (C & 1u) == 0 ? 2u : 1u); }
+__host__ __device__ constexpr uint32_t dec_tile_stride(uint32_t C, int T) { return DEC_LANE_MAJOR ? (uint32_t)T + 4u : 32u + ((C & 3u) == 0 ? 4u : (C & 1u) == 0 ? 2u : 1u); }
 // Balanced schedule (epoch != 0): the launch is ONE resident wave of warps ("slots") and the job list -- job j = the 32/C frames a
 // warp decodes side by side, NT nominal tiles each -- is cut into equal runs of tiles, one run per slot, wherever the cut falls.
 // A plain launch of J jobs on M slots takes ceil(J / M) subframe chains however small the last wave is (cfg2: 2.23 waves cost 3,
@@ -358,18 +411,18 @@ constexpr uint32_t DEC_SLOT_WORDS = DEC_STATE_WORDS * 32;  // word w of lane l a
 template <int ORD, bool WIDE, int SPEC, bool BAL>
 __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : ORD <= 16 ? 128 : DEC_MAXNREG_BIG) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_, uint32_t epoch) {
     constexpr int T = DecCfg<ORD, SPEC>::T, FT = DecCfg<ORD, SPEC>::FT;
-    const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2) : S_;
+    const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2, T) : S_;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // through a shuffle: ptxas otherwise rematerialises this address from SR_CgaCtaId / SR_TID in every pack step (two S2R + four more)
     const uint32_t ring_base = __shfl_sync(FULL, smem_u32(s_dyn) + wib * dec_warp_smem(T, S, FT), 0);
     const uint32_t tile_base = ring_base + 32 * RingBits::STRIDE;
-    const uint32_t ftab = tile_base + T * S * 4;               // bs[FT] | assign[FT] | pcm offset[FT] (u64)
+    const uint32_t ftab = tile_base + dec_tile_words(T, S) * 4;   // bs[FT] | assign[FT] | pcm offset[FT] (u64)
     const uint32_t F = 32 / C;
     const uint32_t n_acc = a.totals->n_accepted;
     const uint32_t fl = lane / C, ch = lane - fl * C;
-    const uint32_t rs4 = S * 4;
-    const uint32_t col = tile_base + lane * 4;
+    const uint32_t rs4 = DEC_LANE_MAJOR ? 4u : S * 4;                                   // bytes between consecutive samples of a lane
+    const uint32_t col = tile_base + (DEC_LANE_MAJOR ? lane * S * 4 : lane * 4);      // this lane's sample 0
     const uint32_t slot = blockIdx.x * DEC_WARPS + wib;
 #if DEC_DEPHASE_NS
     // Warps launched together do identical work and stay in step: all the warps of a scheduler are in the restore phase (FP64 pipe)
@@ -468,7 +521,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
             const uint32_t v = (uint32_t)cval << wasted;
             wasted = 0;
 #pragma unroll 1
-            for (uint32_t t = 0; t < (uint32_t)T; t++) sts32(col + t * rs4, v);
+            for (uint32_t t = 0; t < (uint32_t)T; t++) sts32(col + t * rs4, v);        // (once per subframe)
         }
     }
     double cfD[16], hD[16];                             // MIX only: the 16 most recent taps as doubles (dead code otherwise)
@@ -543,7 +596,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MA
                     if (!ovf) {
                         br.pos = pos;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)r[j]);
+                        if (DEC_LANE_MAJOR) { sts128(row, make_uint4(r[0], r[1], r[2], r[3])); sts128(row + 16, make_uint4(r[4], r[5], r[6], r[7])); }
+                        else for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)r[j]);
                     } else {             // a codeword longer than one window (rare): redo the group carefully
 #pragma unroll 1
                         for (int j = 0; j < 8; j++) sts32(row + j * rs4, (uint32_t)br.rice_careful(k));
@@ -645,7 +699,7 @@ template <int ORD, bool WIDE, int SPEC>
 static void launch_decode_s(const PassArgs& a, uint32_t nacc, uint32_t C, uint32_t B, cudaStream_t st) {
     constexpr int T = DecCfg<ORD, SPEC>::T, FT = DecCfg<ORD, SPEC>::FT;
     const uint32_t F = 32 / C;
-    const uint32_t S = dec_tile_stride(C);
+    const uint32_t S = dec_tile_stride(C, T);
     const uint32_t grid = blocks_for(nacc, F * DEC_WARPS);
     size_t smem = (size_t)DEC_WARPS * dec_warp_smem(T, S, FT);
     static std::atomic<uint64_t> attr_done{0};
