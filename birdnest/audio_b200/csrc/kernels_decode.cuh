@@ -40,10 +40,14 @@ namespace bnf {
 //                  pipe instead: every product and partial sum is an integer below 2^53, so DFMA is exact, the
 //                  quantisation shift is folded into the coefficients (a power of two), floor() is one round-down add of
 //                  1.5*2^52, and the FP64 pipe runs beside the integer pipes the Rice phase of the other warps keeps busy.
-//   pack phase     the warp re-reads the tile row-wise (interleaved order), applies left/side, side/right, mid/side
-//                  decorrelation to stereo pairs and writes packed little-endian 8/16/24-bit PCM, 4 samples per lane.
-// Tile layout: sample t of lane l at word t*S + l, S = 32 + pad chosen so that both the column accesses of the first two
-// phases and the vector row reads of the pack phase are bank-conflict free.
+//   pack phase     the warp re-reads the tile in interleaved order (a lane per 16 consecutive output samples of one frame), applies
+//                  left/side, side/right, mid/side decorrelation to stereo pairs (branch free) and writes packed little-endian
+//                  8/16/24-bit PCM with 16-byte stores.
+// Tile layout (DEC_LANE_MAJOR, the default): sample t of lane l at word l*(T+4) + t -- a lane's samples are contiguous, so the Rice
+// phase stores and the restore phase loads and stores FOUR samples per instruction and the pack phase reads 16-byte runs per channel;
+// T + 4 = 4 (mod 8) keeps the 16-byte accesses of a quarter warp in eight different groups of four banks.  (The column-major layout
+// it replaced, sample t of lane l at word t*S + l with S = 32 + pad, is still selectable: one 4-byte access per sample.)
+// A launch is either plain (one job = 32/C frames per warp) or balanced (template parameter BAL, see k_decode).
 enum : int { M_IDLE = 0, M_CONST = 1, M_VERBATIM = 2, M_PRED = 3 };
 
 #ifndef DEC_MAXNREG
