@@ -634,7 +634,7 @@ enum : uint32_t { PF_NONE = 0, PF_UNPARSE = 1, PF_LOST = 2, PF_EOS = 3 };
 // start, instead of one frame; it records where that subframe ends, and k_spec_resolve keeps the guesses that chain up.
 template <bool LEAN, bool SPEC>
 __global__ void __launch_bounds__(PARSE_THREADS) k_parse(PassArgs a) {
-    extern __shared__ __align__(16) uint8_t s_ring[];
+    extern __shared__ __align__(256) uint8_t s_ring[];
     const uint32_t n = ncand(a);
     const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t i = lane_id;

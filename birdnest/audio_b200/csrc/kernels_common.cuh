@@ -84,7 +84,15 @@ __device__ __forceinline__ int ilog2u(uint32_t v) { return 31 - __clz(v); }
 template <int NBLK_, int DEPTH, int STEADY_ = 0, bool DUP = true>
 struct RingBitsT {
     static constexpr int NBLK = NBLK_, BLK = 16, RB_BYTES = NBLK * BLK;
-    static constexpr int STRIDE = RB_BYTES + BLK;    // per-lane footprint: the ring + the duplicate of block 0
+    static constexpr int STRIDE = DUP ? RB_BYTES + BLK : RB_BYTES;    // per-lane footprint: the ring (+ the duplicate of block 0)
+    // DUP = false: the lane's ring is RB_BYTES-aligned and `sring` holds its address OR-ed with a per-lane swizzle of the block index
+    // (bits 4..): a byte offset x of the ring lives at (x & (RB_BYTES - 4)) ^ sring -- ONE three-input logic instruction where base + masked
+    // offset are two, on every codeword of the branch-free groups (the word after the window is fetched on each step) -- and lanes that
+    // read or fill the same ring offset spread over NBLK groups of four banks as the 144-byte stride of the DUP layout did.
+    __device__ __forceinline__ uint32_t ad(uint32_t x) const { return DUP ? sring + (x & (RB_BYTES - 4)) : ((x & (RB_BYTES - 4)) ^ sring); }
+    __device__ __forceinline__ static uint32_t ring_handle(uint32_t lane_base) {
+        return DUP ? lane_base : (lane_base | (((lane_base / RB_BYTES) & (NBLK - 1)) * BLK));
+    }
     // bytes a refill period can advance + window look-ahead: 8 samples of <= 32 bits plus parameters per 8-sample group
     // (longer codewords take synchronous refills); rings of 16 blocks are checkpointed every 16 samples
     static constexpr uint32_t PERIOD_REACH = (NBLK >= 16 ? 84 : 42) + 16;
@@ -102,7 +110,7 @@ struct RingBitsT {
         // with DUP = false; cfg2 decode 1.70 -> 1.67 ms).  k_parse keeps the other form: the same change made the guessed walks of cfg3 3 % slower.
         const uint8_t* s = (!DUP || RING_LEAN_FETCH) ? g0 + (uint64_t)(in ? b : 0u) * BLK : g0 + (n ? (uint64_t)b * BLK : 0ull);
         const uint32_t slot = b & (NBLK - 1);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + slot * BLK), "l"(s), "r"(n) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ad(slot * BLK)), "l"(s), "r"(n) : "memory");
         if (DUP && slot == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sring + RB_BYTES), "l"(s), "r"(n) : "memory");
     }
     __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -113,7 +121,7 @@ struct RingBitsT {
         const uint32_t n = b < navail ? 16u : 0u;
         const uint8_t* s = g0 + (n ? (uint64_t)b * BLK : 0ull);
         const uint32_t slot = b & (NBLK - 1);
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + slot * BLK), "l"(s), "r"(n), "r"((uint32_t)p) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(ad(slot * BLK)), "l"(s), "r"(n), "r"((uint32_t)p) : "memory");
         if (DUP) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(sring + RB_BYTES), "l"(s), "r"(n), "r"((uint32_t)(p && slot == 0)) : "memory");
     }
     // Request every block the ring has room for (never the slot being read).  STEADY = how many blocks a refill period
@@ -172,7 +180,7 @@ struct RingBitsT {
         for (int d = 0; d <= DEPTH; d++) mark[d] = filled;
     }
     __device__ __forceinline__ void init(uint32_t sring_, const uint8_t* in, uint64_t in_len, uint64_t abs_bit) {
-        sring = sring_;
+        sring = ring_handle(sring_);
         const uint64_t b0 = (abs_bit >> 3) & ~(uint64_t)(BLK - 1);
         g0 = in + b0;
         const uint64_t nb = in_len > b0 ? (in_len - b0) >> 4 : 0;
@@ -182,14 +190,14 @@ struct RingBitsT {
         ensure_now();
     }
     __device__ __forceinline__ void init_idle(uint32_t sring_, const uint8_t* in) {
-        sring = sring_; g0 = in; navail = 0; pos = 0; filled = NBLK;
+        sring = ring_handle(sring_); g0 = in; navail = 0; pos = 0; filled = NBLK;
 #pragma unroll
         for (int d = 0; d <= DEPTH; d++) mark[d] = NBLK;
     }
     __device__ __forceinline__ uint64_t abs_pos(const uint8_t* in) const { return (uint64_t)(g0 - in) * 8 + pos; }
     __device__ __forceinline__ uint32_t window_at(uint32_t p) const {      // 32 bits starting at bit p, MSB first
         const uint32_t bo = (p >> 3) & (RB_BYTES - 4);
-        const uint32_t a = lds32(sring + bo), b = lds32(sring + (DUP ? bo + 4 : ((bo + 4) & (RB_BYTES - 4))));
+        const uint32_t a = lds32(ad(bo)), b = lds32(DUP ? sring + bo + 4 : ad(bo + 4));
         return __funnelshift_l(__byte_perm(b, 0, 0x0123), __byte_perm(a, 0, 0x0123), p);
     }
     __device__ __forceinline__ uint32_t window() const { return window_at(pos); }
@@ -206,13 +214,13 @@ struct RingBitsT {
             w.w0 = __byte_perm(lds32(ad), 0, 0x0123); w.w1 = __byte_perm(lds32(ad + 4), 0, 0x0123); w.w2 = __byte_perm(lds32(ad + 8), 0, 0x0123);
         } else {
             const uint32_t by = p >> 3;
-            w.w0 = __byte_perm(lds32(sring + (by & (RB_BYTES - 4))), 0, 0x0123);
-            w.w1 = __byte_perm(lds32(sring + ((by + 4) & (RB_BYTES - 4))), 0, 0x0123);
-            w.w2 = __byte_perm(lds32(sring + ((by + 8) & (RB_BYTES - 4))), 0, 0x0123);
+            w.w0 = __byte_perm(lds32(ad(by)), 0, 0x0123);
+            w.w1 = __byte_perm(lds32(ad(by + 4)), 0, 0x0123);
+            w.w2 = __byte_perm(lds32(ad(by + 8)), 0, 0x0123);
         }
         return w;
     }
-    __device__ __forceinline__ uint32_t win_next(uint32_t p) const { return __byte_perm(lds32(sring + (((p >> 3) + 12) & (RB_BYTES - 4))), 0, 0x0123); }   // word of p, + 3
+    __device__ __forceinline__ uint32_t win_next(uint32_t p) const { return __byte_perm(lds32(ad((p >> 3) + 12)), 0, 0x0123); }   // word of p, + 3
     __device__ __forceinline__ static uint32_t win_peek(const Win3& w, uint32_t p) { return __funnelshift_l(w.w1, w.w0, p); }
     __device__ __forceinline__ static void win_advance(Win3& w, uint32_t p, uint32_t np, uint32_t nxt) {
         if ((p ^ np) & 32u) { w.w0 = w.w1; w.w1 = w.w2; w.w2 = nxt; }
@@ -267,18 +275,21 @@ struct RingBitsT {
 #ifndef DEC_RING_DEPTH
 #define DEC_RING_DEPTH 1
 #endif
-using ParseBits = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH>;   // no sample tile in k_parse: room for a longer ring and a deeper prefetch
-template <bool LEAN> using ParseBitsT = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH, LEAN ? 3 : 0>;
+#ifndef PARSE_RING_NODUP
+#define PARSE_RING_NODUP 1
+#endif
+using ParseBits = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH, 0, !PARSE_RING_NODUP>;   // no sample tile in k_parse: room for a longer ring and a deeper prefetch
+template <bool LEAN> using ParseBitsT = RingBitsT<PARSE_RING_BLOCKS, PARSE_RING_DEPTH, LEAN ? 3 : 0, !PARSE_RING_NODUP>;
 #ifndef DEC_RING_BLOCKS
 #define DEC_RING_BLOCKS 8
 #endif
-using RingBits = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH>;         // k_decode (16 blocks: one refill checkpoint per 16 samples)
 #ifndef DEC_RING_STEADY_SMALL
 #define DEC_RING_STEADY_SMALL 0
 #endif
 #ifndef DEC_RING_NODUP
 #define DEC_RING_NODUP 1
 #endif
+using RingBits = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, 0, !DEC_RING_NODUP>;         // k_decode: geometry (STRIDE) of the ring every DecRing<ORD> shares
 template <int ORD> using DecRing = RingBitsT<DEC_RING_BLOCKS, DEC_RING_DEPTH, (ORD > 12 ? 2 : DEC_RING_STEADY_SMALL), !DEC_RING_NODUP>;   // orders > 12: few, long subframes
 
 

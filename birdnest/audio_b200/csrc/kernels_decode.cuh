@@ -416,7 +416,7 @@ template <int ORD, bool WIDE, int SPEC, bool BAL>
 __global__ void __launch_bounds__(32 * DEC_WARPS) __maxnreg__(ORD <= 12 ? DEC_MAXNREG : ORD <= 16 ? 128 : DEC_MAXNREG_BIG) k_decode(PassArgs a, uint32_t C_, uint32_t B_, uint32_t S_, uint32_t epoch) {
     constexpr int T = DecCfg<ORD, SPEC>::T, FT = DecCfg<ORD, SPEC>::FT;
     const uint32_t C = SPEC ? (uint32_t)(SPEC >> 2) : C_, B = SPEC ? (uint32_t)(SPEC & 3) : B_, S = SPEC ? dec_tile_stride(SPEC >> 2, T) : S_;
-    extern __shared__ __align__(16) uint8_t s_dyn[];
+    extern __shared__ __align__(128) uint8_t s_dyn[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // through a shuffle: ptxas otherwise rematerialises this address from SR_CgaCtaId / SR_TID in every pack step (two S2R + four more)
     const uint32_t ring_base = __shfl_sync(FULL, smem_u32(s_dyn) + wib * dec_warp_smem(T, S, FT), 0);
