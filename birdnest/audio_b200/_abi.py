@@ -342,19 +342,29 @@ def open_callbacks(read_fn, device=-1, flags=0, read_chunk_frames=0) -> Handle:
     return Handle(h.value, keep=cb)        # the callback object must outlive the handle (lazy pull calls it from bnflac_read)
 
 
+class BatchTable:
+    """The bnflac_span table of a batch (and the result array the library fills), built once for a list of clips that is decoded
+    more than once: filling 100,000 ctypes structs from Python takes ~4 us each -- host-language marshalling, not part of the C ABI
+    (a C# or C++ caller hands over an array it already has)."""
+
+    def __init__(self, clips):
+        n = len(clips)
+        self.n = n
+        self.spans = (Span * max(1, n))()
+        self.keep = list(clips)                       # the table points into these buffers
+        for i, c in enumerate(clips):
+            self.spans[i].data = _addr(c)
+            self.spans[i].len = c.numel() * c.element_size() if hasattr(c, "numel") else len(c)
+        self.res = (ClipResult * max(1, n))()
+
+
 def decode_batch(clips, device=-1, dst=None, dst_is_device=False, packed=False):
     """bnflac_decode_batch: many independent clips in one pipeline pass per (channels, bits) group (BASELINE cfg4).
-    clips: sequence of bytes-like.  Returns (pcm, results) with pcm = bytes (dst=None), or the byte count written
-    into `dst` (a writable host buffer / torch tensor; a device pointer or CUDA tensor with dst_is_device=True).
+    clips: sequence of bytes-like, or a BatchTable built from one.  Returns (pcm, results) with pcm = bytes (dst=None), or the byte
+    count written into `dst` (a writable host buffer / torch tensor; a device pointer or CUDA tensor with dst_is_device=True).
     packed=True: the clips are ascending views into ONE buffer the caller owns (BNFLAC_OPT_PACKED_INPUT: uploaded in place)."""
-    n = len(clips)
-    spans = (Span * max(1, n))()
-    keep = []
-    for i, c in enumerate(clips):
-        keep.append(c)
-        spans[i].data = _addr(c)
-        spans[i].len = c.numel() * c.element_size() if hasattr(c, "numel") else len(c)
-    res = (ClipResult * max(1, n))()
+    tab = clips if isinstance(clips, BatchTable) else BatchTable(clips)
+    n, spans, res = tab.n, tab.spans, tab.res
     o = _opts(device, flags=OPT_PACKED_INPUT if packed else 0)
     w = C.c_uint64()
     if dst is None:
