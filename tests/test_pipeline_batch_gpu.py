@@ -167,6 +167,47 @@ def test_batch_to_device_buffer():
     assert [(r.pcm_offset, r.pcm_bytes) for r in res] == [(r.pcm_offset, r.pcm_bytes) for r in res2]
 
 
+def test_batch_table_is_reusable():
+    """_abi.BatchTable: the bnflac_span table built once, decoded more than once (what bench.py's cfg4 / by_file legs do)."""
+    from birdnest.audio_b200 import _abi
+    clips = [c.flac for c in _clips()] * 2
+    want_pcm, want_res = _abi.decode_batch(clips)
+    table = _abi.BatchTable(clips)
+    for _ in range(3):
+        pcm, res = _abi.decode_batch(table)
+        assert pcm == want_pcm
+        assert [(r.pcm_offset, r.pcm_bytes, r.status) for r in res] == [(r.pcm_offset, r.pcm_bytes, r.status) for r in want_res]
+
+
+def test_batch_gathered_and_uploaded_in_runs():
+    """Large batches are gathered into staging memory in runs, each uploaded while the next is gathered (engine.cu, BNFLAC_BATCH_RUNS;
+    by default one run per 128 MB).  Forced here on a small batch -- the variable is read once per process, hence the subprocess --
+    with run boundaries falling between clips of different formats and sizes."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r"""
+import sys
+sys.path[:0] = [%r, %r, %r, %r]
+import pyoracle
+from test_pipeline_batch_gpu import _clips
+from birdnest.audio_b200 import _abi
+clips = [c.flac for c in _clips()] * 40
+pcm, res = _abi.decode_batch(clips)
+ok = all(pcm[r.pcm_offset:r.pcm_offset + r.pcm_bytes] == pyoracle.decode(b)[0] and r.status == 0 for b, r in zip(clips[:len(_clips())], res))
+ok = ok and all((res[i].pcm_bytes, res[i].status) == (res[i %% len(_clips())].pcm_bytes, 0) for i in range(len(clips)))
+import hashlib
+print(hashlib.md5(pcm).hexdigest(), "ok" if ok else "FAIL")
+""" % (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "corpus"), os.path.join(ROOT, "tests"))
+    outs = []
+    for runs in ("1", "3", "7"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, BNFLAC_BATCH_RUNS=runs))
+        assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (runs, r.stdout[-500:], r.stderr[-1500:])
+        outs.append(r.stdout.split()[0])
+    assert len(set(outs)) == 1, outs
+
+
 def test_packed_batch_is_uploaded_in_place_and_matches():
     """Clips that lie in ascending order inside ONE host buffer (a shard file read in one piece, tar-like 512-byte headers
     full of sync-code look-alikes between them) take the no-gather path: same PCM, same per-clip results as separate buffers."""
